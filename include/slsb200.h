@@ -1,0 +1,123 @@
+/*
+ * slsb200.h — C ABI of libslsb200: column-wise localized H2 state-feedback SLS synthesis on B200.
+ *
+ * This is the drop-in boundary for ONE hot path of aaltoKEPO/SystemLevelControl.jl: the body of
+ * `_SLS_𝓗₂` (reference src/synthesis.jl:34-72) and the `@distributed` loop around it (:23-27).
+ * The Julia host (`SLS_𝓗₂`, src/synthesis.jl:11-32) keeps its signature and calls these symbols
+ * through `ccall`; the Python mirror in systemlevelcontrol.jl_b200/ binds the
+ * same symbols with ctypes.  No C++ types, no exceptions and no callbacks cross this boundary.
+ *
+ * Layout contract (Julia `SparseMatrixCSC{Tv,Int64}` fields, passed zero-copy):
+ *   colptr : int64[ncol+1], 1-based;  rowval : int64[nnz], 1-based, strictly ascending in a column;
+ *   nzval  : double[nnz] (plant / outputs) or uint8 Bool[nnz] (supports).
+ * Ownership: the caller owns every host buffer; the library copies inputs to the device during
+ * `sls_set_*` and keeps no host pointer after a call returns.  Outputs are sized by `sls_plan`
+ * (two-phase sizing) so the library never allocates memory the caller must free.
+ * Errors: return 0 = ok, <0 = argument/layout/capacity error, >0 = CUDA error code; text via
+ * `sls_last_error`.  Numerical outcomes go to `status[]`, never to the return code.
+ * Threading: a handle is not thread-safe; one handle per host thread / per GPU.
+ */
+#ifndef SLSB200_H
+#define SLSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLS_ABI_VERSION 1
+
+/* per-column status bits written by sls_solve* (improves on the reference, which ignores the
+ * solver's termination status: src/synthesis.jl:62-65) */
+#define SLS_STATUS_OK            0
+#define SLS_STATUS_RESIDUAL      1   /* achievability residual above feas_tol: infeasible or inaccurate */
+#define SLS_STATUS_RANK_SKIPPED  2   /* informational: >=1 redundant constraint row was eliminated      */
+#define SLS_STATUS_NO_IMPULSE    4   /* column j is not in its own s_x (Ĩ is a zero column) => Φ = 0    */
+
+typedef struct sls_handle sls_handle;
+
+typedef struct sls_options {
+    int32_t device;      /* CUDA device ordinal                                                        */
+    int32_t flags;       /* reserved, 0                                                                */
+    double  rank_tol;    /* pivot <= rank_tol * diag(D_k) => constraint row treated as redundant; 0 -> 1e-10 */
+    double  feas_tol;    /* max-abs achievability residual above which SLS_STATUS_RESIDUAL is set; 0 -> 1e-9 */
+} sls_options;
+
+typedef struct sls_timing {      /* device times (CUDA events on the handle's stream) of the last plan+solve */
+    float gather_ms;             /* kernel 1: index sets, masks, counts (+ scans)                       */
+    float solve_ms;              /* kernel 2: batched FP64 equality-constrained LS                      */
+    float scatter_ms;            /* kernel 3: CSC scatter                                               */
+    float h2d_ms, d2h_ms;        /* host<->device copies done inside sls_set_* / sls_solve              */
+    int64_t solve_launches, gather_launches, scatter_launches;
+    int64_t ncols, nnz_out;      /* columns synthesised, total stored entries of Φx+Φu                 */
+    double  alg_flops;           /* sum_cols n^2*sum_t(nx_t+nu_t) + (7/3)*T*n^3            */
+    double  alg_bytes;           /* B_col summed over columns                              */
+} sls_timing;
+
+int         sls_abi_version(void);
+/* number of visible CUDA devices, or <0 when the CUDA runtime/driver is unusable (never a CPU fallback) */
+int         sls_device_count(void);
+
+int         sls_create(const sls_options* opts, sls_handle** out);
+void        sls_destroy(sls_handle* h);
+const char* sls_last_error(const sls_handle* h);   /* h may be NULL: returns the last create() error   */
+
+/* Plant blocks read on the path: A (Nx x Nx) and B2 (Nx x Nu) of a StateFeedback plant built by the
+ * 3-argument constructor `Plant(A,B1,B2)` with B1 = I (GeneralizedPlant.jl:105-110): [C1 D12] = I,
+ * D11 = 0, so the cost is the squared Frobenius norm of the free entries (synthesis.jl:50-52,76-86). */
+int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
+                  const int64_t* A_colptr, const int64_t* A_rowval, const double* A_nzval,
+                  const int64_t* B2_colptr, const int64_t* B2_rowval, const double* B2_nzval);
+
+/* 𝓢ₓ[t] (Nx x Nx) and 𝓢ᵤ[t] (Nu x Nx), t = 1..T: arrays of T pointers.  *_nzval (Bool) may be NULL
+ * (= all true).  Index sets use the stored pattern of 𝓢[T] (reduction.jl:14); masks use nzval
+ * (synthesis.jl:58-59). */
+int sls_set_supports(sls_handle* h, int64_t T,
+                     const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
+                     const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval);
+
+/* Kernel 1 on the column list `cols` (1-based disturbance columns, the reference's 𝓘 keyword with
+ * single-column groups, synthesis.jl:11,15; NULL = 1..Nx).  Writes per-tap stored-entry counts of
+ * Φx[t] / Φu[t] (T each) so the caller can allocate exact-size outputs, and optionally n=|s_x|,
+ * m=|s_u| per listed column. */
+int sls_plan(sls_handle* h, const int64_t* cols, int64_t ncols,
+             int64_t* nnz_x, int64_t* nnz_u, int32_t* n_out, int32_t* m_out);
+
+/* sparsity_dim_reduction (reduction.jl:11-27) for one column group cj (1-based, q >= 1):
+ * s_x, s_u in the reference's first-occurrence order (1-based), ii_x Bool per s_x entry.
+ * Ĩ is I(|s_x|)[:, ii_x] (reduction.jl:23) and is implied by ii_x. */
+int sls_reduce(sls_handle* h, const int64_t* cj, int64_t q,
+               int64_t* sx_out, int64_t sx_cap, int64_t* n_sx,
+               int64_t* su_out, int64_t su_cap, int64_t* n_su,
+               uint8_t* iix_out);
+
+/* After sls_plan: the local sub-plant blocks of listed column `k` (0-based position in the plan's
+ * list): dense column-major A~ = A[s_x,s_x] (n x n), B2~ = B2[s_x,s_u] (n x m), and the free-variable
+ * masks Mx (T x n), Mu (T x m) row-major Bool.  Test/inspection entry point for kernel 1. */
+int sls_local_problem(sls_handle* h, int64_t k, double* At, double* B2t, uint8_t* Mx, uint8_t* Mu);
+
+/* Kernels 2+3 on the planned columns.  Outputs: T CSC matrices Φx[t] (Nx x Nx) and Φu[t] (Nu x Nx);
+ * colptr arrays have Nx+1 entries (columns outside the plan are empty), rowval/nzval have the sizes
+ * returned by sls_plan.  status (ncols, may be NULL) and resid (ncols max-abs achievability
+ * residual, may be NULL) are per planned column.  Stored pattern = full in-mask pattern (explicit
+ * zeros kept; the reference's `+=` at synthesis.jl:67 would drop exact 0.0). */
+int sls_solve(sls_handle* h,
+              int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
+              int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
+              int32_t* status, double* resid);
+
+/* Device-resident variants: run kernels 1-3 without any host<->device payload copy (inputs must
+ * already be set).  sls_solve_device leaves Φ in handle-owned device buffers; sls_device_output
+ * returns their device addresses (for NCCL all-gather / the FIR simulation / torch wrapping). */
+int sls_solve_device(sls_handle* h);
+int sls_device_output(sls_handle* h, int64_t t, int which /*0=Φx,1=Φu*/,
+                      const int64_t** d_colptr, const int64_t** d_rowval, const double** d_nzval, int64_t* nnz);
+int sls_device_status(sls_handle* h, const int32_t** d_status, const double** d_resid);
+
+int sls_get_timing(const sls_handle* h, sls_timing* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLSB200_H */

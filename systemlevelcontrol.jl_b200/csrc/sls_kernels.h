@@ -1,0 +1,50 @@
+// sls_kernels.h — host-side launchers of the three kernels (implemented in the .cu files).
+#pragma once
+#include "sls_common.h"
+
+// ---- kernel 1 (sls_gather.cu) ----
+int sls_launch_gather_count(const SlsCsc& A, const SlsSupports& Sx, const SlsSupports& Su, int T, int64_t Nx,
+                            const int32_t* cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
+                            sls_stream_t stream);
+int sls_launch_gather_fill(const SlsCsc& A, const SlsCsc& B2, const SlsSupports& Sx, const SlsSupports& Su,
+                           const SlsPlanView& P, int cap, sls_stream_t stream);
+int sls_launch_scan(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, sls_stream_t stream);
+int sls_launch_local_dense(const SlsCsc& A, const SlsCsc& B2, const SlsPlanView& P, int c,
+                           double* At, double* B2t, uint8_t* Mx, uint8_t* Mu, sls_stream_t stream);
+
+// ---- kernel 2 (sls_solve.cu) ----
+struct SlsSolveArgs {
+    SlsCsc A, B2;            // CSC (column access)
+    SlsCsc Ar, B2r;          // CSC of the transposes == CSR of A, B2 (row access)
+    SlsPlanView P;
+    const int32_t* list;     // planned-column indices of this size class
+    int count;
+    int mcap, nnzcap;        // class maxima of m and of the local nnz (shared-memory carve-up)
+    double* xw;              // packed per-column results, column c at xw[P.tot[c]]
+    double* hist;            // factor history, one slot per resident warp
+    int64_t hist_stride;     // doubles per slot
+    int32_t* status;         // per planned column
+    double* resid;           // per planned column: max-abs achievability residual
+    double rank_tol, feas_tol;
+};
+// size classes (template instantiations) available for the local state dimension n
+int sls_solve_class_of(int n);                 // smallest instantiated N >= n, or -1
+int sls_solve_class_count();
+int sls_solve_class_N(int k);
+// shared memory (bytes per warp) and history doubles per warp for class N
+size_t sls_solve_smem_per_warp(int N, int mcap, int nnzcap, int T, int wu);
+int64_t sls_solve_hist_doubles(int N, int T);
+// launches one class; *slots_io: in = available history slots (warps), out = warps launched
+int sls_launch_solve(int N, const SlsSolveArgs& a, int sm_count, int max_smem, int* warps_launched,
+                     sls_stream_t stream);
+int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem);
+
+// ---- kernel 3 (sls_scatter.cu) ----
+struct SlsScatterArgs {
+    SlsPlanView P;
+    const double* xw;
+    // destination arrays: per tap tt in [0,2T): base pointers (device arrays of pointers)
+    int64_t* const* rowval;  // [2T] -> int64 rowval buffers (1-based out)
+    double* const* nzval;    // [2T]
+};
+int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream);
