@@ -117,6 +117,11 @@ int sls_device_status(sls_handle* h, const int32_t** d_status, const double** d_
 
 int sls_get_timing(const sls_handle* h, sls_timing* out);
 
+/* Calibration for the roofline of kernel 2: measured FP64 throughput of this device in TFLOP/s — a
+ * register-resident DFMA chain (vector pipe) and a DMMA m8n8k4 chain (FP64 tensor path).  Not used by
+ * any synthesis call. */
+int sls_fp64_peak(int device, int iters, double* dfma_tflops, double* dmma_tflops);
+
 #ifdef __cplusplus
 }
 #endif

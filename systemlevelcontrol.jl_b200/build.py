@@ -1,0 +1,73 @@
+"""In-tree build of libslsb200.so (the C-ABI CUDA library, include/slsb200.h) for sm_100a.
+
+    python systemlevelcontrol.jl_b200/build.py            # incremental
+    python systemlevelcontrol.jl_b200/build.py --force
+
+nvcc cross-compiles without a GPU.  The library links the CUDA runtime statically, so it depends on
+nothing but libcuda at run time (no torch, no Python)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libslsb200.so")
+SOURCES = ["sls_api.cu", "sls_gather.cu", "sls_solve.cu", "sls_scatter.cu", "sls_sim.cu", "sls_peak.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libslsb200 cannot be built (there is no CPU fallback)")
+
+
+def _sources():
+    return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    nvcc = _nvcc()
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
+    headers.append(os.path.join(HERE, "..", "include", "slsb200.h"))
+    objs = []
+    logs = []
+    for src in _sources():
+        s = os.path.join(CSRC, src)
+        o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            cmd = [nvcc, *ARCH, *FLAGS, "-c", s, "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            logs.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    if force or _stale(LIB, objs):
+        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    if logs:
+        with open(os.path.join(LIBDIR, "build.log"), "w") as f:
+            f.write("\n".join(logs))
+        if verbose:
+            print("\n".join(logs))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

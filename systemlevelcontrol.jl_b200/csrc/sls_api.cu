@@ -1,0 +1,607 @@
+// sls_api.cu — host side of the C ABI declared in include/slsb200.h.
+//
+// Owns the device copies of the plant (A, B2 and their transposes), of the supports 𝓢ₓ[t], 𝓢ᵤ[t], and the
+// per-plan metadata; sequences kernel 1 (sls_gather.cu), kernel 2 (sls_solve.cu) and kernel 3
+// (sls_scatter.cu) on one stream and times them with CUDA events.  It replaces the per-chunk worker
+// `_SLS_𝓗₂` of the reference (src/synthesis.jl:34-72); the Julia-side `SLS_𝓗₂` (src/synthesis.jl:11-32)
+// keeps its signature and calls these entry points.
+// There is no CPU path here: without a usable CUDA device every entry point fails with an error.
+#include "../../include/slsb200.h"
+#include "sls_kernels.h"
+#include <vector>
+#include <string>
+#include <algorithm>
+#include <new>
+#include <cmath>
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n) {
+        if (n <= bytes && p) return 0;
+        rt::dfree(p); p = nullptr; bytes = 0;
+        int e = rt::alloc(&p, n);
+        if (!e) bytes = n ? n : 1;
+        return e;
+    }
+    void release() { rt::dfree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct DevCsc {                 // device copy of one Julia SparseMatrixCSC{Float64,Int64}
+    DevBuf colptr, rowval, nzval;
+    int64_t ncol = 0, nnz = 0;
+    SlsCsc view() const { return SlsCsc{colptr.as<int64_t>(), rowval.as<int64_t>(), nzval.as<double>()}; }
+    void release() { colptr.release(); rowval.release(); nzval.release(); }
+};
+
+struct DevSupports {            // T Bool CSC matrices, taps concatenated
+    DevBuf colptr, rowval, nzval, tap_off;
+    bool has_nzval = false;
+    int64_t nnz = 0;
+    int maxlen_last = 0;        // longest column of the last tap (bounds kernel 1's candidate list)
+    SlsSupports view() const {
+        return SlsSupports{colptr.as<int64_t>(), rowval.as<int64_t>(), has_nzval ? nzval.as<uint8_t>() : nullptr,
+                           tap_off.as<int64_t>()};
+    }
+    void release() { colptr.release(); rowval.release(); nzval.release(); tap_off.release(); }
+};
+
+struct SolveClass { int N, count, mcap, nnzcap; size_t list_off; };
+
+struct Plan {
+    bool valid = false;
+    int ncols = 0, nstride = 1, mstride = 1, wx = 1, wu = 1, nmax = 0, mmax = 0, cap = 32;
+    DevBuf cols, n, m, sx, su, maskx, masku, jloc, lnnz, lnnzA, lnnzB, pre, tot, colptr, lists;
+    std::vector<int32_t> h_cols, h_n, h_m, h_lnnz;
+    std::vector<int64_t> nnz_tap;       // 2T stored-entry counts (Φx taps then Φu taps)
+    std::vector<int64_t> out_off;       // 2T+1 offsets of each tap inside the output buffers
+    std::vector<SolveClass> classes;
+    int64_t tot_packed = 0;
+    double alg_flops = 0, alg_bytes = 0;
+    void release() {
+        DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists};
+        for (DevBuf* b : all) b->release();
+        valid = false;
+    }
+};
+
+}  // namespace
+
+struct sls_handle {
+    sls_options opt{};
+    int device = 0, sm_count = 0, max_smem = 0;
+    sls_stream_t stream{};
+    std::string err;
+    int64_t Nx = 0, Nu = 0, T = 0;
+    bool have_plant = false, have_supports = false, solved = false;
+    DevCsc A, B2, Ar, B2r;
+    int maxcolA = 0;
+    DevSupports Sx, Su;
+    Plan plan;
+    DevBuf xw, hist, status, resid, out_rowval, out_nzval, out_ptrs;
+    rt::Event ev[8];
+    sls_timing tm{};
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(sls_handle* h, int code, const char* what) {
+    std::string msg = std::string(what);
+    if (code > 0) { msg += ": "; msg += rt::err_str(code); }
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+#define SLS_CK(expr) do { int e_ = (expr); if (e_) return fail(h, e_, #expr); } while (0)
+#define SLS_ARG(cond, msg) do { if (!(cond)) return fail(h, -1, msg); } while (0)
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int sls_abi_version(void) { return SLS_ABI_VERSION; }
+extern "C" int sls_device_count(void) { return rt::device_count(); }
+
+extern "C" const char* sls_last_error(const sls_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int sls_create(const sls_options* opts, sls_handle** out) {
+    sls_handle* h = nullptr;
+    if (!out) return fail(nullptr, -1, "sls_create: out is NULL");
+    *out = nullptr;
+    const int ndev = rt::device_count();
+    if (ndev <= 0) return fail(nullptr, ndev < 0 ? -ndev : 100, "sls_create: no usable CUDA device (this library has no CPU path)");
+    h = new (std::nothrow) sls_handle();
+    if (!h) return fail(nullptr, -2, "sls_create: out of host memory");
+    if (opts) h->opt = *opts;
+    if (h->opt.rank_tol <= 0) h->opt.rank_tol = 1e-10;
+    if (h->opt.feas_tol <= 0) h->opt.feas_tol = 1e-9;
+    h->device = h->opt.device;
+    if (h->device < 0 || h->device >= ndev) { delete h; return fail(nullptr, -1, "sls_create: device ordinal out of range"); }
+    int e = rt::set_device(h->device);
+    if (!e) e = rt::stream_create(&h->stream);
+    for (int i = 0; i < 8 && !e; i++) e = h->ev[i].create();
+    if (e) { delete h; return fail(nullptr, e, "sls_create: CUDA initialisation failed"); }
+    h->sm_count = rt::sm_count(h->device);
+    h->max_smem = rt::max_smem_optin(h->device);
+    *out = h;
+    return 0;
+}
+
+extern "C" void sls_destroy(sls_handle* h) {
+    if (!h) return;
+    rt::set_device(h->device);
+    rt::sync(h->stream);
+    h->A.release(); h->B2.release(); h->Ar.release(); h->B2r.release();
+    h->Sx.release(); h->Su.release(); h->plan.release();
+    DevBuf* all[] = {&h->xw, &h->hist, &h->status, &h->resid, &h->out_rowval, &h->out_nzval, &h->out_ptrs};
+    for (DevBuf* b : all) b->release();
+    for (int i = 0; i < 8; i++) h->ev[i].destroy();
+    rt::stream_destroy(h->stream);
+    delete h;
+}
+
+// ---- plant ----------------------------------------------------------------------------------
+static const char* check_csc(int64_t nrow, int64_t ncol, const int64_t* cp, const int64_t* rv, bool rows) {
+    if (!cp) return "colptr is NULL";
+    if (cp[0] != 1) return "colptr[1] must be 1 (Julia 1-based CSC)";
+    for (int64_t c = 0; c < ncol; c++) if (cp[c + 1] < cp[c]) return "colptr is not monotone";
+    const int64_t nnz = cp[ncol] - 1;
+    if (nnz > 0 && !rv) return "rowval is NULL";
+    if (rows) {
+        for (int64_t c = 0; c < ncol; c++) {
+            int64_t prev = 0;
+            for (int64_t e = cp[c] - 1; e < cp[c + 1] - 1; e++) {
+                if (rv[e] < 1 || rv[e] > nrow) return "rowval out of range";
+                if (rv[e] <= prev) return "rowval not strictly ascending inside a column";
+                prev = rv[e];
+            }
+        }
+    }
+    return nullptr;
+}
+
+// CSC of the transpose (== CSR of M), 1-based like the input
+static void transpose_csc(int64_t nrow, int64_t ncol, const int64_t* cp, const int64_t* rv, const double* nz,
+                          std::vector<int64_t>& tcp, std::vector<int64_t>& trv, std::vector<double>& tnz) {
+    const int64_t nnz = cp[ncol] - 1;
+    tcp.assign(nrow + 1, 0); trv.resize(nnz); tnz.resize(nnz);
+    std::vector<int64_t> cnt(nrow, 0);
+    for (int64_t e = 0; e < nnz; e++) cnt[rv[e] - 1]++;
+    tcp[0] = 1;
+    for (int64_t r = 0; r < nrow; r++) tcp[r + 1] = tcp[r] + cnt[r];
+    std::vector<int64_t> fill(tcp.begin(), tcp.end() - 1);
+    for (int64_t c = 0; c < ncol; c++)
+        for (int64_t e = cp[c] - 1; e < cp[c + 1] - 1; e++) {
+            const int64_t dst = fill[rv[e] - 1]++ - 1;
+            trv[dst] = c + 1; tnz[dst] = nz[e];
+        }
+}
+
+static int upload_csc(sls_handle* h, DevCsc& d, int64_t ncol, const int64_t* cp, const int64_t* rv, const double* nz) {
+    const int64_t nnz = cp[ncol] - 1;
+    d.ncol = ncol; d.nnz = nnz;
+    SLS_CK(d.colptr.ensure((ncol + 1) * sizeof(int64_t)));
+    SLS_CK(d.rowval.ensure(std::max<int64_t>(nnz, 1) * sizeof(int64_t)));
+    SLS_CK(d.nzval.ensure(std::max<int64_t>(nnz, 1) * sizeof(double)));
+    SLS_CK(rt::h2d(d.colptr.p, cp, (ncol + 1) * sizeof(int64_t), h->stream));
+    SLS_CK(rt::h2d(d.rowval.p, rv, nnz * sizeof(int64_t), h->stream));
+    SLS_CK(rt::h2d(d.nzval.p, nz, nnz * sizeof(double), h->stream));
+    return 0;
+}
+
+extern "C" int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
+                             const int64_t* A_colptr, const int64_t* A_rowval, const double* A_nzval,
+                             const int64_t* B2_colptr, const int64_t* B2_rowval, const double* B2_nzval) {
+    if (!h) return -1;
+    SLS_ARG(Nx >= 1 && Nu >= 0 && Nx < (int64_t)1 << 31 && Nu < (int64_t)1 << 31, "sls_set_plant: bad dimensions");
+    SLS_CK(rt::set_device(h->device));
+    const char* m = check_csc(Nx, Nx, A_colptr, A_rowval, true);
+    if (m) return fail(h, -2, (std::string("sls_set_plant: A: ") + m).c_str());
+    m = check_csc(Nx, Nu, B2_colptr, B2_rowval, true);
+    if (m) return fail(h, -2, (std::string("sls_set_plant: B2: ") + m).c_str());
+    SLS_ARG(A_nzval || A_colptr[Nx] == 1, "sls_set_plant: A nzval is NULL");
+    SLS_ARG(B2_nzval || B2_colptr[Nu] == 1, "sls_set_plant: B2 nzval is NULL");
+    h->ev[0].record(h->stream);
+    SLS_CK(upload_csc(h, h->A, Nx, A_colptr, A_rowval, A_nzval));
+    SLS_CK(upload_csc(h, h->B2, Nu, B2_colptr, B2_rowval, B2_nzval));
+    std::vector<int64_t> tcp, trv; std::vector<double> tnz;
+    transpose_csc(Nx, Nx, A_colptr, A_rowval, A_nzval, tcp, trv, tnz);
+    SLS_CK(upload_csc(h, h->Ar, Nx, tcp.data(), trv.data(), tnz.data()));
+    SLS_CK(rt::sync(h->stream));                              // tcp/trv/tnz are reused below
+    transpose_csc(Nx, Nu, B2_colptr, B2_rowval, B2_nzval, tcp, trv, tnz);
+    SLS_CK(upload_csc(h, h->B2r, Nx, tcp.data(), trv.data(), tnz.data()));
+    h->ev[1].record(h->stream);
+    SLS_CK(rt::sync(h->stream));
+    h->tm.h2d_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);
+    int mc = 0;
+    for (int64_t c = 0; c < Nx; c++) mc = std::max<int>(mc, (int)(A_colptr[c + 1] - A_colptr[c]));
+    h->maxcolA = mc;
+    if (h->have_supports && (h->Nx != Nx || h->Nu != Nu)) { h->have_supports = false; }
+    h->Nx = Nx; h->Nu = Nu; h->have_plant = true; h->plan.valid = false; h->solved = false;
+    return 0;
+}
+
+// ---- supports -------------------------------------------------------------------------------
+static int upload_supports(sls_handle* h, DevSupports& d, int64_t T, int64_t nrow, int64_t ncol,
+                           const int64_t* const* cps, const int64_t* const* rvs, const uint8_t* const* nzs,
+                           const char* name) {
+    std::vector<int64_t> off(T + 1, 0);
+    bool any_nz = false, all_nz = true;
+    for (int64_t t = 0; t < T; t++) {
+        const char* m = check_csc(nrow, ncol, cps[t], rvs ? rvs[t] : nullptr, (h->opt.flags & 1) != 0);
+        if (m) return fail(h, -2, (std::string("sls_set_supports: ") + name + ": " + m).c_str());
+        off[t + 1] = off[t] + cps[t][ncol] - 1;
+        if (nzs && nzs[t]) any_nz = true; else all_nz = false;
+    }
+    if (any_nz && !all_nz) return fail(h, -2, "sls_set_supports: nzval must be given for every tap or for none");
+    d.nnz = off[T]; d.has_nzval = any_nz;
+    int ml = 0;
+    for (int64_t c = 0; c < ncol; c++) ml = std::max<int>(ml, (int)(cps[T - 1][c + 1] - cps[T - 1][c]));
+    d.maxlen_last = ml;
+    SLS_CK(d.colptr.ensure(T * (ncol + 1) * sizeof(int64_t)));
+    SLS_CK(d.rowval.ensure(std::max<int64_t>(d.nnz, 1) * sizeof(int64_t)));
+    SLS_CK(d.tap_off.ensure((T + 1) * sizeof(int64_t)));
+    if (any_nz) SLS_CK(d.nzval.ensure(std::max<int64_t>(d.nnz, 1)));
+    for (int64_t t = 0; t < T; t++) {
+        const int64_t nnz = off[t + 1] - off[t];
+        SLS_CK(rt::h2d(d.colptr.as<int64_t>() + t * (ncol + 1), cps[t], (ncol + 1) * sizeof(int64_t), h->stream));
+        SLS_CK(rt::h2d(d.rowval.as<int64_t>() + off[t], rvs[t], nnz * sizeof(int64_t), h->stream));
+        if (any_nz) SLS_CK(rt::h2d(d.nzval.as<uint8_t>() + off[t], nzs[t], nnz, h->stream));
+    }
+    SLS_CK(rt::h2d(d.tap_off.p, off.data(), (T + 1) * sizeof(int64_t), h->stream));
+    SLS_CK(rt::sync(h->stream));                              // `off` is a local
+    return 0;
+}
+
+extern "C" int sls_set_supports(sls_handle* h, int64_t T,
+                                const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
+                                const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval) {
+    if (!h) return -1;
+    SLS_ARG(h->have_plant, "sls_set_supports: call sls_set_plant first");
+    SLS_ARG(T >= 1 && T < 4096, "sls_set_supports: bad T");
+    SLS_ARG(Sx_colptr && Sx_rowval && Su_colptr && Su_rowval, "sls_set_supports: NULL array of pointers");
+    SLS_CK(rt::set_device(h->device));
+    h->have_supports = false; h->plan.valid = false; h->solved = false;
+    h->ev[0].record(h->stream);
+    int e = upload_supports(h, h->Sx, T, h->Nx, h->Nx, Sx_colptr, Sx_rowval, Sx_nzval, "Sx");
+    if (e) return e;
+    e = upload_supports(h, h->Su, T, h->Nu, h->Nx, Su_colptr, Su_rowval, Su_nzval, "Su");
+    if (e) return e;
+    h->ev[1].record(h->stream);
+    SLS_CK(rt::sync(h->stream));
+    h->tm.h2d_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);
+    h->T = T; h->have_supports = true;
+    return 0;
+}
+
+// ---- plan (kernel 1) ------------------------------------------------------------------------
+static SlsPlanView plan_view(const sls_handle* h, const Plan& p) {
+    SlsPlanView v{};
+    v.Nx = h->Nx; v.Nu = h->Nu; v.T = (int32_t)h->T; v.ncols = p.ncols;
+    v.nstride = p.nstride; v.mstride = p.mstride; v.wx = p.wx; v.wu = p.wu;
+    v.cols = p.cols.as<int32_t>(); v.n = p.n.as<int32_t>(); v.m = p.m.as<int32_t>();
+    v.sx = p.sx.as<int32_t>(); v.su = p.su.as<int32_t>();
+    v.maskx = p.maskx.as<uint32_t>(); v.masku = p.masku.as<uint32_t>();
+    v.jloc = p.jloc.as<int32_t>(); v.lnnz = p.lnnz.as<int32_t>(); v.lnnzA = p.lnnzA.as<int32_t>();
+    v.lnnzB = p.lnnzB.as<int32_t>(); v.pre = p.pre.as<uint32_t>(); v.tot = p.tot.as<int64_t>();
+    v.colptr = p.colptr.as<int64_t>();
+    return v;
+}
+
+static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols, bool unique_cols) {
+    const int64_t Nx = h->Nx, T = h->T;
+    p.valid = false;
+    SLS_ARG(h->have_plant && h->have_supports, "plan: plant and supports must be set first");
+    SLS_ARG(ncols >= 0 && ncols < (int64_t)1 << 31, "plan: bad ncols");
+    if (!cols) ncols = Nx;
+    p.ncols = (int)ncols;
+    p.h_cols.resize(ncols);
+    if (!cols) { for (int64_t i = 0; i < ncols; i++) p.h_cols[i] = (int32_t)i; }
+    else {
+        std::vector<uint8_t> seen(unique_cols ? Nx : 0, 0);
+        for (int64_t i = 0; i < ncols; i++) {
+            const int64_t j = cols[i] - 1;
+            if (j < 0 || j >= Nx) return fail(h, -3, "plan: column index out of range (1-based, 1..Nx)");
+            if (unique_cols) { if (seen[j]) return fail(h, -3, "plan: duplicate column"); seen[j] = 1; }
+            p.h_cols[i] = (int32_t)j;
+        }
+    }
+    // candidate-list capacity of kernel 1 (power of two, >= 32)
+    int64_t cand = (int64_t)h->maxcolA * std::max(h->Sx.maxlen_last, h->Su.maxlen_last);
+    int cap = 32; while (cap < cand) cap <<= 1;
+    p.cap = cap;
+    const int nc1 = std::max(p.ncols, 1);
+    SLS_CK(p.cols.ensure(nc1 * sizeof(int32_t)));
+    SLS_CK(p.n.ensure(nc1 * sizeof(int32_t)));
+    SLS_CK(p.m.ensure(nc1 * sizeof(int32_t)));
+    SLS_CK(rt::h2d(p.cols.p, p.h_cols.data(), (size_t)p.ncols * sizeof(int32_t), h->stream));
+    if ((size_t)cap * 4 * sizeof(int32_t) + 4096 > (size_t)h->max_smem)
+        return fail(h, -4, "plan: candidate index list of a column does not fit shared memory");
+    SLS_CK(sls_launch_gather_count(h->A.view(), h->Sx.view(), h->Su.view(), (int)T, Nx, p.cols.as<int32_t>(), p.ncols,
+                                   p.n.as<int32_t>(), p.m.as<int32_t>(), cap, h->stream));
+    p.h_n.assign(nc1, 0); p.h_m.assign(nc1, 0);
+    SLS_CK(rt::d2h(p.h_n.data(), p.n.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(rt::d2h(p.h_m.data(), p.m.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(rt::sync(h->stream));
+    int nmax = 0, mmax = 0;
+    for (int i = 0; i < p.ncols; i++) {
+        if (p.h_n[i] < 0 || p.h_m[i] < 0) return fail(h, -4, "plan: candidate index list overflow in kernel 1");
+        nmax = std::max(nmax, p.h_n[i]); mmax = std::max(mmax, p.h_m[i]);
+    }
+    p.nmax = nmax; p.mmax = mmax;
+    p.nstride = std::max(nmax, 1); p.mstride = std::max(mmax, 1);
+    p.wx = (p.nstride + 31) / 32; p.wu = (p.mstride + 31) / 32;
+    SLS_CK(p.sx.ensure((size_t)nc1 * p.nstride * sizeof(int32_t)));
+    SLS_CK(p.su.ensure((size_t)nc1 * p.mstride * sizeof(int32_t)));
+    SLS_CK(p.maskx.ensure((size_t)nc1 * T * p.wx * sizeof(uint32_t)));
+    SLS_CK(p.masku.ensure((size_t)nc1 * T * p.wu * sizeof(uint32_t)));
+    SLS_CK(p.jloc.ensure(nc1 * sizeof(int32_t)));
+    SLS_CK(p.lnnz.ensure(nc1 * sizeof(int32_t)));
+    SLS_CK(p.lnnzA.ensure(nc1 * sizeof(int32_t)));
+    SLS_CK(p.lnnzB.ensure(nc1 * sizeof(int32_t)));
+    SLS_CK(p.pre.ensure((size_t)nc1 * 2 * T * sizeof(uint32_t)));
+    SLS_CK(p.tot.ensure((size_t)(p.ncols + 1) * sizeof(int64_t)));
+    SLS_CK(p.colptr.ensure((size_t)2 * T * (Nx + 1) * sizeof(int64_t)));
+    SLS_CK(rt::zero(p.colptr.p, (size_t)2 * T * (Nx + 1) * sizeof(int64_t), h->stream));
+    SLS_CK(rt::zero(p.tot.p, (size_t)(p.ncols + 1) * sizeof(int64_t), h->stream));
+    const SlsPlanView v = plan_view(h, p);
+    const size_t fill_smem = (size_t)4 * (cap + p.nstride + p.mstride + p.wx + p.wu) * sizeof(int32_t);
+    if (fill_smem > (size_t)h->max_smem) return fail(h, -4, "plan: index sets do not fit shared memory");
+    SLS_CK(sls_launch_gather_fill(h->A.view(), h->B2.view(), h->Sx.view(), h->Su.view(), v, cap, h->stream));
+    SLS_CK(sls_launch_scan(v.colptr, Nx + 1, (int)(2 * T), v.tot, p.ncols + 1, h->stream));
+    // sizes back to the host
+    p.h_lnnz.assign(nc1, 0);
+    std::vector<int32_t> lA(nc1, 0), lB(nc1, 0);
+    std::vector<int64_t> tot(p.ncols + 1, 0);
+    p.nnz_tap.assign(2 * T, 0);
+    SLS_CK(rt::d2h(p.h_lnnz.data(), p.lnnz.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(rt::d2h(lA.data(), p.lnnzA.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(rt::d2h(lB.data(), p.lnnzB.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(rt::d2h(tot.data(), p.tot.p, (size_t)(p.ncols + 1) * sizeof(int64_t), h->stream));
+    for (int64_t tt = 0; tt < 2 * T; tt++)
+        SLS_CK(rt::d2h(&p.nnz_tap[tt], v.colptr + tt * (Nx + 1) + Nx, sizeof(int64_t), h->stream));
+    SLS_CK(rt::sync(h->stream));
+    p.out_off.assign(2 * T + 1, 0);
+    for (int64_t tt = 0; tt < 2 * T; tt++) { p.nnz_tap[tt] -= 1; p.out_off[tt + 1] = p.out_off[tt] + p.nnz_tap[tt]; }
+    p.tot_packed = tot[p.ncols];
+    if (p.tot_packed != p.out_off[2 * T]) return fail(h, -5, "plan: internal count mismatch");
+    // SURVEY §8d algorithmic work, and the size classes of kernel 2
+    p.alg_flops = 0; p.alg_bytes = 0;
+    for (int i = 0; i < p.ncols; i++) {
+        const double n = p.h_n[i], m = p.h_m[i], v_ = (double)(tot[i + 1] - tot[i]);
+        p.alg_flops += n * n * v_ + (7.0 / 3.0) * (double)T * n * n * n;
+        p.alg_bytes += v_ * 25.0 + 2.0 * T * 24.0 + 16.0 * ((double)lA[i] + n + (double)lB[i] + m);
+    }
+    p.classes.clear();
+    std::vector<int32_t> lists(nc1);
+    size_t off = 0;
+    for (int k = 0; k < sls_solve_class_count(); k++) {
+        const int N = sls_solve_class_N(k);
+        SolveClass c{N, 0, 0, 0, off};
+        for (int i = 0; i < p.ncols; i++) {
+            if (sls_solve_class_of(p.h_n[i]) != N) continue;
+            lists[off + c.count++] = i;
+            c.mcap = std::max(c.mcap, p.h_m[i]); c.nnzcap = std::max(c.nnzcap, p.h_lnnz[i]);
+        }
+        if (c.count) { p.classes.push_back(c); off += c.count; }
+    }
+    SLS_CK(p.lists.ensure(nc1 * sizeof(int32_t)));
+    SLS_CK(rt::h2d(p.lists.p, lists.data(), off * sizeof(int32_t), h->stream));
+    SLS_CK(rt::sync(h->stream));
+    p.valid = true;
+    return 0;
+}
+
+extern "C" int sls_plan(sls_handle* h, const int64_t* cols, int64_t ncols,
+                        int64_t* nnz_x, int64_t* nnz_u, int32_t* n_out, int32_t* m_out) {
+    if (!h) return -1;
+    SLS_CK(rt::set_device(h->device));
+    h->solved = false;
+    h->ev[2].record(h->stream);
+    int e = build_plan(h, h->plan, cols, ncols, true);
+    if (e) return e;
+    h->ev[3].record(h->stream);
+    SLS_CK(rt::sync(h->stream));
+    h->tm.gather_ms = rt::elapsed_ms(h->ev[2], h->ev[3]);
+    h->tm.gather_launches = 3;
+    h->tm.ncols = h->plan.ncols; h->tm.nnz_out = h->plan.tot_packed;
+    h->tm.alg_flops = h->plan.alg_flops; h->tm.alg_bytes = h->plan.alg_bytes;
+    const int64_t T = h->T;
+    for (int64_t t = 0; t < T; t++) {
+        if (nnz_x) nnz_x[t] = h->plan.nnz_tap[t];
+        if (nnz_u) nnz_u[t] = h->plan.nnz_tap[T + t];
+    }
+    for (int i = 0; i < h->plan.ncols; i++) {
+        if (n_out) n_out[i] = h->plan.h_n[i];
+        if (m_out) m_out[i] = h->plan.h_m[i];
+    }
+    return 0;
+}
+
+extern "C" int sls_reduce(sls_handle* h, const int64_t* cj, int64_t q,
+                          int64_t* sx_out, int64_t sx_cap, int64_t* n_sx,
+                          int64_t* su_out, int64_t su_cap, int64_t* n_su, uint8_t* iix_out) {
+    if (!h) return -1;
+    SLS_ARG(cj && q >= 1, "sls_reduce: empty column group");
+    SLS_ARG(n_sx && n_su, "sls_reduce: n_sx / n_su is NULL");
+    SLS_CK(rt::set_device(h->device));
+    Plan p;
+    int e = build_plan(h, p, cj, q, false);
+    if (e) { p.release(); return e; }
+    std::vector<int32_t> sx((size_t)p.ncols * p.nstride), su((size_t)p.ncols * p.mstride);
+    e = rt::d2h(sx.data(), p.sx.p, sx.size() * sizeof(int32_t), h->stream);
+    if (!e) e = rt::d2h(su.data(), p.su.p, su.size() * sizeof(int32_t), h->stream);
+    if (!e) e = rt::sync(h->stream);
+    if (e) { p.release(); return fail(h, e, "sls_reduce: device to host copy"); }
+    // unique(findnz(M[:,cj])[1]): CSC order = cj order, rows ascending inside a column, first occurrences
+    // kept (reduction.jl:14).  Kernel 1 returns each column's rows ascending, so this is a stable merge.
+    auto merge = [&](const std::vector<int32_t>& s, const std::vector<int32_t>& len, int stride, int64_t nrows,
+                     std::vector<int64_t>& out) {
+        std::vector<uint8_t> seen(nrows, 0);
+        for (int c = 0; c < p.ncols; c++)
+            for (int i = 0; i < len[c]; i++) {
+                const int32_t r = s[(size_t)c * stride + i];
+                if (!seen[r]) { seen[r] = 1; out.push_back((int64_t)r + 1); }
+            }
+    };
+    std::vector<int64_t> gx, gu;
+    merge(sx, p.h_n, p.nstride, h->Nx, gx);
+    merge(su, p.h_m, p.mstride, h->Nu, gu);
+    p.release();
+    *n_sx = (int64_t)gx.size(); *n_su = (int64_t)gu.size();
+    if ((sx_out && (int64_t)gx.size() > sx_cap) || (su_out && (int64_t)gu.size() > su_cap))
+        return fail(h, -4, "sls_reduce: output capacity too small (sizes returned in n_sx / n_su)");
+    if (sx_out) std::copy(gx.begin(), gx.end(), sx_out);
+    if (su_out) std::copy(gu.begin(), gu.end(), su_out);
+    if (iix_out) {                                            // indexin(sₓ, cⱼ) .≠ nothing  (reduction.jl:22)
+        std::vector<uint8_t> incj(h->Nx, 0);
+        for (int64_t i = 0; i < q; i++) incj[cj[i] - 1] = 1;
+        for (size_t i = 0; i < gx.size(); i++) iix_out[i] = incj[gx[i] - 1];
+    }
+    return 0;
+}
+
+extern "C" int sls_local_problem(sls_handle* h, int64_t k, double* At, double* B2t, uint8_t* Mx, uint8_t* Mu) {
+    if (!h) return -1;
+    SLS_ARG(h->plan.valid, "sls_local_problem: no plan");
+    SLS_ARG(k >= 0 && k < h->plan.ncols, "sls_local_problem: column position out of range");
+    SLS_CK(rt::set_device(h->device));
+    const int n = h->plan.h_n[k], m = h->plan.h_m[k];
+    const int64_t T = h->T;
+    DevBuf dA, dB, dMx, dMu;
+    int e = dA.ensure((size_t)std::max(n * n, 1) * 8);
+    if (!e) e = dB.ensure((size_t)std::max(n * m, 1) * 8);
+    if (!e) e = dMx.ensure((size_t)std::max<int64_t>(T * n, 1));
+    if (!e) e = dMu.ensure((size_t)std::max<int64_t>(T * m, 1));
+    if (!e) e = sls_launch_local_dense(h->A.view(), h->B2.view(), plan_view(h, h->plan), (int)k, dA.as<double>(),
+                                       dB.as<double>(), dMx.as<uint8_t>(), dMu.as<uint8_t>(), h->stream);
+    if (!e && At) e = rt::d2h(At, dA.p, (size_t)n * n * 8, h->stream);
+    if (!e && B2t) e = rt::d2h(B2t, dB.p, (size_t)n * m * 8, h->stream);
+    if (!e && Mx) e = rt::d2h(Mx, dMx.p, (size_t)T * n, h->stream);
+    if (!e && Mu) e = rt::d2h(Mu, dMu.p, (size_t)T * m, h->stream);
+    if (!e) e = rt::sync(h->stream);
+    dA.release(); dB.release(); dMx.release(); dMu.release();
+    if (e) return fail(h, e, "sls_local_problem");
+    return 0;
+}
+
+// ---- solve (kernels 2 + 3) ------------------------------------------------------------------
+extern "C" int sls_solve_device(sls_handle* h) {
+    if (!h) return -1;
+    Plan& p = h->plan;
+    SLS_ARG(p.valid, "sls_solve: call sls_plan first");
+    SLS_CK(rt::set_device(h->device));
+    const int64_t T = h->T;
+    const int nc1 = std::max(p.ncols, 1);
+    h->solved = false;
+    if (p.nmax > sls_solve_class_N(sls_solve_class_count() - 1))
+        return fail(h, -6, "sls_solve: a column's local state dimension |s_x| exceeds the largest solver size class");
+    SLS_CK(h->xw.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(double)));
+    SLS_CK(h->status.ensure(nc1 * sizeof(int32_t)));
+    SLS_CK(h->resid.ensure(nc1 * sizeof(double)));
+    SLS_CK(h->out_rowval.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(int64_t)));
+    SLS_CK(h->out_nzval.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(double)));
+    SLS_CK(h->out_ptrs.ensure((size_t)4 * T * sizeof(void*)));
+    {
+        std::vector<void*> ptrs(4 * T);
+        for (int64_t tt = 0; tt < 2 * T; tt++) {
+            ptrs[tt] = h->out_rowval.as<int64_t>() + p.out_off[tt];
+            ptrs[2 * T + tt] = h->out_nzval.as<double>() + p.out_off[tt];
+        }
+        SLS_CK(rt::h2d(h->out_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void*), h->stream));
+        SLS_CK(rt::sync(h->stream));
+    }
+    // history slots: sized for the most demanding class
+    size_t hist_bytes = 8;
+    const SlsPlanView v = plan_view(h, p);
+    for (const SolveClass& c : p.classes) {
+        const int maxw = sls_solve_max_resident_warps(c.N, c.mcap, c.nnzcap, (int)T, p.wu, h->sm_count, h->max_smem);
+        if (maxw <= 0) return fail(h, -4, "sls_solve: local problem does not fit shared memory");
+        const int64_t warps = std::min<int64_t>(maxw, ((int64_t)c.count + 3) / 4 * 4);
+        hist_bytes = std::max(hist_bytes, (size_t)warps * sls_solve_hist_doubles(c.N, (int)T) * sizeof(double));
+    }
+    SLS_CK(h->hist.ensure(hist_bytes));
+    h->ev[4].record(h->stream);
+    int64_t launches = 0;
+    for (const SolveClass& c : p.classes) {
+        SlsSolveArgs a{};
+        a.A = h->A.view(); a.B2 = h->B2.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();
+        a.P = v; a.list = p.lists.as<int32_t>() + c.list_off; a.count = c.count;
+        a.mcap = c.mcap; a.nnzcap = c.nnzcap;
+        a.xw = h->xw.as<double>(); a.hist = h->hist.as<double>();
+        a.hist_stride = sls_solve_hist_doubles(c.N, (int)T);
+        a.status = h->status.as<int32_t>(); a.resid = h->resid.as<double>();
+        a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
+        int warps = 0;
+        SLS_CK(sls_launch_solve(c.N, a, h->sm_count, h->max_smem, &warps, h->stream));
+        launches++;
+    }
+    h->ev[5].record(h->stream);
+    SlsScatterArgs s{};
+    s.P = v; s.xw = h->xw.as<double>();
+    s.rowval = reinterpret_cast<int64_t* const*>(h->out_ptrs.as<void*>());
+    s.nzval = reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T);
+    SLS_CK(sls_launch_scatter(s, h->stream));
+    h->ev[6].record(h->stream);
+    SLS_CK(rt::sync(h->stream));
+    h->tm.solve_ms = rt::elapsed_ms(h->ev[4], h->ev[5]);
+    h->tm.scatter_ms = rt::elapsed_ms(h->ev[5], h->ev[6]);
+    h->tm.solve_launches = launches; h->tm.scatter_launches = p.ncols ? 1 : 0;
+    h->solved = true;
+    return 0;
+}
+
+extern "C" int sls_solve(sls_handle* h,
+                         int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
+                         int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
+                         int32_t* status, double* resid) {
+    if (!h) return -1;
+    int e = sls_solve_device(h);
+    if (e) return e;
+    const Plan& p = h->plan;
+    const int64_t T = h->T, Nx = h->Nx;
+    h->ev[6].record(h->stream);
+    for (int64_t tt = 0; tt < 2 * T; tt++) {
+        const bool isu = tt >= T;
+        const int64_t t = isu ? tt - T : tt;
+        int64_t* const* cps = isu ? Pu_colptr : Px_colptr;
+        int64_t* const* rvs = isu ? Pu_rowval : Px_rowval;
+        double* const* nzs = isu ? Pu_nzval : Px_nzval;
+        const int64_t nnz = p.nnz_tap[tt];
+        if (cps && cps[t]) SLS_CK(rt::d2h(cps[t], p.colptr.as<int64_t>() + tt * (Nx + 1), (Nx + 1) * sizeof(int64_t), h->stream));
+        if (rvs && rvs[t]) SLS_CK(rt::d2h(rvs[t], h->out_rowval.as<int64_t>() + p.out_off[tt], nnz * sizeof(int64_t), h->stream));
+        if (nzs && nzs[t]) SLS_CK(rt::d2h(nzs[t], h->out_nzval.as<double>() + p.out_off[tt], nnz * sizeof(double), h->stream));
+    }
+    if (status) SLS_CK(rt::d2h(status, h->status.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    if (resid) SLS_CK(rt::d2h(resid, h->resid.p, (size_t)p.ncols * sizeof(double), h->stream));
+    h->ev[7].record(h->stream);
+    SLS_CK(rt::sync(h->stream));
+    h->tm.d2h_ms = rt::elapsed_ms(h->ev[6], h->ev[7]);
+    return 0;
+}
+
+extern "C" int sls_device_output(sls_handle* h, int64_t t, int which,
+                                 const int64_t** d_colptr, const int64_t** d_rowval, const double** d_nzval, int64_t* nnz) {
+    if (!h) return -1;
+    SLS_ARG(h->solved, "sls_device_output: no solved plan");
+    SLS_ARG(t >= 0 && t < h->T && (which == 0 || which == 1), "sls_device_output: bad tap");
+    const int64_t tt = which ? h->T + t : t;
+    if (d_colptr) *d_colptr = h->plan.colptr.as<int64_t>() + tt * (h->Nx + 1);
+    if (d_rowval) *d_rowval = h->out_rowval.as<int64_t>() + h->plan.out_off[tt];
+    if (d_nzval) *d_nzval = h->out_nzval.as<double>() + h->plan.out_off[tt];
+    if (nnz) *nnz = h->plan.nnz_tap[tt];
+    return 0;
+}
+
+extern "C" int sls_device_status(sls_handle* h, const int32_t** d_status, const double** d_resid) {
+    if (!h) return -1;
+    SLS_ARG(h->solved, "sls_device_status: no solved plan");
+    if (d_status) *d_status = h->status.as<int32_t>();
+    if (d_resid) *d_resid = h->resid.as<double>();
+    return 0;
+}
+
+extern "C" int sls_get_timing(const sls_handle* h, sls_timing* out) {
+    if (!h || !out) return -1;
+    *out = h->tm;
+    return 0;
+}

@@ -1,0 +1,291 @@
+"""Host-side mirror of the reference's interface for the column-wise localized H2 synthesis path.
+
+    Plant(A, B1, B2)                      <- src/types/GeneralizedPlant.jl:105-110,190 (3-argument ctor)
+    SLS_H2(P, [Sx, Su]; I=None)           <- src/synthesis.jl:11-32  (`SLS_𝓗₂`)
+    sparsity_dim_reduction(P, cj, S)      <- src/reduction.jl:11-27
+
+Same names, argument meaning and error behaviour as the Julia functions; sparse matrices are
+scipy CSC on the Python side and are handed to libslsb200 in Julia's `SparseMatrixCSC{Tv,Int64}`
+field layout (1-based int64 colptr/rowval), which is what the Julia shim passes zero-copy.
+All arithmetic happens in the CUDA library (csrc/); nothing here computes Φ on the CPU.
+Python convention: column indices are 0-based (Julia's are 1-based)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _capi
+from ._capi import SlsOptions, SlsTiming, f64p, i32p, i64p, ptr, ptr_array, u8p
+
+__all__ = ["Plant", "JuliaCSC", "SLS_H2", "sparsity_dim_reduction", "Synthesizer"]
+
+
+class JuliaCSC:
+    """Field-for-field image of a Julia `SparseMatrixCSC{Tv,Int64}`: m, n, colptr, rowval, nzval."""
+
+    __slots__ = ("m", "n", "colptr", "rowval", "nzval")
+
+    def __init__(self, m, n, colptr, rowval, nzval):
+        self.m, self.n = int(m), int(n)
+        self.colptr, self.rowval, self.nzval = colptr, rowval, nzval
+
+    @classmethod
+    def from_scipy(cls, M, dtype):
+        M = sp.csc_matrix(M)
+        if not M.has_sorted_indices:
+            M = M.copy()
+            M.sort_indices()
+        colptr = M.indptr.astype(np.int64) + 1
+        rowval = M.indices.astype(np.int64) + 1
+        if dtype == np.bool_:
+            nzval = (M.data != 0).astype(np.uint8)
+        else:
+            nzval = np.ascontiguousarray(M.data, dtype=dtype)
+        return cls(M.shape[0], M.shape[1], colptr, rowval, nzval)
+
+    def to_scipy(self):
+        return sp.csc_matrix((self.nzval, self.rowval - 1, self.colptr - 1), shape=(self.m, self.n))
+
+    @property
+    def nnz(self):
+        return int(self.colptr[-1] - 1)
+
+
+def _as_julia(M, dtype):
+    return M if isinstance(M, JuliaCSC) else JuliaCSC.from_scipy(M, dtype)
+
+
+class Plant:
+    """`Plant(A, B₁, B₂)`: state-feedback generalized plant with the LQR-style defaults of the
+    3-argument constructor — C₁ = [I;0], D₁₂ = [0;I], D₁₁ = 0, C₂ = I (GeneralizedPlant.jl:105-110).
+    Dimension checks follow validate_GeneralizedPlant (GeneralizedPlant.jl:291-311): a mismatch raises
+    ValueError (the reference throws ErrorException)."""
+
+    def __init__(self, A, B1, B2):
+        self.A = sp.csc_matrix(A, dtype=np.float64)
+        self.B1 = sp.csc_matrix(B1, dtype=np.float64)
+        self.B2 = sp.csc_matrix(B2, dtype=np.float64)
+        for M in (self.A, self.B1, self.B2):
+            M.sort_indices()
+        if self.A.shape[0] != self.A.shape[1]:
+            raise ValueError("A must be a square matrix")
+        if self.B1.shape[0] != self.A.shape[0] or self.B2.shape[0] != self.A.shape[0]:
+            raise ValueError("B1 and B2 must have the same number of rows as A")
+        self.Nx = self.A.shape[0]
+        self.Nw = self.B1.shape[1]
+        self.Nu = self.B2.shape[1]
+        self.Nz = self.Nx + self.Nu
+        self.Ny = self.Nx
+        self.feedback = "StateFeedback"
+
+    def _b1_is_identity(self):
+        if self.B1.shape != (self.Nx, self.Nx):
+            return False
+        return (abs(self.B1 - sp.identity(self.Nx, format="csc")).nnz == 0)
+
+
+class Synthesizer:
+    """One libslsb200 handle (one GPU).  Thin, stateful wrapper used by SLS_H2, the tests and bench.py."""
+
+    def __init__(self, device: int = 0, rank_tol: float = 0.0, feas_tol: float = 0.0, flags: int = 0, api=None):
+        self.api = api if api is not None else _capi.default_api()
+        self.h = C.c_void_p()
+        opts = SlsOptions(device, flags, rank_tol, feas_tol)
+        rc = self.api.sls_create(C.byref(opts), C.byref(self.h))
+        if rc != 0:
+            msg = self.api.sls_last_error(None)
+            raise _capi.SlsError(rc, msg.decode() if msg else "")
+        self.Nx = self.Nu = self.T = 0
+        self.ncols = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.api.sls_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        self.api.check(self.h, rc)
+
+    # -- inputs ---------------------------------------------------------------------------------
+    def set_plant(self, A, B2):
+        A = _as_julia(A, np.float64)
+        B2 = _as_julia(B2, np.float64)
+        self.Nx, self.Nu = A.n, B2.n
+        self._ck(self.api.sls_set_plant(self.h, A.n, B2.n, ptr(A.colptr, i64p), ptr(A.rowval, i64p), ptr(A.nzval, f64p),
+                                        ptr(B2.colptr, i64p), ptr(B2.rowval, i64p), ptr(B2.nzval, f64p)))
+
+    def set_supports(self, Sx, Su, pass_nzval=True):
+        Sx = [_as_julia(M, np.bool_) for M in Sx]
+        Su = [_as_julia(M, np.bool_) for M in Su]
+        if len(Sx) != len(Su):
+            raise ValueError("Sx and Su must have the same number of taps")
+        self.T = len(Sx)
+        args = []
+        for S in (Sx, Su):
+            args.append(ptr_array([M.colptr for M in S], i64p))
+            args.append(ptr_array([M.rowval for M in S], i64p))
+            args.append(ptr_array([M.nzval for M in S], u8p) if pass_nzval else None)
+        self._ck(self.api.sls_set_supports(self.h, self.T, *args))
+
+    # -- kernel 1 -------------------------------------------------------------------------------
+    def plan(self, cols=None):
+        """cols: 0-based disturbance columns (None = all).  Returns (nnz_x[T], nnz_u[T], n[ncols], m[ncols])."""
+        T = self.T
+        nnz_x = np.zeros(T, np.int64)
+        nnz_u = np.zeros(T, np.int64)
+        if cols is None:
+            ncols = self.Nx
+            c1 = None
+        else:
+            c1 = np.ascontiguousarray(np.asarray(cols, dtype=np.int64) + 1)
+            ncols = c1.size
+        n = np.zeros(max(ncols, 1), np.int32)
+        m = np.zeros(max(ncols, 1), np.int32)
+        self._ck(self.api.sls_plan(self.h, ptr(c1, i64p), ncols, ptr(nnz_x, i64p), ptr(nnz_u, i64p), ptr(n, i32p), ptr(m, i32p)))
+        self.ncols = ncols
+        self.nnz_x, self.nnz_u = nnz_x, nnz_u
+        self.n, self.m = n[:ncols], m[:ncols]
+        return nnz_x, nnz_u, self.n, self.m
+
+    def reduce(self, cj):
+        """sparsity_dim_reduction index sets for the 0-based column group cj: (sx, su, iix), 0-based."""
+        cj1 = np.ascontiguousarray(np.asarray(cj, dtype=np.int64) + 1)
+        sx = np.zeros(self.Nx, np.int64)
+        su = np.zeros(max(self.Nu, 1), np.int64)
+        iix = np.zeros(self.Nx, np.uint8)
+        nsx = C.c_int64()
+        nsu = C.c_int64()
+        self._ck(self.api.sls_reduce(self.h, ptr(cj1, i64p), cj1.size, ptr(sx, i64p), sx.size, C.byref(nsx),
+                                     ptr(su, i64p), su.size, C.byref(nsu), ptr(iix, u8p)))
+        return sx[:nsx.value] - 1, su[:nsu.value] - 1, iix[:nsx.value].astype(bool)
+
+    def local_problem(self, k):
+        n, m, T = int(self.n[k]), int(self.m[k]), self.T
+        At = np.zeros((n, n), order="F")
+        B2t = np.zeros((n, m), order="F")
+        Mx = np.zeros((T, n), np.uint8)
+        Mu = np.zeros((T, m), np.uint8)
+        self._ck(self.api.sls_local_problem(self.h, k, ptr(At, f64p), ptr(B2t, f64p), ptr(Mx, u8p), ptr(Mu, u8p)))
+        return At, B2t, Mx.astype(bool), Mu.astype(bool)
+
+    # -- kernels 2 + 3 --------------------------------------------------------------------------
+    def alloc_outputs(self, pinned=False):
+        """Caller-owned output buffers in Julia layout, sized by the last plan()."""
+        T, Nx = self.T, self.Nx
+
+        def buf(n, dt):
+            if pinned:
+                import torch
+                t = torch.empty(max(int(n), 1), dtype={np.int64: torch.int64, np.float64: torch.float64}[dt]).pin_memory()
+                self._keep.append(t)
+                return t.numpy()[:int(n)]
+            return np.empty(int(n), dt)
+
+        out = {}
+        for name, nnz in (("x", self.nnz_x), ("u", self.nnz_u)):
+            out[name] = dict(colptr=[buf(Nx + 1, np.int64) for _ in range(T)],
+                             rowval=[buf(nnz[t], np.int64) for t in range(T)],
+                             nzval=[buf(nnz[t], np.float64) for t in range(T)])
+        out["status"] = np.zeros(max(self.ncols, 1), np.int32)
+        out["resid"] = np.zeros(max(self.ncols, 1), np.float64)
+        return out
+
+    def solve(self, out=None):
+        out = out if out is not None else self.alloc_outputs()
+        args = []
+        for name in ("x", "u"):
+            args.append(ptr_array(out[name]["colptr"], i64p))
+            args.append(ptr_array(out[name]["rowval"], i64p))
+            args.append(ptr_array(out[name]["nzval"], f64p))
+        self._ck(self.api.sls_solve(self.h, *args, ptr(out["status"], i32p), ptr(out["resid"], f64p)))
+        return out
+
+    def solve_device(self):
+        self._ck(self.api.sls_solve_device(self.h))
+
+    def timing(self):
+        t = SlsTiming()
+        self._ck(self.api.sls_get_timing(self.h, C.byref(t)))
+        return t.as_dict()
+
+    def outputs_to_scipy(self, out):
+        T, Nx, Nu = self.T, self.Nx, self.Nu
+        Phix = [JuliaCSC(Nx, Nx, out["x"]["colptr"][t], out["x"]["rowval"][t], out["x"]["nzval"][t]).to_scipy() for t in range(T)]
+        Phiu = [JuliaCSC(Nu, Nx, out["u"]["colptr"][t], out["u"]["rowval"][t], out["u"]["nzval"][t]).to_scipy() for t in range(T)]
+        return Phix, Phiu
+
+
+def _check_plant(P):
+    if getattr(P, "feedback", None) != "StateFeedback":
+        return False
+    return True
+
+
+def SLS_H2(P, S, I=None, *, device: int = 0, return_info: bool = False, api=None):
+    """`SLS_𝓗₂(P, 𝓢; 𝓘=nothing)` (src/synthesis.jl:11-32).
+
+    P: Plant (state feedback).  S = [Sx, Su]: two length-T lists of Bool sparse matrices (Nx x Nx, Nu x Nx).
+    I: optional list of column groups; each group must be a single 0-based column (`[[j] for j in ...]`, the
+       reference's default shape, synthesis.jl:15) — plain ints are accepted too.
+    Returns (Phi_x, Phi_u): two length-T lists of scipy CSC matrices, the layout `eachcol(Φ)` gives in Julia
+    (synthesis.jl:27).  The stored pattern is the full in-support mask (explicit zeros kept).
+    Like the reference, a plant that is not state-feedback returns None (synthesis.jl:13 falls through)."""
+    if not _check_plant(P):
+        return None
+    if not P._b1_is_identity():
+        raise NotImplementedError("libslsb200 covers plants built as Plant(A, I, B2) (cost = squared Frobenius norm of Φ); "
+                                  "general B1 / C1 / D12 weights are SURVEY §8f-3")
+    Sx, Su = S
+    cols = None
+    if I is not None:
+        cols = []
+        for g in I:
+            g = np.atleast_1d(np.asarray(g))
+            if g.size != 1:
+                raise NotImplementedError("column groups with more than one column (q > 1) are SURVEY §8f-3")
+            cols.append(int(g[0]))
+    syn = Synthesizer(device=device, api=api)
+    try:
+        syn.set_plant(P.A, P.B2)
+        syn.set_supports(Sx, Su)
+        syn.plan(cols)
+        out = syn.solve()
+        Phix, Phiu = syn.outputs_to_scipy(out)
+        info = dict(status=out["status"][:syn.ncols].copy(), resid=out["resid"][:syn.ncols].copy(),
+                    n=syn.n.copy(), m=syn.m.copy(), timing=syn.timing())
+    finally:
+        syn.close()
+    if return_info:
+        return Phix, Phiu, info
+    return Phix, Phiu
+
+
+def sparsity_dim_reduction(P, cj, S, *, device: int = 0, api=None):
+    """`sparsity_dim_reduction(P, cⱼ, 𝓢)` (src/reduction.jl:11-27), state-feedback branch.
+    Returns (P̃, Ĩ, iiₓ, sₓ, sᵤ) with P̃ = Plant(A[sₓ,sₓ], B₁[sₓ,cⱼ], B₂[sₓ,sᵤ]) (the sub-plant the reference's
+    `view` describes, GeneralizedPlant.jl:266-285), Ĩ = I(|sₓ|)[:, iiₓ] padded to |cⱼ| columns, and 0-based
+    index vectors.  The index sets come from kernel 1 on the GPU."""
+    Sx, Su = S
+    syn = Synthesizer(device=device, api=api)
+    try:
+        syn.set_plant(P.A, P.B2)
+        syn.set_supports([Sx[-1]], [Su[-1]])      # only 𝓢ⱼ[end] is read (reduction.jl:14)
+        sx, su, iix = syn.reduce(cj)
+    finally:
+        syn.close()
+    cj = np.asarray(cj, dtype=np.int64)
+    Pt = Plant(P.A[sx, :][:, sx], P.B1[sx, :][:, cj], P.B2[sx, :][:, su])
+    n, q = sx.size, cj.size
+    It = np.zeros((n, q))
+    sel = np.nonzero(iix)[0]
+    It[sel, np.arange(sel.size)] = 1.0
+    return Pt, It, iix, sx, su

@@ -1,0 +1,68 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# Φ parity tolerance (BASELINE.json north_star): relative Frobenius error per time tap <= 1e-9
+PHI_RTOL = 1e-9
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def golden_taps(g, which):
+    """list of (indptr, indices, data) per tap from a packed golden file"""
+    indptr = g[f"{which}_indptr"]
+    out, off = [], 0
+    for t in range(indptr.shape[0]):
+        nnz = int(indptr[t][-1])
+        out.append((indptr[t], g[f"{which}_indices"][off:off + nnz], g[f"{which}_data"][off:off + nnz]))
+        off += nnz
+    return out
+
+
+def assert_phi_matches(Phi, taps, what, rtol=PHI_RTOL):
+    """pattern bit-exact, values within rtol relative Frobenius error per tap"""
+    worst = 0.0
+    assert len(Phi) == len(taps)
+    for t, (M, (indptr, indices, data)) in enumerate(zip(Phi, taps)):
+        assert np.array_equal(np.asarray(M.indptr, np.int64), indptr), f"{what}[{t}] colptr differs"
+        assert np.array_equal(np.asarray(M.indices, np.int64), indices), f"{what}[{t}] rowval differs"
+        nb = np.linalg.norm(data)
+        err = np.linalg.norm(M.data - data)
+        if nb > 0:
+            worst = max(worst, err / nb)
+            assert err <= rtol * nb, f"{what}[{t}] rel Frobenius error {err / nb:.3e} > {rtol}"
+        else:
+            assert err == 0.0, f"{what}[{t}] expected all-zero tap"
+    return worst
+
+
+@pytest.fixture(scope="session")
+def emu_api():
+    """TEST-ONLY build of the kernels on the SIMT emulator (tests/emu); never used by the package itself."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    import slc_b200
+    return slc_b200._capi.CApi(build_emu.build())
+
+
+@pytest.fixture(scope="session")
+def cuda_api():
+    import slc_b200
+    api = slc_b200._capi.default_api()
+    if api.sls_device_count() <= 0:
+        pytest.fail("CUDA library loaded but no device is usable — GPU tests must run on the GPU box")
+    return api

@@ -1,0 +1,157 @@
+"""Parity checks shared by the GPU tests (CUDA library, `-m gpu`) and the kernel-logic tests that run the
+same kernel sources on the test-only SIMT emulator (`-m "not gpu"`).  Every function takes the bound
+library (`api`) explicitly and compares against the CPU oracle / golden vectors."""
+import numpy as np
+import scipy.sparse as sp
+
+import slc_b200
+from slc_b200 import _capi
+from conftest import PHI_RTOL, assert_phi_matches, golden_taps, load_golden
+from oracle import sls_oracle as O
+
+
+def chain(Nx, jitter=0.0, d=9, T=29, alpha=1.5):
+    A, B1, B2 = O.chain_plant(Nx, jitter=jitter, seed=0)
+    return A, B1, B2, O.make_supports(A, B2, d, T, alpha)
+
+
+def restrict_cols(taps, cols, ncol):
+    """golden taps (all columns) -> taps whose columns outside `cols` are emptied"""
+    out = []
+    keep = np.zeros(ncol, bool); keep[cols] = True
+    for indptr, indices, data in taps:
+        cnt = np.diff(indptr) * keep
+        sel = np.repeat(keep, np.diff(indptr))
+        out.append((np.r_[0, np.cumsum(cnt)].astype(np.int64), indices[sel], data[sel]))
+    return out
+
+
+def check_golden(api, name, plant, cols=None, rtol=PHI_RTOL):
+    g = load_golden(name)
+    A, B1, B2 = plant
+    S = O.make_supports(A, B2, int(g["d"]), int(g["T"]), float(g["alpha"]))
+    P = slc_b200.Plant(A, B1, B2)
+    gcols = g["cols"]
+    use = gcols if cols is None else np.asarray(cols)
+    I = None if (cols is None and gcols.size == A.shape[0]) else [[int(c)] for c in use]
+    Phix, Phiu, info = slc_b200.SLS_H2(P, S, I=I, return_info=True, api=api)
+    tx, tu = golden_taps(g, "x"), golden_taps(g, "u")
+    if cols is not None:
+        tx, tu = restrict_cols(tx, use, A.shape[0]), restrict_cols(tu, use, A.shape[0])
+    wx = assert_phi_matches(Phix, tx, "Phix", rtol)
+    wu = assert_phi_matches(Phiu, tu, "Phiu", rtol)
+    # n, m per column are integer outputs of kernel 1: exact
+    pos = {int(c): i for i, c in enumerate(gcols)}
+    idx = [pos[int(c)] for c in use]
+    assert np.array_equal(info["n"], g["n"][idx]) and np.array_equal(info["m"], g["m"][idx])
+    assert not (info["status"] & _capi.STATUS_RESIDUAL).any()
+    assert info["resid"].max() < 1e-12
+    return max(wx, wu), info
+
+
+def check_reduction_fixture(api):
+    """/root/reference/test/reduction_test.jl:10-24 through sls_reduce (kernel 1)."""
+    A, B1, B2 = O.chain_plant(59)
+    pA = O._pat(A)
+    Sx = [sp.csc_matrix(O._pat_power(pA, 9) != 0)]
+    Su = [sp.csc_matrix((O._pat(sp.csc_matrix(B2).T) @ O._pat_power(pA, 9)) != 0)]
+    P = slc_b200.Plant(A, B1, B2)
+    Pt, It, iix, sx, su = slc_b200.sparsity_dim_reduction(P, np.arange(20), [Sx, Su], api=api)
+    assert np.array_equal(sx, np.arange(30)) and np.array_equal(su, np.arange(10))
+    assert np.array_equal(iix, np.r_[np.ones(20, bool), np.zeros(10, bool)])
+    assert np.array_equal(It, np.eye(30)[:, :20])
+    assert (Pt.A != A[:30, :30]).nnz == 0 and (Pt.B1 != B1[:30, :20]).nnz == 0 and (Pt.B2 != B2[:30, :10]).nnz == 0
+    # first-occurrence order for an unsorted group (reduction.jl:14: unique(findnz(...)[1]))
+    cj = np.array([40, 3])
+    _, _, iix2, sx2, su2 = slc_b200.sparsity_dim_reduction(P, cj, [Sx, Su], api=api)
+    (_, _, _), _, oiix, osx, osu = O.sparsity_dim_reduction(O.Plant(A, B1, B2), cj, [Sx, Su])
+    assert np.array_equal(sx2, osx) and np.array_equal(su2, osu) and np.array_equal(iix2, oiix)
+    assert sx2[0] == 30 and not np.all(np.diff(sx2) > 0)          # genuinely unsorted
+
+
+def check_local_blocks(api, A, B1, B2, S, cols):
+    """kernel 1 outputs (index sets, masks, local A~/B2~) bit-exact against the oracle's gather."""
+    Po = O.Plant(A, B1, B2)
+    prods = O.support_products(Po, S)
+    syn = slc_b200.Synthesizer(api=api)
+    try:
+        syn.set_plant(A, B2)
+        syn.set_supports(*S)
+        _, _, n, m = syn.plan(cols)
+        for k, j in enumerate(cols):
+            (At, _, B2t), It, iix, sx, su = O.sparsity_dim_reduction(Po, [j], S, _prod=prods)
+            Mx, Mu = O.column_masks(S, sx, su, j)
+            gsx, gsu, giix = syn.reduce([j])
+            assert np.array_equal(gsx, sx) and np.array_equal(gsu, su) and np.array_equal(giix, iix)
+            assert n[k] == sx.size and m[k] == su.size
+            dAt, dB2t, dMx, dMu = syn.local_problem(k)
+            assert np.array_equal(dAt, At) and np.array_equal(dB2t, B2t)
+            assert np.array_equal(dMx, Mx) and np.array_equal(dMu, Mu)
+    finally:
+        syn.close()
+
+
+def check_against_oracle(api, A, B1, B2, S, cols, rtol=PHI_RTOL):
+    """Φ columns from the library vs the oracle's exact minimiser on the same columns."""
+    Po = O.Plant(A, B1, B2)
+    Ox, Ou, infos = O.SLS_H2(Po, S, I=cols, return_info=True)
+    Phix, Phiu, info = slc_b200.SLS_H2(slc_b200.Plant(A, B1, B2), S, I=[[int(c)] for c in cols], return_info=True, api=api)
+    worst = 0.0
+    for name, G, H in (("Phix", Phix, Ox), ("Phiu", Phiu, Ou)):
+        taps = [(np.asarray(M.indptr, np.int64), np.asarray(M.indices, np.int64), M.data) for M in H]
+        worst = max(worst, assert_phi_matches(G, taps, name, rtol))
+    return worst, info, infos
+
+
+def check_error_paths(api):
+    A, B1, B2, S = chain(30, d=3, T=6)
+    syn = slc_b200.Synthesizer(api=api)
+    try:
+        with np.testing.assert_raises(_capi.SlsError):
+            syn.plan([0])                                         # nothing set yet
+        syn.set_plant(A, B2)
+        with np.testing.assert_raises(_capi.SlsError):
+            syn.plan([0])                                         # supports missing
+        syn.set_supports(*S)
+        for bad in ([30], [-1], [3, 3]):
+            with np.testing.assert_raises(_capi.SlsError):
+                syn.plan(bad)
+        with np.testing.assert_raises(_capi.SlsError):
+            syn.solve_device()                                    # failed plan leaves no valid plan
+        # malformed CSC
+        J = slc_b200.JuliaCSC.from_scipy(A, np.float64)
+        J.colptr = J.colptr.copy(); J.colptr[0] = 0
+        with np.testing.assert_raises(_capi.SlsError):
+            syn.set_plant(J, B2)
+        # empty column list is legal: all outputs empty
+        syn.set_plant(A, B2); syn.set_supports(*S)
+        nnz_x, nnz_u, n, m = syn.plan([])
+        assert nnz_x.sum() == 0 and nnz_u.sum() == 0
+        out = syn.solve()
+        assert all((cp == 1).all() for cp in out["x"]["colptr"] + out["u"]["colptr"])
+    finally:
+        syn.close()
+
+
+def check_masks_and_flags(api):
+    """stored-false support entries, stored zeros in A, non-nested supports, an infeasible column."""
+    A, B1, B2, S = chain(59)
+    Sx, Su = [M.copy() for M in S[0]], [M.copy() for M in S[1]]
+    # a stored `false` inside 𝓢ₓ[12][:,20] fixes that entry (synthesis.jl:58: `.≠ 1`)
+    M = Sx[11]; e = M.indptr[20] + 1; M.data[e] = False
+    # non-nested: drop one row of tap 15 entirely for column 21
+    M = Sx[14].tolil(); M[24, 21] = False; Sx[14] = sp.csc_matrix(M.tocsc()); Sx[14].eliminate_zeros()
+    # explicitly stored 0.0 in A: `A .≠ 0` drops it (reduction.jl:14)
+    Az = A.tocoo()
+    A2 = sp.csc_matrix((np.r_[Az.data, 0.0], (np.r_[Az.row, 10], np.r_[Az.col, 30])), shape=A.shape)
+    A2.sort_indices()
+    assert A2.nnz == A.nnz + 1
+    cols = [0, 19, 20, 21, 22, 30, 58]
+    worst, info, infos = check_against_oracle(api, A2, B1, B2, [Sx, Su], cols)
+    assert max(i["residual"] for i in infos.values()) < 1e-12        # the modified problems stay feasible
+    assert not (info["status"] & _capi.STATUS_RESIDUAL).any()
+    # infeasible: remove every actuator support => residual flag, like the oracle's residual
+    Su0 = [sp.csc_matrix(M.shape, dtype=bool) for M in Su]
+    Phix, Phiu, info = slc_b200.SLS_H2(slc_b200.Plant(A, B1, B2), [Sx, Su0], I=[[20]], return_info=True, api=api)
+    assert info["status"][0] & _capi.STATUS_RESIDUAL and info["resid"][0] > 1e-3
+    return worst

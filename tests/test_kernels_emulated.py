@@ -1,0 +1,34 @@
+"""Kernel LOGIC tests without a GPU: the very same csrc/*.cu sources compiled by g++ on the test-only SIMT
+emulator (tests/emu).  This is a debugging aid like compute-sanitizer — it proves indexing / algorithm
+logic, not the CUDA build; the parity tests proper are tests/test_parity_gpu.py (`-m gpu`)."""
+import numpy as np
+
+import parity_cases as pc
+from oracle import sls_oracle as O
+
+
+def test_emu_reduction_fixture(emu_api):
+    pc.check_reduction_fixture(emu_api)
+
+
+def test_emu_readme_chain_subset_vs_golden(emu_api):
+    worst, info = pc.check_golden(emu_api, "readme_chain_59", O.chain_plant(59), cols=[0, 1, 5, 29, 30, 57, 58])
+    assert worst < 1e-11
+
+
+def test_emu_local_blocks_bit_exact(emu_api):
+    A, B1, B2, S = pc.chain(59)
+    pc.check_local_blocks(emu_api, A, B1, B2, S, [0, 3, 29, 58])
+
+
+def test_emu_grid_9x9_subset(emu_api):
+    worst, _ = pc.check_golden(emu_api, "grid_9x9_full_d2_T8", O.grid_plant(9, 9, actuation="full"), cols=[0, 4, 40, 44, 80])
+    assert worst < 1e-11
+
+
+def test_emu_error_paths(emu_api):
+    pc.check_error_paths(emu_api)
+
+
+def test_emu_masks_and_flags(emu_api):
+    pc.check_masks_and_flags(emu_api)
