@@ -117,6 +117,12 @@ int sls_device_status(sls_handle* h, const int32_t** d_status, const double** d_
 
 int sls_get_timing(const sls_handle* h, sls_timing* out);
 
+/* Device-side stopwatch on the handle's stream (CUDA events): sls_mark(h,0) ... sls_mark(h,1), then
+ * sls_elapsed_ms waits for mark 1 and returns the device time between the two marks.  bench.py brackets a
+ * whole step (plan + solve, with or without the host copies) with it. */
+int sls_mark(sls_handle* h, int which);
+int sls_elapsed_ms(sls_handle* h, float* ms);
+
 /* Calibration for the roofline of kernel 2: measured FP64 throughput of this device in TFLOP/s — a
  * register-resident DFMA chain (vector pipe) and a DMMA m8n8k4 chain (FP64 tensor path).  Not used by
  * any synthesis call. */

@@ -58,6 +58,8 @@ SIGNATURES = {
                                     C.POINTER(C.c_void_p), i64p]),
     "sls_device_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "sls_get_timing": (C.c_int, [C.c_void_p, C.POINTER(SlsTiming)]),
+    "sls_mark": (C.c_int, [C.c_void_p, C.c_int]),
+    "sls_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "sls_fp64_peak": (C.c_int, [C.c_int, C.c_int, f64p, f64p]),
 }
 

@@ -83,6 +83,7 @@ struct sls_handle {
     Plan plan;
     DevBuf xw, hist, status, resid, out_rowval, out_nzval, out_ptrs;
     rt::Event ev[8];
+    rt::Event marks[2];
     sls_timing tm{};
 };
 
@@ -119,6 +120,7 @@ extern "C" int sls_create(const sls_options* opts, sls_handle** out) {
     int e = rt::set_device(h->device);
     if (!e) e = rt::stream_create(&h->stream);
     for (int i = 0; i < 8 && !e; i++) e = h->ev[i].create();
+    for (int i = 0; i < 2 && !e; i++) e = h->marks[i].create();
     if (e) { delete h; return fail(nullptr, e, "sls_create: CUDA initialisation failed"); }
     h->sm_count = rt::sm_count(h->device);
     h->max_smem = rt::max_smem_optin(h->device);
@@ -135,6 +137,7 @@ extern "C" void sls_destroy(sls_handle* h) {
     DevBuf* all[] = {&h->xw, &h->hist, &h->status, &h->resid, &h->out_rowval, &h->out_nzval, &h->out_ptrs};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < 8; i++) h->ev[i].destroy();
+    for (int i = 0; i < 2; i++) h->marks[i].destroy();
     rt::stream_destroy(h->stream);
     delete h;
 }
@@ -603,5 +606,19 @@ extern "C" int sls_device_status(sls_handle* h, const int32_t** d_status, const 
 extern "C" int sls_get_timing(const sls_handle* h, sls_timing* out) {
     if (!h || !out) return -1;
     *out = h->tm;
+    return 0;
+}
+
+extern "C" int sls_mark(sls_handle* h, int which) {
+    if (!h || which < 0 || which > 1) return -1;
+    SLS_CK(rt::set_device(h->device));
+    h->marks[which].record(h->stream);
+    return 0;
+}
+
+extern "C" int sls_elapsed_ms(sls_handle* h, float* ms) {
+    if (!h || !ms) return -1;
+    SLS_CK(rt::sync(h->stream));
+    *ms = rt::elapsed_ms(h->marks[0], h->marks[1]);
     return 0;
 }

@@ -212,6 +212,14 @@ class Synthesizer:
     def solve_device(self):
         self._ck(self.api.sls_solve_device(self.h))
 
+    def mark(self, which):
+        self._ck(self.api.sls_mark(self.h, which))
+
+    def elapsed_ms(self):
+        ms = C.c_float()
+        self._ck(self.api.sls_elapsed_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
     def timing(self):
         t = SlsTiming()
         self._ck(self.api.sls_get_timing(self.h, C.byref(t)))
