@@ -30,6 +30,23 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+template <class T> struct PinVec {     // pinned host staging array (fast, truly asynchronous D2H)
+    T* p = nullptr;
+    size_t cap = 0, len = 0;
+    int resize(size_t n) {
+        len = n;
+        if (n <= cap && p) return 0;
+        rt::host_free(p); p = nullptr; cap = 0;
+        int e = rt::host_alloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (!e) cap = std::max<size_t>(n, 1);
+        return e;
+    }
+    void release() { rt::host_free(p); p = nullptr; cap = len = 0; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    T* data() { return p; }
+};
+
 struct DevCsc {                 // device copy of one Julia SparseMatrixCSC{Float64,Int64}
     DevBuf colptr, rowval, nzval;
     int64_t ncol = 0, nnz = 0;
@@ -55,7 +72,9 @@ struct Plan {
     bool valid = false;
     int ncols = 0, nstride = 1, mstride = 1, wx = 1, wu = 1, nmax = 0, mmax = 0, cap = 32;
     DevBuf cols, n, m, sx, su, maskx, masku, jloc, lnnz, lnnzA, lnnzB, pre, tot, colptr, lists;
-    std::vector<int32_t> h_cols, h_n, h_m, h_lnnz;
+    std::vector<int32_t> h_cols;
+    PinVec<int32_t> h_n, h_m, h_lnnz, h_lA, h_lB;
+    PinVec<int64_t> h_tot, h_last;
     std::vector<int64_t> nnz_tap;       // 2T stored-entry counts (Φx taps then Φu taps)
     std::vector<int64_t> out_off;       // 2T+1 offsets of each tap inside the output buffers
     std::vector<SolveClass> classes;
@@ -64,6 +83,7 @@ struct Plan {
     void release() {
         DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists};
         for (DevBuf* b : all) b->release();
+        h_n.release(); h_m.release(); h_lnnz.release(); h_lA.release(); h_lB.release(); h_tot.release(); h_last.release();
         valid = false;
     }
 };
@@ -321,7 +341,8 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
         return fail(h, -4, "plan: candidate index list of a column does not fit shared memory");
     SLS_CK(sls_launch_gather_count(h->A.view(), h->Sx.view(), h->Su.view(), (int)T, Nx, p.cols.as<int32_t>(), p.ncols,
                                    p.n.as<int32_t>(), p.m.as<int32_t>(), cap, h->stream));
-    p.h_n.assign(nc1, 0); p.h_m.assign(nc1, 0);
+    SLS_CK(p.h_n.resize(nc1)); SLS_CK(p.h_m.resize(nc1));
+    p.h_n[0] = 0; p.h_m[0] = 0;
     SLS_CK(rt::d2h(p.h_n.data(), p.n.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
     SLS_CK(rt::d2h(p.h_m.data(), p.m.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
     SLS_CK(rt::sync(h->stream));
@@ -352,17 +373,17 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_CK(sls_launch_gather_fill(h->A.view(), h->B2.view(), h->Sx.view(), h->Su.view(), v, cap, h->stream));
     SLS_CK(sls_launch_scan(v.colptr, Nx + 1, (int)(2 * T), v.tot, p.ncols + 1, h->stream));
     // sizes back to the host
-    p.h_lnnz.assign(nc1, 0);
-    std::vector<int32_t> lA(nc1, 0), lB(nc1, 0);
-    std::vector<int64_t> tot(p.ncols + 1, 0);
+    SLS_CK(p.h_lnnz.resize(nc1)); SLS_CK(p.h_lA.resize(nc1)); SLS_CK(p.h_lB.resize(nc1));
+    SLS_CK(p.h_tot.resize(p.ncols + 1)); SLS_CK(p.h_last.resize(2 * T));
+    PinVec<int32_t>& lA = p.h_lA; PinVec<int32_t>& lB = p.h_lB; PinVec<int64_t>& tot = p.h_tot;
     p.nnz_tap.assign(2 * T, 0);
     SLS_CK(rt::d2h(p.h_lnnz.data(), p.lnnz.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
     SLS_CK(rt::d2h(lA.data(), p.lnnzA.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
     SLS_CK(rt::d2h(lB.data(), p.lnnzB.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
     SLS_CK(rt::d2h(tot.data(), p.tot.p, (size_t)(p.ncols + 1) * sizeof(int64_t), h->stream));
-    for (int64_t tt = 0; tt < 2 * T; tt++)
-        SLS_CK(rt::d2h(&p.nnz_tap[tt], v.colptr + tt * (Nx + 1) + Nx, sizeof(int64_t), h->stream));
+    SLS_CK(rt::d2h_strided(p.h_last.data(), v.colptr + Nx, sizeof(int64_t), (size_t)(Nx + 1) * sizeof(int64_t), (size_t)(2 * T), h->stream));
     SLS_CK(rt::sync(h->stream));
+    for (int64_t tt = 0; tt < 2 * T; tt++) p.nnz_tap[tt] = p.h_last[tt];
     p.out_off.assign(2 * T + 1, 0);
     for (int64_t tt = 0; tt < 2 * T; tt++) { p.nnz_tap[tt] -= 1; p.out_off[tt + 1] = p.out_off[tt] + p.nnz_tap[tt]; }
     p.tot_packed = tot[p.ncols];
@@ -377,15 +398,25 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     p.classes.clear();
     std::vector<int32_t> lists(nc1);
     size_t off = 0;
-    for (int k = 0; k < sls_solve_class_count(); k++) {
-        const int N = sls_solve_class_N(k);
-        SolveClass c{N, 0, 0, 0, off};
+    {
+        const int nk = sls_solve_class_count();
+        std::vector<SolveClass> cls(nk);
+        std::vector<int> cls_of_n(p.nmax + 2, -1);
+        for (int n = 0; n <= p.nmax; n++) {
+            const int N = sls_solve_class_of(n);
+            for (int k = 0; k < nk; k++) if (sls_solve_class_N(k) == N) cls_of_n[n] = k;
+        }
+        for (int k = 0; k < nk; k++) cls[k] = SolveClass{sls_solve_class_N(k), 0, 0, 0, 0};
+        for (int i = 0; i < p.ncols; i++) { const int k = cls_of_n[p.h_n[i]]; if (k >= 0) cls[k].count++; }
+        for (int k = 0; k < nk; k++) { cls[k].list_off = off; off += cls[k].count; cls[k].count = 0; }
         for (int i = 0; i < p.ncols; i++) {
-            if (sls_solve_class_of(p.h_n[i]) != N) continue;
-            lists[off + c.count++] = i;
+            const int k = cls_of_n[p.h_n[i]];
+            if (k < 0) continue;
+            SolveClass& c = cls[k];
+            lists[c.list_off + c.count++] = i;
             c.mcap = std::max(c.mcap, p.h_m[i]); c.nnzcap = std::max(c.nnzcap, p.h_lnnz[i]);
         }
-        if (c.count) { p.classes.push_back(c); off += c.count; }
+        for (int k = 0; k < nk; k++) if (cls[k].count) p.classes.push_back(cls[k]);
     }
     SLS_CK(p.lists.ensure(nc1 * sizeof(int32_t)));
     SLS_CK(rt::h2d(p.lists.p, lists.data(), off * sizeof(int32_t), h->stream));
@@ -437,7 +468,7 @@ extern "C" int sls_reduce(sls_handle* h, const int64_t* cj, int64_t q,
     if (e) { p.release(); return fail(h, e, "sls_reduce: device to host copy"); }
     // unique(findnz(M[:,cj])[1]): CSC order = cj order, rows ascending inside a column, first occurrences
     // kept (reduction.jl:14).  Kernel 1 returns each column's rows ascending, so this is a stable merge.
-    auto merge = [&](const std::vector<int32_t>& s, const std::vector<int32_t>& len, int stride, int64_t nrows,
+    auto merge = [&](const std::vector<int32_t>& s, const PinVec<int32_t>& len, int stride, int64_t nrows,
                      std::vector<int64_t>& out) {
         std::vector<uint8_t> seen(nrows, 0);
         for (int c = 0; c < p.ncols; c++)

@@ -17,6 +17,12 @@ inline int h2d(void* d, const void* h, size_t n, sls_stream_t) { memcpy(d, h, n)
 inline int d2h(void* h, const void* d, size_t n, sls_stream_t) { memcpy(h, d, n); return 0; }
 inline int d2d(void* d, const void* s, size_t n, sls_stream_t) { memcpy(d, s, n); return 0; }
 inline int zero(void* d, size_t n, sls_stream_t) { memset(d, 0, n); return 0; }
+inline int d2h_strided(void* h, const void* d, size_t elem, size_t pitch, size_t count, sls_stream_t) {
+    for (size_t i = 0; i < count; i++) memcpy((char*)h + i * elem, (const char*)d + i * pitch, elem);
+    return 0;
+}
+inline int host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+inline void host_free(void* p) { free(p); }
 inline int sync(sls_stream_t) { return 0; }
 inline int last_error() { return 0; }
 inline const char* err_str(int) { return "emu"; }
@@ -36,6 +42,7 @@ inline float elapsed_ms(const Event& a, const Event& b) {
     return std::chrono::duration<float, std::milli>(b.t - a.t).count();
 }
 template <class K> inline int set_max_smem(K, int) { return 0; }
+template <class K> inline int max_blocks_per_sm(K, int, size_t) { return 2; }
 }  // namespace rt
 #define SLS_LAUNCH(kp, grid, block, smem, stream, ...) \
     emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kp(__VA_ARGS__); })
@@ -51,6 +58,11 @@ inline int h2d(void* d, const void* h, size_t n, sls_stream_t s) { return n ? (i
 inline int d2h(void* h, const void* d, size_t n, sls_stream_t s) { return n ? (int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) : 0; }
 inline int d2d(void* d, const void* s_, size_t n, sls_stream_t s) { return n ? (int)cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s) : 0; }
 inline int zero(void* d, size_t n, sls_stream_t s) { return n ? (int)cudaMemsetAsync(d, 0, n, s) : 0; }
+inline int d2h_strided(void* h, const void* d, size_t elem, size_t pitch, size_t count, sls_stream_t s) {
+    return count ? (int)cudaMemcpy2DAsync(h, elem, d, pitch, elem, count, cudaMemcpyDeviceToHost, s) : 0;
+}
+inline int host_alloc(void** p, size_t n) { return (int)cudaMallocHost(p, n ? n : 1); }
+inline void host_free(void* p) { if (p) cudaFreeHost(p); }
 inline int sync(sls_stream_t s) { return (int)cudaStreamSynchronize(s); }
 inline int last_error() { return (int)cudaGetLastError(); }
 inline const char* err_str(int e) { return cudaGetErrorString((cudaError_t)e); }
@@ -69,6 +81,11 @@ struct Event {
 inline float elapsed_ms(const Event& a, const Event& b) { float ms = 0; cudaEventElapsedTime(&ms, a.e, b.e); return ms; }
 template <class K> inline int set_max_smem(K k, int bytes) {
     return (int)cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+template <class K> inline int max_blocks_per_sm(K k, int threads, size_t smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, smem) != cudaSuccess) return 0;
+    return nb;
 }
 }  // namespace rt
 #define SLS_LAUNCH(kp, grid, block, smem, stream, ...) kp<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)

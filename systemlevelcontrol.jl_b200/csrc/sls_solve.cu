@@ -1,54 +1,76 @@
-// sls_solve.cu — kernel 2: batched FP64 equality-constrained least squares, one warp per column.
+// sls_solve.cu — kernel 2: batched FP64 equality-constrained least squares, one warp per column,
+// dense O(n^3) work on the FP64 tensor cores (DMMA m8n8k4), everything register-resident.
 //
 // Replaces the JuMP/Ipopt solve of reference src/synthesis.jl:46-62 for plants built by
 // Plant(A,B1=I,B2) ([C1 D12] = I, D11 = 0; GeneralizedPlant.jl:105-110).  Per column the reference's QP is
 //     min  sum_t ||x_t||^2 + ||u_t||^2      over the in-mask entries (others fixed to 0, synthesis.jl:57-60)
 //     s.t. x_1 = e_j,  x_{t+1} = A~ x_t + B~ u_t (t<T),  0 = A~ x_T + B~ u_T     (synthesis.jl:53-55)
 // i.e. the minimum-norm solution v = G^T lambda, (G G^T) lambda = h, of a rank-deficient but consistent
-// system.  G G^T is block tridiagonal in time with n x n blocks:
+// system.  G G^T is block tridiagonal in time with n x n blocks
 //     D_0 = diag(mx_1),   D_k = diag(mx_{k+1}) + A~ diag(mx_k) A~^T + B~ diag(mu_k) B~^T,   E_k = -A~ diag(mx_k)
-// Forward block elimination (k = 0..T):   S_k = D_k - E_k Z_{k-1} E_k^T,  Z_k = S_k^+,
-//     = diag(mx_{k+1}) + C~ blkdiag(mx_k o (I - Z_{k-1}) o mx_k, diag(mu_k)) C~^T,      C~ = [A~ B~]
-// where S_k^+ is the inverse on the rows whose pivot exceeds rank_tol*diag(D_k) (redundant constraint
-// rows are eliminated — what Ipopt's inertia correction does implicitly), computed by N symmetric
-// Gauss-Jordan sweeps on a register-resident matrix: lane i owns row i (n <= N <= 32), the pivot
-// column is broadcast through shared memory, every lane does N DFMAs per sweep.  The sparse triple
-// product uses a local CSR of C~ gathered from the plant (this is where the local A~/B~ blocks and the
-// FIR constraint block are built in shared memory).  -Z_k goes to a per-warp history slot (packed
-// lower triangle, L2-resident) for the back substitution  lambda_{k-1} = Z_{k-1}(yh_{k-1} + mx_k o A~^T lambda_k),
-// then  x_k = mx_k o (lambda_{k-1} - A~^T lambda_k),  u_k = -mu_k o (B~^T lambda_k).
-// The achievability residual of the computed (x,u) is checked per column and reported in status/resid.
+// Forward block elimination (k = 0..T):   S_k = D_k - E_k Z_{k-1} E_k^T,   Z_k = S_k^+ :
+//     S_k = diag(mx_{k+1}) + B~ diag(mu_k) B~^T + A~ Pi_k A~^T,      Pi_k = mx_k o (I - Z_{k-1}) o mx_k
+// S_k^+ is the inverse on the rows whose pivot exceeds rank_tol * diag(D_k); redundant constraint rows are
+// eliminated (what Ipopt's inertia correction does implicitly).
+//
+// Data layout: an n x n matrix (n <= N = 8*NB <= 32) lives in the registers of one warp as NB x NB blocks
+// of 8 x 8 in the DMMA accumulator layout: lane 4g+q holds X[8bi+g][8bj+2q], X[8bi+g][8bj+2q+1].
+// With the k index of the MMA mapped to even / odd columns, a product  X * W^T  of two blocks that are both
+// in accumulator layout needs NO data movement: A-fragment = (x0 | x1), B-fragment = (w0 | w1).  All
+// products of the recursion have that form because Pi, Z and the pivot-block inverses are symmetric:
+//     T = A~ Pi :  T_ij += A~_il * (Pi_jl)^T         Y = T A~^T :  Y_ij += T_il * (A~_jl)^T
+//     block symmetric sweep (Gauss-Jordan) with pivot block p, P = S_pp^+ :
+//         S_ij -= (S_ip P) * (S_jp)^T,   S_ip <- S_ip P = S_ip * P^T,   S_pi <- P * (S_ip)^T,   S_pp <- -P
+// The 8 x 8 pivot blocks are inverted by 8 scalar symmetric sweeps with rank skipping through warp shuffles.
+// -Z_k goes to a per-warp history slot (packed lower triangle, L2/HBM) for the back substitution
+//     lambda_{k-1} = Z_{k-1}(yh_{k-1} + mx_k o A~^T lambda_k),
+//     x_k = mx_k o (lambda_{k-1} - A~^T lambda_k),   u_k = -mu_k o (B~^T lambda_k).
+// Sparse pieces (A~ x, B~ diag(mu) B~^T, diagonals) use a local CSR/CSC of C~ = [A~ B~] gathered from the
+// plant into shared memory.  The achievability residual of the computed (x,u) is checked per column.
 #include "sls_common.h"
 #include "sls_kernels.h"
 
 #define SOLVE_WPB 4
 
+__device__ __forceinline__ void sls_dmma(double& c0, double& c1, double a, double b) {
+#ifdef SLS_EMU
+    emu::dmma(c0, c1, a, b);
+#else
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#endif
+}
+// acc += X * W^T for two 8x8 blocks in accumulator layout
+__device__ __forceinline__ void sls_mma_xwt(double (&acc)[2], const double (&x)[2], const double (&w)[2]) {
+    sls_dmma(acc[0], acc[1], x[0], w[0]);
+    sls_dmma(acc[0], acc[1], x[1], w[1]);
+}
+
 struct SlsSolveLayout {
-    int N, LDW, LDP, NP, mcap, nnzcap, T, wu;
-    int oWs, oPs, oYh, oCb, oDref, oLam, oTx, oRhs, oXa, oXb, oUc, oG, oValR, oValC;
+    int N, NB, mcap, nnzcap, T, wu;
+    int oAblk, oBBt, oY0, oY1, oG, oDref, oLam, oTx, oRhs, oXa, oXb, oUc, oValR, oValC;
     int oSx, oSu, oMx, oMu, oRptr, oRsplit, oColR, oCptr, oRowC, total;
     __host__ __device__ SlsSolveLayout(int N_, int mcap_, int nnzcap_, int T_, int wu_) {
-        N = N_; mcap = mcap_ < 1 ? 1 : mcap_; nnzcap = nnzcap_ < 1 ? 1 : nnzcap_; T = T_; wu = wu_ < 1 ? 1 : wu_;
-        LDW = N | 1; LDP = (N + 1) & ~1; NP = (N + 1) & ~1;
+        N = N_; NB = N_ / 8; mcap = mcap_ < 1 ? 1 : mcap_; nnzcap = nnzcap_ < 1 ? 1 : nnzcap_; T = T_; wu = wu_ < 1 ? 1 : wu_;
         int o = 0;
 #define SLS_SEC(name, bytes) name = o; o += (bytes); o = (o + 15) & ~15
-        SLS_SEC(oWs, 8 * N * LDW);
-        SLS_SEC(oPs, 8 * (N + mcap) * LDP);
-        SLS_SEC(oYh, 8 * (T + 1) * N);
-        SLS_SEC(oCb, 8 * 2 * NP);
-        SLS_SEC(oDref, 8 * NP);
-        SLS_SEC(oLam, 8 * NP);
+        SLS_SEC(oAblk, 8 * N * N);
+        SLS_SEC(oBBt, 8 * N * N);
+        SLS_SEC(oY0, 8 * N);
+        SLS_SEC(oY1, 8 * N);
+        SLS_SEC(oG, 8 * N);
+        SLS_SEC(oDref, 8 * N);
+        SLS_SEC(oLam, 8 * N);
         SLS_SEC(oTx, 8 * (N + mcap));
-        SLS_SEC(oRhs, 8 * NP);
-        SLS_SEC(oXa, 8 * NP);
-        SLS_SEC(oXb, 8 * NP);
+        SLS_SEC(oRhs, 8 * N);
+        SLS_SEC(oXa, 8 * N);
+        SLS_SEC(oXb, 8 * N);
         SLS_SEC(oUc, 8 * mcap);
-        SLS_SEC(oG, 8 * NP);
         SLS_SEC(oValR, 8 * nnzcap);
         SLS_SEC(oValC, 8 * nnzcap);
         SLS_SEC(oSx, 4 * N);
         SLS_SEC(oSu, 4 * mcap);
-        SLS_SEC(oMx, 4 * T);
+        SLS_SEC(oMx, 4 * (T + 1));
         SLS_SEC(oMu, 4 * T * wu);
         SLS_SEC(oRptr, 2 * (N + 2));
         SLS_SEC(oRsplit, 2 * (N + 2));
@@ -61,21 +83,26 @@ struct SlsSolveLayout {
 };
 
 __device__ __forceinline__ bool sls_bit(const uint32_t* w, int i) { return (w[i >> 5] >> (i & 31)) & 1u; }
+// index of element (r,c) inside a blocked (accumulator-layout friendly) N x N shared-memory matrix
+__device__ __forceinline__ int sls_blk(int NB, int r, int c) { return (((r >> 3) * NB + (c >> 3)) << 6) + ((r & 7) << 3) + (c & 7); }
 
-template <int N>
+template <int NB>
 __global__ void __launch_bounds__(SOLVE_WPB * 32)
 sls_solve_kernel(SlsSolveArgs a) {
+    constexpr int N = 8 * NB;
     SLS_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = sls_lane();
-    const int i = lane;
+    const int i = lane;                      // row owned in the sparse (lane-per-row) phases
+    const int g = lane >> 2, q = lane & 3;   // accumulator-layout coordinates
     const SlsPlanView& P = a.P;
     const int T = P.T;
     const SlsSolveLayout L(N, a.mcap, a.nnzcap, T, P.wu);
     unsigned char* base = smem_raw + (size_t)warp * L.total;
-    double* Ws = reinterpret_cast<double*>(base + L.oWs);
-    double* Ps = reinterpret_cast<double*>(base + L.oPs);
-    double* yh = reinterpret_cast<double*>(base + L.oYh);
-    double* cb = reinterpret_cast<double*>(base + L.oCb);
+    double* Ablk = reinterpret_cast<double*>(base + L.oAblk);
+    double* BBt = reinterpret_cast<double*>(base + L.oBBt);
+    double* ybuf0 = reinterpret_cast<double*>(base + L.oY0);
+    double* ybuf1 = reinterpret_cast<double*>(base + L.oY1);
+    double* gbuf = reinterpret_cast<double*>(base + L.oG);
     double* drefs = reinterpret_cast<double*>(base + L.oDref);
     double* lam_s = reinterpret_cast<double*>(base + L.oLam);
     double* tx = reinterpret_cast<double*>(base + L.oTx);
@@ -83,7 +110,6 @@ sls_solve_kernel(SlsSolveArgs a) {
     double* xa = reinterpret_cast<double*>(base + L.oXa);
     double* xb = reinterpret_cast<double*>(base + L.oXb);
     double* ucur = reinterpret_cast<double*>(base + L.oUc);
-    double* gbuf = reinterpret_cast<double*>(base + L.oG);
     double* valr = reinterpret_cast<double*>(base + L.oValR);
     double* valc = reinterpret_cast<double*>(base + L.oValC);
     int32_t* sx = reinterpret_cast<int32_t*>(base + L.oSx);
@@ -95,33 +121,37 @@ sls_solve_kernel(SlsSolveArgs a) {
     uint16_t* colr = reinterpret_cast<uint16_t*>(base + L.oColR);
     uint16_t* cptr = reinterpret_cast<uint16_t*>(base + L.oCptr);
     uint16_t* rowc = reinterpret_cast<uint16_t*>(base + L.oRowC);
-    constexpr int LDW = (N | 1), LDP = ((N + 1) & ~1);
     const int wu = P.wu;
 
     const int slot = blockIdx.x * SOLVE_WPB + warp;
     const int nslots = gridDim.x * SOLVE_WPB;
-    double* hist = a.hist + (size_t)slot * a.hist_stride;
+    double* hist = a.hist + (size_t)slot * a.hist_stride;      // [T+1][N] yh history, then [T][tri(N)] packed -Z_k
+    double* yhist = hist;
+    double* zhist = hist + (size_t)(T + 1) * N;
+    constexpr int TRI = N * (N + 1) / 2;
 
     for (int idx = slot; idx < a.count; idx += nslots) {
         const int c = a.list[idx];
         const int n = P.n[c], m = P.m[c], jl = P.jloc[c];
-        const int tri = n * (n + 1) / 2;
         const bool act = i < n;
         __syncwarp();
         // ------------------------------------------------------------------ metadata -> shared
         if (act) sx[i] = P.sx[(size_t)c * P.nstride + i];
         for (int l = lane; l < m; l += 32) su[l] = P.su[(size_t)c * P.mstride + l];
         for (int t = lane; t < T; t += 32) mxs[t] = P.maskx[((size_t)c * T + t) * P.wx];
+        if (lane == 0) mxs[T] = 0u;
         for (int t = lane; t < T * wu; t += 32) mus[t] = P.masku[(size_t)c * T * wu + t];
+        for (int e = lane; e < N * N; e += 32) Ablk[e] = 0.0;
         __syncwarp();
-        // ------------------------------------------------------------------ local CSR of C~ = [A~ B~]
+        // ------------------------------------------------------------------ local CSR of C~ = [A~ B~], dense blocks of A~
+        unsigned nzA = 0u;                                    // bit bi*NB+bj: block (bi,bj) of A~ has a stored entry
         {
             int cntA = 0, cntB = 0;
             int64_t ea0 = 0, ea1 = 0, eb0 = 0, eb1 = 0;
             if (act) {
-                const int64_t g = sx[i];
-                ea0 = a.Ar.colptr[g] - 1; ea1 = a.Ar.colptr[g + 1] - 1;
-                eb0 = a.B2r.colptr[g] - 1; eb1 = a.B2r.colptr[g + 1] - 1;
+                const int64_t gr = sx[i];
+                ea0 = a.Ar.colptr[gr] - 1; ea1 = a.Ar.colptr[gr + 1] - 1;
+                eb0 = a.B2r.colptr[gr] - 1; eb1 = a.B2r.colptr[gr + 1] - 1;
                 for (int64_t e = ea0; e < ea1; e++) cntA += (sls_find(sx, n, (int32_t)(a.Ar.rowval[e] - 1)) >= 0);
                 for (int64_t e = eb0; e < eb1; e++) cntB += (sls_find(su, m, (int32_t)(a.B2r.rowval[e] - 1)) >= 0);
             }
@@ -135,7 +165,12 @@ sls_solve_kernel(SlsSolveArgs a) {
                 int o = excl;
                 for (int64_t e = ea0; e < ea1; e++) {
                     const int l = sls_find(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
-                    if (l >= 0) { colr[o] = (uint16_t)l; valr[o] = a.Ar.nzval[e]; o++; }
+                    if (l >= 0) {
+                        const double v = a.Ar.nzval[e];
+                        colr[o] = (uint16_t)l; valr[o] = v; o++;
+                        Ablk[sls_blk(NB, i, l)] = v;
+                        nzA |= 1u << ((i >> 3) * NB + (l >> 3));
+                    }
                 }
                 for (int64_t e = eb0; e < eb1; e++) {
                     const int l = sls_find(su, m, (int32_t)(a.B2r.rowval[e] - 1));
@@ -143,6 +178,8 @@ sls_solve_kernel(SlsSolveArgs a) {
                 }
             }
         }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nzA |= __shfl_xor_sync(SLS_FULL, nzA, d);
         // ------------------------------------------------------------------ local CSC of C~ (columns 0..n+m)
         {
             int carry = 0;
@@ -152,8 +189,8 @@ sls_solve_kernel(SlsSolveArgs a) {
                 int64_t e0 = 0, e1 = 0;
                 const SlsCsc& M = (p < n) ? a.A : a.B2;
                 if (p < n + m) {
-                    const int64_t g = (p < n) ? sx[p] : su[p - n];
-                    e0 = M.colptr[g] - 1; e1 = M.colptr[g + 1] - 1;
+                    const int64_t gc = (p < n) ? sx[p] : su[p - n];
+                    e0 = M.colptr[gc] - 1; e1 = M.colptr[gc + 1] - 1;
                     for (int64_t e = e0; e < e1; e++) cnt += (sls_find(sx, n, (int32_t)(M.rowval[e] - 1)) >= 0);
                 }
                 int incl = cnt;
@@ -174,159 +211,239 @@ sls_solve_kernel(SlsSolveArgs a) {
         __syncwarp();
 
         // ------------------------------------------------------------------ tap 0:  S_0 = diag(mx_1), yh_0 = e
-        double s[N];                       // row i of -Z_k (the sweep works on -Z; signs folded below)
-        const uint32_t m1 = mxs[0];
-#pragma unroll
-        for (int p = 0; p < N; p++) s[p] = (p == i && ((m1 >> p) & 1u)) ? -1.0 : 0.0;
-        if (i < N) yh[i] = (i == jl) ? 1.0 : 0.0;
+        double S[NB][NB][2];                                  // -Z_k ("swept" S_k) in accumulator layout
         {
-            int hp = 0;
+            const uint32_t m1 = mxs[0];
 #pragma unroll
-            for (int p = 0; p < N; p++) {
-                if (p < n) { if (act && i >= p) hist[hp + i - p] = s[p]; hp += n - p; }
-            }
+            for (int bi = 0; bi < NB; bi++)
+#pragma unroll
+                for (int bj = 0; bj < NB; bj++) {
+                    const int r = 8 * bi + g, c0 = 8 * bj + 2 * q;
+                    S[bi][bj][0] = (r == c0 && ((m1 >> r) & 1u)) ? -1.0 : 0.0;
+                    S[bi][bj][1] = (r == c0 + 1 && ((m1 >> r) & 1u)) ? -1.0 : 0.0;
+                }
         }
+        double* yprev = ybuf0;
+        double* ycur = ybuf1;
+        if (i < N) { const double y0 = (i == jl) ? 1.0 : 0.0; yprev[i] = y0; yhist[i] = y0; }
         int status = (jl < 0) ? SLS_ST_NO_IMPULSE : 0;
+        uint32_t mu_prev[4] = {0u, 0u, 0u, 0u};               // wu <= 4 is guaranteed by the launcher (m <= 128)
+        bool bbt_valid = false;
         __syncwarp();
 
         // ------------------------------------------------------------------ forward elimination, taps 1..T
         for (int k = 1; k <= T; k++) {
             const uint32_t mk = mxs[k - 1];
-            const uint32_t mk1 = (k < T) ? mxs[k] : 0u;
+            const uint32_t mk1 = mxs[k];                      // mxs[T] = 0
             const uint32_t* muk = mus + (size_t)(k - 1) * wu;
-            const bool bi = act && ((mk >> i) & 1u);
-            const double* yprev = yh + (size_t)(k - 1) * N;
-            // g = Z_{k-1} yh_{k-1} (masked by mx_k), W row = mx_k o (I - Z_{k-1}) o mx_k
-            double g = 0.0;
+            // (1) g = mx_k o (Z_{k-1} yh_{k-1}) = -(mx_k o (S yprev))
 #pragma unroll
-            for (int p = 0; p < N; p++) g = fma(s[p], yprev[p], g);
-            if (i < N) gbuf[i] = bi ? -g : 0.0;
-            if (act) {
-#pragma unroll
-                for (int p = 0; p < N; p++) {
-                    const double w = (bi && ((mk >> p) & 1u)) ? ((p == i ? 1.0 : 0.0) + s[p]) : 0.0;
-                    Ws[i * LDW + p] = w;
-                }
-            }
-            // zero the B rows of P
-            for (int q = lane; q < m * LDP; q += 32) Ps[n * LDP + q] = 0.0;
-            __syncwarp();
-            // yh_k = A~ (mx_k o g)  (h_k = 0 for k >= 1);  dref = diag(D_k)
-            double dref = 0.0;
-            if (act) {
+            for (int bi = 0; bi < NB; bi++) {
                 double acc = 0.0;
-                dref = ((mk1 >> i) & 1u) ? 1.0 : 0.0;
-                const int r0 = rptr[i], r1 = rsplit[i], r2 = rptr[i + 1];
-                for (int e = r0; e < r1; e++) {
-                    const int l = colr[e]; const double v = valr[e];
-                    acc = fma(v, gbuf[l], acc);
-                    if ((mk >> l) & 1u) dref = fma(v, v, dref);
-                }
-                for (int e = r1; e < r2; e++) {
-                    const int l = colr[e] - n; const double v = valr[e];
-                    if (sls_bit(muk, l)) { dref = fma(v, v, dref); Ps[(n + l) * LDP + i] = v; }
-                }
-                yh[(size_t)k * N + i] = acc;
-            } else if (i < N) {
-                yh[(size_t)k * N + i] = 0.0;
-            }
-            if (i < L.NP) drefs[i] = dref;
-            // stage 1: P = W A~^T  (row i of P; row jj of A~ is read uniformly by all lanes)
-            if (act) {
 #pragma unroll
-                for (int jj = 0; jj < N; jj++) {
-                    double acc = 0.0;
-                    if (jj < n) {
-                        const int r0 = rptr[jj], r1 = rsplit[jj];
-                        for (int e = r0; e < r1; e++) acc = fma(Ws[i * LDW + colr[e]], valr[e], acc);
-                    }
-                    Ps[i * LDP + jj] = acc;
+                for (int bj = 0; bj < NB; bj++) {
+                    const double2 yv = *reinterpret_cast<const double2*>(yprev + 8 * bj + 2 * q);
+                    acc = fma(S[bi][bj][0], yv.x, acc);
+                    acc = fma(S[bi][bj][1], yv.y, acc);
                 }
+                acc += __shfl_xor_sync(SLS_FULL, acc, 1);
+                acc += __shfl_xor_sync(SLS_FULL, acc, 2);
+                const int r = 8 * bi + g;
+                if (q == 0) gbuf[r] = ((mk >> r) & 1u) ? -acc : 0.0;
+            }
+            // (2) B~ diag(mu_k) B~^T into shared memory when the actuator mask changed
+            bool mu_same = bbt_valid;
+#pragma unroll
+            for (int w = 0; w < 4; w++) if (w < wu) mu_same = mu_same && (muk[w] == mu_prev[w]);
+            if (!mu_same) {
+                for (int e = lane; e < N * N; e += 32) BBt[e] = 0.0;
+                __syncwarp();
+                if (act) {
+                    const int r1 = rsplit[i], r2 = rptr[i + 1];
+                    for (int e = r1; e < r2; e++) {
+                        const int l = colr[e] - n;
+                        if (!sls_bit(muk, l)) continue;
+                        const double v = valr[e];
+                        for (int e2 = cptr[n + l]; e2 < cptr[n + l + 1]; e2++) BBt[sls_blk(NB, i, rowc[e2])] += v * valc[e2];
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < 4; w++) if (w < wu) mu_prev[w] = muk[w];
+                bbt_valid = true;
             }
             __syncwarp();
-            // stage 2: S_k row i = diag(mx_{k+1}) + sum_{e in row i of C~} val * P[col][:]
-#pragma unroll
-            for (int p = 0; p < N; p++) s[p] = (p == i && act && ((mk1 >> p) & 1u)) ? 1.0 : 0.0;
-            if (act) {
-                const int r0 = rptr[i], r2 = rptr[i + 1];
-                for (int e = r0; e < r2; e++) {
-                    const double v = valr[e];
-                    const double2* prow = reinterpret_cast<const double2*>(Ps + (size_t)colr[e] * LDP);
-#pragma unroll
-                    for (int p2 = 0; p2 < N / 2; p2++) {
-                        const double2 pv = prow[p2];
-                        s[2 * p2] = fma(v, pv.x, s[2 * p2]);
-                        s[2 * p2 + 1] = fma(v, pv.y, s[2 * p2 + 1]);
+            // (3) yh_k = A~ g ;  dref = diag(D_k)
+            {
+                double acc = 0.0, dref = 0.0;
+                if (act) {
+                    dref = ((mk1 >> i) & 1u) ? 1.0 : 0.0;
+                    const int r0 = rptr[i], r1 = rsplit[i], r2 = rptr[i + 1];
+                    for (int e = r0; e < r1; e++) {
+                        const int l = colr[e]; const double v = valr[e];
+                        acc = fma(v, gbuf[l], acc);
+                        if ((mk >> l) & 1u) dref = fma(v, v, dref);
                     }
-                    if (N & 1) s[N - 1] = fma(v, (Ps + (size_t)colr[e] * LDP)[N - 1], s[N - 1]);
+                    for (int e = r1; e < r2; e++) {
+                        const int l = colr[e] - n; const double v = valr[e];
+                        if (sls_bit(muk, l)) dref = fma(v, v, dref);
+                    }
+                }
+                if (i < N) { ycur[i] = acc; drefs[i] = dref; yhist[(size_t)k * N + i] = acc; }
+            }
+            // (4) Pi = mx_k o (I - Z_{k-1}) o mx_k, in place
+#pragma unroll
+            for (int bi = 0; bi < NB; bi++)
+#pragma unroll
+                for (int bj = 0; bj < NB; bj++) {
+                    const int r = 8 * bi + g, c0 = 8 * bj + 2 * q;
+                    const bool mr = (mk >> r) & 1u;
+                    const bool m0 = mr && ((mk >> c0) & 1u), m1 = mr && ((mk >> (c0 + 1)) & 1u);
+                    S[bi][bj][0] = m0 ? ((r == c0 ? 1.0 : 0.0) + S[bi][bj][0]) : 0.0;
+                    S[bi][bj][1] = m1 ? ((r == c0 + 1 ? 1.0 : 0.0) + S[bi][bj][1]) : 0.0;
+                }
+            // (5) Tm = A~ Pi
+            double Tm[NB][NB][2];
+#pragma unroll
+            for (int bi = 0; bi < NB; bi++) {
+#pragma unroll
+                for (int bj = 0; bj < NB; bj++) { Tm[bi][bj][0] = 0.0; Tm[bi][bj][1] = 0.0; }
+#pragma unroll
+                for (int bl = 0; bl < NB; bl++) {
+                    if (!((nzA >> (bi * NB + bl)) & 1u)) continue;
+                    const double2 av = *reinterpret_cast<const double2*>(Ablk + ((bi * NB + bl) << 6) + (g << 3) + 2 * q);
+                    const double ab[2] = {av.x, av.y};
+#pragma unroll
+                    for (int bj = 0; bj < NB; bj++) sls_mma_xwt(Tm[bi][bj], ab, S[bj][bl]);
                 }
             }
-            // N symmetric sweeps with rank skipping
+            // (6) S_k = diag(mx_{k+1}) + B~ diag(mu_k) B~^T + Tm A~^T
+#pragma unroll
+            for (int bi = 0; bi < NB; bi++)
+#pragma unroll
+                for (int bj = 0; bj < NB; bj++) {
+                    const int r = 8 * bi + g, c0 = 8 * bj + 2 * q;
+                    const double2 bv = *reinterpret_cast<const double2*>(BBt + ((bi * NB + bj) << 6) + (g << 3) + 2 * q);
+                    S[bi][bj][0] = bv.x + ((r == c0 && ((mk1 >> r) & 1u)) ? 1.0 : 0.0);
+                    S[bi][bj][1] = bv.y + ((r == c0 + 1 && ((mk1 >> r) & 1u)) ? 1.0 : 0.0);
+                }
+#pragma unroll
+            for (int bj = 0; bj < NB; bj++)
+#pragma unroll
+                for (int bl = 0; bl < NB; bl++) {
+                    if (!((nzA >> (bj * NB + bl)) & 1u)) continue;
+                    const double2 av = *reinterpret_cast<const double2*>(Ablk + ((bj * NB + bl) << 6) + (g << 3) + 2 * q);
+                    const double ab[2] = {av.x, av.y};
+#pragma unroll
+                    for (int bi = 0; bi < NB; bi++) sls_mma_xwt(S[bi][bj], Tm[bi][bl], ab);
+                }
+            __syncwarp();                                     // drefs / ycur visible
+            // (7) block symmetric sweep with rank skipping:  S <- -(S^+)
             uint32_t keep = 0u;
 #pragma unroll
-            for (int kk = 0; kk < N; kk++) {
-                if (kk < n) {
-                    double* cbk = cb + (kk & 1) * L.NP;
-                    const double cval = s[kk];
-                    if (i < L.NP) cbk[i] = cval;
-                    __syncwarp();
-                    const double d = cbk[kk];
-                    const double dr = drefs[kk];
-                    if (dr != 0.0 && d > a.rank_tol * dr) {
-                        const double pinv = 1.0 / d;
-                        const double f = (i == kk) ? (1.0 - pinv) : cval * pinv;
-                        const double2* cb2 = reinterpret_cast<const double2*>(cbk);
-                        const double nf = -f;
+            for (int p = 0; p < NB; p++) {
+                double d0 = S[p][p][0], d1 = S[p][p][1];
+                uint32_t kb = 0u;
 #pragma unroll
-                        for (int p2 = 0; p2 < N / 2; p2++) {
-                            const double2 cv = cb2[p2];
-                            s[2 * p2] = fma(nf, cv.x, s[2 * p2]);
-                            s[2 * p2 + 1] = fma(nf, cv.y, s[2 * p2 + 1]);
-                        }
-                        if (N & 1) s[N - 1] = fma(nf, cbk[N - 1], s[N - 1]);
-                        s[kk] = (i == kk) ? -pinv : cval * pinv;
-                        keep |= 1u << kk;
+                for (int r = 0; r < 8; r++) {
+                    const double dv = __shfl_sync(SLS_FULL, (r & 1) ? d1 : d0, 4 * r + (r >> 1));
+                    const double dr = drefs[8 * p + r];
+                    if (dr != 0.0 && dv > a.rank_tol * dr) {
+                        const double pinv = 1.0 / dv;
+                        const double rr0 = __shfl_sync(SLS_FULL, d0, 4 * r + q);
+                        const double rr1 = __shfl_sync(SLS_FULL, d1, 4 * r + q);
+                        const double cg = __shfl_sync(SLS_FULL, (r & 1) ? d1 : d0, (lane & ~3) | (r >> 1));
+                        const double f = cg * pinv;
+                        double n0 = fma(-f, rr0, d0), n1 = fma(-f, rr1, d1);
+                        if (g == r) { n0 = rr0 * pinv; n1 = rr1 * pinv; }
+                        if (2 * q == r) n0 = (g == r) ? -pinv : f;
+                        if (2 * q + 1 == r) n1 = (g == r) ? -pinv : f;
+                        d0 = n0; d1 = n1;
+                        kb |= 1u << r;
                     }
                 }
+                {
+                    const bool kr = (kb >> g) & 1u;
+                    d0 = (kr && ((kb >> (2 * q)) & 1u)) ? d0 : 0.0;
+                    d1 = (kr && ((kb >> (2 * q + 1)) & 1u)) ? d1 : 0.0;
+                }
+                keep |= kb << (8 * p);
+                const double Pn[2] = {d0, d1};                // -P, symmetric
+                double Tn[NB][2], Tt[NB][2];                  // Tn_i = -S_ip P,  Tt_i = -P S_pi = -(S_ip P)^T
+#pragma unroll
+                for (int bi = 0; bi < NB; bi++) {
+                    if (bi == p) continue;
+                    Tn[bi][0] = 0.0; Tn[bi][1] = 0.0; Tt[bi][0] = 0.0; Tt[bi][1] = 0.0;
+                    sls_mma_xwt(Tn[bi], S[bi][p], Pn);
+                    sls_mma_xwt(Tt[bi], Pn, S[bi][p]);
+                }
+#pragma unroll
+                for (int bi = 0; bi < NB; bi++) {
+                    if (bi == p) continue;
+#pragma unroll
+                    for (int bj = 0; bj < NB; bj++) {
+                        if (bj == p) continue;
+                        sls_mma_xwt(S[bi][bj], Tn[bi], S[bj][p]);     // S_ij -= (S_ip P) S_jp^T
+                    }
+                }
+#pragma unroll
+                for (int bi = 0; bi < NB; bi++) {
+                    if (bi == p) continue;
+                    S[bi][p][0] = -Tn[bi][0]; S[bi][p][1] = -Tn[bi][1];
+                    S[p][bi][0] = -Tt[bi][0]; S[p][bi][1] = -Tt[bi][1];
+                }
+                S[p][p][0] = d0; S[p][p][1] = d1;
             }
             {
-                const bool ki = (keep >> i) & 1u;
-#pragma unroll
-                for (int p = 0; p < N; p++) s[p] = (ki && ((keep >> p) & 1u)) ? s[p] : 0.0;
-                const unsigned nonempty = __ballot_sync(SLS_FULL, act && dref != 0.0);
+                const unsigned nonempty = __ballot_sync(SLS_FULL, i < N && drefs[i < N ? i : 0] != 0.0);
                 if (keep != nonempty) status |= SLS_ST_RANK_SKIPPED;
             }
-            // history: packed lower triangle of -Z_k, column p holds rows p..n-1
-            {
-                double* hk = hist + (size_t)k * tri;
-                int hp = 0;
+            // (8) history: packed lower triangle (row-major) of -Z_k, k = 1..T-1 (Z_0 is diag(mx_1), Z_T is used at once)
+            if (k < T) {
+                double* hk = zhist + (size_t)k * TRI;
 #pragma unroll
-                for (int p = 0; p < N; p++) {
-                    if (p < n) { if (act && i >= p) hk[hp + i - p] = s[p]; hp += n - p; }
-                }
+                for (int bi = 0; bi < NB; bi++)
+#pragma unroll
+                    for (int bj = 0; bj <= bi; bj++) {
+                        const int r = 8 * bi + g, c0 = 8 * bj + 2 * q;
+                        const int off = r * (r + 1) / 2 + c0;
+                        if (r < n && c0 <= r) hk[off] = S[bi][bj][0];
+                        if (r < n && c0 + 1 <= r) hk[off + 1] = S[bi][bj][1];
+                    }
             }
             __syncwarp();
+            double* tsw = yprev; yprev = ycur; ycur = tsw;
         }
 
-        // ------------------------------------------------------------------ back substitution, k = T..1
-        double lam;
-        {
-            const double* yT = yh + (size_t)T * N;
+        // ------------------------------------------------------------------ lambda_T = Z_T yh_T
+        double lam = 0.0;
+#pragma unroll
+        for (int bi = 0; bi < NB; bi++) {
             double acc = 0.0;
 #pragma unroll
-            for (int p = 0; p < N; p++) acc = fma(s[p], yT[p], acc);
-            lam = -acc;
+            for (int bj = 0; bj < NB; bj++) {
+                const double2 yv = *reinterpret_cast<const double2*>(yprev + 8 * bj + 2 * q);
+                acc = fma(S[bi][bj][0], yv.x, acc);
+                acc = fma(S[bi][bj][1], yv.y, acc);
+            }
+            acc += __shfl_xor_sync(SLS_FULL, acc, 1);
+            acc += __shfl_xor_sync(SLS_FULL, acc, 2);
+            if (q == 0) lam_s[8 * bi + g] = -acc;
         }
+        __syncwarp();
+        if (i < N) lam = lam_s[i];
+        __syncwarp();
+
+        // ------------------------------------------------------------------ back substitution, k = T..1
         double* xnext = xa;   // x_{k+1}
         double* xcur = xb;    // x_k
-        if (i < L.NP) { xnext[i] = 0.0; }
+        if (i < N) { xnext[i] = 0.0; }
         double resmax = 0.0;
         const int64_t xoff = P.tot[c];
         const uint32_t* pre = P.pre + (size_t)c * 2 * T;
         for (int k = T; k >= 1; k--) {
             const uint32_t mk = mxs[k - 1];
             const uint32_t* muk = mus + (size_t)(k - 1) * wu;
-            if (i < L.NP) lam_s[i] = act ? lam : 0.0;
+            if (i < N) lam_s[i] = act ? lam : 0.0;
             __syncwarp();
             // t = C~^T lambda_k
             for (int p = lane; p < n + m; p += 32) {
@@ -349,28 +466,26 @@ sls_solve_kernel(SlsSolveArgs a) {
                     rank0 += __popc(word);
                 }
             }
-            const bool bi = act && ((mk >> i) & 1u);
-            if (i < L.NP) rhs_s[i] = act ? (yh[(size_t)(k - 1) * N + i] + (bi ? tx[i] : 0.0)) : 0.0;
+            const bool bi_ = act && ((mk >> i) & 1u);
+            if (i < N) rhs_s[i] = act ? (yhist[(size_t)(k - 1) * N + i] + (bi_ ? tx[i] : 0.0)) : 0.0;
             __syncwarp();
-            // lambda_{k-1} = Z_{k-1} rhs = -(hist_{k-1} rhs), symmetric packed read
-            double acc = 0.0;
-            if (act) {
-                const double* hk = hist + (size_t)(k - 1) * tri;
-                const int hpi = i * n - (i * (i - 1)) / 2;       // start of packed column i
-                int hp = 0;
-#pragma unroll
-                for (int p = 0; p < N; p++) {
-                    if (p < n) {
-                        const double z = (p <= i) ? hk[hp + i - p] : hk[hpi + p - i];
-                        acc = fma(z, rhs_s[p], acc);
-                        hp += n - p;
-                    }
+            // lambda_{k-1} = Z_{k-1} rhs
+            double lam_prev = 0.0;
+            if (k - 1 == 0) {
+                lam_prev = (act && ((mxs[0] >> i) & 1u)) ? rhs_s[i] : 0.0;
+            } else if (act) {
+                const double* hk = zhist + (size_t)(k - 1) * TRI;
+                const int rowoff = i * (i + 1) / 2;
+                double acc = 0.0;
+                for (int p = 0; p < n; p++) {
+                    const double z = (p <= i) ? hk[rowoff + p] : hk[p * (p + 1) / 2 + i];
+                    acc = fma(z, rhs_s[p], acc);
                 }
+                lam_prev = -acc;
             }
-            const double lam_prev = -acc;
-            const double x = bi ? (lam_prev - tx[i]) : 0.0;
-            if (i < L.NP) xcur[i] = x;
-            if (bi) a.xw[xoff + pre[2 * (k - 1)] + __popc(mk & ((1u << i) - 1u))] = x;
+            const double x = bi_ ? (lam_prev - tx[i]) : 0.0;
+            if (i < N) xcur[i] = x;
+            if (bi_) a.xw[xoff + pre[2 * (k - 1)] + __popc(mk & ((1u << i) - 1u))] = x;
             __syncwarp();
             // residual of constraint block k: A~ x_k + B~ u_k - x_{k+1}
             if (act) {
@@ -394,7 +509,7 @@ sls_solve_kernel(SlsSolveArgs a) {
 }
 
 // ---- host side ------------------------------------------------------------------------------
-static const int kClasses[] = {4, 8, 12, 16, 20, 21, 22, 24, 28, 32};
+static const int kClasses[] = {8, 16, 24, 32};
 int sls_solve_class_count() { return (int)(sizeof(kClasses) / sizeof(int)); }
 int sls_solve_class_N(int k) { return kClasses[k]; }
 int sls_solve_class_of(int n) {
@@ -404,24 +519,36 @@ int sls_solve_class_of(int n) {
 size_t sls_solve_smem_per_warp(int N, int mcap, int nnzcap, int T, int wu) {
     return (size_t)SlsSolveLayout(N, mcap, nnzcap, T, wu).total;
 }
-int64_t sls_solve_hist_doubles(int N, int T) { return (int64_t)(T + 1) * (N * (N + 1) / 2); }
+int64_t sls_solve_hist_doubles(int N, int T) { return (int64_t)(T + 1) * N + (int64_t)T * (N * (N + 1) / 2); }
 
-int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem) {
-    const size_t per_block = sls_solve_smem_per_warp(N, mcap, nnzcap, T, wu) * SOLVE_WPB;
+template <int NB>
+static int resident_warps(int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem) {
+    if (wu > 4) return -1;
+    const size_t per_block = sls_solve_smem_per_warp(8 * NB, mcap, nnzcap, T, wu) * SOLVE_WPB;
     if (per_block > (size_t)max_smem) return -1;
-    int bps = (int)((size_t)(max_smem) / (per_block + 1024));
-    if (bps < 1) bps = 1;
-    if (bps > 4) bps = 4;                       // register budget: 4 blocks x 128 threads
+    auto kp = &sls_solve_kernel<NB>;
+    if (per_block > 48 * 1024) { if (rt::set_max_smem(kp, (int)per_block)) return -1; }
+    const int bps = rt::max_blocks_per_sm(kp, SOLVE_WPB * 32, per_block);
+    if (bps < 1) return -1;
     return bps * sm_count * SOLVE_WPB;
 }
 
-template <int N>
+int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem) {
+    switch (N) {
+        case 8:  return resident_warps<1>(mcap, nnzcap, T, wu, sm_count, max_smem);
+        case 16: return resident_warps<2>(mcap, nnzcap, T, wu, sm_count, max_smem);
+        case 24: return resident_warps<3>(mcap, nnzcap, T, wu, sm_count, max_smem);
+        case 32: return resident_warps<4>(mcap, nnzcap, T, wu, sm_count, max_smem);
+        default: return -1;
+    }
+}
+
+template <int NB>
 static int launch_class(const SlsSolveArgs& a, int sm_count, int max_smem, int* warps_launched, sls_stream_t stream) {
-    const size_t per_block = sls_solve_smem_per_warp(N, a.mcap, a.nnzcap, a.P.T, a.P.wu) * SOLVE_WPB;
-    if (per_block > (size_t)max_smem) return -5;
-    auto kp = &sls_solve_kernel<N>;
-    if (per_block > 48 * 1024) { int e = rt::set_max_smem(kp, (int)per_block); if (e) return e; }
-    const int maxw = sls_solve_max_resident_warps(N, a.mcap, a.nnzcap, a.P.T, a.P.wu, sm_count, max_smem);
+    const size_t per_block = sls_solve_smem_per_warp(8 * NB, a.mcap, a.nnzcap, a.P.T, a.P.wu) * SOLVE_WPB;
+    const int maxw = resident_warps<NB>(a.mcap, a.nnzcap, a.P.T, a.P.wu, sm_count, max_smem);
+    if (maxw <= 0) return -5;
+    auto kp = &sls_solve_kernel<NB>;
     int blocks = (a.count + SOLVE_WPB - 1) / SOLVE_WPB;
     if (blocks > maxw / SOLVE_WPB) blocks = maxw / SOLVE_WPB;
     if (blocks < 1) blocks = 1;
@@ -435,16 +562,10 @@ int sls_launch_solve(int N, const SlsSolveArgs& a, int sm_count, int max_smem, i
     *warps_launched = 0;
     if (a.count == 0) return 0;
     switch (N) {
-        case 4:  return launch_class<4>(a, sm_count, max_smem, warps_launched, stream);
-        case 8:  return launch_class<8>(a, sm_count, max_smem, warps_launched, stream);
-        case 12: return launch_class<12>(a, sm_count, max_smem, warps_launched, stream);
-        case 16: return launch_class<16>(a, sm_count, max_smem, warps_launched, stream);
-        case 20: return launch_class<20>(a, sm_count, max_smem, warps_launched, stream);
-        case 21: return launch_class<21>(a, sm_count, max_smem, warps_launched, stream);
-        case 22: return launch_class<22>(a, sm_count, max_smem, warps_launched, stream);
-        case 24: return launch_class<24>(a, sm_count, max_smem, warps_launched, stream);
-        case 28: return launch_class<28>(a, sm_count, max_smem, warps_launched, stream);
-        case 32: return launch_class<32>(a, sm_count, max_smem, warps_launched, stream);
+        case 8:  return launch_class<1>(a, sm_count, max_smem, warps_launched, stream);
+        case 16: return launch_class<2>(a, sm_count, max_smem, warps_launched, stream);
+        case 24: return launch_class<3>(a, sm_count, max_smem, warps_launched, stream);
+        case 32: return launch_class<4>(a, sm_count, max_smem, warps_launched, stream);
         default: return -6;
     }
 }

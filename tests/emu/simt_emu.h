@@ -44,6 +44,7 @@ namespace emu {
 struct Warp {
     int count = 0; unsigned gen = 0;
     uint64_t slot[32];
+    double fa[32], fb[32];
     int expected = 32;
 };
 struct Fiber {
@@ -117,6 +118,21 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& f) {
     }
     for (int i = 0; i < nt; i++) free(stacks[i]);
     blk() = nullptr;
+}
+// mma.sync.aligned.m8n8k4.row.col.f64: A[row=lane>>2][k=lane&3], B[k=lane&3][col=lane>>2],
+// C/D[row=lane>>2][col=2*(lane&3)+{0,1}]
+inline void dmma(double& c0, double& c1, double a, double b) {
+    Warp& w = my_warp(); int lane = linear_tid() & 31;
+    w.fa[lane] = a; w.fb[lane] = b;
+    warp_barrier();
+    int g = lane >> 2, q = lane & 3;
+    double s0 = c0, s1 = c1;
+    for (int k = 0; k < 4; k++) {
+        s0 = std::fma(w.fa[4 * g + k], w.fb[4 * (2 * q) + k], s0);
+        s1 = std::fma(w.fa[4 * g + k], w.fb[4 * (2 * q + 1) + k], s1);
+    }
+    c0 = s0; c1 = s1;
+    warp_barrier();
 }
 }  // namespace emu
 
