@@ -42,7 +42,7 @@ struct SlsPlanView {            // per planned column c (0 <= c < ncols), writte
     int64_t* colptr;            // [2T][Nx+1]: counts at index j -> scanned in place to Julia colptr (1-based)
 };
 
-__device__ __forceinline__ int sls_find(const int32_t* s, int n, int key) {
+static __device__ __noinline__ int sls_find(const int32_t* s, int n, int key) {
     int lo = 0, hi = n;
     while (lo < hi) { int mid = (lo + hi) >> 1; if (s[mid] < key) lo = mid + 1; else hi = mid; }
     return (lo < n && s[lo] == key) ? lo : -1;

@@ -31,6 +31,8 @@
 #include "sls_kernels.h"
 
 #define SOLVE_WPB 4
+#include <cmath>
+#define SLS_INF ((double)INFINITY)
 
 __device__ __forceinline__ void sls_dmma(double& c0, double& c1, double a, double b) {
 #ifdef SLS_EMU
@@ -38,6 +40,18 @@ __device__ __forceinline__ void sls_dmma(double& c0, double& c1, double a, doubl
 #else
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#endif
+}
+// 1/x for x > 0 to ~1 ulp: hardware seed (rcp.approx.ftz.f64, >= 20 good bits) + 2 Newton steps
+__device__ __forceinline__ double sls_rcp(double x) {
+#ifdef SLS_EMU
+    return 1.0 / x;
+#else
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
 #endif
 }
 // acc += X * W^T for two 8x8 blocks in accumulator layout
@@ -98,12 +112,12 @@ sls_solve_kernel(SlsSolveArgs a) {
     const int T = P.T;
     const SlsSolveLayout L(N, a.mcap, a.nnzcap, T, P.wu);
     unsigned char* base = smem_raw + (size_t)warp * L.total;
-    double* Ablk = reinterpret_cast<double*>(base + L.oAblk);
-    double* BBt = reinterpret_cast<double*>(base + L.oBBt);
+    double* Am = reinterpret_cast<double*>(base + L.oAblk);     // A~ diag(mx_k) as dense 8x8 blocks (accumulator order)
+    double* Dp = reinterpret_cast<double*>(base + L.oBBt);      // diag(mx_{k+1}) + B~ diag(mu_k) B~^T, same layout
     double* ybuf0 = reinterpret_cast<double*>(base + L.oY0);
     double* ybuf1 = reinterpret_cast<double*>(base + L.oY1);
     double* gbuf = reinterpret_cast<double*>(base + L.oG);
-    double* drefs = reinterpret_cast<double*>(base + L.oDref);
+    double* thrs = reinterpret_cast<double*>(base + L.oDref);   // pivot thresholds rank_tol*diag(D_k) (+inf: empty row)
     double* lam_s = reinterpret_cast<double*>(base + L.oLam);
     double* tx = reinterpret_cast<double*>(base + L.oTx);
     double* rhs_s = reinterpret_cast<double*>(base + L.oRhs);
@@ -141,7 +155,7 @@ sls_solve_kernel(SlsSolveArgs a) {
         for (int t = lane; t < T; t += 32) mxs[t] = P.maskx[((size_t)c * T + t) * P.wx];
         if (lane == 0) mxs[T] = 0u;
         for (int t = lane; t < T * wu; t += 32) mus[t] = P.masku[(size_t)c * T * wu + t];
-        for (int e = lane; e < N * N; e += 32) Ablk[e] = 0.0;
+        for (int e = lane; e < N * N; e += 32) Am[e] = 0.0;
         __syncwarp();
         // ------------------------------------------------------------------ local CSR of C~ = [A~ B~], dense blocks of A~
         unsigned nzA = 0u;                                    // bit bi*NB+bj: block (bi,bj) of A~ has a stored entry
@@ -168,7 +182,6 @@ sls_solve_kernel(SlsSolveArgs a) {
                     if (l >= 0) {
                         const double v = a.Ar.nzval[e];
                         colr[o] = (uint16_t)l; valr[o] = v; o++;
-                        Ablk[sls_blk(NB, i, l)] = v;
                         nzA |= 1u << ((i >> 3) * NB + (l >> 3));
                     }
                 }
@@ -212,23 +225,30 @@ sls_solve_kernel(SlsSolveArgs a) {
 
         // ------------------------------------------------------------------ tap 0:  S_0 = diag(mx_1), yh_0 = e
         double S[NB][NB][2];                                  // -Z_k ("swept" S_k) in accumulator layout
+        int rowoff[NB];                                       // r(r+1)/2 of the lane's row in each block row
         {
             const uint32_t m1 = mxs[0];
 #pragma unroll
-            for (int bi = 0; bi < NB; bi++)
+            for (int bi = 0; bi < NB; bi++) {
+                const int r = 8 * bi + g;
+                rowoff[bi] = r * (r + 1) / 2;
 #pragma unroll
                 for (int bj = 0; bj < NB; bj++) {
-                    const int r = 8 * bi + g, c0 = 8 * bj + 2 * q;
+                    const int c0 = 8 * bj + 2 * q;
                     S[bi][bj][0] = (r == c0 && ((m1 >> r) & 1u)) ? -1.0 : 0.0;
                     S[bi][bj][1] = (r == c0 + 1 && ((m1 >> r) & 1u)) ? -1.0 : 0.0;
                 }
+            }
         }
+        const double dg0 = (g == 2 * q) ? 1.0 : 0.0, dg1 = (g == 2 * q + 1) ? 1.0 : 0.0;   // identity inside a diagonal block
         double* yprev = ybuf0;
         double* ycur = ybuf1;
         if (i < N) { const double y0 = (i == jl) ? 1.0 : 0.0; yprev[i] = y0; yhist[i] = y0; }
         int status = (jl < 0) ? SLS_ST_NO_IMPULSE : 0;
         uint32_t mu_prev[4] = {0u, 0u, 0u, 0u};               // wu <= 4 is guaranteed by the launcher (m <= 128)
-        bool bbt_valid = false;
+        uint32_t mk_prev = 0u, mk1_prev = 0u;
+        bool cache_valid = false;
+        unsigned nonempty = 0u;
         __syncwarp();
 
         // ------------------------------------------------------------------ forward elimination, taps 1..T
@@ -251,57 +271,52 @@ sls_solve_kernel(SlsSolveArgs a) {
                 const int r = 8 * bi + g;
                 if (q == 0) gbuf[r] = ((mk >> r) & 1u) ? -acc : 0.0;
             }
-            // (2) B~ diag(mu_k) B~^T into shared memory when the actuator mask changed
-            bool mu_same = bbt_valid;
+            // (2) mask-dependent operands, rebuilt only when a mask changed (constant once the band is full):
+            //     Am = A~ diag(mx_k),  Dp = diag(mx_{k+1}) + B~ diag(mu_k) B~^T,  thr = rank_tol * diag(D_k)
+            bool same = cache_valid && mk == mk_prev && mk1 == mk1_prev;
 #pragma unroll
-            for (int w = 0; w < 4; w++) if (w < wu) mu_same = mu_same && (muk[w] == mu_prev[w]);
-            if (!mu_same) {
-                for (int e = lane; e < N * N; e += 32) BBt[e] = 0.0;
+            for (int w = 0; w < 4; w++) if (w < wu) same = same && (muk[w] == mu_prev[w]);
+            if (!same) {
+                for (int e = lane; e < N * N; e += 32) Dp[e] = 0.0;
                 __syncwarp();
+                double dref = 0.0;
                 if (act) {
-                    const int r1 = rsplit[i], r2 = rptr[i + 1];
+                    const int r0 = rptr[i], r1 = rsplit[i], r2 = rptr[i + 1];
+                    if ((mk1 >> i) & 1u) { dref = 1.0; Dp[sls_blk(NB, i, i)] = 1.0; }
+                    for (int e = r0; e < r1; e++) {
+                        const int l = colr[e]; const double v = valr[e];
+                        const bool on = (mk >> l) & 1u;
+                        Am[sls_blk(NB, i, l)] = on ? v : 0.0;
+                        if (on) dref = fma(v, v, dref);
+                    }
                     for (int e = r1; e < r2; e++) {
                         const int l = colr[e] - n;
                         if (!sls_bit(muk, l)) continue;
                         const double v = valr[e];
-                        for (int e2 = cptr[n + l]; e2 < cptr[n + l + 1]; e2++) BBt[sls_blk(NB, i, rowc[e2])] += v * valc[e2];
+                        dref = fma(v, v, dref);
+                        for (int e2 = cptr[n + l]; e2 < cptr[n + l + 1]; e2++) Dp[sls_blk(NB, i, rowc[e2])] += v * valc[e2];
                     }
                 }
+                if (i < N) thrs[i] = (dref != 0.0) ? a.rank_tol * dref : SLS_INF;
+                nonempty = __ballot_sync(SLS_FULL, dref != 0.0);
 #pragma unroll
                 for (int w = 0; w < 4; w++) if (w < wu) mu_prev[w] = muk[w];
-                bbt_valid = true;
+                mk_prev = mk; mk1_prev = mk1; cache_valid = true;
             }
             __syncwarp();
-            // (3) yh_k = A~ g ;  dref = diag(D_k)
+            // (3) yh_k = A~ g
             {
-                double acc = 0.0, dref = 0.0;
+                double acc = 0.0;
                 if (act) {
-                    dref = ((mk1 >> i) & 1u) ? 1.0 : 0.0;
-                    const int r0 = rptr[i], r1 = rsplit[i], r2 = rptr[i + 1];
-                    for (int e = r0; e < r1; e++) {
-                        const int l = colr[e]; const double v = valr[e];
-                        acc = fma(v, gbuf[l], acc);
-                        if ((mk >> l) & 1u) dref = fma(v, v, dref);
-                    }
-                    for (int e = r1; e < r2; e++) {
-                        const int l = colr[e] - n; const double v = valr[e];
-                        if (sls_bit(muk, l)) dref = fma(v, v, dref);
-                    }
+                    const int r0 = rptr[i], r1 = rsplit[i];
+                    for (int e = r0; e < r1; e++) acc = fma(valr[e], gbuf[colr[e]], acc);
                 }
-                if (i < N) { ycur[i] = acc; drefs[i] = dref; yhist[(size_t)k * N + i] = acc; }
+                if (i < N) { ycur[i] = acc; yhist[(size_t)k * N + i] = acc; }
             }
-            // (4) Pi = mx_k o (I - Z_{k-1}) o mx_k, in place
+            // (4) Pi' = I - Z_{k-1}  (the masks live in Am)
 #pragma unroll
-            for (int bi = 0; bi < NB; bi++)
-#pragma unroll
-                for (int bj = 0; bj < NB; bj++) {
-                    const int r = 8 * bi + g, c0 = 8 * bj + 2 * q;
-                    const bool mr = (mk >> r) & 1u;
-                    const bool m0 = mr && ((mk >> c0) & 1u), m1 = mr && ((mk >> (c0 + 1)) & 1u);
-                    S[bi][bj][0] = m0 ? ((r == c0 ? 1.0 : 0.0) + S[bi][bj][0]) : 0.0;
-                    S[bi][bj][1] = m1 ? ((r == c0 + 1 ? 1.0 : 0.0) + S[bi][bj][1]) : 0.0;
-                }
-            // (5) Tm = A~ Pi
+            for (int bi = 0; bi < NB; bi++) { S[bi][bi][0] += dg0; S[bi][bi][1] += dg1; }
+            // (5) Tm = Am Pi'
             double Tm[NB][NB][2];
 #pragma unroll
             for (int bi = 0; bi < NB; bi++) {
@@ -310,61 +325,58 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
                 for (int bl = 0; bl < NB; bl++) {
                     if (!((nzA >> (bi * NB + bl)) & 1u)) continue;
-                    const double2 av = *reinterpret_cast<const double2*>(Ablk + ((bi * NB + bl) << 6) + (g << 3) + 2 * q);
+                    const double2 av = *reinterpret_cast<const double2*>(Am + ((bi * NB + bl) << 6) + (g << 3) + 2 * q);
                     const double ab[2] = {av.x, av.y};
 #pragma unroll
                     for (int bj = 0; bj < NB; bj++) sls_mma_xwt(Tm[bi][bj], ab, S[bj][bl]);
                 }
             }
-            // (6) S_k = diag(mx_{k+1}) + B~ diag(mu_k) B~^T + Tm A~^T
+            // (6) S_k = Dp + Tm Am^T
 #pragma unroll
             for (int bi = 0; bi < NB; bi++)
 #pragma unroll
                 for (int bj = 0; bj < NB; bj++) {
-                    const int r = 8 * bi + g, c0 = 8 * bj + 2 * q;
-                    const double2 bv = *reinterpret_cast<const double2*>(BBt + ((bi * NB + bj) << 6) + (g << 3) + 2 * q);
-                    S[bi][bj][0] = bv.x + ((r == c0 && ((mk1 >> r) & 1u)) ? 1.0 : 0.0);
-                    S[bi][bj][1] = bv.y + ((r == c0 + 1 && ((mk1 >> r) & 1u)) ? 1.0 : 0.0);
+                    const double2 bv = *reinterpret_cast<const double2*>(Dp + ((bi * NB + bj) << 6) + (g << 3) + 2 * q);
+                    S[bi][bj][0] = bv.x; S[bi][bj][1] = bv.y;
                 }
 #pragma unroll
             for (int bj = 0; bj < NB; bj++)
 #pragma unroll
                 for (int bl = 0; bl < NB; bl++) {
                     if (!((nzA >> (bj * NB + bl)) & 1u)) continue;
-                    const double2 av = *reinterpret_cast<const double2*>(Ablk + ((bj * NB + bl) << 6) + (g << 3) + 2 * q);
+                    const double2 av = *reinterpret_cast<const double2*>(Am + ((bj * NB + bl) << 6) + (g << 3) + 2 * q);
                     const double ab[2] = {av.x, av.y};
 #pragma unroll
                     for (int bi = 0; bi < NB; bi++) sls_mma_xwt(S[bi][bj], Tm[bi][bl], ab);
                 }
-            __syncwarp();                                     // drefs / ycur visible
-            // (7) block symmetric sweep with rank skipping:  S <- -(S^+)
+            // (7) block symmetric sweep with rank skipping:  S <- -(S^+).  A skipped pivot (<= threshold) gets
+            //     pinv = 0, which zeroes its row and column at once (they never feed a kept row).
             uint32_t keep = 0u;
 #pragma unroll
             for (int p = 0; p < NB; p++) {
                 double d0 = S[p][p][0], d1 = S[p][p][1];
                 uint32_t kb = 0u;
+#pragma unroll 1
+                for (int rp = 0; rp < 4; rp++) {
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const double dv = __shfl_sync(SLS_FULL, (r & 1) ? d1 : d0, 4 * r + (r >> 1));
-                    const double dr = drefs[8 * p + r];
-                    if (dr != 0.0 && dv > a.rank_tol * dr) {
-                        const double pinv = 1.0 / dv;
+                    for (int e = 0; e < 2; e++) {
+                        const int r = 2 * rp + e;
+                        const double src = e ? d1 : d0;
+                        const double dv = __shfl_sync(SLS_FULL, src, 4 * r + rp);
+                        const double cg = __shfl_sync(SLS_FULL, src, (lane & ~3) | rp);
                         const double rr0 = __shfl_sync(SLS_FULL, d0, 4 * r + q);
                         const double rr1 = __shfl_sync(SLS_FULL, d1, 4 * r + q);
-                        const double cg = __shfl_sync(SLS_FULL, (r & 1) ? d1 : d0, (lane & ~3) | (r >> 1));
-                        const double f = cg * pinv;
+                        const bool ok = dv > thrs[8 * p + r];
+                        const double pinv = ok ? sls_rcp(dv) : 0.0;
+                        const bool isrow = (g == r);
+                        const double cp = cg * pinv;
+                        const double f = isrow ? (1.0 - pinv) : cp;
                         double n0 = fma(-f, rr0, d0), n1 = fma(-f, rr1, d1);
-                        if (g == r) { n0 = rr0 * pinv; n1 = rr1 * pinv; }
-                        if (2 * q == r) n0 = (g == r) ? -pinv : f;
-                        if (2 * q + 1 == r) n1 = (g == r) ? -pinv : f;
+                        const double cv = isrow ? -pinv : cp;
+                        if (q == rp) { if (e) n1 = cv; else n0 = cv; }
                         d0 = n0; d1 = n1;
-                        kb |= 1u << r;
+                        kb |= (ok ? 1u : 0u) << r;
                     }
-                }
-                {
-                    const bool kr = (kb >> g) & 1u;
-                    d0 = (kr && ((kb >> (2 * q)) & 1u)) ? d0 : 0.0;
-                    d1 = (kr && ((kb >> (2 * q + 1)) & 1u)) ? d1 : 0.0;
                 }
                 keep |= kb << (8 * p);
                 const double Pn[2] = {d0, d1};                // -P, symmetric
@@ -393,10 +405,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 }
                 S[p][p][0] = d0; S[p][p][1] = d1;
             }
-            {
-                const unsigned nonempty = __ballot_sync(SLS_FULL, i < N && drefs[i < N ? i : 0] != 0.0);
-                if (keep != nonempty) status |= SLS_ST_RANK_SKIPPED;
-            }
+            if (keep != nonempty) status |= SLS_ST_RANK_SKIPPED;
             // (8) history: packed lower triangle (row-major) of -Z_k, k = 1..T-1 (Z_0 is diag(mx_1), Z_T is used at once)
             if (k < T) {
                 double* hk = zhist + (size_t)k * TRI;
@@ -405,9 +414,8 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
                     for (int bj = 0; bj <= bi; bj++) {
                         const int r = 8 * bi + g, c0 = 8 * bj + 2 * q;
-                        const int off = r * (r + 1) / 2 + c0;
-                        if (r < n && c0 <= r) hk[off] = S[bi][bj][0];
-                        if (r < n && c0 + 1 <= r) hk[off + 1] = S[bi][bj][1];
+                        if (r < n && c0 <= r) hk[rowoff[bi] + c0] = S[bi][bj][0];
+                        if (r < n && c0 + 1 <= r) hk[rowoff[bi] + c0 + 1] = S[bi][bj][1];
                     }
             }
             __syncwarp();
@@ -469,19 +477,61 @@ sls_solve_kernel(SlsSolveArgs a) {
             const bool bi_ = act && ((mk >> i) & 1u);
             if (i < N) rhs_s[i] = act ? (yhist[(size_t)(k - 1) * N + i] + (bi_ ? tx[i] : 0.0)) : 0.0;
             __syncwarp();
-            // lambda_{k-1} = Z_{k-1} rhs
+            // lambda_{k-1} = Z_{k-1} rhs  (history read back in accumulator layout; symmetric mat-vec)
             double lam_prev = 0.0;
             if (k - 1 == 0) {
                 lam_prev = (act && ((mxs[0] >> i) & 1u)) ? rhs_s[i] : 0.0;
-            } else if (act) {
+            } else {
                 const double* hk = zhist + (size_t)(k - 1) * TRI;
-                const int rowoff = i * (i + 1) / 2;
-                double acc = 0.0;
-                for (int p = 0; p < n; p++) {
-                    const double z = (p <= i) ? hk[rowoff + p] : hk[p * (p + 1) / 2 + i];
-                    acc = fma(z, rhs_s[p], acc);
+                double racc[NB], cacc[NB][2];
+#pragma unroll
+                for (int b = 0; b < NB; b++) { racc[b] = 0.0; cacc[b][0] = 0.0; cacc[b][1] = 0.0; }
+#pragma unroll
+                for (int bi = 0; bi < NB; bi++) {
+                    const int r = 8 * bi + g;
+                    const double vr = rhs_s[r];
+#pragma unroll
+                    for (int bj = 0; bj <= bi; bj++) {
+                        const int c0 = 8 * bj + 2 * q;
+                        const double2 vc = *reinterpret_cast<const double2*>(rhs_s + c0);
+                        double z0 = 0.0, z1 = 0.0;
+                        if (bj < bi) {
+                            if (r < n) { z0 = hk[rowoff[bi] + c0]; z1 = hk[rowoff[bi] + c0 + 1]; }
+                            cacc[bj][0] = fma(z0, vr, cacc[bj][0]);
+                            cacc[bj][1] = fma(z1, vr, cacc[bj][1]);
+                        } else {
+                            // diagonal block: full 8x8 from the packed lower triangle by symmetric addressing
+                            if (r < n && c0 < n) z0 = (c0 <= r) ? hk[rowoff[bi] + c0] : hk[c0 * (c0 + 1) / 2 + r];
+                            if (r < n && c0 + 1 < n) z1 = (c0 + 1 <= r) ? hk[rowoff[bi] + c0 + 1] : hk[(c0 + 1) * (c0 + 2) / 2 + r];
+                        }
+                        racc[bi] = fma(z0, vc.x, racc[bi]);
+                        racc[bi] = fma(z1, vc.y, racc[bi]);
+                    }
                 }
-                lam_prev = -acc;
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    racc[b] += __shfl_xor_sync(SLS_FULL, racc[b], 1);
+                    racc[b] += __shfl_xor_sync(SLS_FULL, racc[b], 2);
+                    if (b < NB - 1) {
+#pragma unroll
+                        for (int d = 4; d < 32; d <<= 1) {
+                            cacc[b][0] += __shfl_xor_sync(SLS_FULL, cacc[b][0], d);
+                            cacc[b][1] += __shfl_xor_sync(SLS_FULL, cacc[b][1], d);
+                        }
+                    }
+                }
+                // row part of row 8b+g sits in every lane of quad g; column part of rows 8b+2q, 8b+2q+1 in every g
+                if (q == 0) {
+#pragma unroll
+                    for (int b = 0; b < NB; b++) gbuf[8 * b + g] = racc[b];
+                }
+                __syncwarp();
+                if (g == 0) {
+#pragma unroll
+                    for (int b = 0; b < NB - 1; b++) { gbuf[8 * b + 2 * q] += cacc[b][0]; gbuf[8 * b + 2 * q + 1] += cacc[b][1]; }
+                }
+                __syncwarp();
+                lam_prev = act ? -gbuf[i] : 0.0;
             }
             const double x = bi_ ? (lam_prev - tx[i]) : 0.0;
             if (i < N) xcur[i] = x;
