@@ -42,10 +42,13 @@ struct SlsPlanView {            // per planned column c (0 <= c < ncols), writte
     int64_t* colptr;            // [2T][Nx+1]: counts at index j -> scanned in place to Julia colptr (1-based)
 };
 
-static __device__ __noinline__ int sls_find(const int32_t* s, int n, int key) {
+__device__ __forceinline__ int sls_find(const int32_t* s, int n, int key) {
     int lo = 0, hi = n;
     while (lo < hi) { int mid = (lo + hi) >> 1; if (s[mid] < key) lo = mid + 1; else hi = mid; }
     return (lo < n && s[lo] == key) ? lo : -1;
 }
 
 __device__ __forceinline__ int sls_lane() { return threadIdx.x & 31; }
+
+// out-of-line copy for cold code (per-column setup of kernel 2): keeps the hot loops' code footprint small
+static __device__ __noinline__ int sls_find_cold(const int32_t* s, int n, int key) { return sls_find(s, n, key); }

@@ -68,6 +68,7 @@ struct SlsSolveLayout {
         N = N_; NB = N_ / 8; mcap = mcap_ < 1 ? 1 : mcap_; nnzcap = nnzcap_ < 1 ? 1 : nnzcap_; T = T_; wu = wu_ < 1 ? 1 : wu_;
         int o = 0;
 #define SLS_SEC(name, bytes) name = o; o += (bytes); o = (o + 15) & ~15
+        // sections whose size depends on N only come first: their offsets are compile-time constants in the kernel
         SLS_SEC(oAblk, 8 * N * N);
         SLS_SEC(oBBt, 8 * N * N);
         SLS_SEC(oY0, 8 * N);
@@ -75,19 +76,19 @@ struct SlsSolveLayout {
         SLS_SEC(oG, 8 * N);
         SLS_SEC(oDref, 8 * N);
         SLS_SEC(oLam, 8 * N);
-        SLS_SEC(oTx, 8 * (N + mcap));
         SLS_SEC(oRhs, 8 * N);
         SLS_SEC(oXa, 8 * N);
         SLS_SEC(oXb, 8 * N);
+        SLS_SEC(oSx, 4 * N);
+        SLS_SEC(oRptr, 2 * (N + 2));
+        SLS_SEC(oRsplit, 2 * (N + 2));
+        SLS_SEC(oTx, 8 * (N + mcap));
         SLS_SEC(oUc, 8 * mcap);
         SLS_SEC(oValR, 8 * nnzcap);
         SLS_SEC(oValC, 8 * nnzcap);
-        SLS_SEC(oSx, 4 * N);
         SLS_SEC(oSu, 4 * mcap);
         SLS_SEC(oMx, 4 * (T + 1));
         SLS_SEC(oMu, 4 * T * wu);
-        SLS_SEC(oRptr, 2 * (N + 2));
-        SLS_SEC(oRsplit, 2 * (N + 2));
         SLS_SEC(oColR, 2 * nnzcap);
         SLS_SEC(oCptr, 2 * (N + mcap + 2));
         SLS_SEC(oRowC, 2 * nnzcap);
@@ -101,7 +102,7 @@ __device__ __forceinline__ bool sls_bit(const uint32_t* w, int i) { return (w[i 
 __device__ __forceinline__ int sls_blk(int NB, int r, int c) { return (((r >> 3) * NB + (c >> 3)) << 6) + ((r & 7) << 3) + (c & 7); }
 
 template <int NB>
-__global__ void __launch_bounds__(SOLVE_WPB * 32)
+__global__ void __launch_bounds__(SOLVE_WPB * 32, (NB <= 3 ? 4 : 2))
 sls_solve_kernel(SlsSolveArgs a) {
     constexpr int N = 8 * NB;
     SLS_DYN_SMEM(smem_raw);
@@ -166,8 +167,8 @@ sls_solve_kernel(SlsSolveArgs a) {
                 const int64_t gr = sx[i];
                 ea0 = a.Ar.colptr[gr] - 1; ea1 = a.Ar.colptr[gr + 1] - 1;
                 eb0 = a.B2r.colptr[gr] - 1; eb1 = a.B2r.colptr[gr + 1] - 1;
-                for (int64_t e = ea0; e < ea1; e++) cntA += (sls_find(sx, n, (int32_t)(a.Ar.rowval[e] - 1)) >= 0);
-                for (int64_t e = eb0; e < eb1; e++) cntB += (sls_find(su, m, (int32_t)(a.B2r.rowval[e] - 1)) >= 0);
+                for (int64_t e = ea0; e < ea1; e++) cntA += (sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1)) >= 0);
+                for (int64_t e = eb0; e < eb1; e++) cntB += (sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1)) >= 0);
             }
             int incl = cntA + cntB;
 #pragma unroll
@@ -178,7 +179,7 @@ sls_solve_kernel(SlsSolveArgs a) {
             if (act) {
                 int o = excl;
                 for (int64_t e = ea0; e < ea1; e++) {
-                    const int l = sls_find(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
+                    const int l = sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
                     if (l >= 0) {
                         const double v = a.Ar.nzval[e];
                         colr[o] = (uint16_t)l; valr[o] = v; o++;
@@ -186,7 +187,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                     }
                 }
                 for (int64_t e = eb0; e < eb1; e++) {
-                    const int l = sls_find(su, m, (int32_t)(a.B2r.rowval[e] - 1));
+                    const int l = sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1));
                     if (l >= 0) { colr[o] = (uint16_t)(n + l); valr[o] = a.B2r.nzval[e]; o++; }
                 }
             }
@@ -204,7 +205,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 if (p < n + m) {
                     const int64_t gc = (p < n) ? sx[p] : su[p - n];
                     e0 = M.colptr[gc] - 1; e1 = M.colptr[gc + 1] - 1;
-                    for (int64_t e = e0; e < e1; e++) cnt += (sls_find(sx, n, (int32_t)(M.rowval[e] - 1)) >= 0);
+                    for (int64_t e = e0; e < e1; e++) cnt += (sls_find_cold(sx, n, (int32_t)(M.rowval[e] - 1)) >= 0);
                 }
                 int incl = cnt;
 #pragma unroll
@@ -213,7 +214,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                     int o = carry + incl - cnt;
                     cptr[p] = (uint16_t)o;
                     for (int64_t e = e0; e < e1; e++) {
-                        const int r = sls_find(sx, n, (int32_t)(M.rowval[e] - 1));
+                        const int r = sls_find_cold(sx, n, (int32_t)(M.rowval[e] - 1));
                         if (r >= 0) { rowc[o] = (uint16_t)r; valc[o] = M.nzval[e]; o++; }
                     }
                 }
