@@ -13,7 +13,7 @@
 // S_k^+ is the inverse on the rows whose pivot exceeds rank_tol * diag(D_k); redundant constraint rows are
 // eliminated (what Ipopt's inertia correction does implicitly).
 //
-// Data layout: an n x n matrix (n <= N = 8*NB <= 32) lives in the registers of one warp as NB x NB blocks
+// Data layout: an n x n matrix (n <= N = 8*NB <= 64) lives in the registers (spilling to L1-backed local memory for N > 32) of one warp as NB x NB blocks
 // of 8 x 8 in the DMMA accumulator layout: lane 4g+q holds X[8bi+g][8bj+2q], X[8bi+g][8bj+2q+1].
 // With the k index of the MMA mapped to even / odd columns, a product  X * W^T  of two blocks that are both
 // in accumulator layout needs NO data movement: A-fragment = (x0 | x1), B-fragment = (w0 | w1).  All
@@ -30,7 +30,7 @@
 #include "sls_common.h"
 #include "sls_kernels.h"
 
-#define SOLVE_WPB 4
+
 #include <cmath>
 #define SLS_INF ((double)INFINITY)
 
@@ -87,7 +87,7 @@ struct SlsSolveLayout {
         SLS_SEC(oValR, 8 * nnzcap);
         SLS_SEC(oValC, 8 * nnzcap);
         SLS_SEC(oSu, 4 * mcap);
-        SLS_SEC(oMx, 4 * (T + 1));
+        SLS_SEC(oMx, 8 * (T + 1));
         SLS_SEC(oMu, 4 * T * wu);
         SLS_SEC(oColR, 2 * nnzcap);
         SLS_SEC(oCptr, 2 * (N + mcap + 2));
@@ -101,13 +101,29 @@ __device__ __forceinline__ bool sls_bit(const uint32_t* w, int i) { return (w[i 
 // index of element (r,c) inside a blocked (accumulator-layout friendly) N x N shared-memory matrix
 __device__ __forceinline__ int sls_blk(int NB, int r, int c) { return (((r >> 3) * NB + (c >> 3)) << 6) + ((r & 7) << 3) + (c & 7); }
 
+// free-variable mask of one tap over the local state index: 32 bits for n <= 32, 64 bits for n <= 64
+template <int NB> struct SlsMask { typedef uint32_t type; };
+template <> struct SlsMask<5> { typedef uint64_t type; };
+template <> struct SlsMask<6> { typedef uint64_t type; };
+template <> struct SlsMask<7> { typedef uint64_t type; };
+template <> struct SlsMask<8> { typedef uint64_t type; };
+__device__ __forceinline__ bool sls_mbit(uint32_t m, int r) { return (m >> r) & 1u; }
+__device__ __forceinline__ bool sls_mbit(uint64_t m, int r) { return (m >> r) & 1ull; }
+__device__ __forceinline__ int sls_mrank(uint32_t m, int r) { return __popc(m & ((1u << r) - 1u)); }
+__device__ __forceinline__ int sls_mrank(uint64_t m, int r) { return __popcll(m & ((1ull << r) - 1ull)); }
+
+// warps per block / minimum resident blocks per SM of each size class (registers: 128 per thread up to N = 24)
+template <int NB> struct SlsCfg { static const int WPB = (NB <= 4) ? 4 : 1; static const int MINB = (NB <= 3) ? 4 : ((NB == 4) ? 2 : 1); };
+
 template <int NB>
-__global__ void __launch_bounds__(SOLVE_WPB * 32, (NB <= 3 ? 4 : 2))
+__global__ void __launch_bounds__(SlsCfg<NB>::WPB * 32, SlsCfg<NB>::MINB)
 sls_solve_kernel(SlsSolveArgs a) {
     constexpr int N = 8 * NB;
+    constexpr int WPB = SlsCfg<NB>::WPB;
+    constexpr int RPL = (N + 31) / 32;       // rows per lane in the sparse (lane-per-row) phases
+    typedef typename SlsMask<NB>::type mask_t;
     SLS_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = sls_lane();
-    const int i = lane;                      // row owned in the sparse (lane-per-row) phases
     const int g = lane >> 2, q = lane & 3;   // accumulator-layout coordinates
     const SlsPlanView& P = a.P;
     const int T = P.T;
@@ -129,7 +145,7 @@ sls_solve_kernel(SlsSolveArgs a) {
     double* valc = reinterpret_cast<double*>(base + L.oValC);
     int32_t* sx = reinterpret_cast<int32_t*>(base + L.oSx);
     int32_t* su = reinterpret_cast<int32_t*>(base + L.oSu);
-    uint32_t* mxs = reinterpret_cast<uint32_t*>(base + L.oMx);
+    mask_t* mxs = reinterpret_cast<mask_t*>(base + L.oMx);
     uint32_t* mus = reinterpret_cast<uint32_t*>(base + L.oMu);
     uint16_t* rptr = reinterpret_cast<uint16_t*>(base + L.oRptr);
     uint16_t* rsplit = reinterpret_cast<uint16_t*>(base + L.oRsplit);
@@ -138,8 +154,8 @@ sls_solve_kernel(SlsSolveArgs a) {
     uint16_t* rowc = reinterpret_cast<uint16_t*>(base + L.oRowC);
     const int wu = P.wu;
 
-    const int slot = blockIdx.x * SOLVE_WPB + warp;
-    const int nslots = gridDim.x * SOLVE_WPB;
+    const int slot = blockIdx.x * WPB + warp;
+    const int nslots = gridDim.x * WPB;
     double* hist = a.hist + (size_t)slot * a.hist_stride;      // [T+1][N] yh history, then [T][tri(N)] packed -Z_k
     double* yhist = hist;
     double* zhist = hist + (size_t)(T + 1) * N;
@@ -148,49 +164,59 @@ sls_solve_kernel(SlsSolveArgs a) {
     for (int idx = slot; idx < a.count; idx += nslots) {
         const int c = a.list[idx];
         const int n = P.n[c], m = P.m[c], jl = P.jloc[c];
-        const bool act = i < n;
         __syncwarp();
         // ------------------------------------------------------------------ metadata -> shared
-        if (act) sx[i] = P.sx[(size_t)c * P.nstride + i];
+        for (int i = lane; i < n; i += 32) sx[i] = P.sx[(size_t)c * P.nstride + i];
         for (int l = lane; l < m; l += 32) su[l] = P.su[(size_t)c * P.mstride + l];
-        for (int t = lane; t < T; t += 32) mxs[t] = P.maskx[((size_t)c * T + t) * P.wx];
-        if (lane == 0) mxs[T] = 0u;
+        for (int t = lane; t < T; t += 32) {
+            const uint32_t* w = P.maskx + ((size_t)c * T + t) * P.wx;
+            mask_t v = (mask_t)w[0];
+            if (sizeof(mask_t) == 8 && P.wx > 1) v |= (mask_t)((uint64_t)w[1] << 32);
+            mxs[t] = v;
+        }
+        if (lane == 0) mxs[T] = (mask_t)0;
         for (int t = lane; t < T * wu; t += 32) mus[t] = P.masku[(size_t)c * T * wu + t];
         for (int e = lane; e < N * N; e += 32) Am[e] = 0.0;
         __syncwarp();
-        // ------------------------------------------------------------------ local CSR of C~ = [A~ B~], dense blocks of A~
-        unsigned nzA = 0u;                                    // bit bi*NB+bj: block (bi,bj) of A~ has a stored entry
+        // ------------------------------------------------------------------ local CSR of C~ = [A~ B~]
+        uint64_t nzA = 0ull;                                  // bit bi*NB+bj: block (bi,bj) of A~ has a stored entry
         {
-            int cntA = 0, cntB = 0;
-            int64_t ea0 = 0, ea1 = 0, eb0 = 0, eb1 = 0;
-            if (act) {
-                const int64_t gr = sx[i];
-                ea0 = a.Ar.colptr[gr] - 1; ea1 = a.Ar.colptr[gr + 1] - 1;
-                eb0 = a.B2r.colptr[gr] - 1; eb1 = a.B2r.colptr[gr + 1] - 1;
-                for (int64_t e = ea0; e < ea1; e++) cntA += (sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1)) >= 0);
-                for (int64_t e = eb0; e < eb1; e++) cntB += (sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1)) >= 0);
-            }
-            int incl = cntA + cntB;
+            int carry = 0;
+#pragma unroll 1
+            for (int rr = 0; rr < RPL; rr++) {
+                const int i = lane + 32 * rr;
+                const bool act = i < n;
+                int cntA = 0, cntB = 0;
+                int64_t ea0 = 0, ea1 = 0, eb0 = 0, eb1 = 0;
+                if (act) {
+                    const int64_t gr = sx[i];
+                    ea0 = a.Ar.colptr[gr] - 1; ea1 = a.Ar.colptr[gr + 1] - 1;
+                    eb0 = a.B2r.colptr[gr] - 1; eb1 = a.B2r.colptr[gr + 1] - 1;
+                    for (int64_t e = ea0; e < ea1; e++) cntA += (sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1)) >= 0);
+                    for (int64_t e = eb0; e < eb1; e++) cntB += (sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1)) >= 0);
+                }
+                int incl = cntA + cntB;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(SLS_FULL, incl, d); if (lane >= d) incl += o; }
-            const int excl = incl - (cntA + cntB);
-            if (act) { rptr[i] = (uint16_t)excl; rsplit[i] = (uint16_t)(excl + cntA); }
-            if (i == n - 1 || (n == 0 && i == 0)) rptr[n] = (uint16_t)(n ? incl : 0);
-            if (act) {
-                int o = excl;
-                for (int64_t e = ea0; e < ea1; e++) {
-                    const int l = sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
-                    if (l >= 0) {
-                        const double v = a.Ar.nzval[e];
-                        colr[o] = (uint16_t)l; valr[o] = v; o++;
-                        nzA |= 1u << ((i >> 3) * NB + (l >> 3));
+                for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(SLS_FULL, incl, d); if (lane >= d) incl += o; }
+                const int excl = carry + incl - (cntA + cntB);
+                if (act) {
+                    rptr[i] = (uint16_t)excl; rsplit[i] = (uint16_t)(excl + cntA);
+                    int o = excl;
+                    for (int64_t e = ea0; e < ea1; e++) {
+                        const int l = sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
+                        if (l >= 0) {
+                            colr[o] = (uint16_t)l; valr[o] = a.Ar.nzval[e]; o++;
+                            nzA |= 1ull << ((i >> 3) * NB + (l >> 3));
+                        }
+                    }
+                    for (int64_t e = eb0; e < eb1; e++) {
+                        const int l = sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1));
+                        if (l >= 0) { colr[o] = (uint16_t)(n + l); valr[o] = a.B2r.nzval[e]; o++; }
                     }
                 }
-                for (int64_t e = eb0; e < eb1; e++) {
-                    const int l = sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1));
-                    if (l >= 0) { colr[o] = (uint16_t)(n + l); valr[o] = a.B2r.nzval[e]; o++; }
-                }
+                carry += __shfl_sync(SLS_FULL, incl, 31);
             }
+            if (lane == 0) rptr[n] = (uint16_t)carry;
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) nzA |= __shfl_xor_sync(SLS_FULL, nzA, d);
@@ -228,7 +254,7 @@ sls_solve_kernel(SlsSolveArgs a) {
         double S[NB][NB][2];                                  // -Z_k ("swept" S_k) in accumulator layout
         int rowoff[NB];                                       // r(r+1)/2 of the lane's row in each block row
         {
-            const uint32_t m1 = mxs[0];
+            const mask_t m1 = mxs[0];
 #pragma unroll
             for (int bi = 0; bi < NB; bi++) {
                 const int r = 8 * bi + g;
@@ -236,26 +262,30 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
                 for (int bj = 0; bj < NB; bj++) {
                     const int c0 = 8 * bj + 2 * q;
-                    S[bi][bj][0] = (r == c0 && ((m1 >> r) & 1u)) ? -1.0 : 0.0;
-                    S[bi][bj][1] = (r == c0 + 1 && ((m1 >> r) & 1u)) ? -1.0 : 0.0;
+                    S[bi][bj][0] = (r == c0 && sls_mbit(m1, r)) ? -1.0 : 0.0;
+                    S[bi][bj][1] = (r == c0 + 1 && sls_mbit(m1, r)) ? -1.0 : 0.0;
                 }
             }
         }
         const double dg0 = (g == 2 * q) ? 1.0 : 0.0, dg1 = (g == 2 * q + 1) ? 1.0 : 0.0;   // identity inside a diagonal block
         double* yprev = ybuf0;
         double* ycur = ybuf1;
-        if (i < N) { const double y0 = (i == jl) ? 1.0 : 0.0; yprev[i] = y0; yhist[i] = y0; }
+#pragma unroll
+        for (int rr = 0; rr < RPL; rr++) {
+            const int i = lane + 32 * rr;
+            if (i < N) { const double y0 = (i == jl) ? 1.0 : 0.0; yprev[i] = y0; yhist[i] = y0; }
+        }
         int status = (jl < 0) ? SLS_ST_NO_IMPULSE : 0;
         uint32_t mu_prev[4] = {0u, 0u, 0u, 0u};               // wu <= 4 is guaranteed by the launcher (m <= 128)
-        uint32_t mk_prev = 0u, mk1_prev = 0u;
+        mask_t mk_prev = 0, mk1_prev = 0;
         bool cache_valid = false;
-        unsigned nonempty = 0u;
+        uint64_t nonempty = 0ull;
         __syncwarp();
 
         // ------------------------------------------------------------------ forward elimination, taps 1..T
         for (int k = 1; k <= T; k++) {
-            const uint32_t mk = mxs[k - 1];
-            const uint32_t mk1 = mxs[k];                      // mxs[T] = 0
+            const mask_t mk = mxs[k - 1];
+            const mask_t mk1 = mxs[k];                        // mxs[T] = 0
             const uint32_t* muk = mus + (size_t)(k - 1) * wu;
             // (1) g = mx_k o (Z_{k-1} yh_{k-1}) = -(mx_k o (S yprev))
 #pragma unroll
@@ -270,7 +300,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 acc += __shfl_xor_sync(SLS_FULL, acc, 1);
                 acc += __shfl_xor_sync(SLS_FULL, acc, 2);
                 const int r = 8 * bi + g;
-                if (q == 0) gbuf[r] = ((mk >> r) & 1u) ? -acc : 0.0;
+                if (q == 0) gbuf[r] = sls_mbit(mk, r) ? -acc : 0.0;
             }
             // (2) mask-dependent operands, rebuilt only when a mask changed (constant once the band is full):
             //     Am = A~ diag(mx_k),  Dp = diag(mx_{k+1}) + B~ diag(mu_k) B~^T,  thr = rank_tol * diag(D_k)
@@ -280,35 +310,42 @@ sls_solve_kernel(SlsSolveArgs a) {
             if (!same) {
                 for (int e = lane; e < N * N; e += 32) Dp[e] = 0.0;
                 __syncwarp();
-                double dref = 0.0;
-                if (act) {
-                    const int r0 = rptr[i], r1 = rsplit[i], r2 = rptr[i + 1];
-                    if ((mk1 >> i) & 1u) { dref = 1.0; Dp[sls_blk(NB, i, i)] = 1.0; }
-                    for (int e = r0; e < r1; e++) {
-                        const int l = colr[e]; const double v = valr[e];
-                        const bool on = (mk >> l) & 1u;
-                        Am[sls_blk(NB, i, l)] = on ? v : 0.0;
-                        if (on) dref = fma(v, v, dref);
+                nonempty = 0ull;
+#pragma unroll
+                for (int rr = 0; rr < RPL; rr++) {
+                    const int i = lane + 32 * rr;
+                    double dref = 0.0;
+                    if (i < n) {
+                        const int r0 = rptr[i], r1 = rsplit[i], r2 = rptr[i + 1];
+                        if (sls_mbit(mk1, i)) { dref = 1.0; Dp[sls_blk(NB, i, i)] = 1.0; }
+                        for (int e = r0; e < r1; e++) {
+                            const int l = colr[e]; const double v = valr[e];
+                            const bool on = sls_mbit(mk, l);
+                            Am[sls_blk(NB, i, l)] = on ? v : 0.0;
+                            if (on) dref = fma(v, v, dref);
+                        }
+                        for (int e = r1; e < r2; e++) {
+                            const int l = colr[e] - n;
+                            if (!sls_bit(muk, l)) continue;
+                            const double v = valr[e];
+                            dref = fma(v, v, dref);
+                            for (int e2 = cptr[n + l]; e2 < cptr[n + l + 1]; e2++) Dp[sls_blk(NB, i, rowc[e2])] += v * valc[e2];
+                        }
                     }
-                    for (int e = r1; e < r2; e++) {
-                        const int l = colr[e] - n;
-                        if (!sls_bit(muk, l)) continue;
-                        const double v = valr[e];
-                        dref = fma(v, v, dref);
-                        for (int e2 = cptr[n + l]; e2 < cptr[n + l + 1]; e2++) Dp[sls_blk(NB, i, rowc[e2])] += v * valc[e2];
-                    }
+                    if (i < N) thrs[i] = (dref != 0.0) ? a.rank_tol * dref : SLS_INF;
+                    nonempty |= (uint64_t)__ballot_sync(SLS_FULL, dref != 0.0) << (32 * rr);
                 }
-                if (i < N) thrs[i] = (dref != 0.0) ? a.rank_tol * dref : SLS_INF;
-                nonempty = __ballot_sync(SLS_FULL, dref != 0.0);
 #pragma unroll
                 for (int w = 0; w < 4; w++) if (w < wu) mu_prev[w] = muk[w];
                 mk_prev = mk; mk1_prev = mk1; cache_valid = true;
             }
             __syncwarp();
             // (3) yh_k = A~ g
-            {
+#pragma unroll
+            for (int rr = 0; rr < RPL; rr++) {
+                const int i = lane + 32 * rr;
                 double acc = 0.0;
-                if (act) {
+                if (i < n) {
                     const int r0 = rptr[i], r1 = rsplit[i];
                     for (int e = r0; e < r1; e++) acc = fma(valr[e], gbuf[colr[e]], acc);
                 }
@@ -325,7 +362,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 for (int bj = 0; bj < NB; bj++) { Tm[bi][bj][0] = 0.0; Tm[bi][bj][1] = 0.0; }
 #pragma unroll
                 for (int bl = 0; bl < NB; bl++) {
-                    if (!((nzA >> (bi * NB + bl)) & 1u)) continue;
+                    if (!((nzA >> (bi * NB + bl)) & 1ull)) continue;
                     const double2 av = *reinterpret_cast<const double2*>(Am + ((bi * NB + bl) << 6) + (g << 3) + 2 * q);
                     const double ab[2] = {av.x, av.y};
 #pragma unroll
@@ -344,7 +381,7 @@ sls_solve_kernel(SlsSolveArgs a) {
             for (int bj = 0; bj < NB; bj++)
 #pragma unroll
                 for (int bl = 0; bl < NB; bl++) {
-                    if (!((nzA >> (bj * NB + bl)) & 1u)) continue;
+                    if (!((nzA >> (bj * NB + bl)) & 1ull)) continue;
                     const double2 av = *reinterpret_cast<const double2*>(Am + ((bj * NB + bl) << 6) + (g << 3) + 2 * q);
                     const double ab[2] = {av.x, av.y};
 #pragma unroll
@@ -352,7 +389,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 }
             // (7) block symmetric sweep with rank skipping:  S <- -(S^+).  A skipped pivot (<= threshold) gets
             //     pinv = 0, which zeroes its row and column at once (they never feed a kept row).
-            uint32_t keep = 0u;
+            uint64_t keep = 0ull;
 #pragma unroll
             for (int p = 0; p < NB; p++) {
                 double d0 = S[p][p][0], d1 = S[p][p][1];
@@ -379,7 +416,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                         kb |= (ok ? 1u : 0u) << r;
                     }
                 }
-                keep |= kb << (8 * p);
+                keep |= (uint64_t)kb << (8 * p);
                 const double Pn[2] = {d0, d1};                // -P, symmetric
                 double Tn[NB][2], Tt[NB][2];                  // Tn_i = -S_ip P,  Tt_i = -P S_pi = -(S_ip P)^T
 #pragma unroll
@@ -424,7 +461,6 @@ sls_solve_kernel(SlsSolveArgs a) {
         }
 
         // ------------------------------------------------------------------ lambda_T = Z_T yh_T
-        double lam = 0.0;
 #pragma unroll
         for (int bi = 0; bi < NB; bi++) {
             double acc = 0.0;
@@ -436,23 +472,23 @@ sls_solve_kernel(SlsSolveArgs a) {
             }
             acc += __shfl_xor_sync(SLS_FULL, acc, 1);
             acc += __shfl_xor_sync(SLS_FULL, acc, 2);
-            if (q == 0) lam_s[8 * bi + g] = -acc;
+            const int r = 8 * bi + g;
+            if (q == 0) lam_s[r] = (r < n) ? -acc : 0.0;
         }
-        __syncwarp();
-        if (i < N) lam = lam_s[i];
         __syncwarp();
 
         // ------------------------------------------------------------------ back substitution, k = T..1
+        // lam_s holds lambda_k (zero beyond n) at the top of every iteration
         double* xnext = xa;   // x_{k+1}
         double* xcur = xb;    // x_k
-        if (i < N) { xnext[i] = 0.0; }
+#pragma unroll
+        for (int rr = 0; rr < RPL; rr++) { const int i = lane + 32 * rr; if (i < N) xnext[i] = 0.0; }
         double resmax = 0.0;
         const int64_t xoff = P.tot[c];
         const uint32_t* pre = P.pre + (size_t)c * 2 * T;
         for (int k = T; k >= 1; k--) {
-            const uint32_t mk = mxs[k - 1];
+            const mask_t mk = mxs[k - 1];
             const uint32_t* muk = mus + (size_t)(k - 1) * wu;
-            if (i < N) lam_s[i] = act ? lam : 0.0;
             __syncwarp();
             // t = C~^T lambda_k
             for (int p = lane; p < n + m; p += 32) {
@@ -475,13 +511,19 @@ sls_solve_kernel(SlsSolveArgs a) {
                     rank0 += __popc(word);
                 }
             }
-            const bool bi_ = act && ((mk >> i) & 1u);
-            if (i < N) rhs_s[i] = act ? (yhist[(size_t)(k - 1) * N + i] + (bi_ ? tx[i] : 0.0)) : 0.0;
+#pragma unroll
+            for (int rr = 0; rr < RPL; rr++) {
+                const int i = lane + 32 * rr;
+                if (i < N) rhs_s[i] = (i < n) ? (yhist[(size_t)(k - 1) * N + i] + (sls_mbit(mk, i) ? tx[i] : 0.0)) : 0.0;
+            }
             __syncwarp();
-            // lambda_{k-1} = Z_{k-1} rhs  (history read back in accumulator layout; symmetric mat-vec)
-            double lam_prev = 0.0;
+            // lambda_{k-1} = Z_{k-1} rhs  (history read back in accumulator layout; symmetric mat-vec) -> gbuf
             if (k - 1 == 0) {
-                lam_prev = (act && ((mxs[0] >> i) & 1u)) ? rhs_s[i] : 0.0;
+#pragma unroll
+                for (int rr = 0; rr < RPL; rr++) {
+                    const int i = lane + 32 * rr;
+                    if (i < N) gbuf[i] = (i < n && sls_mbit(mxs[0], i)) ? -rhs_s[i] : 0.0;
+                }
             } else {
                 const double* hk = zhist + (size_t)(k - 1) * TRI;
                 double racc[NB], cacc[NB][2];
@@ -531,27 +573,40 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
                     for (int b = 0; b < NB - 1; b++) { gbuf[8 * b + 2 * q] += cacc[b][0]; gbuf[8 * b + 2 * q + 1] += cacc[b][1]; }
                 }
-                __syncwarp();
-                lam_prev = act ? -gbuf[i] : 0.0;
             }
-            const double x = bi_ ? (lam_prev - tx[i]) : 0.0;
-            if (i < N) xcur[i] = x;
-            if (bi_) a.xw[xoff + pre[2 * (k - 1)] + __popc(mk & ((1u << i) - 1u))] = x;
+            __syncwarp();
+            // gbuf = -lambda_{k-1} (history stores -Z);  x_k = mx_k o (lambda_{k-1} - A~^T lambda_k)
+#pragma unroll
+            for (int rr = 0; rr < RPL; rr++) {
+                const int i = lane + 32 * rr;
+                const bool on = (i < n) && sls_mbit(mk, i);
+                const double lam_prev = (i < n) ? -gbuf[i] : 0.0;
+                const double x = on ? (lam_prev - tx[i]) : 0.0;
+                if (i < N) { xcur[i] = x; lam_s[i] = lam_prev; }
+                if (on) a.xw[xoff + pre[2 * (k - 1)] + sls_mrank(mk, i)] = x;
+            }
             __syncwarp();
             // residual of constraint block k: A~ x_k + B~ u_k - x_{k+1}
-            if (act) {
-                double r = -xnext[i];
-                const int r0 = rptr[i], r1 = rsplit[i], r2 = rptr[i + 1];
-                for (int e = r0; e < r1; e++) r = fma(valr[e], xcur[colr[e]], r);
-                for (int e = r1; e < r2; e++) r = fma(valr[e], ucur[colr[e] - n], r);
-                resmax = fmax(resmax, fabs(r));
+#pragma unroll
+            for (int rr = 0; rr < RPL; rr++) {
+                const int i = lane + 32 * rr;
+                if (i < n) {
+                    double r = -xnext[i];
+                    const int r0 = rptr[i], r1 = rsplit[i], r2 = rptr[i + 1];
+                    for (int e = r0; e < r1; e++) r = fma(valr[e], xcur[colr[e]], r);
+                    for (int e = r1; e < r2; e++) r = fma(valr[e], ucur[colr[e] - n], r);
+                    resmax = fmax(resmax, fabs(r));
+                }
             }
-            __syncwarp();
             double* tswap = xnext; xnext = xcur; xcur = tswap;
-            lam = lam_prev;
         }
+        __syncwarp();
         // block 0: x_1 = e
-        if (act) resmax = fmax(resmax, fabs(((i == jl) ? 1.0 : 0.0) - xnext[i]));
+#pragma unroll
+        for (int rr = 0; rr < RPL; rr++) {
+            const int i = lane + 32 * rr;
+            if (i < n) resmax = fmax(resmax, fabs(((i == jl) ? 1.0 : 0.0) - xnext[i]));
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) resmax = fmax(resmax, __shfl_xor_sync(SLS_FULL, resmax, d));
         if (!(resmax <= a.feas_tol)) status |= SLS_ST_RESIDUAL;
@@ -560,7 +615,7 @@ sls_solve_kernel(SlsSolveArgs a) {
 }
 
 // ---- host side ------------------------------------------------------------------------------
-static const int kClasses[] = {8, 16, 24, 32};
+static const int kClasses[] = {8, 16, 24, 32, 40, 48, 56, 64};
 int sls_solve_class_count() { return (int)(sizeof(kClasses) / sizeof(int)); }
 int sls_solve_class_N(int k) { return kClasses[k]; }
 int sls_solve_class_of(int n) {
@@ -574,49 +629,51 @@ int64_t sls_solve_hist_doubles(int N, int T) { return (int64_t)(T + 1) * N + (in
 
 template <int NB>
 static int resident_warps(int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem) {
+    constexpr int WPB = SlsCfg<NB>::WPB;
     if (wu > 4) return -1;
-    const size_t per_block = sls_solve_smem_per_warp(8 * NB, mcap, nnzcap, T, wu) * SOLVE_WPB;
+    const size_t per_block = sls_solve_smem_per_warp(8 * NB, mcap, nnzcap, T, wu) * WPB;
     if (per_block > (size_t)max_smem) return -1;
     auto kp = &sls_solve_kernel<NB>;
     if (per_block > 48 * 1024) { if (rt::set_max_smem(kp, (int)per_block)) return -1; }
-    const int bps = rt::max_blocks_per_sm(kp, SOLVE_WPB * 32, per_block);
+    const int bps = rt::max_blocks_per_sm(kp, WPB * 32, per_block);
     if (bps < 1) return -1;
-    return bps * sm_count * SOLVE_WPB;
-}
-
-int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem) {
-    switch (N) {
-        case 8:  return resident_warps<1>(mcap, nnzcap, T, wu, sm_count, max_smem);
-        case 16: return resident_warps<2>(mcap, nnzcap, T, wu, sm_count, max_smem);
-        case 24: return resident_warps<3>(mcap, nnzcap, T, wu, sm_count, max_smem);
-        case 32: return resident_warps<4>(mcap, nnzcap, T, wu, sm_count, max_smem);
-        default: return -1;
-    }
+    return bps * sm_count * WPB;
 }
 
 template <int NB>
 static int launch_class(const SlsSolveArgs& a, int sm_count, int max_smem, int* warps_launched, sls_stream_t stream) {
-    const size_t per_block = sls_solve_smem_per_warp(8 * NB, a.mcap, a.nnzcap, a.P.T, a.P.wu) * SOLVE_WPB;
+    constexpr int WPB = SlsCfg<NB>::WPB;
+    const size_t per_block = sls_solve_smem_per_warp(8 * NB, a.mcap, a.nnzcap, a.P.T, a.P.wu) * WPB;
     const int maxw = resident_warps<NB>(a.mcap, a.nnzcap, a.P.T, a.P.wu, sm_count, max_smem);
     if (maxw <= 0) return -5;
     auto kp = &sls_solve_kernel<NB>;
-    int blocks = (a.count + SOLVE_WPB - 1) / SOLVE_WPB;
-    if (blocks > maxw / SOLVE_WPB) blocks = maxw / SOLVE_WPB;
+    int blocks = (a.count + WPB - 1) / WPB;
+    if (blocks > maxw / WPB) blocks = maxw / WPB;
     if (blocks < 1) blocks = 1;
-    *warps_launched = blocks * SOLVE_WPB;
-    SLS_LAUNCH(kp, blocks, SOLVE_WPB * 32, per_block, stream, a);
+    *warps_launched = blocks * WPB;
+    SLS_LAUNCH(kp, blocks, WPB * 32, per_block, stream, a);
     return rt::last_error();
+}
+
+#define SLS_FOR_CLASSES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+
+int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem) {
+    switch (N / 8) {
+#define X(nb) case nb: return resident_warps<nb>(mcap, nnzcap, T, wu, sm_count, max_smem);
+        SLS_FOR_CLASSES(X)
+#undef X
+        default: return -1;
+    }
 }
 
 int sls_launch_solve(int N, const SlsSolveArgs& a, int sm_count, int max_smem, int* warps_launched,
                      sls_stream_t stream) {
     *warps_launched = 0;
     if (a.count == 0) return 0;
-    switch (N) {
-        case 8:  return launch_class<1>(a, sm_count, max_smem, warps_launched, stream);
-        case 16: return launch_class<2>(a, sm_count, max_smem, warps_launched, stream);
-        case 24: return launch_class<3>(a, sm_count, max_smem, warps_launched, stream);
-        case 32: return launch_class<4>(a, sm_count, max_smem, warps_launched, stream);
+    switch (N / 8) {
+#define X(nb) case nb: return launch_class<nb>(a, sm_count, max_smem, warps_launched, stream);
+        SLS_FOR_CLASSES(X)
+#undef X
         default: return -6;
     }
 }

@@ -45,6 +45,38 @@ def test_grid_9x9_vs_golden(cuda_api):
     assert worst < 1e-10
 
 
+def test_grid_13x13_wide_solver_vs_golden(cuda_api):
+    """n up to 61, m up to 85: the 64-bit-mask / N=64 size classes of kernel 2 (BASELINE config #4 shapes)."""
+    worst, info = pc.check_golden(cuda_api, "grid_13x13_full_d4_T20_subset", O.grid_plant(13, 13, actuation="full"))
+    assert info["n"].max() == 61 and info["m"].max() == 85
+    assert worst < 1e-9
+
+
+def test_config4_grid_properties(cuda_api):
+    """BASELINE config #4 at 60 x 60 (same d=4, T=20 local problems as 300 x 300): invariants on all columns and
+    oracle parity on a few."""
+    from slc_b200 import workloads as W
+    nr = nc = 60
+    A, B1, B2 = W.grid_plant(nr, nc)
+    Sx, Su = W.grid_supports(nr, nc, 4, 20, 1.5)
+    S = [[M.to_scipy().astype(bool) for M in Sx], [M.to_scipy().astype(bool) for M in Su]]
+    P = slc_b200.Plant(A, B1, B2)
+    Phix, Phiu, info = slc_b200.SLS_H2(P, S, return_info=True, api=cuda_api)
+    assert not (info["status"] & _capi.STATUS_RESIDUAL).any() and info["resid"].max() < 1e-12
+    Nx = nr * nc
+    I = sp.identity(Nx, format="csc")
+    r = abs(Phix[0] - I).max()
+    for t in range(20):
+        nxt = Phix[t + 1] if t + 1 < 20 else sp.csc_matrix((Nx, Nx))
+        R = nxt - A @ Phix[t] - B2 @ Phiu[t]
+        r = max(r, abs(R).max() if R.nnz else 0.0)
+        assert np.array_equal(Phix[t].indices, S[0][t].indices) and np.array_equal(Phiu[t].indices, S[1][t].indices)
+    assert r < 1e-12
+    cols = [0, 59, 1830, 1831, 3599]
+    worst, _, _ = pc.check_against_oracle(cuda_api, A, B1, B2, S, cols)
+    assert worst < 1e-9
+
+
 def test_error_paths(cuda_api):
     pc.check_error_paths(cuda_api)
 
