@@ -50,6 +50,11 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="columns in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="chain", choices=["chain", "grid"],
+                    help="chain = BASELINE config #3 (the headline, default); grid = config #4 (300x300, d=4, T=20, B2=I)")
+    ap.add_argument("--allgather", action="store_true",
+                    help="N>1: also time an NCCL all-gather of the device-resident Phi value slabs (only needed when every "
+                         "GPU must hold the whole Phi; not part of value/e2e)")
     return ap.parse_args()
 
 
@@ -206,8 +211,18 @@ def run_ours(args, rank, world, local_rank):
     Nx = nx_local * world
     c0, c1 = rank * nx_local, (rank + 1) * nx_local
     halo = 1                                                   # kernel 1 reads 𝓢[T][:,k] for k in nz(A[:,j]): j±1
-    A, B1, B2 = W.chain_plant(Nx)
-    Sx, Su = W.chain_supports(Nx, D, T, ALPHA, max(0, c0 - halo), min(Nx, c1 + halo))
+    wl_d, wl_T = D, T
+    if args.workload == "grid":
+        assert world == 1, "the grid workload is a single-GPU measurement"
+        side = int(round(np.sqrt(90_000 if args.nx == NX_PER_GPU else args.nx)))
+        nx_local = Nx = side * side
+        c0, c1 = 0, Nx
+        wl_d, wl_T = 4, 20
+        A, B1, B2 = W.grid_plant(side, side)
+        Sx, Su = W.grid_supports(side, side, wl_d, wl_T, ALPHA)
+    else:
+        A, B1, B2 = W.chain_plant(Nx)
+        Sx, Su = W.chain_supports(Nx, D, T, ALPHA, max(0, c0 - halo), min(Nx, c1 + halo))
     Aj = slc_b200.JuliaCSC.from_scipy(A, np.float64)
     B2j = slc_b200.JuliaCSC.from_scipy(B2, np.float64)
     keep = []
@@ -287,6 +302,30 @@ def run_ours(args, rank, world, local_rank):
         e2e_ms = float(np.mean(e2e))
         assert out["resid"][:syn.ncols].max() < 1e-9, "e2e result failed its own feasibility check"
 
+    ag_ms = None
+    if args.allgather and dist is not None:
+        import ctypes as C
+
+        class _Dev:                                             # device buffer -> torch tensor without a copy
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        pz, nnz, total = C.c_void_p(), C.c_int64(), 0
+        syn._ck(syn.api.sls_device_output(syn.h, 0, 0, None, None, C.byref(pz), C.byref(nnz)))
+        total = int(tm["nnz_out"])
+        mine = torch.as_tensor(_Dev(pz.value, total), device=f"cuda:{local_rank}")
+        cap = torch.tensor([total], device="cuda"); dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+        send = torch.zeros(int(cap.item()), dtype=torch.float64, device="cuda"); send[:total] = mine
+        recv = torch.empty(world * int(cap.item()), dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            dist.all_gather_into_tensor(recv, send)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dist.all_gather_into_tensor(recv, send)
+        e1.record(); torch.cuda.synchronize()
+        ag_ms = e0.elapsed_time(e1) / 5
+
     def allmax(x):
         if dist is None:
             return x
@@ -298,6 +337,8 @@ def run_ours(args, rank, world, local_rank):
     if e2e_ms is not None:
         e2e_ms = allmax(e2e_ms)
     launches_all = int(allmax(float(launches)))
+    if ag_ms is not None:
+        ag_ms = allmax(ag_ms)
 
     if rank == 0:
         peaks = {}
@@ -318,7 +359,9 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": ncols_all * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"chain Nx={nx_local}/GPU ({Nx} total), Nu=Nx/3, d={D}, T={T}, alpha={ALPHA} (BASELINE config #3)",
+            "config": {"workload": (f"chain Nx={nx_local}/GPU ({Nx} total), Nu=Nx/3, d={D}, T={T}, alpha={ALPHA} (BASELINE config #3)"
+                                    if args.workload == "chain" else
+                                    f"grid {int(np.sqrt(Nx))}x{int(np.sqrt(Nx))} Nx={Nx}, B2=I, d={wl_d}, T={wl_T}, alpha={ALPHA} (BASELINE config #4)"),
                        "columns_per_gpu": nx_local, "parallelism": f"column-sharded x{world}, no collective",
                        "l2": "inputs (0.57 GB supports) and outputs (1.06 GB) exceed the 126 MB L2; no flush needed",
                        "nnz_out_per_gpu": int(tm["nnz_out"])},
@@ -333,6 +376,8 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches_all,
             "clocks": clocks,
         }
+        if ag_ms is not None:
+            line["allgather"] = {"ms": ag_ms, "bytes_per_rank": int(tm["nnz_out"]) * 8, "what": "NCCL all_gather_into_tensor of the F64 value slabs"}
         if e2e_ms is not None:
             line["e2e"] = {"value": ncols_all / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                            "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)}
