@@ -72,7 +72,10 @@ struct Plan {
     bool valid = false;
     int ncols = 0, nstride = 1, mstride = 1, wx = 1, wu = 1, nmax = 0, mmax = 0, cap = 32;
     DevBuf cols, n, m, sx, su, maskx, masku, jloc, lnnz, lnnzA, lnnzB, pre, tot, colptr, lists;
-    std::vector<int32_t> h_cols;
+    std::vector<int32_t> h_cols, h_lists;
+    bool cols_sorted = true;            // planned columns strictly ascending => a planned-index range is a CSC column range
+    PinVec<int32_t> h_status; PinVec<double> h_resid;
+    PinVec<int64_t> h_seg;              // [(nchunk+1)][2T] output offsets of the D2H pipeline's chunk boundaries
     PinVec<int32_t> h_n, h_m, h_lnnz, h_lA, h_lB;
     PinVec<int64_t> h_tot, h_last;
     std::vector<int64_t> nnz_tap;       // 2T stored-entry counts (Φx taps then Φu taps)
@@ -83,6 +86,7 @@ struct Plan {
     void release() {
         DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists};
         for (DevBuf* b : all) b->release();
+        h_seg.release(); h_status.release(); h_resid.release();
         h_n.release(); h_m.release(); h_lnnz.release(); h_lA.release(); h_lB.release(); h_tot.release(); h_last.release();
         valid = false;
     }
@@ -93,7 +97,8 @@ struct Plan {
 struct sls_handle {
     sls_options opt{};
     int device = 0, sm_count = 0, max_smem = 0;
-    sls_stream_t stream{};
+    sls_stream_t stream{}, copy_stream{};
+    rt::Event chunk_ev[16];
     std::string err;
     int64_t Nx = 0, Nu = 0, T = 0;
     bool have_plant = false, have_supports = false, solved = false;
@@ -139,6 +144,8 @@ extern "C" int sls_create(const sls_options* opts, sls_handle** out) {
     if (h->device < 0 || h->device >= ndev) { delete h; return fail(nullptr, -1, "sls_create: device ordinal out of range"); }
     int e = rt::set_device(h->device);
     if (!e) e = rt::stream_create(&h->stream);
+    if (!e) e = rt::stream_create(&h->copy_stream);
+    for (int i = 0; i < 16 && !e; i++) e = h->chunk_ev[i].create();
     for (int i = 0; i < 8 && !e; i++) e = h->ev[i].create();
     for (int i = 0; i < 2 && !e; i++) e = h->marks[i].create();
     if (e) { delete h; return fail(nullptr, e, "sls_create: CUDA initialisation failed"); }
@@ -152,12 +159,15 @@ extern "C" void sls_destroy(sls_handle* h) {
     if (!h) return;
     rt::set_device(h->device);
     rt::sync(h->stream);
+    rt::sync(h->copy_stream);
     h->A.release(); h->B2.release(); h->Ar.release(); h->B2r.release();
     h->Sx.release(); h->Su.release(); h->plan.release();
     DevBuf* all[] = {&h->xw, &h->hist, &h->status, &h->resid, &h->out_rowval, &h->out_nzval, &h->out_ptrs};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < 8; i++) h->ev[i].destroy();
     for (int i = 0; i < 2; i++) h->marks[i].destroy();
+    for (int i = 0; i < 16; i++) h->chunk_ev[i].destroy();
+    rt::stream_destroy(h->copy_stream);
     rt::stream_destroy(h->stream);
     delete h;
 }
@@ -328,6 +338,8 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
             p.h_cols[i] = (int32_t)j;
         }
     }
+    p.cols_sorted = true;
+    for (int64_t i = 1; i < ncols; i++) if (p.h_cols[i] <= p.h_cols[i - 1]) { p.cols_sorted = false; break; }
     // candidate-list capacity of kernel 1 (power of two, >= 32)
     int64_t cand = (int64_t)h->maxcolA * std::max(h->Sx.maxlen_last, h->Su.maxlen_last);
     int cap = 32; while (cap < cand) cap <<= 1;
@@ -418,6 +430,7 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
         }
         for (int k = 0; k < nk; k++) if (cls[k].count) p.classes.push_back(cls[k]);
     }
+    p.h_lists = lists;
     SLS_CK(p.lists.ensure(nc1 * sizeof(int32_t)));
     SLS_CK(rt::h2d(p.lists.p, lists.data(), off * sizeof(int32_t), h->stream));
     SLS_CK(rt::sync(h->stream));
@@ -519,12 +532,21 @@ extern "C" int sls_local_problem(sls_handle* h, int64_t k, double* At, double* B
 }
 
 // ---- solve (kernels 2 + 3) ------------------------------------------------------------------
-extern "C" int sls_solve_device(sls_handle* h) {
-    if (!h) return -1;
+namespace {
+struct HostOut {
+    int64_t* const* cps[2]; int64_t* const* rvs[2]; double* const* nzs[2];
+    int32_t* status; double* resid;
+};
+}
+
+// Runs kernel 2 and kernel 3 on the planned columns.  With host outputs (`ho`) and ascending columns the
+// work is cut into contiguous column chunks: while chunk c+1 is being solved, chunk c's CSC segments of all
+// 2T taps travel device->host on a second stream, so the D2H time hides behind kernel 2.
+static int run_solve(sls_handle* h, const HostOut* ho) {
     Plan& p = h->plan;
     SLS_ARG(p.valid, "sls_solve: call sls_plan first");
     SLS_CK(rt::set_device(h->device));
-    const int64_t T = h->T;
+    const int64_t T = h->T, Nx = h->Nx;
     const int nc1 = std::max(p.ncols, 1);
     h->solved = false;
     if (p.nmax > sls_solve_class_N(sls_solve_class_count() - 1))
@@ -535,6 +557,10 @@ extern "C" int sls_solve_device(sls_handle* h) {
     SLS_CK(h->out_rowval.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(int64_t)));
     SLS_CK(h->out_nzval.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(double)));
     SLS_CK(h->out_ptrs.ensure((size_t)4 * T * sizeof(void*)));
+    int nchunk = 1;
+    if (ho && p.cols_sorted && p.ncols >= 16384) nchunk = (h->opt.flags & 2) ? 1 : 4;      // flags bit 1: no D2H pipeline
+    std::vector<int> cb(nchunk + 1);
+    for (int c = 0; c <= nchunk; c++) cb[c] = (int)((int64_t)p.ncols * c / nchunk);
     {
         std::vector<void*> ptrs(4 * T);
         for (int64_t tt = 0; tt < 2 * T; tt++) {
@@ -542,6 +568,15 @@ extern "C" int sls_solve_device(sls_handle* h) {
             ptrs[2 * T + tt] = h->out_nzval.as<double>() + p.out_off[tt];
         }
         SLS_CK(rt::h2d(h->out_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void*), h->stream));
+        if (nchunk > 1) {
+            // 0-based position, inside every tap's arrays, of the first stored entry of each chunk boundary column
+            SLS_CK(p.h_seg.resize((size_t)(nchunk + 1) * 2 * T));
+            for (int c = 0; c <= nchunk; c++) {
+                const int64_t col = (cb[c] < p.ncols) ? p.h_cols[cb[c]] : Nx;
+                SLS_CK(rt::d2h_strided(p.h_seg.data() + (size_t)c * 2 * T, p.colptr.as<int64_t>() + col, sizeof(int64_t),
+                                       (size_t)(Nx + 1) * sizeof(int64_t), (size_t)(2 * T), h->stream));
+            }
+        }
         SLS_CK(rt::sync(h->stream));
     }
     // history slots: sized for the most demanding class
@@ -555,33 +590,86 @@ extern "C" int sls_solve_device(sls_handle* h) {
     }
     SLS_CK(h->hist.ensure(hist_bytes));
     h->ev[4].record(h->stream);
-    int64_t launches = 0;
-    for (const SolveClass& c : p.classes) {
-        SlsSolveArgs a{};
-        a.A = h->A.view(); a.B2 = h->B2.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();
-        a.P = v; a.list = p.lists.as<int32_t>() + c.list_off; a.count = c.count;
-        a.mcap = c.mcap; a.nnzcap = c.nnzcap;
-        a.xw = h->xw.as<double>(); a.hist = h->hist.as<double>();
-        a.hist_stride = sls_solve_hist_doubles(c.N, (int)T);
-        a.status = h->status.as<int32_t>(); a.resid = h->resid.as<double>();
-        a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
-        int warps = 0;
-        SLS_CK(sls_launch_solve(c.N, a, h->sm_count, h->max_smem, &warps, h->stream));
-        launches++;
+    if (ho) {                                                  // colptr arrays are final since sls_plan
+        SLS_CK(rt::stream_wait(h->copy_stream, h->ev[4]));
+        for (int64_t tt = 0; tt < 2 * T; tt++) {
+            const int x = tt >= T; const int64_t t = x ? tt - T : tt;
+            if (ho->cps[x] && ho->cps[x][t])
+                SLS_CK(rt::d2h(ho->cps[x][t], p.colptr.as<int64_t>() + tt * (Nx + 1), (Nx + 1) * sizeof(int64_t), h->copy_stream));
+        }
     }
-    h->ev[5].record(h->stream);
-    SlsScatterArgs s{};
-    s.P = v; s.xw = h->xw.as<double>();
-    s.rowval = reinterpret_cast<int64_t* const*>(h->out_ptrs.as<void*>());
-    s.nzval = reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T);
-    SLS_CK(sls_launch_scatter(s, h->stream));
+    int64_t launches = 0, scatters = 0;
+    for (int ch = 0; ch < nchunk; ch++) {
+        for (const SolveClass& c : p.classes) {
+            const int32_t* lb = p.h_lists.data() + c.list_off;
+            const int lo = (int)(std::lower_bound(lb, lb + c.count, cb[ch]) - lb);
+            const int hi = (int)(std::lower_bound(lb, lb + c.count, cb[ch + 1]) - lb);
+            if (hi <= lo) continue;
+            SlsSolveArgs a{};
+            a.A = h->A.view(); a.B2 = h->B2.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();
+            a.P = v; a.list = p.lists.as<int32_t>() + c.list_off + lo; a.count = hi - lo;
+            a.mcap = c.mcap; a.nnzcap = c.nnzcap;
+            a.xw = h->xw.as<double>(); a.hist = h->hist.as<double>();
+            a.hist_stride = sls_solve_hist_doubles(c.N, (int)T);
+            a.status = h->status.as<int32_t>(); a.resid = h->resid.as<double>();
+            a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
+            int warps = 0;
+            SLS_CK(sls_launch_solve(c.N, a, h->sm_count, h->max_smem, &warps, h->stream));
+            launches++;
+        }
+        if (nchunk == 1) h->ev[5].record(h->stream);
+        SlsScatterArgs s{};
+        s.P = v; s.xw = h->xw.as<double>(); s.c_begin = cb[ch]; s.c_end = cb[ch + 1];
+        s.rowval = reinterpret_cast<int64_t* const*>(h->out_ptrs.as<void*>());
+        s.nzval = reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T);
+        SLS_CK(sls_launch_scatter(s, h->stream));
+        if (cb[ch + 1] > cb[ch]) scatters++;
+        if (ho) {
+            h->chunk_ev[ch].record(h->stream);
+            SLS_CK(rt::stream_wait(h->copy_stream, h->chunk_ev[ch]));
+            for (int64_t tt = 0; tt < 2 * T; tt++) {
+                const int x = tt >= T; const int64_t t = x ? tt - T : tt;
+                int64_t o0 = 0, o1 = p.nnz_tap[tt];
+                if (nchunk > 1) { o0 = p.h_seg[(size_t)ch * 2 * T + tt] - 1; o1 = p.h_seg[(size_t)(ch + 1) * 2 * T + tt] - 1; }
+                if (o1 <= o0) continue;
+                if (ho->rvs[x] && ho->rvs[x][t])
+                    SLS_CK(rt::d2h(ho->rvs[x][t] + o0, h->out_rowval.as<int64_t>() + p.out_off[tt] + o0, (o1 - o0) * sizeof(int64_t), h->copy_stream));
+                if (ho->nzs[x] && ho->nzs[x][t])
+                    SLS_CK(rt::d2h(ho->nzs[x][t] + o0, h->out_nzval.as<double>() + p.out_off[tt] + o0, (o1 - o0) * sizeof(double), h->copy_stream));
+            }
+        }
+    }
     h->ev[6].record(h->stream);
+    if (ho) { SLS_CK(rt::stream_wait(h->stream, h->chunk_ev[nchunk - 1])); }
     SLS_CK(rt::sync(h->stream));
-    h->tm.solve_ms = rt::elapsed_ms(h->ev[4], h->ev[5]);
-    h->tm.scatter_ms = rt::elapsed_ms(h->ev[5], h->ev[6]);
-    h->tm.solve_launches = launches; h->tm.scatter_launches = p.ncols ? 1 : 0;
+    if (ho) {
+        // per-column outcomes go through pinned staging: the caller's arrays may be pageable, and a pageable
+        // cudaMemcpyAsync would block the host in the middle of the pipeline
+        SLS_CK(p.h_status.resize(nc1)); SLS_CK(p.h_resid.resize(nc1));
+        if (ho->status) SLS_CK(rt::d2h(p.h_status.data(), h->status.p, (size_t)p.ncols * sizeof(int32_t), h->copy_stream));
+        if (ho->resid) SLS_CK(rt::d2h(p.h_resid.data(), h->resid.p, (size_t)p.ncols * sizeof(double), h->copy_stream));
+        h->ev[7].record(h->copy_stream);
+        SLS_CK(rt::sync(h->copy_stream));
+        if (ho->status) memcpy(ho->status, p.h_status.data(), (size_t)p.ncols * sizeof(int32_t));
+        if (ho->resid) memcpy(ho->resid, p.h_resid.data(), (size_t)p.ncols * sizeof(double));
+        SLS_CK(rt::stream_wait(h->stream, h->ev[7]));          // later marks on the main stream see the copies
+        h->tm.d2h_ms = rt::elapsed_ms(h->ev[6], h->ev[7]);     // D2H tail left exposed after the last kernel
+    }
+    if (nchunk == 1) {
+        h->tm.solve_ms = rt::elapsed_ms(h->ev[4], h->ev[5]);
+        h->tm.scatter_ms = rt::elapsed_ms(h->ev[5], h->ev[6]);
+    } else {
+        h->tm.solve_ms = rt::elapsed_ms(h->ev[4], h->ev[6]);   // kernels 2 and 3 interleaved per chunk
+        h->tm.scatter_ms = 0.f;
+    }
+    h->tm.solve_launches = launches; h->tm.scatter_launches = scatters;
     h->solved = true;
     return 0;
+}
+
+extern "C" int sls_solve_device(sls_handle* h) {
+    if (!h) return -1;
+    return run_solve(h, nullptr);
 }
 
 extern "C" int sls_solve(sls_handle* h,
@@ -589,28 +677,8 @@ extern "C" int sls_solve(sls_handle* h,
                          int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
                          int32_t* status, double* resid) {
     if (!h) return -1;
-    int e = sls_solve_device(h);
-    if (e) return e;
-    const Plan& p = h->plan;
-    const int64_t T = h->T, Nx = h->Nx;
-    h->ev[6].record(h->stream);
-    for (int64_t tt = 0; tt < 2 * T; tt++) {
-        const bool isu = tt >= T;
-        const int64_t t = isu ? tt - T : tt;
-        int64_t* const* cps = isu ? Pu_colptr : Px_colptr;
-        int64_t* const* rvs = isu ? Pu_rowval : Px_rowval;
-        double* const* nzs = isu ? Pu_nzval : Px_nzval;
-        const int64_t nnz = p.nnz_tap[tt];
-        if (cps && cps[t]) SLS_CK(rt::d2h(cps[t], p.colptr.as<int64_t>() + tt * (Nx + 1), (Nx + 1) * sizeof(int64_t), h->stream));
-        if (rvs && rvs[t]) SLS_CK(rt::d2h(rvs[t], h->out_rowval.as<int64_t>() + p.out_off[tt], nnz * sizeof(int64_t), h->stream));
-        if (nzs && nzs[t]) SLS_CK(rt::d2h(nzs[t], h->out_nzval.as<double>() + p.out_off[tt], nnz * sizeof(double), h->stream));
-    }
-    if (status) SLS_CK(rt::d2h(status, h->status.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
-    if (resid) SLS_CK(rt::d2h(resid, h->resid.p, (size_t)p.ncols * sizeof(double), h->stream));
-    h->ev[7].record(h->stream);
-    SLS_CK(rt::sync(h->stream));
-    h->tm.d2h_ms = rt::elapsed_ms(h->ev[6], h->ev[7]);
-    return 0;
+    HostOut ho{{Px_colptr, Pu_colptr}, {Px_rowval, Pu_rowval}, {Px_nzval, Pu_nzval}, status, resid};
+    return run_solve(h, &ho);
 }
 
 extern "C" int sls_device_output(sls_handle* h, int64_t t, int which,

@@ -43,6 +43,7 @@ int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int
 struct SlsScatterArgs {
     SlsPlanView P;
     const double* xw;
+    int c_begin, c_end;      // planned-column range handled by this launch
     // destination arrays: per tap tt in [0,2T): base pointers (device arrays of pointers)
     int64_t* const* rowval;  // [2T] -> int64 rowval buffers (1-based out)
     double* const* nzval;    // [2T]

@@ -41,6 +41,7 @@ struct Event {
 inline float elapsed_ms(const Event& a, const Event& b) {
     return std::chrono::duration<float, std::milli>(b.t - a.t).count();
 }
+inline int stream_wait(sls_stream_t, const Event&) { return 0; }
 template <class K> inline int set_max_smem(K, int) { return 0; }
 template <class K> inline int max_blocks_per_sm(K, int, size_t) { return 2; }
 }  // namespace rt
@@ -79,6 +80,7 @@ struct Event {
     void record(sls_stream_t s) { cudaEventRecord(e, s); }
 };
 inline float elapsed_ms(const Event& a, const Event& b) { float ms = 0; cudaEventElapsedTime(&ms, a.e, b.e); return ms; }
+inline int stream_wait(sls_stream_t s, const Event& ev) { return (int)cudaStreamWaitEvent(s, ev.e, 0); }
 template <class K> inline int set_max_smem(K k, int bytes) {
     return (int)cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }

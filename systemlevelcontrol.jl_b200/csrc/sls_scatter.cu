@@ -33,11 +33,11 @@ sls_scatter_kernel(SlsScatterArgs a) {
     const int T = P.T;
     const bool isu = tt >= T;
     const int t = isu ? tt - T : tt;
-    const int c0 = (blockIdx.x * SCATTER_WPB + warp) * 32;
-    if (c0 >= P.ncols) return;
+    const int c0 = a.c_begin + (blockIdx.x * SCATTER_WPB + warp) * 32;
+    if (c0 >= a.c_end) return;
     int32_t* pref = pref_s[warp];
     const int c = c0 + lane;
-    const bool valid = c < P.ncols;
+    const bool valid = c < a.c_end;
     const int nw = isu ? P.wu : P.wx;
     const uint32_t* mbase = isu ? P.masku : P.maskx;
     int cnt = 0;
@@ -72,9 +72,9 @@ sls_scatter_kernel(SlsScatterArgs a) {
 }
 
 int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream) {
-    if (a.P.ncols == 0) return 0;
+    if (a.c_end <= a.c_begin) return 0;
     const int per_block = SCATTER_WPB * 32;
-    dim3 grid((a.P.ncols + per_block - 1) / per_block, 2 * a.P.T, 1);
+    dim3 grid((a.c_end - a.c_begin + per_block - 1) / per_block, 2 * a.P.T, 1);
     auto kp = &sls_scatter_kernel;
     SLS_LAUNCH(kp, grid, SCATTER_WPB * 32, 0, stream, a);
     return rt::last_error();

@@ -32,6 +32,7 @@
 
 
 #include <cmath>
+#include <cstdlib>
 #define SLS_INF ((double)INFINITY)
 
 __device__ __forceinline__ void sls_dmma(double& c0, double& c1, double a, double b) {
@@ -63,7 +64,7 @@ __device__ __forceinline__ void sls_mma_xwt(double (&acc)[2], const double (&x)[
 struct SlsSolveLayout {
     int N, NB, mcap, nnzcap, T, wu;
     int oAblk, oBBt, oY0, oY1, oG, oDref, oLam, oTx, oRhs, oXa, oXb, oUc, oValR, oValC;
-    int oSx, oSu, oMx, oMu, oRptr, oRsplit, oColR, oCptr, oRowC, total;
+    int oSx, oSu, oMx, oMu, oPre, oRptr, oRsplit, oColR, oCptr, oRowC, total;
     __host__ __device__ SlsSolveLayout(int N_, int mcap_, int nnzcap_, int T_, int wu_) {
         N = N_; NB = N_ / 8; mcap = mcap_ < 1 ? 1 : mcap_; nnzcap = nnzcap_ < 1 ? 1 : nnzcap_; T = T_; wu = wu_ < 1 ? 1 : wu_;
         int o = 0;
@@ -89,6 +90,7 @@ struct SlsSolveLayout {
         SLS_SEC(oSu, 4 * mcap);
         SLS_SEC(oMx, 8 * (T + 1));
         SLS_SEC(oMu, 4 * T * wu);
+        SLS_SEC(oPre, 4 * 2 * T);
         SLS_SEC(oColR, 2 * nnzcap);
         SLS_SEC(oCptr, 2 * (N + mcap + 2));
         SLS_SEC(oRowC, 2 * nnzcap);
@@ -147,6 +149,7 @@ sls_solve_kernel(SlsSolveArgs a) {
     int32_t* su = reinterpret_cast<int32_t*>(base + L.oSu);
     mask_t* mxs = reinterpret_cast<mask_t*>(base + L.oMx);
     uint32_t* mus = reinterpret_cast<uint32_t*>(base + L.oMu);
+    uint32_t* pre = reinterpret_cast<uint32_t*>(base + L.oPre);
     uint16_t* rptr = reinterpret_cast<uint16_t*>(base + L.oRptr);
     uint16_t* rsplit = reinterpret_cast<uint16_t*>(base + L.oRsplit);
     uint16_t* colr = reinterpret_cast<uint16_t*>(base + L.oColR);
@@ -176,6 +179,7 @@ sls_solve_kernel(SlsSolveArgs a) {
         }
         if (lane == 0) mxs[T] = (mask_t)0;
         for (int t = lane; t < T * wu; t += 32) mus[t] = P.masku[(size_t)c * T * wu + t];
+        for (int t = lane; t < 2 * T; t += 32) pre[t] = P.pre[(size_t)c * 2 * T + t];
         for (int e = lane; e < N * N; e += 32) Am[e] = 0.0;
         __syncwarp();
         // ------------------------------------------------------------------ local CSR of C~ = [A~ B~]
@@ -364,9 +368,11 @@ sls_solve_kernel(SlsSolveArgs a) {
                 for (int bl = 0; bl < NB; bl++) {
                     if (!((nzA >> (bi * NB + bl)) & 1ull)) continue;
                     const double2 av = *reinterpret_cast<const double2*>(Am + ((bi * NB + bl) << 6) + (g << 3) + 2 * q);
-                    const double ab[2] = {av.x, av.y};
+                    // even-k halves of all NB accumulators first, then the odd-k halves: back-to-back DMMAs are independent
 #pragma unroll
-                    for (int bj = 0; bj < NB; bj++) sls_mma_xwt(Tm[bi][bj], ab, S[bj][bl]);
+                    for (int bj = 0; bj < NB; bj++) sls_dmma(Tm[bi][bj][0], Tm[bi][bj][1], av.x, S[bj][bl][0]);
+#pragma unroll
+                    for (int bj = 0; bj < NB; bj++) sls_dmma(Tm[bi][bj][0], Tm[bi][bj][1], av.y, S[bj][bl][1]);
                 }
             }
             // (6) S_k = Dp + Tm Am^T
@@ -383,9 +389,10 @@ sls_solve_kernel(SlsSolveArgs a) {
                 for (int bl = 0; bl < NB; bl++) {
                     if (!((nzA >> (bj * NB + bl)) & 1ull)) continue;
                     const double2 av = *reinterpret_cast<const double2*>(Am + ((bj * NB + bl) << 6) + (g << 3) + 2 * q);
-                    const double ab[2] = {av.x, av.y};
 #pragma unroll
-                    for (int bi = 0; bi < NB; bi++) sls_mma_xwt(S[bi][bj], Tm[bi][bl], ab);
+                    for (int bi = 0; bi < NB; bi++) sls_dmma(S[bi][bj][0], S[bi][bj][1], Tm[bi][bl][0], av.x);
+#pragma unroll
+                    for (int bi = 0; bi < NB; bi++) sls_dmma(S[bi][bj][0], S[bi][bj][1], Tm[bi][bl][1], av.y);
                 }
             // (7) block symmetric sweep with rank skipping:  S <- -(S^+).  A skipped pivot (<= threshold) gets
             //     pinv = 0, which zeroes its row and column at once (they never feed a kept row).
@@ -394,11 +401,13 @@ sls_solve_kernel(SlsSolveArgs a) {
             for (int p = 0; p < NB; p++) {
                 double d0 = S[p][p][0], d1 = S[p][p][1];
                 uint32_t kb = 0u;
+                const uint32_t actp = (uint32_t)(nonempty >> (8 * p)) & 0xffu;   // non-empty rows of D_k in this block
 #pragma unroll 1
                 for (int rp = 0; rp < 4; rp++) {
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
                         const int r = 2 * rp + e;
+                        if (!((actp >> r) & 1u)) continue;   // empty constraint row: its row/column of S_k is exactly zero
                         const double src = e ? d1 : d0;
                         const double dv = __shfl_sync(SLS_FULL, src, 4 * r + rp);
                         const double cg = __shfl_sync(SLS_FULL, src, (lane & ~3) | rp);
@@ -420,19 +429,26 @@ sls_solve_kernel(SlsSolveArgs a) {
                 const double Pn[2] = {d0, d1};                // -P, symmetric
                 double Tn[NB][2], Tt[NB][2];                  // Tn_i = -S_ip P,  Tt_i = -P S_pi = -(S_ip P)^T
 #pragma unroll
-                for (int bi = 0; bi < NB; bi++) {
-                    if (bi == p) continue;
-                    Tn[bi][0] = 0.0; Tn[bi][1] = 0.0; Tt[bi][0] = 0.0; Tt[bi][1] = 0.0;
-                    sls_mma_xwt(Tn[bi], S[bi][p], Pn);
-                    sls_mma_xwt(Tt[bi], Pn, S[bi][p]);
+                for (int bi = 0; bi < NB; bi++) { Tn[bi][0] = 0.0; Tn[bi][1] = 0.0; Tt[bi][0] = 0.0; Tt[bi][1] = 0.0; }
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+#pragma unroll
+                    for (int bi = 0; bi < NB; bi++) {
+                        if (bi == p) continue;
+                        sls_dmma(Tn[bi][0], Tn[bi][1], S[bi][p][e], Pn[e]);
+                        sls_dmma(Tt[bi][0], Tt[bi][1], Pn[e], S[bi][p][e]);
+                    }
                 }
 #pragma unroll
-                for (int bi = 0; bi < NB; bi++) {
-                    if (bi == p) continue;
+                for (int e = 0; e < 2; e++) {
 #pragma unroll
-                    for (int bj = 0; bj < NB; bj++) {
-                        if (bj == p) continue;
-                        sls_mma_xwt(S[bi][bj], Tn[bi], S[bj][p]);     // S_ij -= (S_ip P) S_jp^T
+                    for (int bi = 0; bi < NB; bi++) {
+                        if (bi == p) continue;
+#pragma unroll
+                        for (int bj = 0; bj < NB; bj++) {
+                            if (bj == p) continue;
+                            sls_dmma(S[bi][bj][0], S[bi][bj][1], Tn[bi][e], S[bj][p][e]);   // S_ij -= (S_ip P) S_jp^T
+                        }
                     }
                 }
 #pragma unroll
@@ -485,7 +501,6 @@ sls_solve_kernel(SlsSolveArgs a) {
         for (int rr = 0; rr < RPL; rr++) { const int i = lane + 32 * rr; if (i < N) xnext[i] = 0.0; }
         double resmax = 0.0;
         const int64_t xoff = P.tot[c];
-        const uint32_t* pre = P.pre + (size_t)c * 2 * T;
         for (int k = T; k >= 1; k--) {
             const mask_t mk = mxs[k - 1];
             const uint32_t* muk = mus + (size_t)(k - 1) * wu;
@@ -635,8 +650,9 @@ static int resident_warps(int mcap, int nnzcap, int T, int wu, int sm_count, int
     if (per_block > (size_t)max_smem) return -1;
     auto kp = &sls_solve_kernel<NB>;
     if (per_block > 48 * 1024) { if (rt::set_max_smem(kp, (int)per_block)) return -1; }
-    const int bps = rt::max_blocks_per_sm(kp, WPB * 32, per_block);
+    int bps = rt::max_blocks_per_sm(kp, WPB * 32, per_block);
     if (bps < 1) return -1;
+    if (const char* cap = getenv("SLS_MAX_BPS")) { const int c = atoi(cap); if (c >= 1 && c < bps) bps = c; }   // tuning knob
     return bps * sm_count * WPB;
 }
 
