@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SLS_ABI_VERSION 1
+#define SLS_ABI_VERSION 2
 
 /* per-column status bits written by sls_solve* (improves on the reference, which ignores the
  * solver's termination status: src/synthesis.jl:62-65) */
@@ -53,6 +53,8 @@ typedef struct sls_timing {      /* device times (CUDA events on the handle's st
     int64_t ncols, nnz_out;      /* columns synthesised, total stored entries of Φx+Φu                 */
     double  alg_flops;           /* sum_cols n^2*sum_t(nx_t+nu_t) + (7/3)*T*n^3            */
     double  alg_bytes;           /* B_col summed over columns                              */
+    float sim_ms;                /* sls_simulate: device time of the simulation kernel                  */
+    int32_t sim_window, sim_uwindow;   /* largest state / input window over the scenarios             */
 } sls_timing;
 
 int         sls_abi_version(void);
@@ -116,6 +118,14 @@ int sls_device_output(sls_handle* h, int64_t t, int which /*0=Φx,1=Φu*/,
 int sls_device_status(sls_handle* h, const int32_t** d_status, const double** d_resid);
 
 int sls_get_timing(const sls_handle* h, sls_timing* out);
+
+/* Batched closed-loop FIR simulation (README.md:62-71) of the controller left on the device by the last
+ * sls_solve / sls_solve_device: scenario s applies w(t) = delta(t - dist_time[s]) e_{dist_col[s]} (both 1-based)
+ * and runs x, beta, u for `steps` steps from rest.  Outputs (host, any may be NULL): xnorm[s*steps + t-1] = ||x(t)||_2,
+ * unorm likewise for u(t); x_out / u_out are dense [nscen][steps][Nx] / [nscen][steps][Nu] trajectories (small cases).
+ * Every disturbance column's neighbourhood must be among the planned columns (unplanned columns have Phi = 0). */
+int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const int64_t* dist_col, const int64_t* dist_time,
+                 double* xnorm, double* unorm, double* x_out, double* u_out);
 
 /* Device-side stopwatch on the handle's stream (CUDA events): sls_mark(h,0) ... sls_mark(h,1), then
  * sls_elapsed_ms waits for mark 1 and returns the device time between the two marks.  bench.py brackets a

@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libslsb200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 STATUS_OK, STATUS_RESIDUAL, STATUS_RANK_SKIPPED, STATUS_NO_IMPULSE = 0, 1, 2, 4
 
 i64p = C.POINTER(C.c_int64)
@@ -34,7 +34,8 @@ class SlsTiming(C.Structure):
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("solve_launches", C.c_int64), ("gather_launches", C.c_int64), ("scatter_launches", C.c_int64),
                 ("ncols", C.c_int64), ("nnz_out", C.c_int64),
-                ("alg_flops", C.c_double), ("alg_bytes", C.c_double)]
+                ("alg_flops", C.c_double), ("alg_bytes", C.c_double),
+                ("sim_ms", C.c_float), ("sim_window", C.c_int32), ("sim_uwindow", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -58,6 +59,7 @@ SIGNATURES = {
                                     C.POINTER(C.c_void_p), i64p]),
     "sls_device_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "sls_get_timing": (C.c_int, [C.c_void_p, C.POINTER(SlsTiming)]),
+    "sls_simulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, i64p, i64p, f64p, f64p, f64p, f64p]),
     "sls_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "sls_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "sls_fp64_peak": (C.c_int, [C.c_int, C.c_int, f64p, f64p]),

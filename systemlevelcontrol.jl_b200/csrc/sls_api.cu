@@ -681,6 +681,79 @@ extern "C" int sls_solve(sls_handle* h,
     return run_solve(h, &ho);
 }
 
+// ---- closed-loop FIR simulation --------------------------------------------------------------
+extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const int64_t* dist_col, const int64_t* dist_time,
+                            double* xnorm, double* unorm, double* x_out, double* u_out) {
+    if (!h) return -1;
+    SLS_ARG(h->solved, "sls_simulate: no synthesised controller on the device (call sls_solve first)");
+    SLS_ARG(nscen >= 0 && nscen < (int64_t)1 << 30 && steps >= 2 && dist_col && dist_time, "sls_simulate: bad arguments");
+    SLS_CK(rt::set_device(h->device));
+    const int64_t Nx = h->Nx, Nu = h->Nu, T = h->T;
+    for (int64_t s = 0; s < nscen; s++)
+        if (dist_col[s] < 1 || dist_col[s] > Nx || dist_time[s] < 1) return fail(h, -3, "sls_simulate: scenario out of range");
+    if (nscen == 0) return 0;
+    const Plan& p = h->plan;
+    DevBuf dcol, dtime, dnw, dnu, dxn, dun, dxo, duo, dovf;
+    int e = 0;
+    auto cleanup = [&]() { DevBuf* all[] = {&dcol, &dtime, &dnw, &dnu, &dxn, &dun, &dxo, &duo, &dovf}; for (DevBuf* b : all) b->release(); };
+#define SIM_CK(expr) do { e = (expr); if (e) { cleanup(); return fail(h, e, #expr); } } while (0)
+    SIM_CK(dcol.ensure(nscen * 8)); SIM_CK(dtime.ensure(nscen * 8));
+    SIM_CK(dnw.ensure(nscen * 4)); SIM_CK(dnu.ensure(nscen * 4)); SIM_CK(dovf.ensure(4));
+    SIM_CK(rt::h2d(dcol.p, dist_col, nscen * 8, h->stream));
+    SIM_CK(rt::h2d(dtime.p, dist_time, nscen * 8, h->stream));
+    SIM_CK(rt::zero(dovf.p, 4, h->stream));
+    SlsSimArgs a{};
+    a.Nx = Nx; a.Nu = Nu; a.steps = steps; a.T = (int)T; a.nscen = (int)nscen;
+    a.colptr = p.colptr.as<int64_t>();
+    a.rowval = reinterpret_cast<const int64_t* const*>(h->out_ptrs.as<void*>());
+    a.nzval = reinterpret_cast<const double* const*>(h->out_ptrs.as<void*>() + 2 * T);
+    a.A = h->A.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();
+    a.dcol = dcol.as<int64_t>(); a.dtime = dtime.as<int64_t>(); a.overflow = dovf.as<int>();
+    // pass 1: window sizes (scratch capacity = as much as 4 warps can have)
+    int cap = 1024;
+    while ((size_t)4 * 3 * (cap * 2) * sizeof(int32_t) <= (size_t)h->max_smem && cap < 8192) cap *= 2;
+    SIM_CK(sls_launch_sim_size(a, dnw.as<int32_t>(), dnu.as<int32_t>(), cap, h->stream));
+    std::vector<int32_t> nw(nscen), nu(nscen);
+    SIM_CK(rt::d2h(nw.data(), dnw.p, nscen * 4, h->stream));
+    SIM_CK(rt::d2h(nu.data(), dnu.p, nscen * 4, h->stream));
+    SIM_CK(rt::sync(h->stream));
+    int wmax = 1, umax = 1;
+    for (int64_t s = 0; s < nscen; s++) {
+        if (nw[s] < 0 || nu[s] < 0) { cleanup(); return fail(h, -4, "sls_simulate: a scenario's window does not fit shared memory"); }
+        wmax = std::max(wmax, nw[s]); umax = std::max(umax, nu[s]);
+    }
+    const int wcap = (wmax + 1) & ~1, ucap = (umax + 1) & ~1;
+    // scratch of the main kernel: as large as pass 1's if shared memory allows (it must hold the window so far plus
+    // one append round = the T columns of one state); overflow is detected on the device
+    int cap2 = cap;
+    while ((size_t)4 * sls_sim_smem_per_warp(cap2, wcap, ucap, (int)T) > (size_t)h->max_smem && cap2 > 256) cap2 /= 2;
+    if ((size_t)4 * sls_sim_smem_per_warp(cap2, wcap, ucap, (int)T) > (size_t)h->max_smem) {
+        cleanup(); return fail(h, -4, "sls_simulate: windows do not fit shared memory");
+    }
+    const size_t nn = (size_t)nscen * steps;
+    SIM_CK(dxn.ensure(nn * 8)); SIM_CK(dun.ensure(nn * 8));
+    SIM_CK(rt::zero(dxn.p, nn * 8, h->stream)); SIM_CK(rt::zero(dun.p, nn * 8, h->stream));
+    a.xnorm = dxn.as<double>(); a.unorm = dun.as<double>();
+    if (x_out) { SIM_CK(dxo.ensure(nn * Nx * 8)); SIM_CK(rt::zero(dxo.p, nn * Nx * 8, h->stream)); a.xout = dxo.as<double>(); }
+    if (u_out) { SIM_CK(duo.ensure(nn * std::max<int64_t>(Nu, 1) * 8)); SIM_CK(rt::zero(duo.p, nn * std::max<int64_t>(Nu, 1) * 8, h->stream)); a.uout = duo.as<double>(); }
+    h->ev[0].record(h->stream);
+    SIM_CK(sls_launch_sim(a, cap2, wcap, ucap, h->stream));
+    h->ev[1].record(h->stream);
+    int ovf = 0;
+    SIM_CK(rt::d2h(&ovf, dovf.p, 4, h->stream));
+    if (xnorm) SIM_CK(rt::d2h(xnorm, dxn.p, nn * 8, h->stream));
+    if (unorm) SIM_CK(rt::d2h(unorm, dun.p, nn * 8, h->stream));
+    if (x_out) SIM_CK(rt::d2h(x_out, dxo.p, nn * Nx * 8, h->stream));
+    if (u_out) SIM_CK(rt::d2h(u_out, duo.p, nn * Nu * 8, h->stream));
+    SIM_CK(rt::sync(h->stream));
+#undef SIM_CK
+    h->tm.sim_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);
+    h->tm.sim_window = wmax; h->tm.sim_uwindow = umax;
+    cleanup();
+    if (ovf) return fail(h, -4, "sls_simulate: window scratch overflow");
+    return 0;
+}
+
 extern "C" int sls_device_output(sls_handle* h, int64_t t, int which,
                                  const int64_t** d_colptr, const int64_t** d_rowval, const double** d_nzval, int64_t* nnz) {
     if (!h) return -1;

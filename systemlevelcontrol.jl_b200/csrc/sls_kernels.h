@@ -49,3 +49,21 @@ struct SlsScatterArgs {
     double* const* nzval;    // [2T]
 };
 int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream);
+
+// ---- closed-loop FIR simulation (sls_sim.cu) ----
+struct SlsSimArgs {
+    int64_t Nx, Nu, steps;
+    int T, nscen;
+    const int64_t* colptr;            // [2T][Nx+1] Julia colptr of Phi_x taps then Phi_u taps
+    const int64_t* const* rowval;     // [2T] device pointers
+    const double* const* nzval;       // [2T]
+    SlsCsc A, Ar, B2r;                // A by columns; A and B2 by rows
+    const int64_t* dcol;              // [nscen] 1-based disturbance column j_s
+    const int64_t* dtime;             // [nscen] 1-based disturbance time t_s
+    double* xnorm; double* unorm;     // [nscen][steps] or null
+    double* xout; double* uout;       // dense [nscen][steps][Nx] / [nscen][steps][Nu] or null
+    int* overflow;
+};
+__host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, int T);
+int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, sls_stream_t stream);
+int sls_launch_sim(const SlsSimArgs& a, int cap, int wcap, int ucap, sls_stream_t stream);

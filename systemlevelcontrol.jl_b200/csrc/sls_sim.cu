@@ -1,0 +1,291 @@
+// sls_sim.cu — batched closed-loop FIR simulation of the synthesised controller (BASELINE config #5).
+//
+// Implements, per disturbance scenario s with w(t) = delta(t - t_s) e_{j_s}, the recursion of the reference's
+// README (README.md:62-71, 1-based t, x(1) = beta(1) = 0, what(s) := x(s) - beta(s)):
+//     beta(t+1) = sum_{tau=1}^{min(t,T-1)} Phi_x[tau+1] * what(t+1-tau)
+//     u(t)      = sum_{tau=1}^{min(t,T)}   Phi_u[tau]   * what(t+1-tau)
+//     x(t+1)    = A x(t) + B1 w(t) + B2 u(t)                       (B1 = I)
+// on the device-resident Phi of the handle's last solve.  One warp per scenario.  The closed-loop response of a
+// localized controller to an impulse at j never leaves a small neighbourhood of j (that is what (d,T)-localization
+// buys), so every scenario runs on a WINDOW of states: W = the 2-level closure of j under the column patterns of
+// Phi_x (all taps), plus one hop of A.  Inside the window the recursion is exact; contributions that would land
+// outside it are second-generation round-off (<= 1e-32 relative: the estimate what(s) is exactly e_j at s = t_s+1
+// and pure round-off afterwards, and a round-off disturbance at a window state is itself confined to that state's
+// own support, which the 2-level closure contains).
+// Phi columns are streamed from L2/HBM each step (window columns x taps); what-history, x, beta, u live in
+// shared memory.  Deterministic: columns are applied one after another, rows inside a column are distinct.
+#include "../../include/slsb200.h"
+#include "sls_common.h"
+#include "sls_kernels.h"
+#include <climits>
+
+#define SIM_WPB 4
+
+__host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, int T) {
+    size_t b = ((size_t)T * wcap + 3 * (size_t)wcap + ucap) * sizeof(double) + ((size_t)wcap + ucap + 2 * (size_t)cap) * sizeof(int32_t);
+    return (b + 15) & ~(size_t)15;
+}
+
+
+// append the rows of column gc of every tap in [tt0, tt1) to buf[cnt..]; returns new count or -1 on overflow
+__device__ int sls_sim_append(const SlsSimArgs& a, int tt0, int tt1, int64_t gc, int32_t* buf, int cnt, int cap) {
+    const int lane = sls_lane();
+    for (int tt = tt0; tt < tt1; tt++) {
+        const int64_t* cp = a.colptr + (int64_t)tt * (a.Nx + 1);
+        const int64_t e0 = cp[gc] - 1, e1 = cp[gc + 1] - 1;
+        const int len = (int)(e1 - e0);
+        if (cnt + len > cap) return -1;
+        const int64_t* rv = a.rowval[tt];
+        for (int i = lane; i < len; i += 32) buf[cnt + i] = (int32_t)(rv[e0 + i] - 1);
+        cnt += len;
+    }
+    return cnt;
+}
+
+// in-place sort + unique of buf[0..cnt) (warp-cooperative bitonic sort, cnt <= cap, cap a power of two)
+__device__ int sls_sim_sort_unique(int32_t* buf, int cnt, int cap) {
+    const int lane = sls_lane();
+    int P = 32;
+    while (P < cnt) P <<= 1;
+    if (P > cap) P = cap;
+    for (int i = cnt + lane; i < P; i += 32) buf[i] = INT_MAX;
+    __syncwarp();
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < P; i += 32) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int x = buf[i], y = buf[ixj];
+                    const bool asc = (i & k) == 0;
+                    if ((x > y) == asc) { buf[i] = y; buf[ixj] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    int n = 0, prev_last = -1;
+    for (int b0 = 0; b0 < P; b0 += 32) {
+        const int v = buf[b0 + lane];
+        int pv = __shfl_up_sync(SLS_FULL, v, 1);
+        if (lane == 0) pv = prev_last;
+        const bool keep = (v != INT_MAX) && (v != pv);
+        const unsigned bal = __ballot_sync(SLS_FULL, keep);
+        __syncwarp();
+        if (keep) buf[n + __popc(bal & ((1u << lane) - 1u))] = v;
+        n += __popc(bal);
+        prev_last = __shfl_sync(SLS_FULL, v, 31);
+        __syncwarp();
+    }
+    return n;
+}
+
+// window of scenario column j: returns |W| (rows in buf[0..|W|)), or -1 on overflow.  `tmp` holds a copy of level 1.
+__device__ int sls_sim_window(const SlsSimArgs& a, int64_t j, int32_t* buf, int32_t* tmp, int cap, int tmpcap) {
+    const int lane = sls_lane();
+    const int T = a.T;
+    // level 1: rows of Phi_x[:, j] over all taps, and j itself
+    if (lane == 0) buf[0] = (int32_t)j;
+    __syncwarp();
+    int cnt = sls_sim_append(a, 0, T, j, buf, 1, cap);
+    if (cnt < 0) return -1;
+    __syncwarp();
+    int n1 = sls_sim_sort_unique(buf, cnt, cap);
+    if (n1 > tmpcap) return -1;
+    for (int i = lane; i < n1; i += 32) tmp[i] = buf[i];
+    __syncwarp();
+    // level 2: add the rows of Phi_x[:, c] for every c of level 1
+    int n = n1;
+    for (int k = 0; k < n1; k++) {
+        cnt = sls_sim_append(a, 0, T, tmp[k], buf, n, cap);
+        if (cnt < 0) return -1;
+        __syncwarp();
+        n = sls_sim_sort_unique(buf, cnt, cap);
+    }
+    // one hop of A (x(t+1) = A x(t) reaches the neighbours of the support): rows r with A[r, c] != 0, c in W
+    {
+        const int nw = n;
+        cnt = nw;
+        for (int k0 = 0; k0 < nw; k0 += 32) {
+            // sequential over window columns to keep the append deterministic and bounded
+            for (int kk = k0; kk < min(k0 + 32, nw); kk++) {
+                const int64_t gc = buf[kk];
+                const int64_t e0 = a.A.colptr[gc] - 1, e1 = a.A.colptr[gc + 1] - 1;
+                const int len = (int)(e1 - e0);
+                if (cnt + len > cap) return -1;
+                for (int i = lane; i < len; i += 32) buf[cnt + i] = (int32_t)(a.A.rowval[e0 + i] - 1);
+                cnt += len;
+            }
+            __syncwarp();
+        }
+        n = sls_sim_sort_unique(buf, cnt, cap);
+    }
+    return n;
+}
+
+// input window: rows of Phi_u[:, c] for c in W (all taps)
+__device__ int sls_sim_uwindow(const SlsSimArgs& a, const int32_t* W, int nw, int32_t* buf, int cap) {
+    const int T = a.T;
+    int n = 0;
+    for (int k = 0; k < nw; k++) {
+        const int cnt = sls_sim_append(a, T, 2 * T, W[k], buf, n, cap);
+        if (cnt < 0) return -1;
+        __syncwarp();
+        n = sls_sim_sort_unique(buf, cnt, cap);
+    }
+    return n;
+}
+
+// pass 1: window sizes per scenario
+__global__ void __launch_bounds__(SIM_WPB * 32)
+sls_sim_size_kernel(SlsSimArgs a, int32_t* nw_out, int32_t* nu_out, int cap) {
+    SLS_DYN_SMEM(smem);
+    const int warp = threadIdx.x >> 5, lane = sls_lane();
+    const int s = blockIdx.x * SIM_WPB + warp;
+    if (s >= a.nscen) return;
+    int32_t* buf = reinterpret_cast<int32_t*>(smem) + (size_t)warp * 3 * cap;
+    int32_t* tmp = buf + cap;
+    int32_t* ub = tmp + cap;
+    const int64_t j = a.dcol[s] - 1;
+    const int nw = sls_sim_window(a, j, buf, tmp, cap, cap);
+    __syncwarp();
+    int nu = -1;
+    if (nw >= 0) {
+        for (int i = lane; i < nw; i += 32) tmp[i] = buf[i];
+        __syncwarp();
+        nu = sls_sim_uwindow(a, tmp, nw, ub, cap);
+    }
+    if (lane == 0) { nw_out[s] = nw; nu_out[s] = nu; }
+}
+
+// pass 2: the simulation.  shared memory per warp: scratch[3*cap] int32 | W[wcap] Wu[ucap] int32 |
+//         what[T][wcap], x[wcap], xn[wcap], beta[wcap], u[ucap] doubles
+__global__ void __launch_bounds__(SIM_WPB * 32)
+sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
+    SLS_DYN_SMEM(smem);
+    const int warp = threadIdx.x >> 5, lane = sls_lane();
+    const int s = blockIdx.x * SIM_WPB + warp;
+    if (s >= a.nscen) return;
+    const int T = a.T;
+    const size_t per_warp = sls_sim_smem_per_warp(cap, wcap, ucap, T);
+    unsigned char* base = smem + (size_t)warp * per_warp;
+    double* what = reinterpret_cast<double*>(base);
+    double* x = what + (size_t)T * wcap;
+    double* xn = x + wcap;
+    double* beta = xn + wcap;
+    double* u = beta + wcap;
+    int32_t* W = reinterpret_cast<int32_t*>(u + ucap);
+    int32_t* Wu = W + wcap;
+    int32_t* scratch = Wu + ucap;
+    const int64_t j = a.dcol[s] - 1;
+    const int64_t ts = a.dtime[s];                             // 1-based disturbance time
+    // ---- windows
+    int nw = sls_sim_window(a, j, scratch, scratch + cap, cap, cap);
+    __syncwarp();
+    if (nw < 0 || nw > wcap) { if (lane == 0) atomicOr(a.overflow, 1); return; }
+    for (int i = lane; i < nw; i += 32) W[i] = scratch[i];
+    __syncwarp();
+    int nu = sls_sim_uwindow(a, W, nw, scratch, cap);
+    __syncwarp();
+    if (nu < 0 || nu > ucap) { if (lane == 0) atomicOr(a.overflow, 1); return; }
+    for (int i = lane; i < nu; i += 32) Wu[i] = scratch[i];
+    for (int i = lane; i < T * wcap; i += 32) what[i] = 0.0;
+    for (int i = lane; i < wcap; i += 32) { x[i] = 0.0; xn[i] = 0.0; beta[i] = 0.0; }
+    for (int i = lane; i < ucap; i += 32) u[i] = 0.0;
+    __syncwarp();
+    const int jl = sls_find(W, nw, (int32_t)j);
+    double* xnorm = a.xnorm ? a.xnorm + (size_t)s * a.steps : nullptr;
+    double* unorm = a.unorm ? a.unorm + (size_t)s * a.steps : nullptr;
+    // everything is exactly zero up to and including t = ts (x(ts) = 0); norms of those steps stay 0 (pre-zeroed)
+    for (int64_t t = (ts < 1 ? 1 : ts); t <= a.steps - 1; t++) {
+        // beta(t+1), u(t) from what(t+1-tau)
+        for (int i = lane; i < nw; i += 32) beta[i] = 0.0;
+        for (int i = lane; i < nu; i += 32) u[i] = 0.0;
+        __syncwarp();
+        const int taumax = (int)(t < T ? t : T);
+        for (int tau = 1; tau <= taumax; tau++) {
+            const int64_t src = t + 1 - tau;
+            if (src <= ts) break;                              // what(s) = 0 exactly for s <= ts
+            const double* wv = what + (size_t)(src % T) * wcap;
+            const int ttx = tau;                               // Phi_x[tau+1] -> 0-based tap index tau   (tau <= T-1)
+            const int ttu = T + tau - 1;                       // Phi_u[tau]   -> 0-based tap index tau-1
+            for (int cl = 0; cl < nw; cl++) {
+                const double wc = wv[cl];
+                if (wc == 0.0) continue;
+                const int64_t gc = W[cl];
+                if (tau <= T - 1) {
+                    const int64_t* cp = a.colptr + (int64_t)ttx * (a.Nx + 1);
+                    const int64_t e0 = cp[gc] - 1, e1 = cp[gc + 1] - 1;
+                    const int64_t* rv = a.rowval[ttx]; const double* nz = a.nzval[ttx];
+                    for (int64_t e = e0 + lane; e < e1; e += 32) {
+                        const int lr = sls_find(W, nw, (int32_t)(rv[e] - 1));
+                        if (lr >= 0) beta[lr] = fma(nz[e], wc, beta[lr]);
+                    }
+                }
+                {
+                    const int64_t* cp = a.colptr + (int64_t)ttu * (a.Nx + 1);
+                    const int64_t e0 = cp[gc] - 1, e1 = cp[gc + 1] - 1;
+                    const int64_t* rv = a.rowval[ttu]; const double* nz = a.nzval[ttu];
+                    for (int64_t e = e0 + lane; e < e1; e += 32) {
+                        const int lr = sls_find(Wu, nu, (int32_t)(rv[e] - 1));
+                        if (lr >= 0) u[lr] = fma(nz[e], wc, u[lr]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        // x(t+1) = A x(t) + w(t) + B2 u(t) on the window rows
+        double un = 0.0, xnn = 0.0;
+        for (int i = lane; i < nu; i += 32) un = fma(u[i], u[i], un);
+        for (int lr = lane; lr < nw; lr += 32) {
+            const int64_t gr = W[lr];
+            double acc = (t == ts && lr == jl) ? 1.0 : 0.0;
+            for (int64_t e = a.Ar.colptr[gr] - 1; e < a.Ar.colptr[gr + 1] - 1; e++) {
+                const int lc = sls_find(W, nw, (int32_t)(a.Ar.rowval[e] - 1));
+                if (lc >= 0) acc = fma(a.Ar.nzval[e], x[lc], acc);
+            }
+            for (int64_t e = a.B2r.colptr[gr] - 1; e < a.B2r.colptr[gr + 1] - 1; e++) {
+                const int lc = sls_find(Wu, nu, (int32_t)(a.B2r.rowval[e] - 1));
+                if (lc >= 0) acc = fma(a.B2r.nzval[e], u[lc], acc);
+            }
+            xn[lr] = acc;
+            xnn = fma(acc, acc, xnn);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { un += __shfl_xor_sync(SLS_FULL, un, d); xnn += __shfl_xor_sync(SLS_FULL, xnn, d); }
+        if (lane == 0) {
+            if (unorm) unorm[t - 1] = sqrt(un);
+            if (xnorm) xnorm[t] = sqrt(xnn);
+        }
+        if (a.uout) for (int i = lane; i < nu; i += 32) a.uout[((size_t)s * a.steps + (t - 1)) * a.Nu + Wu[i]] = u[i];
+        __syncwarp();
+        // what(t+1) = x(t+1) - beta(t+1);  x <- x(t+1)
+        double* wn = what + (size_t)((t + 1) % T) * wcap;
+        for (int lr = lane; lr < nw; lr += 32) {
+            const double xv = xn[lr];
+            wn[lr] = xv - beta[lr];
+            x[lr] = xv;
+            if (a.xout) a.xout[((size_t)s * a.steps + t) * a.Nx + W[lr]] = xv;
+        }
+        __syncwarp();
+    }
+}
+
+int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, sls_stream_t stream) {
+    if (a.nscen == 0) return 0;
+    const int grid = (a.nscen + SIM_WPB - 1) / SIM_WPB;
+    const size_t smem = (size_t)SIM_WPB * 3 * cap * sizeof(int32_t);
+    auto kp = &sls_sim_size_kernel;
+    if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
+    SLS_LAUNCH(kp, grid, SIM_WPB * 32, smem, stream, a, nw_out, nu_out, cap);
+    return rt::last_error();
+}
+
+int sls_launch_sim(const SlsSimArgs& a, int cap, int wcap, int ucap, sls_stream_t stream) {
+    if (a.nscen == 0) return 0;
+    const int grid = (a.nscen + SIM_WPB - 1) / SIM_WPB;
+    const size_t smem = (size_t)SIM_WPB * sls_sim_smem_per_warp(cap, wcap, ucap, a.T);
+    auto kp = &sls_sim_kernel;
+    if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
+    SLS_LAUNCH(kp, grid, SIM_WPB * 32, smem, stream, a, cap, wcap, ucap);
+    return rt::last_error();
+}

@@ -212,6 +212,21 @@ class Synthesizer:
     def solve_device(self):
         self._ck(self.api.sls_solve_device(self.h))
 
+    def simulate(self, dist_col, dist_time, steps, dense=False):
+        """Batched closed-loop FIR simulation (README.md:62-71) of the controller of the last solve.
+        dist_col: 0-based disturbed states j_s; dist_time: 1-based impulse times t_s (README's t).
+        Returns dict(xnorm[nscen, steps], unorm[nscen, steps][, x[nscen, steps, Nx], u[nscen, steps, Nu]])."""
+        dc = np.ascontiguousarray(np.asarray(dist_col, dtype=np.int64) + 1)
+        dt = np.ascontiguousarray(np.asarray(dist_time, dtype=np.int64))
+        ns = dc.size
+        out = dict(xnorm=np.zeros((ns, steps)), unorm=np.zeros((ns, steps)))
+        if dense:
+            out["x"] = np.zeros((ns, steps, self.Nx))
+            out["u"] = np.zeros((ns, steps, max(self.Nu, 1)))
+        self._ck(self.api.sls_simulate(self.h, ns, steps, ptr(dc, i64p), ptr(dt, i64p), ptr(out["xnorm"], f64p),
+                                       ptr(out["unorm"], f64p), ptr(out.get("x"), f64p), ptr(out.get("u"), f64p)))
+        return out
+
     def mark(self, which):
         self._ck(self.api.sls_mark(self.h, which))
 

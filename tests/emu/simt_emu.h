@@ -222,7 +222,7 @@ template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return 
 template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
-using std::max; using std::min;
+using std::max; using std::min; using std::sqrt;
 
 struct double2 { double x, y; };
 inline double2 make_double2(double a, double b) { return double2{a, b}; }

@@ -155,3 +155,36 @@ def check_masks_and_flags(api):
     Phix, Phiu, info = slc_b200.SLS_H2(slc_b200.Plant(A, B1, B2), [Sx, Su0], I=[[20]], return_info=True, api=api)
     assert info["status"][0] & _capi.STATUS_RESIDUAL and info["resid"][0] > 1e-3
     return worst
+
+
+def check_simulation(api, Nx, scenarios, steps=120, tol=1e-13):
+    """sls_simulate (windowed, on device) against the oracle's dense README recursion, scenario by scenario."""
+    A, B1, B2, S = chain(Nx)
+    syn = slc_b200.Synthesizer(api=api)
+    try:
+        syn.set_plant(A, B2)
+        syn.set_supports(*S)
+        syn.plan(None)
+        out = syn.solve()
+        Phix, Phiu = syn.outputs_to_scipy(out)
+        sim = syn.simulate([j for j, _ in scenarios], [t for _, t in scenarios], steps, dense=True)
+        tm = syn.timing()
+    finally:
+        syn.close()
+    Po = O.Plant(A, B1, B2)
+    T = len(Phix)
+    worst = 0.0
+    for s, (j, ts) in enumerate(scenarios):
+        w = np.zeros((Nx, steps)); w[j, ts - 1] = 1.0
+        x, u, beta = O.simulate_closed_loop(Po, Phix, Phiu, w, steps)
+        worst = max(worst, np.abs(sim["x"][s].T - x).max(), np.abs(sim["u"][s].T - u).max())
+        assert np.abs(sim["xnorm"][s] - np.linalg.norm(x, axis=0)).max() < tol
+        assert np.abs(sim["unorm"][s] - np.linalg.norm(u, axis=0)).max() < tol
+        # closed-loop identity: x(ts+k) = Phi_x[k][:, j], zero after the FIR horizon
+        for k in range(1, T + 1):
+            if ts + k <= steps:
+                assert np.abs(sim["x"][s][ts + k - 1] - Phix[k - 1][:, j].toarray().ravel()).max() < 1e-12
+        if ts + T + 1 <= steps:
+            assert np.abs(sim["x"][s][ts + T:]).max() < 1e-12
+    assert worst < tol, worst
+    return worst, tm

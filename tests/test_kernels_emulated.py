@@ -32,3 +32,8 @@ def test_emu_error_paths(emu_api):
 
 def test_emu_masks_and_flags(emu_api):
     pc.check_masks_and_flags(emu_api)
+
+
+def test_emu_closed_loop_simulation(emu_api):
+    worst, tm = pc.check_simulation(emu_api, 100, [(50, 5), (0, 1), (99, 60), (7, 119)], steps=120)
+    assert tm["sim_window"] < 100        # genuinely windowed: 2-level closure (radius 18) + one hop = 39 states

@@ -177,3 +177,45 @@ def test_sharded_equals_single_bit_for_bit(cuda_api):
                 assert np.array_equal(F[:, a:b].indices, Q[:, a:b].indices)
                 assert np.array_equal(F[:, a:b].data, Q[:, a:b].data)
                 assert Q[:, :a].nnz == 0 and Q[:, b:].nnz == 0
+
+
+def test_closed_loop_simulation_vs_oracle(cuda_api):
+    """README.md:62-71 through sls_simulate: README scenario (j=30, t=50, 250 steps) + edge/late scenarios."""
+    worst, tm = pc.check_simulation(cuda_api, 59, [(29, 50), (0, 1), (58, 200), (30, 249)], steps=250)
+    rng = np.random.default_rng(0)
+    scen = [(int(j), int(t)) for j, t in zip(rng.integers(0, 400, 24), rng.integers(1, 100, 24))]
+    worst, tm = pc.check_simulation(cuda_api, 400, scen, steps=130)
+    assert tm["sim_window"] == 39 and tm["sim_uwindow"] <= 20
+
+
+def test_config5_simulation_100k_4096_scenarios(cuda_api):
+    """BASELINE config #5: Nx = 100 000 controller, 4 096 random impulse scenarios, 250 steps (seed 0).  Checked
+    through the closed-loop identity on norms: ||x(ts+k)|| = ||Phi_x[k][:,j]||, 0 after the FIR horizon."""
+    Nx, ns, steps = 100_000, 4096, 250
+    from slc_b200 import workloads as W
+    A, B1, B2 = W.chain_plant(Nx)
+    Sx, Su = W.chain_supports(Nx, 9, 29, 1.5)
+    syn = slc_b200.Synthesizer(api=cuda_api)
+    try:
+        syn.set_plant(A, B2); syn.set_supports(Sx, Su); syn.plan(None)
+        out = syn.solve()
+        rng = np.random.default_rng(0)
+        js = rng.integers(0, Nx, ns); ts = rng.integers(1, steps - 29, ns)
+        sim = syn.simulate(js, ts, steps)
+        tm = syn.timing()
+    finally:
+        syn.close()
+    T = 29
+    colnorm = np.zeros((T, Nx))
+    for t in range(T):
+        cp = out["x"]["colptr"][t] - 1
+        sq = np.add.reduceat(np.r_[out["x"]["nzval"][t] ** 2, 0.0], cp[:-1])
+        sq[cp[:-1] == cp[1:]] = 0.0
+        colnorm[t] = np.sqrt(sq)
+    for s in range(0, ns, 7):
+        j, t0 = int(js[s]), int(ts[s])
+        got = sim["xnorm"][s]
+        assert np.abs(got[:t0]).max() == 0.0
+        assert np.abs(got[t0:t0 + T] - colnorm[:, j]).max() < 1e-12
+        assert np.abs(got[t0 + T:]).max() < 1e-12
+    print("config5 sim_ms", tm["sim_ms"])
