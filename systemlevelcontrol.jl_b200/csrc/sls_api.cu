@@ -380,7 +380,7 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_CK(rt::zero(p.colptr.p, (size_t)2 * T * (Nx + 1) * sizeof(int64_t), h->stream));
     SLS_CK(rt::zero(p.tot.p, (size_t)(p.ncols + 1) * sizeof(int64_t), h->stream));
     const SlsPlanView v = plan_view(h, p);
-    const size_t fill_smem = (size_t)4 * (cap + p.nstride + p.mstride + p.wx + p.wu) * sizeof(int32_t);
+    const size_t fill_smem = (size_t)4 * sls_gather_fill_words(cap, p.nstride, p.mstride, p.wx, p.wu, (int)T) * sizeof(int32_t);
     if (fill_smem > (size_t)h->max_smem) return fail(h, -4, "plan: index sets do not fit shared memory");
     SLS_CK(sls_launch_gather_fill(h->A.view(), h->B2.view(), h->Sx.view(), h->Su.view(), v, cap, h->stream));
     SLS_CK(sls_launch_scan(v.colptr, Nx + 1, (int)(2 * T), v.tot, p.ncols + 1, h->stream));

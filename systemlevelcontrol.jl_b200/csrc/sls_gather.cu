@@ -85,36 +85,45 @@ sls_gather_count_kernel(SlsCsc A, SlsSupports Sx, SlsSupports Su, int T, int64_t
     if (lane == 0) { n_out[c] = n; m_out[c] = m; }
 }
 
-// Set the mask bits of one tap for one column: rows of S[t][:,j] (with nzval true) found in s.
-__device__ __forceinline__ void sls_warp_mask(const SlsSupports& S, int t, int64_t Nx, int64_t j,
-                                              const int32_t* s, int n, uint32_t* words) {
-    const int lane = sls_lane();
-    const int64_t* cp = S.colptr + (int64_t)t * (Nx + 1);
-    const int64_t base = S.tap_off[t];
-    const int64_t s0 = base + cp[j] - 1, s1 = base + cp[j + 1] - 1;
-    for (int64_t e = s0 + lane; e < s1; e += 32) {
-        const bool on = S.nzval ? (S.nzval[e] != 0) : true;   // `𝓢[t][s,cⱼ] .≠ 1` fixes the entry (synthesis.jl:58-59)
-        const int idx = sls_find(s, n, (int32_t)(S.rowval[e] - 1));
-        if (on && idx >= 0) atomicOr(&words[idx >> 5], 1u << (idx & 31));
-    }
+// 32-bit words of shared memory one warp of kernel 1b needs (kept even so that the int64 section stays aligned)
+__host__ __device__ int sls_gather_fill_words(int cap, int nstride, int mstride, int wx, int wu, int T) {
+    const int w = 4 * T + cap + nstride + mstride + T * (wx + wu) + (2 * T + 1) + 2 * T;
+    return (w + 1) & ~1;
 }
 
 // kernel 1b: index sets, ii_x, masks, per-tap counts, packed-result offsets, local nnz.
-// shared memory per warp: cap + nstride + mstride int32, wx + wu uint32.
+// The 2T support columns 𝓢ₓ[t][:,j], 𝓢ᵤ[t][:,j] of a disturbance column are read as ONE flattened list
+// (segment table + prefix sums in shared memory), so all their loads are independent and in flight together
+// instead of 2T dependent colptr -> rowval round trips.
 __global__ void __launch_bounds__(GATHER_WPB * 32)
 sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsPlanView P, int cap) {
     SLS_DYN_SMEM(smem);
     const int warp = threadIdx.x >> 5, lane = sls_lane();
     const int c = blockIdx.x * GATHER_WPB + warp;
     if (c >= P.ncols) return;
-    const int per_warp = cap + P.nstride + P.mstride + P.wx + P.wu;
-    int32_t* buf = reinterpret_cast<int32_t*>(smem) + (size_t)warp * per_warp;
+    const int T = P.T;
+    const int nmw = P.wx + P.wu;
+    const int per_warp = sls_gather_fill_words(cap, P.nstride, P.mstride, P.wx, P.wu, T);
+    int32_t* wbase = reinterpret_cast<int32_t*>(smem) + (size_t)warp * per_warp;
+    int64_t* seg0 = reinterpret_cast<int64_t*>(wbase);          // [2T] first entry of each support column
+    int32_t* buf = wbase + 4 * T;
     int32_t* sx = buf + cap;
     int32_t* su = sx + P.nstride;
-    uint32_t* mw = reinterpret_cast<uint32_t*>(su + P.mstride);
-    const int T = P.T;
+    uint32_t* mw = reinterpret_cast<uint32_t*>(su + P.mstride); // [T][wx+wu] mask words of every tap
+    int32_t* pfx = reinterpret_cast<int32_t*>(mw + T * nmw);    // [2T+1] prefix sums of the segment lengths
+    int32_t* cnt = pfx + 2 * T + 1;                             // [2T] stored entries per tap (x taps, then u taps)
     const int64_t Nx = P.Nx;
     const int64_t j = P.cols[c];
+
+    // segment table first: these loads overlap with the index-set work below
+    for (int tt = lane; tt < 2 * T; tt += 32) {
+        const SlsSupports& S = (tt < T) ? Sx : Su;
+        const int t = (tt < T) ? tt : tt - T;
+        const int64_t* cp = S.colptr + (int64_t)t * (Nx + 1);
+        const int64_t s0 = S.tap_off[t] + cp[j] - 1, s1 = S.tap_off[t] + cp[j + 1] - 1;
+        seg0[tt] = s0; cnt[tt] = (int)(s1 - s0);
+    }
+    for (int w = lane; w < T * nmw; w += 32) mw[w] = 0u;
 
     const int n = sls_warp_index_set(A, Sx, T, Nx, j, buf, cap);
     for (int i = lane; i < n; i += 32) { sx[i] = buf[i]; P.sx[(size_t)c * P.nstride + i] = buf[i]; }
@@ -124,26 +133,63 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
     __syncwarp();
     if (lane == 0) { P.n[c] = n; P.m[c] = m; P.jloc[c] = sls_find(sx, n, (int32_t)j); }
 
-    uint32_t run = 0;
-    for (int t = 0; t < T; t++) {
-        for (int w = lane; w < P.wx + P.wu; w += 32) mw[w] = 0u;
-        __syncwarp();
-        sls_warp_mask(Sx, t, Nx, j, sx, n, mw);
-        sls_warp_mask(Su, t, Nx, j, su, m, mw + P.wx);
-        __syncwarp();
-        uint32_t cx = 0, cu = 0;
-        for (int w = 0; w < P.wx; w++) cx += __popc(mw[w]);
-        for (int w = 0; w < P.wu; w++) cu += __popc(mw[P.wx + w]);
-        for (int w = lane; w < P.wx; w += 32) P.maskx[((size_t)c * T + t) * P.wx + w] = mw[w];
-        for (int w = lane; w < P.wu; w += 32) P.masku[((size_t)c * T + t) * P.wu + w] = mw[P.wx + w];
-        if (lane == 0) {
-            P.colptr[(int64_t)t * (Nx + 1) + j] = cx;
-            P.colptr[(int64_t)(T + t) * (Nx + 1) + j] = cu;
-            P.pre[(size_t)c * 2 * T + 2 * t] = run;
-            P.pre[(size_t)c * 2 * T + 2 * t + 1] = run + cx;
+    // prefix sums of the 2T segment lengths
+    {
+        int carry = 0;
+        for (int t0 = 0; t0 < 2 * T; t0 += 32) {
+            const int tt = t0 + lane;
+            const int v = (tt < 2 * T) ? cnt[tt] : 0;
+            int incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(SLS_FULL, incl, d); if (lane >= d) incl += o; }
+            if (tt < 2 * T) pfx[tt] = carry + incl - v;
+            carry += __shfl_sync(SLS_FULL, incl, 31);
         }
-        run += cx + cu;
-        __syncwarp();
+        if (lane == 0) pfx[2 * T] = carry;
+    }
+    __syncwarp();
+    const int total = pfx[2 * T];
+    for (int f = lane; f < total; f += 32) {
+        int lo = 0, hi = 2 * T;                               // largest tt with pfx[tt] <= f
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pfx[mid] <= f) lo = mid; else hi = mid; }
+        const int tt = lo;
+        const bool isu = tt >= T;
+        const int t = isu ? tt - T : tt;
+        const SlsSupports& S = isu ? Su : Sx;
+        const int64_t e = seg0[tt] + (f - pfx[tt]);
+        const bool on = S.nzval ? (S.nzval[e] != 0) : true;   // `𝓢[t][s,cⱼ] .≠ 1` fixes the entry (synthesis.jl:58-59)
+        const int idx = isu ? sls_find(su, m, (int32_t)(S.rowval[e] - 1)) : sls_find(sx, n, (int32_t)(S.rowval[e] - 1));
+        if (on && idx >= 0) atomicOr(&mw[t * nmw + (isu ? P.wx : 0) + (idx >> 5)], 1u << (idx & 31));
+    }
+    __syncwarp();
+    // per-tap counts, masks to global, colptr counts
+    for (int tt = lane; tt < 2 * T; tt += 32) {
+        const bool isu = tt >= T;
+        const int t = isu ? tt - T : tt;
+        const uint32_t* w = mw + t * nmw + (isu ? P.wx : 0);
+        const int nwd = isu ? P.wu : P.wx;
+        int k = 0;
+        for (int q = 0; q < nwd; q++) k += __popc(w[q]);
+        cnt[tt] = k;
+        P.colptr[(int64_t)tt * (Nx + 1) + j] = k;
+        uint32_t* dst = isu ? P.masku + ((size_t)c * T + t) * P.wu : P.maskx + ((size_t)c * T + t) * P.wx;
+        for (int q = 0; q < nwd; q++) dst[q] = w[q];
+    }
+    __syncwarp();
+    // offsets of the (x_t, u_t) segments inside the column's packed result: order x_0 u_0 x_1 u_1 ...
+    uint32_t run = 0;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        const int t = t0 + lane;
+        const int cx = (t < T) ? cnt[t] : 0, cu = (t < T) ? cnt[T + t] : 0;
+        int incl = cx + cu;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(SLS_FULL, incl, d); if (lane >= d) incl += o; }
+        if (t < T) {
+            const uint32_t off = run + (uint32_t)(incl - cx - cu);
+            P.pre[(size_t)c * 2 * T + 2 * t] = off;
+            P.pre[(size_t)c * 2 * T + 2 * t + 1] = off + (uint32_t)cx;
+        }
+        run += (uint32_t)__shfl_sync(SLS_FULL, incl, 31);
     }
     // local nnz: A[sx,sx] by columns, B2[sx,su] by columns, and the full column lengths of B2[:,su]
     int cntA = 0, cntB = 0, cntBfull = 0;
@@ -262,7 +308,7 @@ int sls_launch_gather_fill(const SlsCsc& A, const SlsCsc& B2, const SlsSupports&
                            const SlsPlanView& P, int cap, sls_stream_t stream) {
     if (P.ncols == 0) return 0;
     const int grid = (P.ncols + GATHER_WPB - 1) / GATHER_WPB;
-    const size_t smem = (size_t)GATHER_WPB * (cap + P.nstride + P.mstride + P.wx + P.wu) * sizeof(int32_t);
+    const size_t smem = (size_t)GATHER_WPB * sls_gather_fill_words(cap, P.nstride, P.mstride, P.wx, P.wu, P.T) * sizeof(int32_t);
     auto kp = &sls_gather_fill_kernel;
     if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
     SLS_LAUNCH(kp, grid, GATHER_WPB * 32, smem, stream, A, B2, Sx, Su, P, cap);

@@ -6,6 +6,7 @@
 int sls_launch_gather_count(const SlsCsc& A, const SlsSupports& Sx, const SlsSupports& Su, int T, int64_t Nx,
                             const int32_t* cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
                             sls_stream_t stream);
+__host__ __device__ int sls_gather_fill_words(int cap, int nstride, int mstride, int wx, int wu, int T);
 int sls_launch_gather_fill(const SlsCsc& A, const SlsCsc& B2, const SlsSupports& Sx, const SlsSupports& Su,
                            const SlsPlanView& P, int cap, sls_stream_t stream);
 int sls_launch_scan(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, sls_stream_t stream);
