@@ -693,9 +693,9 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
         if (dist_col[s] < 1 || dist_col[s] > Nx || dist_time[s] < 1) return fail(h, -3, "sls_simulate: scenario out of range");
     if (nscen == 0) return 0;
     const Plan& p = h->plan;
-    DevBuf dcol, dtime, dnw, dnu, dxn, dun, dxo, duo, dovf;
+    DevBuf dcol, dtime, dnw, dnu, dxn, dun, dxo, duo, dovf, dW, dWu;
     int e = 0;
-    auto cleanup = [&]() { DevBuf* all[] = {&dcol, &dtime, &dnw, &dnu, &dxn, &dun, &dxo, &duo, &dovf}; for (DevBuf* b : all) b->release(); };
+    auto cleanup = [&]() { DevBuf* all[] = {&dcol, &dtime, &dnw, &dnu, &dxn, &dun, &dxo, &duo, &dovf, &dW, &dWu}; for (DevBuf* b : all) b->release(); };
 #define SIM_CK(expr) do { e = (expr); if (e) { cleanup(); return fail(h, e, #expr); } } while (0)
     SIM_CK(dcol.ensure(nscen * 8)); SIM_CK(dtime.ensure(nscen * 8));
     SIM_CK(dnw.ensure(nscen * 4)); SIM_CK(dnu.ensure(nscen * 4)); SIM_CK(dovf.ensure(4));
@@ -712,7 +712,7 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     // pass 1: window sizes (scratch capacity = as much as 4 warps can have)
     int cap = 1024;
     while ((size_t)4 * 3 * (cap * 2) * sizeof(int32_t) <= (size_t)h->max_smem && cap < 8192) cap *= 2;
-    SIM_CK(sls_launch_sim_size(a, dnw.as<int32_t>(), dnu.as<int32_t>(), cap, h->stream));
+    SIM_CK(sls_launch_sim_size(a, dnw.as<int32_t>(), dnu.as<int32_t>(), cap, nullptr, nullptr, 0, 0, h->stream));
     std::vector<int32_t> nw(nscen), nu(nscen);
     SIM_CK(rt::d2h(nw.data(), dnw.p, nscen * 4, h->stream));
     SIM_CK(rt::d2h(nu.data(), dnu.p, nscen * 4, h->stream));
@@ -723,10 +723,11 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
         wmax = std::max(wmax, nw[s]); umax = std::max(umax, nu[s]);
     }
     const int wcap = (wmax + 1) & ~1, ucap = (umax + 1) & ~1;
-    // scratch of the main kernel: as large as pass 1's if shared memory allows (it must hold the window so far plus
-    // one append round = the T columns of one state); overflow is detected on the device
-    int cap2 = cap;
-    while ((size_t)4 * sls_sim_smem_per_warp(cap2, wcap, ucap, (int)T) > (size_t)h->max_smem && cap2 > 256) cap2 /= 2;
+    // window pass: the same kernel again, now storing the windows with exact strides
+    SIM_CK(dW.ensure((size_t)nscen * wcap * 4)); SIM_CK(dWu.ensure((size_t)nscen * ucap * 4));
+    SIM_CK(sls_launch_sim_size(a, dnw.as<int32_t>(), dnu.as<int32_t>(), cap, dW.as<int32_t>(), dWu.as<int32_t>(), wcap, ucap, h->stream));
+    a.nw = dnw.as<int32_t>(); a.nu = dnu.as<int32_t>(); a.Wg = dW.as<int32_t>(); a.Wug = dWu.as<int32_t>();
+    const int cap2 = 0;
     if ((size_t)4 * sls_sim_smem_per_warp(cap2, wcap, ucap, (int)T) > (size_t)h->max_smem) {
         cleanup(); return fail(h, -4, "sls_simulate: windows do not fit shared memory");
     }

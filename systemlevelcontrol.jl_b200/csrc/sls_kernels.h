@@ -63,8 +63,11 @@ struct SlsSimArgs {
     const int64_t* dtime;             // [nscen] 1-based disturbance time t_s
     double* xnorm; double* unorm;     // [nscen][steps] or null
     double* xout; double* uout;       // dense [nscen][steps][Nx] / [nscen][steps][Nu] or null
+    const int32_t* nw; const int32_t* nu;       // window sizes per scenario
+    const int32_t* Wg; const int32_t* Wug;      // windows [nscen][wcap], [nscen][ucap] (ascending global indices)
     int* overflow;
 };
 __host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, int T);
-int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, sls_stream_t stream);
+int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, int32_t* Wg, int32_t* Wug,
+                        int wcap, int ucap, sls_stream_t stream);
 int sls_launch_sim(const SlsSimArgs& a, int cap, int wcap, int ucap, sls_stream_t stream);

@@ -22,7 +22,8 @@
 #define SIM_WPB 4
 
 __host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, int T) {
-    size_t b = ((size_t)T * wcap + 3 * (size_t)wcap + ucap) * sizeof(double) + ((size_t)wcap + ucap + 2 * (size_t)cap) * sizeof(int32_t);
+    (void)cap;   // the windows are computed by the sizing/window passes; the simulation itself needs no scratch
+    size_t b = ((size_t)T * wcap + 3 * (size_t)wcap + ucap) * sizeof(double) + ((size_t)wcap + ucap) * sizeof(int32_t);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -136,7 +137,7 @@ __device__ int sls_sim_uwindow(const SlsSimArgs& a, const int32_t* W, int nw, in
 
 // pass 1: window sizes per scenario
 __global__ void __launch_bounds__(SIM_WPB * 32)
-sls_sim_size_kernel(SlsSimArgs a, int32_t* nw_out, int32_t* nu_out, int cap) {
+sls_sim_size_kernel(SlsSimArgs a, int32_t* nw_out, int32_t* nu_out, int cap, int32_t* Wg, int32_t* Wug, int wcap, int ucap) {
     SLS_DYN_SMEM(smem);
     const int warp = threadIdx.x >> 5, lane = sls_lane();
     const int s = blockIdx.x * SIM_WPB + warp;
@@ -153,11 +154,15 @@ sls_sim_size_kernel(SlsSimArgs a, int32_t* nw_out, int32_t* nu_out, int cap) {
         __syncwarp();
         nu = sls_sim_uwindow(a, tmp, nw, ub, cap);
     }
+    if (Wg && nw >= 0 && nu >= 0 && nw <= wcap && nu <= ucap) {           // second call: store the windows (exact strides)
+        for (int i = lane; i < nw; i += 32) Wg[(size_t)s * wcap + i] = tmp[i];
+        for (int i = lane; i < nu; i += 32) Wug[(size_t)s * ucap + i] = ub[i];
+    }
     if (lane == 0) { nw_out[s] = nw; nu_out[s] = nu; }
 }
 
-// pass 2: the simulation.  shared memory per warp: scratch[3*cap] int32 | W[wcap] Wu[ucap] int32 |
-//         what[T][wcap], x[wcap], xn[wcap], beta[wcap], u[ucap] doubles
+// pass 2: the simulation.  shared memory per warp: what[T][wcap], x[wcap], xn[wcap], beta[wcap], u[ucap] doubles |
+//         W[wcap] Wu[ucap] int32 (loaded from the window pass)
 __global__ void __launch_bounds__(SIM_WPB * 32)
 sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
     SLS_DYN_SMEM(smem);
@@ -174,19 +179,13 @@ sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
     double* u = beta + wcap;
     int32_t* W = reinterpret_cast<int32_t*>(u + ucap);
     int32_t* Wu = W + wcap;
-    int32_t* scratch = Wu + ucap;
     const int64_t j = a.dcol[s] - 1;
     const int64_t ts = a.dtime[s];                             // 1-based disturbance time
-    // ---- windows
-    int nw = sls_sim_window(a, j, scratch, scratch + cap, cap, cap);
-    __syncwarp();
-    if (nw < 0 || nw > wcap) { if (lane == 0) atomicOr(a.overflow, 1); return; }
-    for (int i = lane; i < nw; i += 32) W[i] = scratch[i];
-    __syncwarp();
-    int nu = sls_sim_uwindow(a, W, nw, scratch, cap);
-    __syncwarp();
-    if (nu < 0 || nu > ucap) { if (lane == 0) atomicOr(a.overflow, 1); return; }
-    for (int i = lane; i < nu; i += 32) Wu[i] = scratch[i];
+    // ---- windows (computed by the window pass)
+    const int nw = a.nw[s], nu = a.nu[s];
+    if (nw < 0 || nu < 0 || nw > wcap || nu > ucap) { if (lane == 0) atomicOr(a.overflow, 1); return; }
+    for (int i = lane; i < nw; i += 32) W[i] = a.Wg[(size_t)s * wcap + i];
+    for (int i = lane; i < nu; i += 32) Wu[i] = a.Wug[(size_t)s * ucap + i];
     for (int i = lane; i < T * wcap; i += 32) what[i] = 0.0;
     for (int i = lane; i < wcap; i += 32) { x[i] = 0.0; xn[i] = 0.0; beta[i] = 0.0; }
     for (int i = lane; i < ucap; i += 32) u[i] = 0.0;
@@ -270,13 +269,14 @@ sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
     }
 }
 
-int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, sls_stream_t stream) {
+int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, int32_t* Wg, int32_t* Wug,
+                        int wcap, int ucap, sls_stream_t stream) {
     if (a.nscen == 0) return 0;
     const int grid = (a.nscen + SIM_WPB - 1) / SIM_WPB;
     const size_t smem = (size_t)SIM_WPB * 3 * cap * sizeof(int32_t);
     auto kp = &sls_sim_size_kernel;
     if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
-    SLS_LAUNCH(kp, grid, SIM_WPB * 32, smem, stream, a, nw_out, nu_out, cap);
+    SLS_LAUNCH(kp, grid, SIM_WPB * 32, smem, stream, a, nw_out, nu_out, cap, Wg, Wug, wcap, ucap);
     return rt::last_error();
 }
 
