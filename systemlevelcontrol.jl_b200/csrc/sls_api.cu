@@ -259,17 +259,15 @@ static int upload_supports(sls_handle* h, DevSupports& d, int64_t T, int64_t nro
                            const char* name) {
     std::vector<int64_t> off(T + 1, 0);
     bool any_nz = false, all_nz = true;
-    for (int64_t t = 0; t < T; t++) {
-        const char* m = check_csc(nrow, ncol, cps[t], rvs ? rvs[t] : nullptr, (h->opt.flags & 1) != 0);
-        if (m) return fail(h, -2, (std::string("sls_set_supports: ") + name + ": " + m).c_str());
+    for (int64_t t = 0; t < T; t++) {                          // cheap checks first: enough to size and start the copies
+        if (!cps[t]) return fail(h, -2, (std::string("sls_set_supports: ") + name + ": colptr is NULL").c_str());
+        if (cps[t][0] != 1 || cps[t][ncol] < 1) return fail(h, -2, (std::string("sls_set_supports: ") + name + ": colptr[1] must be 1 (Julia 1-based CSC)").c_str());
+        if (cps[t][ncol] > 1 && !(rvs && rvs[t])) return fail(h, -2, (std::string("sls_set_supports: ") + name + ": rowval is NULL").c_str());
         off[t + 1] = off[t] + cps[t][ncol] - 1;
         if (nzs && nzs[t]) any_nz = true; else all_nz = false;
     }
     if (any_nz && !all_nz) return fail(h, -2, "sls_set_supports: nzval must be given for every tap or for none");
     d.nnz = off[T]; d.has_nzval = any_nz;
-    int ml = 0;
-    for (int64_t c = 0; c < ncol; c++) ml = std::max<int>(ml, (int)(cps[T - 1][c + 1] - cps[T - 1][c]));
-    d.maxlen_last = ml;
     SLS_CK(d.colptr.ensure(T * (ncol + 1) * sizeof(int64_t)));
     SLS_CK(d.rowval.ensure(std::max<int64_t>(d.nnz, 1) * sizeof(int64_t)));
     SLS_CK(d.tap_off.ensure((T + 1) * sizeof(int64_t)));
@@ -281,6 +279,13 @@ static int upload_supports(sls_handle* h, DevSupports& d, int64_t T, int64_t nro
         if (any_nz) SLS_CK(rt::h2d(d.nzval.as<uint8_t>() + off[t], nzs[t], nnz, h->stream));
     }
     SLS_CK(rt::h2d(d.tap_off.p, off.data(), (T + 1) * sizeof(int64_t), h->stream));
+    // full layout validation on the host while the copies are in flight (a failure leaves have_supports = false)
+    const char* bad = nullptr;
+    for (int64_t t = 0; t < T && !bad; t++) bad = check_csc(nrow, ncol, cps[t], rvs ? rvs[t] : nullptr, (h->opt.flags & 1) != 0);
+    int ml = 0;
+    if (!bad) for (int64_t c = 0; c < ncol; c++) ml = std::max<int>(ml, (int)(cps[T - 1][c + 1] - cps[T - 1][c]));
+    d.maxlen_last = ml;
+    if (bad) { rt::sync(h->stream); return fail(h, -2, (std::string("sls_set_supports: ") + name + ": " + bad).c_str()); }
     SLS_CK(rt::sync(h->stream));                              // `off` is a local
     return 0;
 }
@@ -394,23 +399,11 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_CK(rt::d2h(lB.data(), p.lnnzB.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
     SLS_CK(rt::d2h(tot.data(), p.tot.p, (size_t)(p.ncols + 1) * sizeof(int64_t), h->stream));
     SLS_CK(rt::d2h_strided(p.h_last.data(), v.colptr + Nx, sizeof(int64_t), (size_t)(Nx + 1) * sizeof(int64_t), (size_t)(2 * T), h->stream));
-    SLS_CK(rt::sync(h->stream));
-    for (int64_t tt = 0; tt < 2 * T; tt++) p.nnz_tap[tt] = p.h_last[tt];
-    p.out_off.assign(2 * T + 1, 0);
-    for (int64_t tt = 0; tt < 2 * T; tt++) { p.nnz_tap[tt] -= 1; p.out_off[tt + 1] = p.out_off[tt] + p.nnz_tap[tt]; }
-    p.tot_packed = tot[p.ncols];
-    if (p.tot_packed != p.out_off[2 * T]) return fail(h, -5, "plan: internal count mismatch");
-    // SURVEY §8d algorithmic work, and the size classes of kernel 2
-    p.alg_flops = 0; p.alg_bytes = 0;
-    for (int i = 0; i < p.ncols; i++) {
-        const double n = p.h_n[i], m = p.h_m[i], v_ = (double)(tot[i + 1] - tot[i]);
-        p.alg_flops += n * n * v_ + (7.0 / 3.0) * (double)T * n * n * n;
-        p.alg_bytes += v_ * 25.0 + 2.0 * T * 24.0 + 16.0 * ((double)lA[i] + n + (double)lB[i] + m);
-    }
+    // size classes of kernel 2 (by n, known since the count pass): binned on the host while kernel 1b runs
     p.classes.clear();
-    std::vector<int32_t> lists(nc1);
-    size_t off = 0;
+    p.h_lists.assign(nc1, 0);
     {
+        size_t off = 0;
         const int nk = sls_solve_class_count();
         std::vector<SolveClass> cls(nk);
         std::vector<int> cls_of_n(p.nmax + 2, -1);
@@ -425,15 +418,30 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
             const int k = cls_of_n[p.h_n[i]];
             if (k < 0) continue;
             SolveClass& c = cls[k];
-            lists[c.list_off + c.count++] = i;
-            c.mcap = std::max(c.mcap, p.h_m[i]); c.nnzcap = std::max(c.nnzcap, p.h_lnnz[i]);
+            p.h_lists[c.list_off + c.count++] = i;
+            c.mcap = std::max(c.mcap, p.h_m[i]);
         }
         for (int k = 0; k < nk; k++) if (cls[k].count) p.classes.push_back(cls[k]);
+        SLS_CK(p.lists.ensure(nc1 * sizeof(int32_t)));
+        SLS_CK(rt::h2d(p.lists.p, p.h_lists.data(), off * sizeof(int32_t), h->stream));
     }
-    p.h_lists = lists;
-    SLS_CK(p.lists.ensure(nc1 * sizeof(int32_t)));
-    SLS_CK(rt::h2d(p.lists.p, lists.data(), off * sizeof(int32_t), h->stream));
     SLS_CK(rt::sync(h->stream));
+    for (int64_t tt = 0; tt < 2 * T; tt++) p.nnz_tap[tt] = p.h_last[tt];
+    p.out_off.assign(2 * T + 1, 0);
+    for (int64_t tt = 0; tt < 2 * T; tt++) { p.nnz_tap[tt] -= 1; p.out_off[tt + 1] = p.out_off[tt] + p.nnz_tap[tt]; }
+    p.tot_packed = tot[p.ncols];
+    if (p.tot_packed != p.out_off[2 * T]) return fail(h, -5, "plan: internal count mismatch");
+    // SURVEY §8d algorithmic work, and the size classes of kernel 2
+    p.alg_flops = 0; p.alg_bytes = 0;
+    for (int i = 0; i < p.ncols; i++) {
+        const double n = p.h_n[i], m = p.h_m[i], v_ = (double)(tot[i + 1] - tot[i]);
+        p.alg_flops += n * n * v_ + (7.0 / 3.0) * (double)T * n * n * n;
+        p.alg_bytes += v_ * 25.0 + 2.0 * T * 24.0 + 16.0 * ((double)lA[i] + n + (double)lB[i] + m);
+    }
+    for (SolveClass& c : p.classes) {
+        c.nnzcap = 0;
+        for (int k = 0; k < c.count; k++) c.nnzcap = std::max(c.nnzcap, p.h_lnnz[p.h_lists[c.list_off + k]]);
+    }
     p.valid = true;
     return 0;
 }
