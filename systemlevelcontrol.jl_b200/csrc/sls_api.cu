@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <new>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -559,14 +561,16 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
     h->solved = false;
     if (p.nmax > sls_solve_class_N(sls_solve_class_count() - 1))
         return fail(h, -6, "sls_solve: a column's local state dimension |s_x| exceeds the largest solver size class");
-    SLS_CK(h->xw.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(double)));
     SLS_CK(h->status.ensure(nc1 * sizeof(int32_t)));
     SLS_CK(h->resid.ensure(nc1 * sizeof(double)));
     SLS_CK(h->out_rowval.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(int64_t)));
     SLS_CK(h->out_nzval.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(double)));
     SLS_CK(h->out_ptrs.ensure((size_t)4 * T * sizeof(void*)));
     int nchunk = 1;
-    if (ho && p.cols_sorted && p.ncols >= 16384) nchunk = (h->opt.flags & 2) ? 1 : 4;      // flags bit 1: no D2H pipeline
+    if (ho && p.cols_sorted && p.ncols >= 16384) {
+        nchunk = (h->opt.flags & 2) ? 1 : 4;                   // flags bit 1: no D2H pipeline
+        if (const char* ev = getenv("SLS_D2H_CHUNKS")) { const int c = atoi(ev); if (c >= 1 && c <= 16) nchunk = c; }
+    }
     std::vector<int> cb(nchunk + 1);
     for (int c = 0; c <= nchunk; c++) cb[c] = (int)((int64_t)p.ncols * c / nchunk);
     {
@@ -607,6 +611,17 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         }
     }
     int64_t launches = 0, scatters = 0;
+    {
+        // kernel 3 (rowval) is independent of kernel 2: it runs on the second stream beside the first solve chunk
+        SLS_CK(rt::stream_wait(h->copy_stream, h->ev[4]));
+        SlsScatterArgs s{};
+        s.P = v; s.c_begin = 0; s.c_end = p.ncols;
+        s.rowval = reinterpret_cast<int64_t* const*>(h->out_ptrs.as<void*>());
+        h->ev[5].record(h->copy_stream);
+        SLS_CK(sls_launch_scatter(s, h->copy_stream));
+        h->chunk_ev[15].record(h->copy_stream);
+        if (p.ncols) scatters++;
+    }
     for (int ch = 0; ch < nchunk; ch++) {
         for (const SolveClass& c : p.classes) {
             const int32_t* lb = p.h_lists.data() + c.list_off;
@@ -617,7 +632,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
             a.A = h->A.view(); a.B2 = h->B2.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();
             a.P = v; a.list = p.lists.as<int32_t>() + c.list_off + lo; a.count = hi - lo;
             a.mcap = c.mcap; a.nnzcap = c.nnzcap;
-            a.xw = h->xw.as<double>(); a.hist = h->hist.as<double>();
+            a.out_nzval = reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T); a.hist = h->hist.as<double>();
             a.hist_stride = sls_solve_hist_doubles(c.N, (int)T);
             a.status = h->status.as<int32_t>(); a.resid = h->resid.as<double>();
             a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
@@ -625,13 +640,6 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
             SLS_CK(sls_launch_solve(c.N, a, h->sm_count, h->max_smem, &warps, h->stream));
             launches++;
         }
-        if (nchunk == 1) h->ev[5].record(h->stream);
-        SlsScatterArgs s{};
-        s.P = v; s.xw = h->xw.as<double>(); s.c_begin = cb[ch]; s.c_end = cb[ch + 1];
-        s.rowval = reinterpret_cast<int64_t* const*>(h->out_ptrs.as<void*>());
-        s.nzval = reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T);
-        SLS_CK(sls_launch_scatter(s, h->stream));
-        if (cb[ch + 1] > cb[ch]) scatters++;
         if (ho) {
             h->chunk_ev[ch].record(h->stream);
             SLS_CK(rt::stream_wait(h->copy_stream, h->chunk_ev[ch]));
@@ -647,8 +655,8 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
             }
         }
     }
+    SLS_CK(rt::stream_wait(h->stream, h->chunk_ev[15]));       // join: rowval scatter done
     h->ev[6].record(h->stream);
-    if (ho) { SLS_CK(rt::stream_wait(h->stream, h->chunk_ev[nchunk - 1])); }
     SLS_CK(rt::sync(h->stream));
     if (ho) {
         // per-column outcomes go through pinned staging: the caller's arrays may be pageable, and a pageable
@@ -663,13 +671,8 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         SLS_CK(rt::stream_wait(h->stream, h->ev[7]));          // later marks on the main stream see the copies
         h->tm.d2h_ms = rt::elapsed_ms(h->ev[6], h->ev[7]);     // D2H tail left exposed after the last kernel
     }
-    if (nchunk == 1) {
-        h->tm.solve_ms = rt::elapsed_ms(h->ev[4], h->ev[5]);
-        h->tm.scatter_ms = rt::elapsed_ms(h->ev[5], h->ev[6]);
-    } else {
-        h->tm.solve_ms = rt::elapsed_ms(h->ev[4], h->ev[6]);   // kernels 2 and 3 interleaved per chunk
-        h->tm.scatter_ms = 0.f;
-    }
+    h->tm.solve_ms = rt::elapsed_ms(h->ev[4], h->ev[6]);       // kernel 2 (all classes / chunks); kernel 3 runs beside it
+    h->tm.scatter_ms = rt::elapsed_ms(h->ev[5], h->chunk_ev[15]);   // kernel 3 alone, on the second stream (overlapped)
     h->tm.solve_launches = launches; h->tm.scatter_launches = scatters;
     h->solved = true;
     return 0;

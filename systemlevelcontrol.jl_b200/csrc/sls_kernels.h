@@ -21,7 +21,7 @@ struct SlsSolveArgs {
     const int32_t* list;     // planned-column indices of this size class
     int count;
     int mcap, nnzcap;        // class maxima of m and of the local nnz (shared-memory carve-up)
-    double* xw;              // packed per-column results, column c at xw[P.tot[c]]
+    double* const* out_nzval;  // [2T] device pointers: nzval arrays of the Φx taps then the Φu taps (written directly)
     double* hist;            // factor history, one slot per resident warp
     int64_t hist_stride;     // doubles per slot
     int32_t* status;         // per planned column
@@ -43,11 +43,9 @@ int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int
 // ---- kernel 3 (sls_scatter.cu) ----
 struct SlsScatterArgs {
     SlsPlanView P;
-    const double* xw;
     int c_begin, c_end;      // planned-column range handled by this launch
     // destination arrays: per tap tt in [0,2T): base pointers (device arrays of pointers)
     int64_t* const* rowval;  // [2T] -> int64 rowval buffers (1-based out)
-    double* const* nzval;    // [2T]
 };
 int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream);
 

@@ -1,12 +1,11 @@
-// sls_scatter.cu — kernel 3: scatter of the per-column results into the per-tap CSC patterns.
+// sls_scatter.cu — kernel 3: the index half of the scatter into the per-tap CSC patterns.
 //
 // Replaces reference src/synthesis.jl:65-67: `sparse(rows=s_x, cols=j, vals=value.(Φ̃ₓ[t]) .* mask)` followed
-// by the Θ(Nx) `Φ̃ += …` re-allocation per column.  Kernel 2 leaves each column's in-mask values packed
-// column-major ([x_1 | u_1 | x_2 | u_2 | ...]); the outputs are 2T tap-major CSC arrays.  This is a
-// segmented transpose: one warp handles 32 consecutive planned columns of one tap, flattens their
-// (column, rank) pairs over the lanes so that nzval/rowval are written as full coalesced 256-byte
-// stores, and derives rowval (Int64, 1-based, ascending) from the mask bits and s_x / s_u.
-// HBM-bound; algorithmic bytes per stored entry: 8 (value read) + 8 + 8 (nzval + rowval written).
+// by the Θ(Nx) `Φ̃ += …` re-allocation per column.  The values (nzval) are written straight into the 2T tap-major
+// CSC arrays by kernel 2's back substitution; this kernel writes the matching rowval (Int64, 1-based, ascending),
+// derived from the mask bits and s_x / s_u.  It does not depend on kernel 2 and runs beside it on a second
+// stream.  One warp handles 32 consecutive planned columns of one tap and flattens their (column, rank) pairs
+// over the lanes so that rowval is written as full coalesced 256-byte stores.  HBM-bound.
 #include "sls_common.h"
 #include "sls_kernels.h"
 
@@ -54,7 +53,6 @@ sls_scatter_kernel(SlsScatterArgs a) {
     const int E = pref[32];
     const int64_t* colptr = P.colptr + (int64_t)tt * (P.Nx + 1);
     int64_t* rowval = a.rowval[tt];
-    double* nzval = a.nzval[tt];
     for (int e = lane; e < E; e += 32) {
         int lo = 0, hi = 32;                                  // largest cc with pref[cc] <= e
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pref[mid] <= e) lo = mid; else hi = mid; }
@@ -65,8 +63,6 @@ sls_scatter_kernel(SlsScatterArgs a) {
         const uint32_t* mw = mbase + ((size_t)cc * T + t) * nw;
         const int li = sls_select_bit(mw, nw, r);
         const int32_t grow = isu ? P.su[(size_t)cc * P.mstride + li] : P.sx[(size_t)cc * P.nstride + li];
-        const int64_t src = P.tot[cc] + P.pre[(size_t)cc * 2 * T + 2 * t + (isu ? 1 : 0)] + r;
-        nzval[dst] = a.xw[src];
         rowval[dst] = (int64_t)grow + 1;
     }
 }

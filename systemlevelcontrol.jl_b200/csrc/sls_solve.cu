@@ -90,7 +90,7 @@ struct SlsSolveLayout {
         SLS_SEC(oSu, 4 * mcap);
         SLS_SEC(oMx, 8 * (T + 1));
         SLS_SEC(oMu, 4 * T * wu);
-        SLS_SEC(oPre, 4 * 2 * T);
+        SLS_SEC(oPre, 8 * 2 * T);
         SLS_SEC(oColR, 2 * nnzcap);
         SLS_SEC(oCptr, 2 * (N + mcap + 2));
         SLS_SEC(oRowC, 2 * nnzcap);
@@ -149,7 +149,7 @@ sls_solve_kernel(SlsSolveArgs a) {
     int32_t* su = reinterpret_cast<int32_t*>(base + L.oSu);
     mask_t* mxs = reinterpret_cast<mask_t*>(base + L.oMx);
     uint32_t* mus = reinterpret_cast<uint32_t*>(base + L.oMu);
-    uint32_t* pre = reinterpret_cast<uint32_t*>(base + L.oPre);
+    int64_t* obase = reinterpret_cast<int64_t*>(base + L.oPre);   // [2T] first stored entry of column j in every output tap
     uint16_t* rptr = reinterpret_cast<uint16_t*>(base + L.oRptr);
     uint16_t* rsplit = reinterpret_cast<uint16_t*>(base + L.oRsplit);
     uint16_t* colr = reinterpret_cast<uint16_t*>(base + L.oColR);
@@ -179,7 +179,7 @@ sls_solve_kernel(SlsSolveArgs a) {
         }
         if (lane == 0) mxs[T] = (mask_t)0;
         for (int t = lane; t < T * wu; t += 32) mus[t] = P.masku[(size_t)c * T * wu + t];
-        for (int t = lane; t < 2 * T; t += 32) pre[t] = P.pre[(size_t)c * 2 * T + t];
+        for (int t = lane; t < 2 * T; t += 32) obase[t] = P.colptr[(int64_t)t * (P.Nx + 1) + P.cols[c]] - 1;
         for (int e = lane; e < N * N; e += 32) Am[e] = 0.0;
         __syncwarp();
         // ------------------------------------------------------------------ local CSR of C~ = [A~ B~]
@@ -500,7 +500,6 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
         for (int rr = 0; rr < RPL; rr++) { const int i = lane + 32 * rr; if (i < N) xnext[i] = 0.0; }
         double resmax = 0.0;
-        const int64_t xoff = P.tot[c];
         for (int k = T; k >= 1; k--) {
             const mask_t mk = mxs[k - 1];
             const uint32_t* muk = mus + (size_t)(k - 1) * wu;
@@ -522,7 +521,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                     const bool on = (l < m) && ((word >> lane) & 1u);
                     const double u = on ? -tx[n + l] : 0.0;
                     if (l < m) ucur[l] = u;
-                    if (on) a.xw[xoff + pre[2 * (k - 1) + 1] + rank0 + __popc(word & ((1u << lane) - 1u))] = u;
+                    if (on) a.out_nzval[T + k - 1][obase[T + k - 1] + rank0 + __popc(word & ((1u << lane) - 1u))] = u;
                     rank0 += __popc(word);
                 }
             }
@@ -598,7 +597,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 const double lam_prev = (i < n) ? -gbuf[i] : 0.0;
                 const double x = on ? (lam_prev - tx[i]) : 0.0;
                 if (i < N) { xcur[i] = x; lam_s[i] = lam_prev; }
-                if (on) a.xw[xoff + pre[2 * (k - 1)] + sls_mrank(mk, i)] = x;
+                if (on) a.out_nzval[k - 1][obase[k - 1] + sls_mrank(mk, i)] = x;
             }
             __syncwarp();
             // residual of constraint block k: A~ x_k + B~ u_k - x_{k+1}
