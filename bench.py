@@ -36,6 +36,9 @@ sys.path.insert(0, ROOT)
 
 NX_PER_GPU = 100_000
 D, T, ALPHA = 9, 29, 1.5
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
+# (profiles/r01_step_kernels_ncu_raw.txt): kernel 2 N=24 class; kernel 1b + kernel 3
+NCU_TRAFFIC = {("chain", 100_000, "solve"): 9.86e9, ("chain", 100_000, "gather_scatter"): 0.747e9 + 0.577e9}
 METRIC = "Phi synthesis throughput, localized H2 state feedback (chain Nx=100k/GPU, d=9, T=29)"
 UNIT = "columns/s"
 
@@ -367,11 +370,13 @@ def run_ours(args, rank, world, local_rank):
                        "nnz_out_per_gpu": int(tm["nnz_out"])},
             "kernel_ms": {"gather": float(np.mean(k_ms["gather_ms"])), "solve": solve_ms, "scatter": float(np.mean(k_ms["scatter_ms"]))},
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": dfma.value, "unit": "TFLOP/s", "frac": ach_tf / dfma.value,
-                         "traffic": None, "kernel": "sls_solve_kernel (kernel 2, all size classes of one step)",
+                         "traffic": NCU_TRAFFIC.get((args.workload, nx_local, "solve")),
+                         "kernel": "sls_solve_kernel (kernel 2, all size classes of one step; kernel 3 overlaps on a 2nd stream)",
                          "flops_per_launch": tm["alg_flops"], "peak_source": "sls_fp64_peak DFMA chain, measured in this run",
                          "dmma_peak": dmma.value},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                             "traffic": None, "kernel": "kernels 1+3 (gather incl. host sizing round trips, scatter)",
+                             "traffic": NCU_TRAFFIC.get((args.workload, nx_local, "gather_scatter")),
+                             "kernel": "kernels 1+3 (gather incl. host sizing round trips; rowval scatter timed alone on its stream)",
                              "bytes_per_launch": tm["alg_bytes"], "peak_source": hbm_src},
             "gpu_launches": launches_all,
             "clocks": clocks,
