@@ -503,6 +503,17 @@ sls_solve_kernel(SlsSolveArgs a) {
         for (int k = T; k >= 1; k--) {
             const mask_t mk = mxs[k - 1];
             const uint32_t* muk = mus + (size_t)(k - 1) * wu;
+#ifndef SLS_EMU
+            // the next iteration's history (-Z_{k-2}, yh_{k-2}) is fetched towards L1 now: its loads sit at the head
+            // of a serial chain and would otherwise pay L2/HBM latency every tap
+            if (k >= 3) {
+                const char* hz = reinterpret_cast<const char*>(zhist + (size_t)(k - 2) * TRI);
+                for (int o = lane * 128; o < (int)(n * (n + 1) / 2 * sizeof(double)); o += 32 * 128)
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(hz + o));
+                if (lane == 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(yhist + (size_t)(k - 2) * N));
+                if (lane == 1 && N > 16) asm volatile("prefetch.global.L1 [%0];" :: "l"(yhist + (size_t)(k - 2) * N + 16));
+            }
+#endif
             __syncwarp();
             // t = C~^T lambda_k
             for (int p = lane; p < n + m; p += 32) {
