@@ -282,6 +282,7 @@ def run_ours(args, rank, world, local_rank):
 
     # e2e: host buffers in, host buffers out
     e2e_ms = None
+    e2e_ds_ms = None
     d2h_bytes = 0
     if not args.no_e2e:
         out = syn.alloc_outputs(pinned=True)
@@ -304,6 +305,20 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         e2e_ms = float(np.mean(e2e))
         assert out["resid"][:syn.ncols].max() < 1e-9, "e2e result failed its own feasibility check"
+        # variant: supports generated on the device (sls_make_supports) instead of shipped over PCIe
+        e2e_ds_ms = None
+        if args.workload == "chain" and world == 1:
+            def e2e_ds_step():
+                syn.mark(0)
+                syn.set_plant(Aj, B2j)
+                syn.make_supports(D, T, ALPHA)
+                syn.plan(cols)
+                syn.solve(out)
+                syn.mark(1)
+                return syn.elapsed_ms()
+            e2e_ds_step()
+            e2e_ds_ms = float(np.mean([e2e_ds_step() for _ in range(3)]))
+            syn.set_supports(Sx, Su)
 
     ag_ms = None
     if args.allgather and dist is not None:
@@ -386,6 +401,10 @@ def run_ours(args, rank, world, local_rank):
         if e2e_ms is not None:
             line["e2e"] = {"value": ncols_all / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                            "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)}
+            if e2e_ds_ms is not None:
+                line["e2e_device_supports"] = {"value": ncols_all / (e2e_ds_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ds_ms,
+                                               "what": "same, but the supports are built on the device by sls_make_supports(d,T,alpha) "
+                                                       "instead of being copied from the host (not the reference-facing signature)"}
         if not args.no_cpu_baseline and world == 1:
             arm = CpuArm()
             n = args.cpu_sample or 64 * arm.cores

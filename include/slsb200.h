@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SLS_ABI_VERSION 2
+#define SLS_ABI_VERSION 3
 
 /* per-column status bits written by sls_solve* (improves on the reference, which ignores the
  * solver's termination status: src/synthesis.jl:62-65) */
@@ -78,6 +78,15 @@ int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
 int sls_set_supports(sls_handle* h, int64_t T,
                      const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
                      const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval);
+
+/* Alternative to sls_set_supports: build the (d,T)-localized supports of the README on the device from the plant
+ * already set (README.md:52-54):  𝓢ₓ[t] = (A .≠ 0)^min(d, floor(α(t-1))) .≠ 0,
+ *                                 𝓢ᵤ[t] = (B₂' .≠ 0)*(A .≠ 0)^min(d+1, floor(α(t-1))) .≠ 0,   t = 1..T.
+ * Nothing but d, T, α crosses the bus.  nnz_x / nnz_u (T each, may be NULL) return the stored entries per tap so
+ * that sls_get_supports can copy a tap back in Julia layout (all stored values are `true`). */
+int sls_make_supports(sls_handle* h, int64_t d, int64_t T, double alpha, int64_t* nnz_x, int64_t* nnz_u);
+int sls_get_supports(sls_handle* h, int which /*0=𝓢ₓ,1=𝓢ᵤ*/, int64_t t /*0-based tap*/,
+                     int64_t* colptr, int64_t* rowval, uint8_t* nzval);
 
 /* Kernel 1 on the column list `cols` (1-based disturbance columns, the reference's 𝓘 keyword with
  * single-column groups, synthesis.jl:11,15; NULL = 1..Nx).  Writes per-tap stored-entry counts of

@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libslsb200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 STATUS_OK, STATUS_RESIDUAL, STATUS_RANK_SKIPPED, STATUS_NO_IMPULSE = 0, 1, 2, 4
 
 i64p = C.POINTER(C.c_int64)
@@ -50,6 +50,8 @@ SIGNATURES = {
     "sls_last_error": (C.c_char_p, [C.c_void_p]),
     "sls_set_plant": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, i64p, i64p, f64p, i64p, i64p, f64p]),
     "sls_set_supports": (C.c_int, [C.c_void_p, C.c_int64, i64pp, i64pp, u8pp, i64pp, i64pp, u8pp]),
+    "sls_make_supports": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_double, i64p, i64p]),
+    "sls_get_supports": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, i64p, i64p, u8p]),
     "sls_plan": (C.c_int, [C.c_void_p, i64p, C.c_int64, i64p, i64p, i32p, i32p]),
     "sls_reduce": (C.c_int, [C.c_void_p, i64p, C.c_int64, i64p, C.c_int64, i64p, i64p, C.c_int64, i64p, u8p]),
     "sls_local_problem": (C.c_int, [C.c_void_p, C.c_int64, f64p, f64p, u8p, u8p]),

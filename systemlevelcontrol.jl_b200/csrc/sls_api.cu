@@ -61,6 +61,7 @@ struct DevSupports {            // T Bool CSC matrices, taps concatenated
     bool has_nzval = false;
     int64_t nnz = 0;
     int maxlen_last = 0;        // longest column of the last tap (bounds kernel 1's candidate list)
+    std::vector<int64_t> h_tap_off;   // host copy of tap_off (sls_get_supports)
     SlsSupports view() const {
         return SlsSupports{colptr.as<int64_t>(), rowval.as<int64_t>(), has_nzval ? nzval.as<uint8_t>() : nullptr,
                            tap_off.as<int64_t>()};
@@ -281,6 +282,7 @@ static int upload_supports(sls_handle* h, DevSupports& d, int64_t T, int64_t nro
         if (any_nz) SLS_CK(rt::h2d(d.nzval.as<uint8_t>() + off[t], nzs[t], nnz, h->stream));
     }
     SLS_CK(rt::h2d(d.tap_off.p, off.data(), (T + 1) * sizeof(int64_t), h->stream));
+    d.h_tap_off = off;
     // full layout validation on the host while the copies are in flight (a failure leaves have_supports = false)
     const char* bad = nullptr;
     for (int64_t t = 0; t < T && !bad; t++) bad = check_csc(nrow, ncol, cps[t], rvs ? rvs[t] : nullptr, (h->opt.flags & 1) != 0);
@@ -310,6 +312,136 @@ extern "C" int sls_set_supports(sls_handle* h, int64_t T,
     SLS_CK(rt::sync(h->stream));
     h->tm.h2d_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);
     h->T = T; h->have_supports = true;
+    return 0;
+}
+
+// ---- supports generated on the device (README.md:52-54) ----------------------------------------
+static int make_both_families(sls_handle* h, int64_t T, const std::vector<int>& kx, const std::vector<int>& ku,
+                              int nlev, int64_t* nnz_x, int64_t* nnz_u) {
+    const int64_t Nx = h->Nx;
+    auto distinct_of = [](const std::vector<int>& v) {
+        std::vector<int> d(v.begin(), v.end());
+        std::sort(d.begin(), d.end());
+        d.erase(std::unique(d.begin(), d.end()), d.end());
+        return d;
+    };
+    const std::vector<int> dx = distinct_of(kx), du = distinct_of(ku);
+    const int nsx = (int)dx.size(), nsu = (int)du.size();
+    std::vector<int32_t> sx(nlev + 1, -1), su(nlev + 1, -1);
+    for (int k = 0; k < nsx; k++) sx[dx[k]] = k;
+    for (int k = 0; k < nsu; k++) su[du[k]] = k;
+    DevBuf dsx, dsu, dcpx, dcpu, dtot, doffx, doffu, dovf;
+    int e = 0;
+    auto cleanup = [&]() { DevBuf* all[] = {&dsx, &dsu, &dcpx, &dcpu, &dtot, &doffx, &doffu, &dovf}; for (DevBuf* b : all) b->release(); };
+#define MS_CK(expr) do { e = (expr); if (e) { cleanup(); return fail(h, e, #expr); } } while (0)
+    MS_CK(dsx.ensure((nlev + 1) * 4)); MS_CK(dsu.ensure((nlev + 1) * 4));
+    MS_CK(dcpx.ensure((size_t)nsx * (Nx + 1) * 8)); MS_CK(dcpu.ensure((size_t)nsu * (Nx + 1) * 8));
+    MS_CK(dtot.ensure(16)); MS_CK(doffx.ensure((size_t)nsx * 8)); MS_CK(doffu.ensure((size_t)nsu * 8)); MS_CK(dovf.ensure(4));
+    MS_CK(rt::h2d(dsx.p, sx.data(), (nlev + 1) * 4, h->stream));
+    MS_CK(rt::h2d(dsu.p, su.data(), (nlev + 1) * 4, h->stream));
+    MS_CK(rt::zero(dcpx.p, (size_t)nsx * (Nx + 1) * 8, h->stream));
+    MS_CK(rt::zero(dcpu.p, (size_t)nsu * (Nx + 1) * 8, h->stream));
+    MS_CK(rt::zero(dtot.p, 16, h->stream)); MS_CK(rt::zero(dovf.p, 4, h->stream));
+    SlsSuppArgs a{};
+    a.A = h->A.view(); a.B2r = h->B2r.view(); a.Nx = Nx; a.Nu = h->Nu; a.nlev = nlev; a.cap = 2048;
+    a.ex_slot = dsx.as<int32_t>(); a.eu_slot = dsu.as<int32_t>();
+    a.xcolptr = dcpx.as<int64_t>(); a.ucolptr = dcpu.as<int64_t>();
+    a.overflow = dovf.as<int>();
+    MS_CK(sls_launch_supports(a, false, h->stream));
+    MS_CK(sls_launch_scan(dcpx.as<int64_t>(), Nx + 1, nsx, dtot.as<int64_t>(), 1, h->stream));
+    MS_CK(sls_launch_scan(dcpu.as<int64_t>(), Nx + 1, nsu, dtot.as<int64_t>(), 1, h->stream));
+    std::vector<int64_t> lastx(nsx), lastu(nsu), offx(nsx + 1, 0), offu(nsu + 1, 0);
+    int ovf = 0;
+    MS_CK(rt::d2h_strided(lastx.data(), dcpx.as<int64_t>() + Nx, 8, (size_t)(Nx + 1) * 8, (size_t)nsx, h->stream));
+    MS_CK(rt::d2h_strided(lastu.data(), dcpu.as<int64_t>() + Nx, 8, (size_t)(Nx + 1) * 8, (size_t)nsu, h->stream));
+    MS_CK(rt::d2h(&ovf, dovf.p, 4, h->stream));
+    MS_CK(rt::sync(h->stream));
+    if (ovf) { cleanup(); return fail(h, -4, "sls_make_supports: a reachability set does not fit shared memory"); }
+    for (int k = 0; k < nsx; k++) offx[k + 1] = offx[k] + lastx[k] - 1;
+    for (int k = 0; k < nsu; k++) offu[k + 1] = offu[k] + lastu[k] - 1;
+    DevSupports& X = h->Sx; DevSupports& U = h->Su;
+    X.nnz = offx[nsx]; U.nnz = offu[nsu]; X.has_nzval = U.has_nzval = false;
+    MS_CK(X.rowval.ensure(std::max<int64_t>(X.nnz, 1) * 8));
+    MS_CK(U.rowval.ensure(std::max<int64_t>(U.nnz, 1) * 8));
+    MS_CK(rt::h2d(doffx.p, offx.data(), (size_t)nsx * 8, h->stream));
+    MS_CK(rt::h2d(doffu.p, offu.data(), (size_t)nsu * 8, h->stream));
+    a.xrow = X.rowval.as<int64_t>(); a.urow = U.rowval.as<int64_t>();
+    a.xoff = doffx.as<int64_t>(); a.uoff = doffu.as<int64_t>();
+    MS_CK(sls_launch_supports(a, true, h->stream));
+    // per-tap views: colptr copies, shared rowval through tap_off
+    MS_CK(X.colptr.ensure((size_t)T * (Nx + 1) * 8)); MS_CK(U.colptr.ensure((size_t)T * (Nx + 1) * 8));
+    MS_CK(X.tap_off.ensure((T + 1) * 8)); MS_CK(U.tap_off.ensure((T + 1) * 8));
+    X.h_tap_off.assign(T + 1, 0); U.h_tap_off.assign(T + 1, 0);
+    for (int64_t t = 0; t < T; t++) {
+        const int k = sx[kx[t]], l = su[ku[t]];
+        MS_CK(rt::d2d(X.colptr.as<int64_t>() + t * (Nx + 1), dcpx.as<int64_t>() + (int64_t)k * (Nx + 1), (Nx + 1) * 8, h->stream));
+        MS_CK(rt::d2d(U.colptr.as<int64_t>() + t * (Nx + 1), dcpu.as<int64_t>() + (int64_t)l * (Nx + 1), (Nx + 1) * 8, h->stream));
+        X.h_tap_off[t] = offx[k]; U.h_tap_off[t] = offu[l];
+        if (nnz_x) nnz_x[t] = lastx[k] - 1;
+        if (nnz_u) nnz_u[t] = lastu[l] - 1;
+    }
+    X.h_tap_off[T] = X.nnz; U.h_tap_off[T] = U.nnz;
+    MS_CK(rt::h2d(X.tap_off.p, X.h_tap_off.data(), (T + 1) * 8, h->stream));
+    MS_CK(rt::h2d(U.tap_off.p, U.h_tap_off.data(), (T + 1) * 8, h->stream));
+    // longest column of the last tap of each family (bounds kernel 1's candidate list)
+    {
+        std::vector<int64_t> cpx(Nx + 1), cpu_(Nx + 1);
+        MS_CK(rt::d2h(cpx.data(), dcpx.as<int64_t>() + (int64_t)sx[kx[T - 1]] * (Nx + 1), (Nx + 1) * 8, h->stream));
+        MS_CK(rt::d2h(cpu_.data(), dcpu.as<int64_t>() + (int64_t)su[ku[T - 1]] * (Nx + 1), (Nx + 1) * 8, h->stream));
+        MS_CK(rt::d2h(&ovf, dovf.p, 4, h->stream));
+        MS_CK(rt::sync(h->stream));
+        int mlx = 0, mlu = 0;
+        for (int64_t c = 0; c < Nx; c++) { mlx = std::max<int>(mlx, (int)(cpx[c + 1] - cpx[c])); mlu = std::max<int>(mlu, (int)(cpu_[c + 1] - cpu_[c])); }
+        X.maxlen_last = mlx; U.maxlen_last = mlu;
+    }
+#undef MS_CK
+    cleanup();
+    if (ovf) return fail(h, -4, "sls_make_supports: a reachability set does not fit shared memory");
+    return 0;
+}
+
+extern "C" int sls_make_supports(sls_handle* h, int64_t d, int64_t T, double alpha, int64_t* nnz_x, int64_t* nnz_u) {
+    if (!h) return -1;
+    SLS_ARG(h->have_plant, "sls_make_supports: call sls_set_plant first");
+    SLS_ARG(T >= 1 && T < 4096 && d >= 0 && d < 4096 && alpha >= 0, "sls_make_supports: bad d, T or alpha");
+    SLS_CK(rt::set_device(h->device));
+    h->have_supports = false; h->plan.valid = false; h->solved = false;
+    std::vector<int> kx(T), ku(T);
+    int nlev = 0;
+    for (int64_t t = 1; t <= T; t++) {
+        const double k = std::floor(alpha * (double)(t - 1));              // Julia: floor(α*(t-1)) in Float64
+        kx[t - 1] = (int)std::min<double>((double)d, k);
+        ku[t - 1] = (int)std::min<double>((double)(d + 1), k);
+        nlev = std::max(nlev, std::max(kx[t - 1], ku[t - 1]));
+    }
+    h->ev[0].record(h->stream);
+    int e = make_both_families(h, T, kx, ku, nlev, nnz_x, nnz_u);
+    if (e) return e;
+    h->ev[1].record(h->stream);
+    SLS_CK(rt::sync(h->stream));
+    h->tm.h2d_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);
+    h->T = T; h->have_supports = true;
+    return 0;
+}
+
+extern "C" int sls_get_supports(sls_handle* h, int which, int64_t t, int64_t* colptr, int64_t* rowval, uint8_t* nzval) {
+    if (!h) return -1;
+    SLS_ARG(h->have_supports, "sls_get_supports: no supports on the device");
+    SLS_ARG((which == 0 || which == 1) && t >= 0 && t < h->T, "sls_get_supports: bad tap");
+    SLS_CK(rt::set_device(h->device));
+    const DevSupports& d = which ? h->Su : h->Sx;
+    const int64_t Nx = h->Nx;
+    std::vector<int64_t> cp(Nx + 1);
+    SLS_CK(rt::d2h(cp.data(), d.colptr.as<int64_t>() + t * (Nx + 1), (Nx + 1) * 8, h->stream));
+    SLS_CK(rt::sync(h->stream));
+    const int64_t nnz = cp[Nx] - 1;
+    if (colptr) std::copy(cp.begin(), cp.end(), colptr);
+    if (rowval && nnz) SLS_CK(rt::d2h(rowval, d.rowval.as<int64_t>() + d.h_tap_off[t], nnz * 8, h->stream));
+    if (nzval && nnz) {
+        if (d.has_nzval) SLS_CK(rt::d2h(nzval, d.nzval.as<uint8_t>() + d.h_tap_off[t], nnz, h->stream));
+        else memset(nzval, 1, nnz);
+    }
+    SLS_CK(rt::sync(h->stream));
     return 0;
 }
 

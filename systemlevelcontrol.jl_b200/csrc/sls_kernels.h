@@ -69,3 +69,17 @@ __host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, in
 int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, int32_t* Wg, int32_t* Wug,
                         int wcap, int ucap, sls_stream_t stream);
 int sls_launch_sim(const SlsSimArgs& a, int cap, int wcap, int ucap, sls_stream_t stream);
+
+// ---- support generation (sls_supports.cu) ----
+struct SlsSuppArgs {
+    SlsCsc A, B2r;                    // A by columns (pattern graph), B2 by rows
+    int64_t Nx, Nu;
+    int nlev, cap;                    // largest exponent; shared-memory set capacity (power of two)
+    const int32_t* ex_slot;           // [nlev+1] pattern slot of exponent s among the distinct x exponents, or -1
+    const int32_t* eu_slot;           // same for the u exponents
+    int64_t* xcolptr; int64_t* ucolptr;     // [nslots][Nx+1]: counts at [slot][j] (count pass) -> Julia colptr after the scan
+    int64_t* xrow; int64_t* urow;           // rowval of all slots back to back (fill pass)
+    const int64_t* xoff; const int64_t* uoff;   // [nslots] offsets of each slot inside xrow / urow
+    int* overflow;
+};
+int sls_launch_supports(const SlsSuppArgs& a, bool fill, sls_stream_t stream);

@@ -136,6 +136,28 @@ class Synthesizer:
             args.append(ptr_array([M.nzval for M in S], u8p) if pass_nzval else None)
         self._ck(self.api.sls_set_supports(self.h, self.T, *args))
 
+    def make_supports(self, d, T, alpha):
+        """README.md:52-54 on the device (no host-side supports, no PCIe transfer).  Returns (nnz_x[T], nnz_u[T])."""
+        nnz_x = np.zeros(T, np.int64)
+        nnz_u = np.zeros(T, np.int64)
+        self._ck(self.api.sls_make_supports(self.h, d, T, float(alpha), ptr(nnz_x, i64p), ptr(nnz_u, i64p)))
+        self.T = T
+        self._supp_nnz = (nnz_x, nnz_u)
+        return nnz_x, nnz_u
+
+    def get_supports(self):
+        """Device-generated supports back on the host: (Sx, Su) lists of JuliaCSC (Bool, all true)."""
+        out = []
+        for which, nrow in ((0, self.Nx), (1, self.Nu)):
+            taps = []
+            for t in range(self.T):
+                nnz = int(self._supp_nnz[which][t])
+                cp = np.zeros(self.Nx + 1, np.int64); rv = np.zeros(max(nnz, 1), np.int64); nz = np.zeros(max(nnz, 1), np.uint8)
+                self._ck(self.api.sls_get_supports(self.h, which, t, ptr(cp, i64p), ptr(rv, i64p), ptr(nz, u8p)))
+                taps.append(JuliaCSC(nrow, self.Nx, cp, rv[:nnz], nz[:nnz]))
+            out.append(taps)
+        return out
+
     # -- kernel 1 -------------------------------------------------------------------------------
     def plan(self, cols=None):
         """cols: 0-based disturbance columns (None = all).  Returns (nnz_x[T], nnz_u[T], n[ncols], m[ncols])."""

@@ -188,3 +188,31 @@ def check_simulation(api, Nx, scenarios, steps=120, tol=1e-13):
             assert np.abs(sim["x"][s][ts + T:]).max() < 1e-12
     assert worst < tol, worst
     return worst, tm
+
+
+def check_device_supports(api, plant, d, T, alpha):
+    """sls_make_supports (device) == the README's Boolean matrix powers (oracle.make_supports), entry for entry;
+    and a synthesis on device-generated supports == the synthesis on host-supplied ones, bit for bit."""
+    A, B1, B2 = plant
+    Ox, Ou = O.make_supports(A, B2, d, T, alpha)
+    syn = slc_b200.Synthesizer(api=api)
+    try:
+        syn.set_plant(A, B2)
+        nnz_x, nnz_u = syn.make_supports(d, T, alpha)
+        Sx, Su = syn.get_supports()
+        for t in range(T):
+            for J, M in ((Sx[t], Ox[t]), (Su[t], Ou[t])):
+                M = M.tocsc(); M.sort_indices()
+                assert np.array_equal(J.colptr - 1, M.indptr) and np.array_equal(J.rowval - 1, M.indices) and J.nzval.all()
+        assert np.array_equal(nnz_x, [M.nnz for M in Ox]) and np.array_equal(nnz_u, [M.nnz for M in Ou])
+        syn.plan(None)
+        a = syn.solve()
+        syn.set_supports(Ox, Ou)
+        syn.plan(None)
+        b = syn.solve()
+        for name in ("x", "u"):
+            for t in range(T):
+                assert np.array_equal(a[name]["rowval"][t], b[name]["rowval"][t])
+                assert np.array_equal(a[name]["nzval"][t], b[name]["nzval"][t])
+    finally:
+        syn.close()

@@ -37,3 +37,8 @@ def test_emu_masks_and_flags(emu_api):
 def test_emu_closed_loop_simulation(emu_api):
     worst, tm = pc.check_simulation(emu_api, 100, [(50, 5), (0, 1), (99, 60), (7, 119)], steps=120)
     assert tm["sim_window"] < 100        # genuinely windowed: 2-level closure (radius 18) + one hop = 39 states
+
+
+def test_emu_device_supports(emu_api):
+    pc.check_device_supports(emu_api, O.chain_plant(40), 9, 29, 1.5)
+    pc.check_device_supports(emu_api, O.grid_plant(6, 7, actuation="full"), 2, 6, 1.5)

@@ -219,3 +219,12 @@ def test_config5_simulation_100k_4096_scenarios(cuda_api):
         assert np.abs(got[t0:t0 + T] - colnorm[:, j]).max() < 1e-12
         assert np.abs(got[t0 + T:]).max() < 1e-12
     print("config5 sim_ms", tm["sim_ms"])
+
+
+def test_device_generated_supports(cuda_api):
+    """README.md:52-54 on the device, against the matrix-power construction."""
+    pc.check_device_supports(cuda_api, O.chain_plant(59), 9, 29, 1.5)
+    pc.check_device_supports(cuda_api, O.chain_plant(300, jitter=0.1), 5, 12, 2.0)
+    pc.check_device_supports(cuda_api, O.grid_plant(11, 9, actuation="full"), 3, 10, 1.5)
+    A, B1, B2 = O.grid_plant(8, 8, actuation="checker")          # B2 is a strict selection: Nu < Nx
+    pc.check_device_supports(cuda_api, (A, B1, B2), 2, 7, 1.0)
