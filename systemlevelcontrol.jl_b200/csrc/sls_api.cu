@@ -836,9 +836,9 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
         if (dist_col[s] < 1 || dist_col[s] > Nx || dist_time[s] < 1) return fail(h, -3, "sls_simulate: scenario out of range");
     if (nscen == 0) return 0;
     const Plan& p = h->plan;
-    DevBuf dcol, dtime, dnw, dnu, dxn, dun, dxo, duo, dovf, dW, dWu;
+    DevBuf dcol, dtime, dnw, dnu, dxn, dun, dxo, duo, dovf, dW, dWu, dnent, dtapcnt, dpkoff, dpkcnt, dpkrow, dpkval;
     int e = 0;
-    auto cleanup = [&]() { DevBuf* all[] = {&dcol, &dtime, &dnw, &dnu, &dxn, &dun, &dxo, &duo, &dovf, &dW, &dWu}; for (DevBuf* b : all) b->release(); };
+    auto cleanup = [&]() { DevBuf* all[] = {&dcol, &dtime, &dnw, &dnu, &dxn, &dun, &dxo, &duo, &dovf, &dW, &dWu, &dnent, &dtapcnt, &dpkoff, &dpkcnt, &dpkrow, &dpkval}; for (DevBuf* b : all) b->release(); };
 #define SIM_CK(expr) do { e = (expr); if (e) { cleanup(); return fail(h, e, #expr); } } while (0)
     SIM_CK(dcol.ensure(nscen * 8)); SIM_CK(dtime.ensure(nscen * 8));
     SIM_CK(dnw.ensure(nscen * 4)); SIM_CK(dnu.ensure(nscen * 4)); SIM_CK(dovf.ensure(4));
@@ -870,6 +870,26 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     SIM_CK(dW.ensure((size_t)nscen * wcap * 4)); SIM_CK(dWu.ensure((size_t)nscen * ucap * 4));
     SIM_CK(sls_launch_sim_size(a, dnw.as<int32_t>(), dnu.as<int32_t>(), cap, dW.as<int32_t>(), dWu.as<int32_t>(), wcap, ucap, h->stream));
     a.nw = dnw.as<int32_t>(); a.nu = dnu.as<int32_t>(); a.Wg = dW.as<int32_t>(); a.Wug = dWu.as<int32_t>();
+    // pack pass: Phi restricted to every scenario's window, local row indices, in consumption order
+    if (wcap > 65535 || ucap > 65535) { cleanup(); return fail(h, -4, "sls_simulate: window too large"); }
+    SIM_CK(dnent.ensure(nscen * 8)); SIM_CK(dtapcnt.ensure((size_t)nscen * 2 * T * 4)); SIM_CK(dpkoff.ensure(nscen * 8));
+    SIM_CK(sls_launch_sim_pack(a, false, wcap, ucap, dnent.as<int64_t>(), dtapcnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, h->stream));
+    {
+        std::vector<int64_t> nent(nscen), off(nscen);
+        SIM_CK(rt::d2h(nent.data(), dnent.p, nscen * 8, h->stream));
+        SIM_CK(rt::sync(h->stream));
+        int64_t run = 0;
+        for (int64_t s = 0; s < nscen; s++) { off[s] = run; run += nent[s]; }
+        SIM_CK(rt::h2d(dpkoff.p, off.data(), nscen * 8, h->stream));
+        SIM_CK(dpkcnt.ensure((size_t)nscen * 2 * T * wcap * 2));
+        SIM_CK(dpkrow.ensure((size_t)std::max<int64_t>(run, 1) * 2));
+        SIM_CK(dpkval.ensure((size_t)std::max<int64_t>(run, 1) * 8));
+        SIM_CK(sls_launch_sim_pack(a, true, wcap, ucap, dnent.as<int64_t>(), dtapcnt.as<uint32_t>(), dpkoff.as<int64_t>(),
+                                   dpkcnt.as<uint16_t>(), dpkrow.as<uint16_t>(), dpkval.as<double>(), h->stream));
+        SIM_CK(rt::sync(h->stream));                           // `off` is a local
+    }
+    a.pk_off = dpkoff.as<int64_t>(); a.pk_tapcnt = dtapcnt.as<uint32_t>(); a.pk_cnt = dpkcnt.as<uint16_t>();
+    a.pk_row = dpkrow.as<uint16_t>(); a.pk_val = dpkval.as<double>();
     const int cap2 = 0;
     if ((size_t)4 * sls_sim_smem_per_warp(cap2, wcap, ucap, (int)T) > (size_t)h->max_smem) {
         cleanup(); return fail(h, -4, "sls_simulate: windows do not fit shared memory");

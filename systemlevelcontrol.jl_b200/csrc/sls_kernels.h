@@ -63,12 +63,18 @@ struct SlsSimArgs {
     double* xout; double* uout;       // dense [nscen][steps][Nx] / [nscen][steps][Nu] or null
     const int32_t* nw; const int32_t* nu;       // window sizes per scenario
     const int32_t* Wg; const int32_t* Wug;      // windows [nscen][wcap], [nscen][ucap] (ascending global indices)
+    const int64_t* pk_off;                      // [nscen] first packed entry of the scenario
+    const uint32_t* pk_tapcnt;                  // [nscen][2T] packed entries per tap
+    const uint16_t* pk_cnt;                     // [nscen][2T][wcap] packed entries per (tap, window column)
+    const uint16_t* pk_row; const double* pk_val;   // packed Phi restricted to the window: local row, value
     int* overflow;
 };
 __host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, int T);
 int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, int32_t* Wg, int32_t* Wug,
                         int wcap, int ucap, sls_stream_t stream);
 int sls_launch_sim(const SlsSimArgs& a, int cap, int wcap, int ucap, sls_stream_t stream);
+int sls_launch_sim_pack(const SlsSimArgs& a, bool fill, int wcap, int ucap, int64_t* nent, uint32_t* tapcnt, const int64_t* pk_off,
+                        uint16_t* pk_cnt, uint16_t* pk_row, double* pk_val, sls_stream_t stream);
 
 // ---- support generation (sls_supports.cu) ----
 struct SlsSuppArgs {

@@ -23,7 +23,7 @@
 
 __host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, int T) {
     (void)cap;   // the windows are computed by the sizing/window passes; the simulation itself needs no scratch
-    size_t b = ((size_t)T * wcap + 3 * (size_t)wcap + ucap) * sizeof(double) + ((size_t)wcap + ucap) * sizeof(int32_t);
+    size_t b = ((size_t)T * wcap + 3 * (size_t)wcap + ucap) * sizeof(double) + ((size_t)wcap + ucap + 2 * (size_t)T + 2) * sizeof(int32_t);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -161,6 +161,58 @@ sls_sim_size_kernel(SlsSimArgs a, int32_t* nw_out, int32_t* nu_out, int cap, int
     if (lane == 0) { nw_out[s] = nw; nu_out[s] = nu; }
 }
 
+// pack pass: the columns of Phi restricted to the scenario's window, with LOCAL row indices, in the order the
+// simulation consumes them (tap-major, then window column): vals/rows back to back, cnt[tt][cl] entries per column.
+// COUNT mode only sizes (nent[s], tapcnt[s][2T]); FILL mode writes.  Rows inside a column stay ascending.
+template <bool FILL>
+__global__ void __launch_bounds__(SIM_WPB * 32)
+sls_sim_pack_kernel(SlsSimArgs a, int wcap, int ucap, int64_t* nent, uint32_t* tapcnt, const int64_t* pk_off,
+                    uint16_t* pk_cnt, uint16_t* pk_row, double* pk_val) {
+    SLS_DYN_SMEM(smem);
+    const int warp = threadIdx.x >> 5, lane = sls_lane();
+    const int s = blockIdx.x * SIM_WPB + warp;
+    if (s >= a.nscen) return;
+    const int T = a.T;
+    int32_t* W = reinterpret_cast<int32_t*>(smem) + (size_t)warp * (wcap + ucap);
+    int32_t* Wu = W + wcap;
+    const int nw = a.nw[s], nu = a.nu[s];
+    if (nw < 0 || nu < 0 || nw > wcap || nu > ucap) return;
+    for (int i = lane; i < nw; i += 32) W[i] = a.Wg[(size_t)s * wcap + i];
+    for (int i = lane; i < nu; i += 32) Wu[i] = a.Wug[(size_t)s * ucap + i];
+    __syncwarp();
+    int64_t run = 0;
+    const int64_t base = FILL ? pk_off[s] : 0;
+    for (int tt = 0; tt < 2 * T; tt++) {
+        const bool isu = tt >= T;
+        const int64_t* cp = a.colptr + (int64_t)tt * (a.Nx + 1);
+        const int64_t* rv = a.rowval[tt]; const double* nz = a.nzval[tt];
+        const int32_t* Wr = isu ? Wu : W; const int nr = isu ? nu : nw;
+        uint32_t tapn = 0;
+        for (int cl = 0; cl < nw; cl++) {
+            int cnt = 0;
+            if (tt != 0) {                                     // Phi_x[1] is never used by the recursion
+                const int64_t gc = W[cl];
+                const int64_t e0 = cp[gc] - 1, e1 = cp[gc + 1] - 1;
+                for (int64_t eb = e0; eb < e1; eb += 32) {
+                    const int64_t e = eb + lane;
+                    int lr = -1;
+                    if (e < e1) lr = sls_find(Wr, nr, (int32_t)(rv[e] - 1));
+                    const unsigned bal = __ballot_sync(SLS_FULL, lr >= 0);
+                    if (FILL && lr >= 0) {
+                        const int64_t dst = base + run + cnt + __popc(bal & ((1u << lane) - 1u));
+                        pk_row[dst] = (uint16_t)lr; pk_val[dst] = nz[e];
+                    }
+                    cnt += __popc(bal);
+                }
+            }
+            if (FILL && lane == 0) pk_cnt[((size_t)s * 2 * T + tt) * wcap + cl] = (uint16_t)cnt;
+            run += cnt; tapn += (uint32_t)cnt;
+        }
+        if (!FILL && lane == 0) tapcnt[(size_t)s * 2 * T + tt] = tapn;
+    }
+    if (!FILL && lane == 0) nent[s] = run;
+}
+
 // pass 2: the simulation.  shared memory per warp: what[T][wcap], x[wcap], xn[wcap], beta[wcap], u[ucap] doubles |
 //         W[wcap] Wu[ucap] int32 (loaded from the window pass)
 __global__ void __launch_bounds__(SIM_WPB * 32)
@@ -179,8 +231,15 @@ sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
     double* u = beta + wcap;
     int32_t* W = reinterpret_cast<int32_t*>(u + ucap);
     int32_t* Wu = W + wcap;
+    uint32_t* tapoff = reinterpret_cast<uint32_t*>(Wu + ucap);  // [2T+1] offsets of each tap inside the scenario's packed Phi
     const int64_t j = a.dcol[s] - 1;
     const int64_t ts = a.dtime[s];                             // 1-based disturbance time
+    const int64_t pkbase = a.pk_off[s];
+    if (lane == 0) {
+        uint32_t run = 0;
+        for (int tt = 0; tt < 2 * T; tt++) { tapoff[tt] = run; run += a.pk_tapcnt[(size_t)s * 2 * T + tt]; }
+        tapoff[2 * T] = run;
+    }
     // ---- windows (computed by the window pass)
     const int nw = a.nw[s], nu = a.nu[s];
     if (nw < 0 || nu < 0 || nw > wcap || nu > ucap) { if (lane == 0) atomicOr(a.overflow, 1); return; }
@@ -204,31 +263,29 @@ sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
             const int64_t src = t + 1 - tau;
             if (src <= ts) break;                              // what(s) = 0 exactly for s <= ts
             const double* wv = what + (size_t)(src % T) * wcap;
-            const int ttx = tau;                               // Phi_x[tau+1] -> 0-based tap index tau   (tau <= T-1)
-            const int ttu = T + tau - 1;                       // Phi_u[tau]   -> 0-based tap index tau-1
-            for (int cl = 0; cl < nw; cl++) {
-                const double wc = wv[cl];
-                if (wc == 0.0) continue;
-                const int64_t gc = W[cl];
-                if (tau <= T - 1) {
-                    const int64_t* cp = a.colptr + (int64_t)ttx * (a.Nx + 1);
-                    const int64_t e0 = cp[gc] - 1, e1 = cp[gc + 1] - 1;
-                    const int64_t* rv = a.rowval[ttx]; const double* nz = a.nzval[ttx];
-                    for (int64_t e = e0 + lane; e < e1; e += 32) {
-                        const int lr = sls_find(W, nw, (int32_t)(rv[e] - 1));
-                        if (lr >= 0) beta[lr] = fma(nz[e], wc, beta[lr]);
+#pragma unroll 1
+            for (int fam = 0; fam < 2; fam++) {
+                if (fam == 0 && tau > T - 1) continue;         // beta uses Phi_x[tau+1], tau <= T-1
+                const int tt = fam ? (T + tau - 1) : tau;      // 0-based tap: Phi_x[tau+1] -> tau, Phi_u[tau] -> T+tau-1
+                double* acc = fam ? u : beta;
+                int64_t ptr = pkbase + tapoff[tt];
+                const uint16_t* cnts = a.pk_cnt + ((size_t)s * 2 * T + tt) * wcap;
+                for (int cl0 = 0; cl0 < nw; cl0 += 32) {
+                    const int mycnt = (cl0 + lane < nw) ? (int)cnts[cl0 + lane] : 0;
+                    const int kmax = (nw - cl0 < 32) ? (nw - cl0) : 32;
+                    for (int k = 0; k < kmax; k++) {
+                        const int len = __shfl_sync(SLS_FULL, mycnt, k);
+                        const double wc = wv[cl0 + k];
+                        if (len != 0 && wc != 0.0) {
+                            for (int i = lane; i < len; i += 32) {
+                                const int lr = a.pk_row[ptr + i];
+                                acc[lr] = fma(a.pk_val[ptr + i], wc, acc[lr]);
+                            }
+                            __syncwarp();
+                        }
+                        ptr += len;
                     }
                 }
-                {
-                    const int64_t* cp = a.colptr + (int64_t)ttu * (a.Nx + 1);
-                    const int64_t e0 = cp[gc] - 1, e1 = cp[gc + 1] - 1;
-                    const int64_t* rv = a.rowval[ttu]; const double* nz = a.nzval[ttu];
-                    for (int64_t e = e0 + lane; e < e1; e += 32) {
-                        const int lr = sls_find(Wu, nu, (int32_t)(rv[e] - 1));
-                        if (lr >= 0) u[lr] = fma(nz[e], wc, u[lr]);
-                    }
-                }
-                __syncwarp();
             }
         }
         __syncwarp();
@@ -287,5 +344,22 @@ int sls_launch_sim(const SlsSimArgs& a, int cap, int wcap, int ucap, sls_stream_
     auto kp = &sls_sim_kernel;
     if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
     SLS_LAUNCH(kp, grid, SIM_WPB * 32, smem, stream, a, cap, wcap, ucap);
+    return rt::last_error();
+}
+
+int sls_launch_sim_pack(const SlsSimArgs& a, bool fill, int wcap, int ucap, int64_t* nent, uint32_t* tapcnt, const int64_t* pk_off,
+                        uint16_t* pk_cnt, uint16_t* pk_row, double* pk_val, sls_stream_t stream) {
+    if (a.nscen == 0) return 0;
+    const int grid = (a.nscen + SIM_WPB - 1) / SIM_WPB;
+    const size_t smem = (size_t)SIM_WPB * (wcap + ucap) * sizeof(int32_t);
+    if (fill) {
+        auto kp = &sls_sim_pack_kernel<true>;
+        if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
+        SLS_LAUNCH(kp, grid, SIM_WPB * 32, smem, stream, a, wcap, ucap, nent, tapcnt, pk_off, pk_cnt, pk_row, pk_val);
+    } else {
+        auto kp = &sls_sim_pack_kernel<false>;
+        if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
+        SLS_LAUNCH(kp, grid, SIM_WPB * 32, smem, stream, a, wcap, ucap, nent, tapcnt, pk_off, pk_cnt, pk_row, pk_val);
+    }
     return rt::last_error();
 }
