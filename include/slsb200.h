@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SLS_ABI_VERSION 3
+#define SLS_ABI_VERSION 4
 
 /* per-column status bits written by sls_solve* (improves on the reference, which ignores the
  * solver's termination status: src/synthesis.jl:62-65) */
@@ -117,6 +117,26 @@ int sls_solve(sls_handle* h,
               int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
               int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
               int32_t* status, double* resid);
+
+/* One-shot, pipelined form of sls_set_supports + sls_plan(all columns) + sls_solve — what `SLS_𝓗₂(P, [𝓢ₓ,𝓢ᵤ])` with the
+ * default 𝓘 = 1..Nx does (src/synthesis.jl:11-32).  The columns are cut into contiguous chunks and the host->device
+ * copy of chunk c+1's support columns, kernels 1-3 of chunk c and the device->host copy of chunk c-1's CSC segments
+ * overlap; results are bit-for-bit those of the three-call path.  Because the stored pattern of Φ[t] is a subset of
+ * the stored pattern of 𝓢[t], the caller sizes rowval/nzval of tap t by cap_x[t] / cap_u[t] (NULL = nnz(𝓢[t])) and
+ * receives the stored-entry counts in nnz_x / nnz_u (T each; Julia: `resize!`).  colptr arrays have Nx+1 entries.
+ * Pinned (page-locked) host buffers make the copies truly asynchronous; pageable buffers work but serialise.
+ * first_col (1-based), ncols: a contiguous column range — one GPU's shard of the `@distributed` loop (synthesis.jl:16,
+ * 23-27); ncols <= 0 means all of 1..Nx.  Only the support columns of the range and its halo (the columns reached
+ * through nz(A[:,j])) are read and uploaded; status / resid have ncols entries; columns outside the range are empty.
+ * Afterwards device-resident accessors (sls_device_output, sls_simulate) and plans of other columns need the
+ * three-call path (sls_set_supports, sls_plan, sls_solve_device). */
+int sls_synthesize(sls_handle* h, int64_t T,
+                   const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
+                   const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval,
+                   int64_t first_col, int64_t ncols, const int64_t* cap_x, const int64_t* cap_u,
+                   int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
+                   int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
+                   int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid);
 
 /* Device-resident variants: run kernels 1-3 without any host<->device payload copy (inputs must
  * already be set).  sls_solve_device leaves Φ in handle-owned device buffers; sls_device_output

@@ -15,6 +15,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <atomic>
 
 namespace {
 
@@ -75,7 +77,7 @@ struct Plan {
     bool valid = false;
     int ncols = 0, nstride = 1, mstride = 1, wx = 1, wu = 1, nmax = 0, mmax = 0, cap = 32;
     DevBuf cols, n, m, sx, su, maskx, masku, jloc, lnnz, lnnzA, lnnzB, pre, tot, colptr, lists;
-    std::vector<int32_t> h_cols, h_lists;
+    PinVec<int32_t> h_cols, h_lists;    // pinned: read by kernel copies (sls_kcopy)
     bool cols_sorted = true;            // planned columns strictly ascending => a planned-index range is a CSC column range
     PinVec<int32_t> h_status; PinVec<double> h_resid;
     PinVec<int64_t> h_seg;              // [(nchunk+1)][2T] output offsets of the D2H pipeline's chunk boundaries
@@ -89,11 +91,29 @@ struct Plan {
     void release() {
         DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists};
         for (DevBuf* b : all) b->release();
-        h_seg.release(); h_status.release(); h_resid.release();
+        h_seg.release(); h_status.release(); h_resid.release(); h_cols.release(); h_lists.release();
         h_n.release(); h_m.release(); h_lnnz.release(); h_lA.release(); h_lB.release(); h_tot.release(); h_last.release();
         valid = false;
     }
 };
+
+// one column chunk of the pipelined one-shot path (sls_synthesize): its own plan and output buffers, so that the
+// chunk's D2H copies never alias a later chunk's kernels
+struct PipeCtx {
+    Plan plan;
+    DevBuf out_rowval, out_nzval, out_ptrs, status, resid, base;
+    PinVec<void*> h_ptrs; PinVec<int64_t> h_base;
+    rt::Event ev_plan, ev_scat, ev_solved, ev_out;
+    int create() { int e = ev_plan.create(); if (!e) e = ev_scat.create(); if (!e) e = ev_solved.create(); if (!e) e = ev_out.create(); return e; }
+    void release() {
+        plan.release();
+        DevBuf* all[] = {&out_rowval, &out_nzval, &out_ptrs, &status, &resid, &base};
+        for (DevBuf* b : all) b->release();
+        h_ptrs.release(); h_base.release();
+        ev_plan.destroy(); ev_scat.destroy(); ev_solved.destroy(); ev_out.destroy();
+    }
+};
+#define SLS_PIPE_MAX 64
 
 }  // namespace
 
@@ -113,6 +133,15 @@ struct sls_handle {
     rt::Event ev[8];
     rt::Event marks[2];
     sls_timing tm{};
+    // pipelined one-shot path
+    sls_stream_t in_stream{}, scat_stream{}, out2_stream{};
+    rt::Event pipe_done2;
+    rt::Event pipe_in[SLS_PIPE_MAX];
+    rt::Event pipe_done;
+    std::vector<PipeCtx*> pipe;
+    DevBuf pipe_colptr;
+    PinVec<int32_t> pipe_status; PinVec<double> pipe_resid;
+    std::vector<int32_t> h_Akmax, h_Akmin;   // largest / smallest row index (0-based) stored in each column of A
 };
 
 static thread_local std::string g_create_err;
@@ -148,6 +177,12 @@ extern "C" int sls_create(const sls_options* opts, sls_handle** out) {
     int e = rt::set_device(h->device);
     if (!e) e = rt::stream_create(&h->stream);
     if (!e) e = rt::stream_create(&h->copy_stream);
+    if (!e) e = rt::stream_create(&h->in_stream);
+    if (!e) e = rt::stream_create(&h->scat_stream);
+    if (!e) e = rt::stream_create(&h->out2_stream);
+    if (!e) e = h->pipe_done2.create();
+    for (int i = 0; i < SLS_PIPE_MAX && !e; i++) e = h->pipe_in[i].create();
+    if (!e) e = h->pipe_done.create();
     for (int i = 0; i < 16 && !e; i++) e = h->chunk_ev[i].create();
     for (int i = 0; i < 8 && !e; i++) e = h->ev[i].create();
     for (int i = 0; i < 2 && !e; i++) e = h->marks[i].create();
@@ -163,6 +198,18 @@ extern "C" void sls_destroy(sls_handle* h) {
     rt::set_device(h->device);
     rt::sync(h->stream);
     rt::sync(h->copy_stream);
+    rt::sync(h->in_stream);
+    rt::sync(h->scat_stream);
+    rt::sync(h->out2_stream);
+    for (PipeCtx* x : h->pipe) { x->release(); delete x; }
+    h->pipe.clear();
+    h->pipe_colptr.release(); h->pipe_status.release(); h->pipe_resid.release();
+    for (int i = 0; i < SLS_PIPE_MAX; i++) h->pipe_in[i].destroy();
+    h->pipe_done.destroy();
+    rt::stream_destroy(h->in_stream);
+    rt::stream_destroy(h->scat_stream);
+    rt::stream_destroy(h->out2_stream);
+    h->pipe_done2.destroy();
     h->A.release(); h->B2.release(); h->Ar.release(); h->B2r.release();
     h->Sx.release(); h->Su.release(); h->plan.release();
     DevBuf* all[] = {&h->xw, &h->hist, &h->status, &h->resid, &h->out_rowval, &h->out_nzval, &h->out_ptrs};
@@ -251,6 +298,12 @@ extern "C" int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
     int mc = 0;
     for (int64_t c = 0; c < Nx; c++) mc = std::max<int>(mc, (int)(A_colptr[c + 1] - A_colptr[c]));
     h->maxcolA = mc;
+    h->h_Akmax.assign(Nx, 0); h->h_Akmin.assign(Nx, 0);
+    for (int64_t c = 0; c < Nx; c++) {
+        const bool any = A_colptr[c + 1] > A_colptr[c];
+        h->h_Akmax[c] = any ? (int32_t)(A_rowval[A_colptr[c + 1] - 2] - 1) : (int32_t)c;
+        h->h_Akmin[c] = any ? (int32_t)(A_rowval[A_colptr[c] - 1] - 1) : (int32_t)c;
+    }
     if (h->have_supports && (h->Nx != Nx || h->Nu != Nu)) { h->have_supports = false; }
     h->Nx = Nx; h->Nu = Nu; h->have_plant = true; h->plan.valid = false; h->solved = false;
     return 0;
@@ -466,7 +519,7 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_ARG(ncols >= 0 && ncols < (int64_t)1 << 31, "plan: bad ncols");
     if (!cols) ncols = Nx;
     p.ncols = (int)ncols;
-    p.h_cols.resize(ncols);
+    SLS_CK(p.h_cols.resize(std::max<int64_t>(ncols, 1)));
     if (!cols) { for (int64_t i = 0; i < ncols; i++) p.h_cols[i] = (int32_t)i; }
     else {
         std::vector<uint8_t> seen(unique_cols ? Nx : 0, 0);
@@ -487,15 +540,15 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_CK(p.cols.ensure(nc1 * sizeof(int32_t)));
     SLS_CK(p.n.ensure(nc1 * sizeof(int32_t)));
     SLS_CK(p.m.ensure(nc1 * sizeof(int32_t)));
-    SLS_CK(rt::h2d(p.cols.p, p.h_cols.data(), (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(sls_kcopy(p.cols.p, p.h_cols.data(), (size_t)p.ncols * sizeof(int32_t), h->stream));
     if ((size_t)cap * 4 * sizeof(int32_t) + 4096 > (size_t)h->max_smem)
         return fail(h, -4, "plan: candidate index list of a column does not fit shared memory");
     SLS_CK(sls_launch_gather_count(h->A.view(), h->Sx.view(), h->Su.view(), (int)T, Nx, p.cols.as<int32_t>(), p.ncols,
                                    p.n.as<int32_t>(), p.m.as<int32_t>(), cap, h->stream));
     SLS_CK(p.h_n.resize(nc1)); SLS_CK(p.h_m.resize(nc1));
     p.h_n[0] = 0; p.h_m[0] = 0;
-    SLS_CK(rt::d2h(p.h_n.data(), p.n.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
-    SLS_CK(rt::d2h(p.h_m.data(), p.m.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(sls_kcopy(p.h_n.data(), p.n.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(sls_kcopy(p.h_m.data(), p.m.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
     SLS_CK(rt::sync(h->stream));
     int nmax = 0, mmax = 0;
     for (int i = 0; i < p.ncols; i++) {
@@ -528,14 +581,15 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_CK(p.h_tot.resize(p.ncols + 1)); SLS_CK(p.h_last.resize(2 * T));
     PinVec<int32_t>& lA = p.h_lA; PinVec<int32_t>& lB = p.h_lB; PinVec<int64_t>& tot = p.h_tot;
     p.nnz_tap.assign(2 * T, 0);
-    SLS_CK(rt::d2h(p.h_lnnz.data(), p.lnnz.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
-    SLS_CK(rt::d2h(lA.data(), p.lnnzA.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
-    SLS_CK(rt::d2h(lB.data(), p.lnnzB.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
-    SLS_CK(rt::d2h(tot.data(), p.tot.p, (size_t)(p.ncols + 1) * sizeof(int64_t), h->stream));
-    SLS_CK(rt::d2h_strided(p.h_last.data(), v.colptr + Nx, sizeof(int64_t), (size_t)(Nx + 1) * sizeof(int64_t), (size_t)(2 * T), h->stream));
+    SLS_CK(sls_kcopy(p.h_lnnz.data(), p.lnnz.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(sls_kcopy(lA.data(), p.lnnzA.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(sls_kcopy(lB.data(), p.lnnzB.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(sls_kcopy(tot.data(), p.tot.p, (size_t)(p.ncols + 1) * sizeof(int64_t), h->stream));
+    SLS_CK(sls_kgather64(p.h_last.data(), v.colptr + Nx, (size_t)(Nx + 1), (int)(2 * T), h->stream));
     // size classes of kernel 2 (by n, known since the count pass): binned on the host while kernel 1b runs
     p.classes.clear();
-    p.h_lists.assign(nc1, 0);
+    SLS_CK(p.h_lists.resize(nc1));
+    std::fill(p.h_lists.data(), p.h_lists.data() + nc1, 0);
     {
         size_t off = 0;
         const int nk = sls_solve_class_count();
@@ -557,7 +611,7 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
         }
         for (int k = 0; k < nk; k++) if (cls[k].count) p.classes.push_back(cls[k]);
         SLS_CK(p.lists.ensure(nc1 * sizeof(int32_t)));
-        SLS_CK(rt::h2d(p.lists.p, p.h_lists.data(), off * sizeof(int32_t), h->stream));
+        SLS_CK(sls_kcopy(p.lists.p, p.h_lists.data(), off * sizeof(int32_t), h->stream));
     }
     SLS_CK(rt::sync(h->stream));
     for (int64_t tt = 0; tt < 2 * T; tt++) p.nnz_tap[tt] = p.h_last[tt];
@@ -822,6 +876,319 @@ extern "C" int sls_solve(sls_handle* h,
     if (!h) return -1;
     HostOut ho{{Px_colptr, Pu_colptr}, {Px_rowval, Pu_rowval}, {Px_nzval, Pu_nzval}, status, resid};
     return run_solve(h, &ho);
+}
+
+
+// ---- pipelined one-shot synthesis -------------------------------------------------------------
+// sls_set_supports + sls_plan + sls_solve for ALL columns 1..Nx in one call, cut into contiguous column chunks so
+// that the three PCIe/compute stages overlap:   H2D of chunk c+1's support columns (in_stream)
+//                                             | kernels 1-3 of chunk c (stream; kernel 3 on scat_stream)
+//                                             | D2H of chunk c-1's CSC segments (copy_stream).
+// Every chunk is an ordinary plan on a contiguous column list over the shared device copy of the supports (whose
+// rowval/nzval arrive slice by slice, in final position), with its own output buffers.  Results are bit-for-bit
+// those of the three-call path.
+namespace {
+struct CopyBatch {                                          // slice copies of one chunk and direction, issued as one call
+    std::vector<void*> dst, src; std::vector<size_t> len;
+    void add(void* d, const void* s_, size_t n) { if (n) { dst.push_back(d); src.push_back(const_cast<void*>(s_)); len.push_back(n); } }
+    int flush(sls_stream_t st) { int e = rt::copy_batch(dst.data(), src.data(), len.data(), len.size(), st); dst.clear(); src.clear(); len.clear(); return e; }
+};
+struct PipeSupp {
+    DevSupports* d; const int64_t* const* cps; const int64_t* const* rvs; const uint8_t* const* nzs;
+    int64_t nrow; const char* name;
+};
+}
+
+static int pipe_prepare(sls_handle* h, PipeSupp& f, int64_t T, int64_t ncol) {
+    DevSupports& d = *f.d;
+    std::vector<int64_t> off(T + 1, 0);
+    bool any_nz = false, all_nz = true;
+    for (int64_t t = 0; t < T; t++) {
+        if (!f.cps[t]) return fail(h, -2, (std::string("sls_synthesize: ") + f.name + ": colptr is NULL").c_str());
+        if (f.cps[t][0] != 1 || f.cps[t][ncol] < 1) return fail(h, -2, (std::string("sls_synthesize: ") + f.name + ": colptr[1] must be 1 (Julia 1-based CSC)").c_str());
+        if (f.cps[t][ncol] > 1 && !(f.rvs && f.rvs[t])) return fail(h, -2, (std::string("sls_synthesize: ") + f.name + ": rowval is NULL").c_str());
+        off[t + 1] = off[t] + f.cps[t][ncol] - 1;
+        if (f.nzs && f.nzs[t]) any_nz = true; else all_nz = false;
+    }
+    if (any_nz && !all_nz) return fail(h, -2, "sls_synthesize: nzval must be given for every tap or for none");
+    d.nnz = off[T]; d.has_nzval = any_nz;
+    SLS_CK(d.colptr.ensure(T * (ncol + 1) * sizeof(int64_t)));
+    SLS_CK(d.rowval.ensure(std::max<int64_t>(d.nnz, 1) * sizeof(int64_t)));
+    SLS_CK(d.tap_off.ensure((T + 1) * sizeof(int64_t)));
+    if (any_nz) SLS_CK(d.nzval.ensure(std::max<int64_t>(d.nnz, 1)));
+    d.h_tap_off = off;
+    int ml = 0;
+    const int64_t* cl = f.cps[T - 1];
+    for (int64_t c = 0; c < ncol; c++) ml = std::max<int>(ml, (int)std::min<int64_t>(std::max<int64_t>(cl[c + 1] - cl[c], 0), 1 << 30));
+    d.maxlen_last = ml;
+    SLS_CK(rt::h2d(d.tap_off.p, d.h_tap_off.data(), (T + 1) * sizeof(int64_t), h->in_stream));   // pageable: before the big copies
+    for (int64_t t = 0; t < T; t++)
+        SLS_CK(rt::h2d(d.colptr.as<int64_t>() + t * (ncol + 1), f.cps[t], (ncol + 1) * sizeof(int64_t), h->in_stream));
+    // the Bool values are 1/9 of the bytes but would be half of the slice copies (each copy costs ~10 us of driver
+    // time): they go up whole, once per tap, ahead of the column chunks
+    if (any_nz)
+        for (int64_t t = 0; t < T; t++)
+            SLS_CK(rt::h2d(d.nzval.as<uint8_t>() + off[t], f.nzs[t], (size_t)(off[t + 1] - off[t]), h->in_stream));
+    return 0;
+}
+
+// validates and enqueues the support columns [c0, c1) of every tap of one family
+// (runs on the feeder thread: errors are returned as a message, never through the handle)
+static int pipe_enqueue_slice(sls_handle* h, PipeSupp& f, int64_t T, int64_t ncol, int64_t c0, int64_t c1, CopyBatch& cbatch,
+                              std::string& msg) {
+    DevSupports& d = *f.d;
+    const bool rows = (h->opt.flags & 1) != 0;
+    for (int64_t t = 0; t < T; t++) {
+        const int64_t* cp = f.cps[t];
+        for (int64_t c = c0; c < c1; c++)
+            if (cp[c + 1] < cp[c]) { msg = std::string("sls_synthesize: ") + f.name + ": colptr is not monotone"; return -2; }
+        if (cp[c0] < 1 || cp[c1] > cp[ncol]) { msg = std::string("sls_synthesize: ") + f.name + ": colptr is not monotone"; return -2; }
+        const int64_t s0 = cp[c0] - 1, s1 = cp[c1] - 1;
+        if (rows)
+            for (int64_t c = c0; c < c1; c++) {
+                int64_t prev = 0;
+                for (int64_t e = cp[c] - 1; e < cp[c + 1] - 1; e++) {
+                    if (f.rvs[t][e] < 1 || f.rvs[t][e] > f.nrow || f.rvs[t][e] <= prev) {
+                        msg = std::string("sls_synthesize: ") + f.name + ": rowval out of range or not strictly ascending"; return -2;
+                    }
+                    prev = f.rvs[t][e];
+                }
+            }
+        if (s1 > s0) {
+            cbatch.add(d.rowval.as<int64_t>() + d.h_tap_off[t] + s0, f.rvs[t] + s0, (s1 - s0) * sizeof(int64_t));
+        }
+    }
+    return 0;
+}
+
+static void pipe_drain(sls_handle* h) {
+    rt::sync(h->in_stream); rt::sync(h->stream); rt::sync(h->scat_stream); rt::sync(h->copy_stream); rt::sync(h->out2_stream);
+}
+
+extern "C" int sls_synthesize(sls_handle* h, int64_t T,
+                              const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
+                              const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval,
+                              int64_t first_col, int64_t ncols, const int64_t* cap_x, const int64_t* cap_u,
+                              int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
+                              int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
+                              int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid) {
+    if (!h) return -1;
+    SLS_ARG(h->have_plant, "sls_synthesize: call sls_set_plant first");
+    SLS_ARG(T >= 1 && T < 4096, "sls_synthesize: bad T");
+    SLS_ARG(Sx_colptr && Sx_rowval && Su_colptr && Su_rowval, "sls_synthesize: NULL array of pointers");
+    SLS_CK(rt::set_device(h->device));
+    const int64_t Nx = h->Nx, Nu = h->Nu;
+    if (ncols <= 0) { first_col = 1; ncols = Nx; }
+    SLS_ARG(first_col >= 1 && first_col + ncols - 1 <= Nx, "sls_synthesize: column range out of 1..Nx");
+    const int64_t r0 = first_col - 1, r1 = r0 + ncols;          // 0-based half-open column range
+    h->have_supports = false; h->plan.valid = false; h->solved = false;
+    // chunk count: every chunk costs ~230 slice copies of ~10 us driver/engine time each way, against the pipeline's
+    // fill and drain time (measured on config #3: 4-5 chunks best, 8 chunks +2 ms)
+    int K = (ncols >= 16384) ? 4 : 1;
+    if (const char* ev = getenv("SLS_PIPE_CHUNKS")) { const int c = atoi(ev); if (c >= 1) K = c; }
+    K = (int)std::min<int64_t>(std::min<int64_t>(K, SLS_PIPE_MAX), ncols);
+    std::vector<int64_t> cb(K + 1), ub(K + 1);
+    for (int c = 0; c <= K; c++) cb[c] = r0 + ncols * c / K;
+    // support columns to upload: the range itself plus the columns kernel 1 reaches through nz(A[:,j]) (the halo)
+    // upload chunk c ends where the reach of plan chunk c ends, so that chunk c never waits for chunk c+1's copy
+    ub = cb;
+    for (int c = 0; c < K; c++) {
+        int64_t hi = cb[c + 1];
+        for (int64_t j = cb[c]; j < cb[c + 1]; j++) { ub[0] = std::min<int64_t>(ub[0], h->h_Akmin[j]); hi = std::max<int64_t>(hi, (int64_t)h->h_Akmax[j] + 1); }
+        ub[c + 1] = std::max(ub[c], hi);
+    }
+    for (int c = 1; c <= K; c++) ub[c] = std::max(ub[c], ub[c - 1]);
+    while ((int)h->pipe.size() < K) {
+        PipeCtx* x = new (std::nothrow) PipeCtx();
+        if (!x) return fail(h, -2, "sls_synthesize: out of host memory");
+        int e = x->create();
+        if (e) { x->release(); delete x; return fail(h, e, "sls_synthesize: event creation"); }
+        h->pipe.push_back(x);
+    }
+    h->ev[0].record(h->stream);
+    SLS_CK(rt::stream_wait(h->in_stream, h->ev[0]));            // earlier work on the main stream may still read the supports
+    PipeSupp fam[2] = {{&h->Sx, Sx_colptr, Sx_rowval, Sx_nzval, Nx, "Sx"}, {&h->Su, Su_colptr, Su_rowval, Su_nzval, Nu, "Su"}};
+    for (int f = 0; f < 2; f++) { int e = pipe_prepare(h, fam[f], T, Nx); if (e) { pipe_drain(h); return e; } }
+    h->T = T;
+    SLS_CK(h->pipe_colptr.ensure((size_t)2 * T * (Nx + 1) * sizeof(int64_t)));
+    SLS_CK(h->pipe_status.resize(ncols)); SLS_CK(h->pipe_resid.resize(ncols));
+    // Feeder thread: validates and enqueues the support slices of every chunk on the copy-in stream as fast as the
+    // driver accepts them (~230 copies per chunk), so that their per-call cost stays off the thread that launches
+    // the kernels.  `fed` = chunks whose copy-in event has been recorded.
+    std::atomic<int> fed{0}, feed_err{0};
+    std::atomic<bool> feed_stop{false};
+    std::string feed_msg;
+    std::thread feeder([&]() {
+        rt::set_device(h->device);
+        CopyBatch cbatch;
+        for (int c = 0; c < K && !feed_stop.load(); c++) {
+            int e = 0;
+            for (int f = 0; f < 2 && !e; f++) e = pipe_enqueue_slice(h, fam[f], T, Nx, ub[c], ub[c + 1], cbatch, feed_msg);
+            if (!e) { e = cbatch.flush(h->in_stream); if (e) feed_msg = "sls_synthesize: host to device copy"; }
+            if (e) { feed_err.store(e); return; }
+            h->pipe_in[c].record(h->in_stream);
+            fed.store(c + 1, std::memory_order_release);
+        }
+    });
+    auto wait_fed = [&](int c) -> int {                         // host-side wait until chunk c's copy-in event exists
+        while (fed.load(std::memory_order_acquire) <= c) {
+            if (feed_err.load()) return feed_err.load();
+            std::this_thread::yield();
+        }
+        return 0;
+    };
+    CopyBatch obatch;
+    auto chunk_of = [&](int64_t col) { int c = 0; while (c < K - 1 && col >= ub[c + 1]) c++; return c; };
+    std::vector<int64_t> base(2 * T, 0);
+    std::vector<int64_t> cols;
+    int64_t launches = 0, nnz_total = 0;
+    double flops = 0, bytes = 0;
+    int e = 0;
+#define PIPE_CK(expr) { e = (expr); if (e) { fail(h, e, #expr); break; } }
+    h->have_supports = true;                                    // build_plan's precondition; reset on failure below
+    for (int c = 0; c < K && !e; c++) {
+        const int64_t c0 = cb[c], c1 = cb[c + 1];
+        // kernel 1 of column j reads the support columns k in nz(A[:,j]): wait for the chunk holding the largest one
+        int32_t kmax = (int32_t)(c1 - 1);
+        for (int64_t j = c0; j < c1; j++) kmax = std::max(kmax, h->h_Akmax[j]);
+        const int need = chunk_of(kmax);
+        e = wait_fed(need);
+        if (e) { fail(h, e, feed_msg.c_str()); break; }
+        PIPE_CK(rt::stream_wait(h->stream, h->pipe_in[need]));
+        PipeCtx& x = *h->pipe[c];
+        Plan& p = x.plan;
+        cols.resize(c1 - c0);
+        for (int64_t j = c0; j < c1; j++) cols[j - c0] = j + 1;
+        e = build_plan(h, p, cols.data(), c1 - c0, false);
+        if (e) break;
+        if (p.nmax > sls_solve_class_N(sls_solve_class_count() - 1)) { e = fail(h, -6, "sls_synthesize: a column's local state dimension |s_x| exceeds the largest solver size class"); break; }
+        for (int64_t tt = 0; tt < 2 * T && !e; tt++) {
+            const int x_ = tt >= T; const int64_t t = x_ ? tt - T : tt;
+            const int64_t* capv = x_ ? cap_u : cap_x;
+            const int64_t cap = capv ? capv[t] : (fam[x_].cps[t][Nx] - 1);
+            if (base[tt] + p.nnz_tap[tt] > cap) e = fail(h, -4, "sls_synthesize: output capacity of a tap is too small");
+        }
+        if (e) break;
+        const int nc1 = std::max(p.ncols, 1);
+        PIPE_CK(x.status.ensure(nc1 * sizeof(int32_t)));
+        PIPE_CK(x.resid.ensure(nc1 * sizeof(double)));
+        PIPE_CK(x.out_rowval.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(int64_t)));
+        PIPE_CK(x.out_nzval.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(double)));
+        PIPE_CK(x.out_ptrs.ensure((size_t)4 * T * sizeof(void*)));
+        PIPE_CK(x.base.ensure((size_t)2 * T * sizeof(int64_t)));
+        PIPE_CK(x.h_ptrs.resize(4 * T)); PIPE_CK(x.h_base.resize(2 * T));
+        for (int64_t tt = 0; tt < 2 * T; tt++) {
+            x.h_ptrs[tt] = x.out_rowval.as<int64_t>() + p.out_off[tt];
+            x.h_ptrs[2 * T + tt] = x.out_nzval.as<double>() + p.out_off[tt];
+            x.h_base[tt] = base[tt];
+        }
+        PIPE_CK(sls_kcopy(x.out_ptrs.p, x.h_ptrs.data(), (size_t)4 * T * sizeof(void*), h->stream));
+        PIPE_CK(sls_kcopy(x.base.p, x.h_base.data(), (size_t)2 * T * sizeof(int64_t), h->stream));
+        const SlsPlanView v = plan_view(h, p);
+        size_t hist_bytes = 8;
+        for (const SolveClass& cl : p.classes) {
+            const int maxw = sls_solve_max_resident_warps(cl.N, cl.mcap, cl.nnzcap, (int)T, p.wu, h->sm_count, h->max_smem);
+            if (maxw <= 0) { e = fail(h, -4, "sls_synthesize: local problem does not fit shared memory"); break; }
+            const int64_t warps = std::min<int64_t>(maxw, ((int64_t)cl.count + 3) / 4 * 4);
+            hist_bytes = std::max(hist_bytes, (size_t)warps * sls_solve_hist_doubles(cl.N, (int)T) * sizeof(double));
+        }
+        if (e) break;
+        PIPE_CK(h->hist.ensure(hist_bytes));
+        // the caller's colptr = the chunk's colptr + entries of the earlier chunks (columns c0+1..c1; chunk 0 also writes [0])
+        const int64_t j0 = (c == 0) ? 0 : c0 + 1, j1 = (c == K - 1) ? Nx : c1;   // columns outside the range are empty
+        PIPE_CK(sls_launch_colptr_rebase(h->pipe_colptr.as<int64_t>(), p.colptr.as<int64_t>(), x.base.as<int64_t>(), Nx + 1, (int)(2 * T), j0, j1, h->stream));
+        x.ev_plan.record(h->stream);
+        // kernel 3 beside kernel 2
+        PIPE_CK(rt::stream_wait(h->scat_stream, x.ev_plan));
+        {
+            SlsScatterArgs sa{};
+            sa.P = v; sa.c_begin = 0; sa.c_end = p.ncols;
+            sa.rowval = reinterpret_cast<int64_t* const*>(x.out_ptrs.as<void*>());
+            PIPE_CK(sls_launch_scatter(sa, h->scat_stream));
+        }
+        x.ev_scat.record(h->scat_stream);
+        for (const SolveClass& cl : p.classes) {
+            SlsSolveArgs a{};
+            a.A = h->A.view(); a.B2 = h->B2.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();
+            a.P = v; a.list = p.lists.as<int32_t>() + cl.list_off; a.count = cl.count;
+            a.mcap = cl.mcap; a.nnzcap = cl.nnzcap;
+            a.out_nzval = reinterpret_cast<double* const*>(x.out_ptrs.as<void*>() + 2 * T); a.hist = h->hist.as<double>();
+            a.hist_stride = sls_solve_hist_doubles(cl.N, (int)T);
+            a.status = x.status.as<int32_t>(); a.resid = x.resid.as<double>();
+            a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
+            int warps = 0;
+            PIPE_CK(sls_launch_solve(cl.N, a, h->sm_count, h->max_smem, &warps, h->stream));
+            launches++;
+        }
+        if (e) break;
+        x.ev_solved.record(h->stream);
+        // device -> host, in the order the data becomes final: colptr, rowval, then nzval / status / residual
+        PIPE_CK(rt::stream_wait(h->copy_stream, x.ev_plan));
+        if (c == K - 1) {                                       // colptr: whole arrays once (58 copies instead of 58 per chunk)
+            for (int64_t tt = 0; tt < 2 * T; tt++) {
+                const int x_ = tt >= T; const int64_t t = x_ ? tt - T : tt;
+                int64_t* const* hc = x_ ? Pu_colptr : Px_colptr;
+                if (hc && hc[t]) obatch.add(hc[t], h->pipe_colptr.as<int64_t>() + tt * (Nx + 1), (size_t)(Nx + 1) * sizeof(int64_t));
+            }
+            PIPE_CK(obatch.flush(h->copy_stream));
+        }
+        PIPE_CK(rt::stream_wait(h->copy_stream, x.ev_scat));
+        for (int64_t tt = 0; tt < 2 * T; tt++) {
+            const int x_ = tt >= T; const int64_t t = x_ ? tt - T : tt;
+            int64_t* const* hr = x_ ? Pu_rowval : Px_rowval;
+            if (hr && hr[t]) obatch.add(hr[t] + base[tt], x.out_rowval.as<int64_t>() + p.out_off[tt], (size_t)p.nnz_tap[tt] * sizeof(int64_t));
+        }
+        PIPE_CK(obatch.flush(h->copy_stream));
+        sls_stream_t vstream = getenv("SLS_PIPE_ONE_OUT") ? h->copy_stream : h->out2_stream;   // values on their own stream
+        PIPE_CK(rt::stream_wait(vstream, x.ev_solved));
+        for (int64_t tt = 0; tt < 2 * T; tt++) {
+            const int x_ = tt >= T; const int64_t t = x_ ? tt - T : tt;
+            double* const* hz = x_ ? Pu_nzval : Px_nzval;
+            if (hz && hz[t]) obatch.add(hz[t] + base[tt], x.out_nzval.as<double>() + p.out_off[tt], (size_t)p.nnz_tap[tt] * sizeof(double));
+        }
+        if (status) obatch.add(h->pipe_status.data() + (c0 - r0), x.status.p, (size_t)p.ncols * sizeof(int32_t));
+        if (resid) obatch.add(h->pipe_resid.data() + (c0 - r0), x.resid.p, (size_t)p.ncols * sizeof(double));
+        PIPE_CK(obatch.flush(vstream));
+        x.ev_out.record(vstream);
+        for (int64_t tt = 0; tt < 2 * T; tt++) base[tt] += p.nnz_tap[tt];
+        nnz_total += p.tot_packed; flops += p.alg_flops; bytes += p.alg_bytes;
+    }
+#undef PIPE_CK
+    if (e) feed_stop.store(true);
+    feeder.join();
+    if (!e && feed_err.load()) e = fail(h, feed_err.load(), feed_msg.c_str());
+    if (e) { pipe_drain(h); h->have_supports = false; return e; }
+    h->pipe_done.record(h->copy_stream);
+    h->pipe_done2.record(h->out2_stream);
+    SLS_CK(rt::stream_wait(h->stream, h->pipe_done));           // later marks on the main stream see the copies
+    SLS_CK(rt::stream_wait(h->stream, h->pipe_done2));
+    SLS_CK(rt::stream_wait(h->stream, h->pipe_in[K - 1]));
+    h->ev[1].record(h->stream);
+    SLS_CK(rt::sync(h->stream));
+    SLS_CK(rt::sync(h->scat_stream));
+    if (status) memcpy(status, h->pipe_status.data(), (size_t)ncols * sizeof(int32_t));
+    if (resid) memcpy(resid, h->pipe_resid.data(), (size_t)ncols * sizeof(double));
+    for (int64_t t = 0; t < T; t++) {
+        if (nnz_x) nnz_x[t] = base[t];
+        if (nnz_u) nnz_u[t] = base[T + t];
+    }
+    if (getenv("SLS_PIPE_TRACE")) {                            // per-chunk completion times on the device clock (ms since the call)
+        for (int c = 0; c < K; c++)
+            fprintf(stderr, "[pipe] chunk %d: in %.2f plan %.2f scat %.2f solved %.2f out %.2f\n", c,
+                    rt::elapsed_ms(h->ev[0], h->pipe_in[c]), rt::elapsed_ms(h->ev[0], h->pipe[c]->ev_plan),
+                    rt::elapsed_ms(h->ev[0], h->pipe[c]->ev_scat), rt::elapsed_ms(h->ev[0], h->pipe[c]->ev_solved),
+                    rt::elapsed_ms(h->ev[0], h->pipe[c]->ev_out));
+        fprintf(stderr, "[pipe] total %.2f\n", rt::elapsed_ms(h->ev[0], h->ev[1]));
+    }
+    h->tm = sls_timing{};
+    h->tm.solve_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);       // whole pipelined call (copies, kernels 1-3) on the device clock
+    h->tm.solve_launches = launches; h->tm.gather_launches = 3 * K; h->tm.scatter_launches = 2 * K;
+    h->tm.ncols = ncols; h->tm.nnz_out = nnz_total; h->tm.alg_flops = flops; h->tm.alg_bytes = bytes;
+    // the support columns of the range (+halo) stay on the device; a later sls_plan of other columns needs
+    // sls_set_supports.  The outputs live in per-chunk buffers, so the
+    // device-resident accessors (sls_device_output, sls_simulate) need a sls_plan + sls_solve_device first
+    h->plan.valid = false; h->solved = false;
+    return 0;
 }
 
 // ---- closed-loop FIR simulation --------------------------------------------------------------

@@ -6,6 +6,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #ifdef SLS_EMU
 #include "simt_emu.h"
@@ -19,6 +20,10 @@ inline int d2d(void* d, const void* s, size_t n, sls_stream_t) { memcpy(d, s, n)
 inline int zero(void* d, size_t n, sls_stream_t) { memset(d, 0, n); return 0; }
 inline int d2h_strided(void* h, const void* d, size_t elem, size_t pitch, size_t count, sls_stream_t) {
     for (size_t i = 0; i < count; i++) memcpy((char*)h + i * elem, (const char*)d + i * pitch, elem);
+    return 0;
+}
+inline int copy_batch(void** dsts, void** srcs, size_t* sizes, size_t n, sls_stream_t) {
+    for (size_t i = 0; i < n; i++) memcpy(dsts[i], srcs[i], sizes[i]);
     return 0;
 }
 inline int host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
@@ -61,6 +66,14 @@ inline int d2d(void* d, const void* s_, size_t n, sls_stream_t s) { return n ? (
 inline int zero(void* d, size_t n, sls_stream_t s) { return n ? (int)cudaMemsetAsync(d, 0, n, s) : 0; }
 inline int d2h_strided(void* h, const void* d, size_t elem, size_t pitch, size_t count, sls_stream_t s) {
     return count ? (int)cudaMemcpy2DAsync(h, elem, d, pitch, elem, count, cudaMemcpyDeviceToHost, s) : 0;
+}
+// a list of independent copies (any direction), in stream order
+inline int copy_batch(void** dsts, void** srcs, size_t* sizes, size_t n, sls_stream_t s) {
+    for (size_t i = 0; i < n; i++) {
+        cudaError_t e = cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyDefault, s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
 }
 inline int host_alloc(void** p, size_t n) { return (int)cudaMallocHost(p, n ? n : 1); }
 inline void host_free(void* p) { if (p) cudaFreeHost(p); }

@@ -75,3 +75,48 @@ int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream) {
     SLS_LAUNCH(kp, grid, SCATTER_WPB * 32, 0, stream, a);
     return rt::last_error();
 }
+
+// colptr of one column chunk of the pipelined one-shot path (sls_synthesize): the chunk's plan holds, per tap, a
+// colptr scanned over its own columns only; the caller's colptr is that plus the entries of the earlier chunks.
+//     dst[tt][j] = src[tt][j] + base[tt]      for j in [j0, j1]   (0-based positions inside the Nx+1 array)
+__global__ void sls_colptr_rebase_kernel(int64_t* dst, const int64_t* src, const int64_t* base, int64_t len, int64_t j0, int64_t j1) {
+    const int tt = blockIdx.y;
+    const int64_t j = j0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j <= j1) dst[(int64_t)tt * len + j] = src[(int64_t)tt * len + j] + base[tt];
+}
+
+int sls_launch_colptr_rebase(int64_t* dst, const int64_t* src, const int64_t* base, int64_t len, int narr, int64_t j0, int64_t j1,
+                             sls_stream_t stream) {
+    if (j1 < j0 || narr <= 0) return 0;
+    dim3 grid((unsigned)((j1 - j0 + 1 + 255) / 256), narr, 1);
+    auto kp = &sls_colptr_rebase_kernel;
+    SLS_LAUNCH(kp, grid, 256, 0, stream, dst, src, base, len, j0, j1);
+    return rt::last_error();
+}
+
+// Small metadata transfers of the plan (column lists, per-column sizes) as kernels over mapped pinned host memory
+// instead of copy-engine commands: in the pipelined path the copy engines' queues hold megabytes of support /
+// output slices, and a 50 KB size read-back queued behind them would stall kernel 1 of the next chunk for
+// milliseconds.  Either pointer may be device memory or pinned host memory (UVA); 4-byte granularity.
+__global__ void sls_kcopy_kernel(uint32_t* dst, const uint32_t* src, size_t nwords) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int sls_kcopy(void* dst, const void* src, size_t bytes, sls_stream_t stream) {
+    if (!bytes) return 0;
+    const size_t nwords = (bytes + 3) / 4;
+    const int grid = (int)((nwords + 255) / 256 < 296 ? (nwords + 255) / 256 : 296);
+    auto kp = &sls_kcopy_kernel;
+    SLS_LAUNCH(kp, grid, 256, 0, stream, reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const uint32_t*>(src), nwords);
+    return rt::last_error();
+}
+// dst[i] = src[i * pitch], i < count  (the last colptr entry of every tap)
+__global__ void sls_kgather64_kernel(int64_t* dst, const int64_t* src, size_t pitch, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = src[(size_t)i * pitch];
+}
+int sls_kgather64(int64_t* dst, const int64_t* src, size_t pitch, int count, sls_stream_t stream) {
+    if (count <= 0) return 0;
+    auto kp = &sls_kgather64_kernel;
+    SLS_LAUNCH(kp, (count + 127) / 128, 128, 0, stream, dst, src, pitch, count);
+    return rt::last_error();
+}

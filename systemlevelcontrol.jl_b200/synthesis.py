@@ -231,6 +231,65 @@ class Synthesizer:
         self._ck(self.api.sls_solve(self.h, *args, ptr(out["status"], i32p), ptr(out["resid"], f64p)))
         return out
 
+    def synthesize(self, Sx, Su, pass_nzval=True, out=None, pinned=False, col_range=None):
+        """One-shot pipelined `set_supports + plan(all columns) + solve` (sls_synthesize): H2D of the next column
+        chunk, kernels 1-3 and D2H of the previous chunk overlap.  Output taps are allocated at the support's size
+        (the stored pattern of Phi[t] is a subset of S[t]'s) and trimmed to the returned counts.
+        col_range = (c0, c1): 0-based half-open contiguous column range (one GPU's shard); None = all columns."""
+        Sx = [_as_julia(M, np.bool_) for M in Sx]
+        Su = [_as_julia(M, np.bool_) for M in Su]
+        if len(Sx) != len(Su):
+            raise ValueError("Sx and Su must have the same number of taps")
+        self.T = T = len(Sx)
+        if out is None:
+            self.nnz_x = np.array([M.nnz for M in Sx], np.int64)
+            self.nnz_u = np.array([M.nnz for M in Su], np.int64)
+            self.ncols = self.Nx
+            out = self.alloc_outputs(pinned=pinned)
+        c0, c1 = (0, self.Nx) if col_range is None else (int(col_range[0]), int(col_range[1]))
+        cap_x = np.array([a.size for a in out["x"]["rowval"]], np.int64)
+        cap_u = np.array([a.size for a in out["u"]["rowval"]], np.int64)
+        args = []
+        for S in (Sx, Su):
+            args.append(ptr_array([M.colptr for M in S], i64p))
+            args.append(ptr_array([M.rowval for M in S], i64p))
+            args.append(ptr_array([M.nzval for M in S], u8p) if pass_nzval else None)
+        oargs = []
+        for name in ("x", "u"):
+            oargs.append(ptr_array(out[name]["colptr"], i64p))
+            oargs.append(ptr_array(out[name]["rowval"], i64p))
+            oargs.append(ptr_array(out[name]["nzval"], f64p))
+        nnz_x = np.zeros(T, np.int64); nnz_u = np.zeros(T, np.int64)
+        self._ck(self.api.sls_synthesize(self.h, T, *args, c0 + 1, c1 - c0, ptr(cap_x, i64p), ptr(cap_u, i64p), *oargs,
+                                         ptr(nnz_x, i64p), ptr(nnz_u, i64p), ptr(out["status"], i32p), ptr(out["resid"], f64p)))
+        self.nnz_x, self.nnz_u, self.ncols = nnz_x, nnz_u, c1 - c0
+        for name, nnz in (("x", nnz_x), ("u", nnz_u)):
+            out[name]["rowval"] = [a[:int(nnz[t])] for t, a in enumerate(out[name]["rowval"])]
+            out[name]["nzval"] = [a[:int(nnz[t])] for t, a in enumerate(out[name]["nzval"])]
+        return out
+
+    def synthesize_values_only(self, Sx, Su, out, pass_nzval=True, col_range=None):
+        """sls_synthesize with NULL rowval outputs (colptr and nzval only).  Returns (nnz_x, nnz_u): where
+        nnz_x[t] == nnz(Sx[t][:, range]) the pattern of Phi_x[t] is exactly Sx[t]'s and its rowval can be aliased."""
+        Sx = [_as_julia(M, np.bool_) for M in Sx]
+        Su = [_as_julia(M, np.bool_) for M in Su]
+        T = len(Sx)
+        c0, c1 = (0, self.Nx) if col_range is None else (int(col_range[0]), int(col_range[1]))
+        cap_x = np.array([a.size for a in out["x"]["nzval"]], np.int64)
+        cap_u = np.array([a.size for a in out["u"]["nzval"]], np.int64)
+        args = []
+        for S in (Sx, Su):
+            args.append(ptr_array([M.colptr for M in S], i64p))
+            args.append(ptr_array([M.rowval for M in S], i64p))
+            args.append(ptr_array([M.nzval for M in S], u8p) if pass_nzval else None)
+        oargs = []
+        for name in ("x", "u"):
+            oargs += [ptr_array(out[name]["colptr"], i64p), None, ptr_array(out[name]["nzval"], f64p)]
+        nnz_x = np.zeros(T, np.int64); nnz_u = np.zeros(T, np.int64)
+        self._ck(self.api.sls_synthesize(self.h, T, *args, c0 + 1, c1 - c0, ptr(cap_x, i64p), ptr(cap_u, i64p), *oargs,
+                                         ptr(nnz_x, i64p), ptr(nnz_u, i64p), ptr(out["status"], i32p), ptr(out["resid"], f64p)))
+        return nnz_x, nnz_u
+
     def solve_device(self):
         self._ck(self.api.sls_solve_device(self.h))
 
@@ -301,12 +360,17 @@ def SLS_H2(P, S, I=None, *, device: int = 0, return_info: bool = False, api=None
     syn = Synthesizer(device=device, api=api)
     try:
         syn.set_plant(P.A, P.B2)
-        syn.set_supports(Sx, Su)
-        syn.plan(cols)
-        out = syn.solve()
-        Phix, Phiu = syn.outputs_to_scipy(out)
-        info = dict(status=out["status"][:syn.ncols].copy(), resid=out["resid"][:syn.ncols].copy(),
-                    n=syn.n.copy(), m=syn.m.copy(), timing=syn.timing())
+        if cols is None and not return_info:
+            out = syn.synthesize(Sx, Su)              # the default 𝓘 = 1..Nx: one pipelined call
+            Phix, Phiu = syn.outputs_to_scipy(out)
+            info = None
+        else:
+            syn.set_supports(Sx, Su)
+            syn.plan(cols)
+            out = syn.solve()
+            Phix, Phiu = syn.outputs_to_scipy(out)
+            info = dict(status=out["status"][:syn.ncols].copy(), resid=out["resid"][:syn.ncols].copy(),
+                        n=syn.n.copy(), m=syn.m.copy(), timing=syn.timing())
     finally:
         syn.close()
     if return_info:

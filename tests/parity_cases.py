@@ -2,6 +2,7 @@
 same kernel sources on the test-only SIMT emulator (`-m "not gpu"`).  Every function takes the bound
 library (`api`) explicitly and compares against the CPU oracle / golden vectors."""
 import numpy as np
+import pytest
 import scipy.sparse as sp
 
 import slc_b200
@@ -215,4 +216,58 @@ def check_device_supports(api, plant, d, T, alpha):
                 assert np.array_equal(a[name]["rowval"][t], b[name]["rowval"][t])
                 assert np.array_equal(a[name]["nzval"][t], b[name]["nzval"][t])
     finally:
+        syn.close()
+
+
+def check_pipelined(api, plant, S, chunks, pass_nzval=True):
+    """sls_synthesize (one-shot, column-chunked pipeline) == sls_set_supports + sls_plan + sls_solve, bit for bit."""
+    import os
+    A, B1, B2 = plant
+    syn = slc_b200.Synthesizer(api=api)
+    old = os.environ.get("SLS_PIPE_CHUNKS")
+    try:
+        syn.set_plant(A, B2)
+        syn.set_supports(*S, pass_nzval=pass_nzval)
+        syn.plan(None)
+        ref = syn.solve()
+        nnz_ref = (syn.nnz_x.copy(), syn.nnz_u.copy())
+        for K in chunks:
+            os.environ["SLS_PIPE_CHUNKS"] = str(K)
+            out = syn.synthesize(*S, pass_nzval=pass_nzval)
+            assert np.array_equal(syn.nnz_x, nnz_ref[0]) and np.array_equal(syn.nnz_u, nnz_ref[1]), K
+            for fam in ("x", "u"):
+                for t in range(syn.T):
+                    for part in ("colptr", "rowval", "nzval"):
+                        assert np.array_equal(out[fam][part][t], ref[fam][part][t]), (K, fam, t, part)
+            assert np.array_equal(out["status"][:syn.Nx], ref["status"][:syn.Nx])
+            assert np.array_equal(out["resid"][:syn.Nx], ref["resid"][:syn.Nx])
+        # a contiguous column range (one GPU's shard) == the three-call path on that column list
+        c0, c1 = syn.Nx // 3, (2 * syn.Nx) // 3 + 1
+        syn.set_supports(*S, pass_nzval=pass_nzval)
+        syn.plan(np.arange(c0, c1))
+        ref2 = syn.solve()
+        os.environ["SLS_PIPE_CHUNKS"] = str(chunks[-1])
+        out2 = syn.synthesize(*S, pass_nzval=pass_nzval, col_range=(c0, c1))
+        for fam in ("x", "u"):
+            for t in range(syn.T):
+                for part in ("colptr", "rowval", "nzval"):
+                    assert np.array_equal(out2[fam][part][t], ref2[fam][part][t]), ("range", fam, t, part)
+        assert np.array_equal(out2["status"][:c1 - c0], ref2["status"][:c1 - c0])
+        assert np.array_equal(out2["resid"][:c1 - c0], ref2["resid"][:c1 - c0])
+        # too-small output capacity is an argument error, not a crash
+        syn.nnz_x, syn.nnz_u, syn.ncols = nnz_ref[0], nnz_ref[1], syn.Nx
+        small = syn.alloc_outputs()
+        small["x"]["rowval"][-1] = small["x"]["rowval"][-1][:-1]
+        small["x"]["nzval"][-1] = small["x"]["nzval"][-1][:-1]
+        with pytest.raises(_capi.SlsError) as ei:
+            syn.synthesize(*S, out=small)
+        assert ei.value.code == -4
+        # the handle is still usable afterwards
+        out = syn.synthesize(*S)
+        assert np.array_equal(out["x"]["nzval"][0], ref["x"]["nzval"][0])
+    finally:
+        if old is None:
+            os.environ.pop("SLS_PIPE_CHUNKS", None)
+        else:
+            os.environ["SLS_PIPE_CHUNKS"] = old
         syn.close()

@@ -42,3 +42,8 @@ def test_emu_closed_loop_simulation(emu_api):
 def test_emu_device_supports(emu_api):
     pc.check_device_supports(emu_api, O.chain_plant(40), 9, 29, 1.5)
     pc.check_device_supports(emu_api, O.grid_plant(6, 7, actuation="full"), 2, 6, 1.5)
+
+
+def test_emu_pipelined_one_shot_equals_three_call(emu_api):
+    A, B1, B2, S = pc.chain(24, d=3, T=8)
+    pc.check_pipelined(emu_api, (A, B1, B2), S, chunks=[1, 5])

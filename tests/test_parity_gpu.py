@@ -228,3 +228,40 @@ def test_device_generated_supports(cuda_api):
     pc.check_device_supports(cuda_api, O.grid_plant(11, 9, actuation="full"), 3, 10, 1.5)
     A, B1, B2 = O.grid_plant(8, 8, actuation="checker")          # B2 is a strict selection: Nu < Nx
     pc.check_device_supports(cuda_api, (A, B1, B2), 2, 7, 1.0)
+
+
+def test_pipelined_one_shot_equals_three_call_small(cuda_api):
+    A, B1, B2, S = pc.chain(59)
+    pc.check_pipelined(cuda_api, (A, B1, B2), S, chunks=[1, 3, 7])
+    pc.check_pipelined(cuda_api, (A, B1, B2), S, chunks=[4], pass_nzval=False)
+
+
+def test_pipelined_one_shot_config3_100k_bit_for_bit(cuda_api):
+    """BASELINE config #3 through sls_synthesize (default 8 column chunks, pinned buffers, copies overlapped with the
+    kernels) == the three-call path, bit for bit; plus a 2-shard split of the columns."""
+    from slc_b200 import workloads as W
+    Nx = 100_000
+    A, B1, B2 = W.chain_plant(Nx)
+    Sx, Su = W.chain_supports(Nx, 9, 29, 1.5)
+    syn = slc_b200.Synthesizer(api=cuda_api)
+    try:
+        syn.set_plant(A, B2)
+        syn.set_supports(Sx, Su)
+        syn.plan(None)
+        ref = syn.solve()
+        out = syn.synthesize(Sx, Su, pinned=True)
+        for fam in ("x", "u"):
+            for t in range(29):
+                for part in ("colptr", "rowval", "nzval"):
+                    assert np.array_equal(out[fam][part][t], ref[fam][part][t]), (fam, t, part)
+        assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["resid"], ref["resid"])
+        assert out["resid"].max() < 1e-12
+        # two shards: the entries of every tap are the concatenation of the shards' entries
+        h0 = syn.synthesize(Sx, Su, col_range=(0, Nx // 2))
+        h1 = syn.synthesize(Sx, Su, col_range=(Nx // 2, Nx))
+        for fam in ("x", "u"):
+            for t in (0, 7, 28):
+                assert np.array_equal(np.concatenate([h0[fam]["nzval"][t], h1[fam]["nzval"][t]]), ref[fam]["nzval"][t])
+                assert np.array_equal(np.concatenate([h0[fam]["rowval"][t], h1[fam]["rowval"][t]]), ref[fam]["rowval"][t])
+    finally:
+        syn.close()
