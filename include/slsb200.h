@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SLS_ABI_VERSION 4
+#define SLS_ABI_VERSION 5
 
 /* per-column status bits written by sls_solve* (improves on the reference, which ignores the
  * solver's termination status: src/synthesis.jl:62-65) */
@@ -71,6 +71,14 @@ const char* sls_last_error(const sls_handle* h);   /* h may be NULL: returns the
 int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
                   const int64_t* A_colptr, const int64_t* A_rowval, const double* A_nzval,
                   const int64_t* B2_colptr, const int64_t* B2_rowval, const double* B2_nzval);
+
+/* Diagonal cost weights — the 6-argument `Plant(A,B1,B2,C1,D11,D12)` (GeneralizedPlant.jl:101-103) with
+ * C1 = [diag(wx); 0], D12 = [0; diag(wu)], D11 = 0:  cost = sum_t ||wx .* Φx[t][:,j]||^2 + ||wu .* Φu[t][:,j]||^2
+ * (synthesis.jl:50,76-77).  wx (Nx) / wu (Nu) positive; NULL = ones; both NULL clears the weights.  Must be called
+ * BEFORE sls_set_plant (it invalidates the plant on the device: the weighted problem is solved as the unweighted one
+ * of the similarity-scaled plant Wx A Wx^-1, Wx B2 Wu^-1 and Φ is scaled back on the device).  resid[] then refers
+ * to the scaled variables.  A diagonal B1 only rescales the cost of each column and does not change Φ. */
+int sls_set_weights(sls_handle* h, int64_t Nx, int64_t Nu, const double* wx, const double* wu);
 
 /* 𝓢ₓ[t] (Nx x Nx) and 𝓢ᵤ[t] (Nu x Nx), t = 1..T: arrays of T pointers.  *_nzval (Bool) may be NULL
  * (= all true).  Index sets use the stored pattern of 𝓢[T] (reduction.jl:14); masks use nzval

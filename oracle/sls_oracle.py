@@ -34,7 +34,7 @@ import scipy.sparse as sp
 
 __all__ = [
     "chain_plant", "grid_plant", "make_supports", "Plant", "sparsity_dim_reduction",
-    "column_problem", "solve_column", "SLS_H2", "simulate_closed_loop",
+    "column_problem", "solve_column", "SLS_H2", "SLS_H2_general", "solve_group_general", "cost_blocks", "simulate_closed_loop",
     "achievability_residual",
 ]
 
@@ -146,19 +146,26 @@ def make_supports(A, B2, d: int, T: int, alpha: float):
 
 
 class Plant:
-    """Minimal stand-in for GeneralizedPlant{Float64,StateFeedback} built by the 3-argument
-    constructor (GeneralizedPlant.jl:105-110): C1 = [I;0], D12 = [0;I], D11 = 0, C2 = I."""
+    """Minimal stand-in for GeneralizedPlant{Float64,StateFeedback}.  3-argument form (GeneralizedPlant.jl:105-110):
+    C1 = [I;0], D12 = [0;I], D11 = 0, C2 = I.  6-argument form (GeneralizedPlant.jl:101-103): explicit C1 (Nz x Nx),
+    D11 (Nz x Nw, 0 -> zeros), D12 (Nz x Nu)."""
 
-    def __init__(self, A, B1, B2):
+    def __init__(self, A, B1, B2, C1=None, D11=None, D12=None):
         self.A = sp.csc_matrix(A, dtype=np.float64)
         self.B1 = sp.csc_matrix(B1, dtype=np.float64)
         self.B2 = sp.csc_matrix(B2, dtype=np.float64)
-        for M in (self.A, self.B1, self.B2):
-            M.sort_indices()
         self.Nx = self.A.shape[0]
         self.Nw = self.B1.shape[1]
         self.Nu = self.B2.shape[1]
-        self.Nz = self.Nx + self.Nu
+        if C1 is None:
+            CD = sp.identity(self.Nx + self.Nu, format="csc", dtype=np.float64)
+            C1, D12 = CD[:, :self.Nx], CD[:, self.Nx:]
+        self.C1 = sp.csc_matrix(C1, dtype=np.float64)
+        self.D12 = sp.csc_matrix(D12, dtype=np.float64)
+        self.Nz = self.C1.shape[0]
+        self.D11 = sp.csc_matrix((self.Nz, self.Nw)) if (D11 is None or np.isscalar(D11)) else sp.csc_matrix(D11, dtype=np.float64)
+        for M in (self.A, self.B1, self.B2, self.C1, self.D11, self.D12):
+            M.sort_indices()
         self.Ny = self.Nx
 
 
@@ -200,12 +207,25 @@ def sparsity_dim_reduction(P: Plant, cj, S, _prod=None):
     At = P.A[sx, :][:, sx].toarray()
     B1t = P.B1[sx, :][:, cj].toarray()
     B2t = P.B2[sx, :][:, su].toarray()
+    P._last_cost_blocks = cost_blocks(P, cj, sx, su)
     iix = np.isin(sx, cj)                                          # reduction.jl:22
     n, q = sx.size, cj.size
     It = np.zeros((n, q))
     sel = np.nonzero(iix)[0]
     It[sel, np.arange(sel.size)] = 1.0                             # reduction.jl:23
     return (At, B1t, B2t), It, iix, sx, su
+
+
+def cost_blocks(P: Plant, cj, sx, su):
+    """[C1~ D12~] and D11~ of the reduced plant: rows [s_x; Nx+s_u] of C1, D12, D11 (reduction.jl:15,
+    GeneralizedPlant.jl:266-271), columns s_x / s_u / c_j.  Returns (L, D11t) dense."""
+    rows = np.concatenate([np.asarray(sx, np.int64), P.Nx + np.asarray(su, np.int64)])
+    if rows.size and rows.max() >= P.Nz:
+        raise ValueError("the reduced plant selects rows [s_x; Nx+s_u] of C1/D12/D11: needs Nz >= Nx+Nu rows")
+    C1t = P.C1[rows, :][:, sx].toarray()
+    D12t = P.D12[rows, :][:, su].toarray()
+    D11t = P.D11[rows, :][:, np.asarray(cj, np.int64)].toarray()
+    return np.hstack([C1t, D12t]), D11t
 
 
 # --------------------------------------------------------------------------------------
@@ -276,6 +296,101 @@ def solve_column(At, B2t, It, Mx, Mu, rcond=1e-11):
     nz_rows = int((np.abs(G).sum(axis=1) > 0).sum())
     return X, U, dict(residual=res, rank=int(rank), rows=nz_rows, cost=float(v @ v),
                       smin=float(sv[rank - 1]) if rank else 0.0, smax=float(sv[0]) if sv.size else 0.0)
+
+
+def solve_group_general(At, B2t, It, Mxs, Mus, L, R, D, rcond=1e-11):
+    """Exact minimiser of the reference's general per-group problem (synthesis.jl:46-62, 76-77):
+        min  sum_t || L [X_t; U_t] R + D ||_F^2     X_t (n x q), U_t (m x q), off-mask entries fixed to 0
+        s.t. X_1 = I~,  X_{t+1} = A~ X_t + B2~ U_t,  0 = A~ X_T + B2~ U_T          (column by column)
+    with L = [C1~ D12~], R = B1~[ii_x,:] (q x q), D = D11~.  Mxs/Mus: per-column masks (lists of T x n / T x m).
+    Null-space method on the stacked system; minimum-norm among minimisers when the cost is not strictly convex.
+    Returns X (T x n x q), U (T x m x q), info."""
+    q = len(Mxs)
+    T, n = Mxs[0].shape
+    m = Mus[0].shape[1]
+    Gs, hs, offs, nvs = [], [], [], []
+    for c in range(q):
+        G, h, (xoff, uoff) = column_problem(At, B2t, It[:, [c]], Mxs[c], Mus[c])
+        Gs.append(G); hs.append(h); offs.append((xoff, uoff)); nvs.append(G.shape[1])
+    start = np.concatenate([[0], np.cumsum(nvs)])
+    nv = int(start[-1])
+    G = np.zeros((sum(g.shape[0] for g in Gs), nv)); h = np.concatenate(hs)
+    r = 0
+    for c in range(q):
+        G[r:r + Gs[c].shape[0], start[c]:start[c + 1]] = Gs[c]; r += Gs[c].shape[0]
+    # cost rows: for every tap t, vec(L V_t R + D)  =  sum_c' (R[c',c] * L[:, var]) ...
+    nzr = L.shape[0]
+    F = np.zeros((T * nzr * q, nv)); f0 = np.zeros(T * nzr * q)
+    for t in range(T):
+        for cout in range(q):                                    # column of the (Nz x q) block L V R + D
+            rows = slice((t * q + cout) * nzr, (t * q + cout + 1) * nzr)
+            f0[rows] = D[:, cout] if D.size else 0.0
+            for cin in range(q):
+                rr = R[cin, cout]
+                if rr == 0.0:
+                    continue
+                xoff, uoff = offs[cin]
+                fx = np.nonzero(xoff[t] >= 0)[0]; fu = np.nonzero(uoff[t] >= 0)[0]
+                F[rows, start[cin] + xoff[t, fx]] += rr * L[:, fx]
+                F[rows, start[cin] + uoff[t, fu]] += rr * L[:, n + fu]
+    vp, _, rank, sv = np.linalg.lstsq(G, h, rcond=rcond)
+    res = float(np.linalg.norm(G @ vp - h))
+    U_, s_, Vt = np.linalg.svd(G, full_matrices=True)
+    rk = int((s_ > rcond * (s_[0] if s_.size else 1.0)).sum())
+    N = Vt[rk:].T                                                # null space of G
+    if N.shape[1]:
+        z = np.linalg.lstsq(F @ N, -(F @ vp + f0), rcond=rcond)[0]
+        v = vp + N @ z
+    else:
+        v = vp
+    X = np.zeros((T, n, q)); U = np.zeros((T, m, q))
+    for c in range(q):
+        xoff, uoff = offs[c]
+        vc = v[start[c]:start[c + 1]]
+        X[:, :, c][xoff >= 0] = vc[xoff[xoff >= 0]]
+        U[:, :, c][uoff >= 0] = vc[uoff[uoff >= 0]]
+    return X, U, dict(residual=res, rank=rk, cost=float(np.sum((F @ v + f0) ** 2)))
+
+
+def SLS_H2_general(P: Plant, S, I=None):
+    """synthesis.jl:11-72 in full generality for state-feedback plants: column groups of any size (the 𝓘 keyword,
+    synthesis.jl:15), general [C1 D12], B1 and D11 in the cost (synthesis.jl:42-43,50,76-77).  Dense, slow: small cases."""
+    Sx, Su = S
+    T = len(Sx)
+    groups = [[j] for j in range(P.Nx)] if I is None else [list(map(int, np.atleast_1d(g))) for g in I]
+    prods = support_products(P, S)
+    ex = [([], [], []) for _ in range(T)]
+    eu = [([], [], []) for _ in range(T)]
+    for cj in groups:
+        (At, B1t, B2t), It, iix, sx, su = sparsity_dim_reduction(P, cj, S, _prod=prods)
+        L, D = P._last_cost_blocks
+        R = B1t[iix, :]                                          # synthesis.jl:42
+        if R.shape[0] != len(cj):
+            raise ValueError("B1~[ii_x,:] is not square: a group column is missing from its own s_x")
+        Mxs, Mus = zip(*[column_masks(S, sx, su, j) for j in cj])
+        X, U, _ = solve_group_general(At, B2t, It, list(Mxs), list(Mus), L, R, D)
+        for c, j in enumerate(cj):
+            for t in range(T):
+                fx = np.nonzero(Mxs[c][t])[0]
+                ex[t][0].append(sx[fx]); ex[t][1].append(np.full(fx.size, j)); ex[t][2].append(X[t, fx, c])
+                fu = np.nonzero(Mus[c][t])[0]
+                eu[t][0].append(su[fu]); eu[t][1].append(np.full(fu.size, j)); eu[t][2].append(U[t, fu, c])
+    return _build_taps(ex, (P.Nx, P.Nx)), _build_taps(eu, (P.Nu, P.Nx))
+
+
+def _build_taps(e, shape):
+    out = []
+    for r, c, v in e:
+        r = np.concatenate(r) if r else np.zeros(0, np.int64)
+        c = np.concatenate(c) if c else np.zeros(0, np.int64)
+        v = np.concatenate(v) if v else np.zeros(0)
+        order = np.lexsort((r, c))
+        r, c, v = r[order], c[order], v[order]
+        indptr = np.zeros(shape[1] + 1, dtype=np.int64)
+        np.add.at(indptr, c + 1, 1)
+        indptr = np.cumsum(indptr)
+        out.append(sp.csc_matrix((v, r.astype(np.int64), indptr), shape=shape))
+    return out
 
 
 def SLS_H2(P: Plant, S, I=None, return_info=False):

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sls_local_problem": (C.c_int, [C.c_void_p, C.c_int64, f64p, f64p, u8p, u8p]),
     "sls_solve": (C.c_int, [C.c_void_p, i64pp, i64pp, f64pp, i64pp, i64pp, f64pp, i32p, f64p]),
     "sls_solve_device": (C.c_int, [C.c_void_p]),
+    "sls_set_weights": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, f64p, f64p]),
     "sls_synthesize": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(i64p), C.POINTER(i64p), C.POINTER(u8p),
                                  C.POINTER(i64p), C.POINTER(i64p), C.POINTER(u8p), C.c_int64, C.c_int64, i64p, i64p,
                                  C.POINTER(i64p), C.POINTER(i64p), C.POINTER(f64p),

@@ -141,6 +141,9 @@ struct sls_handle {
     std::vector<PipeCtx*> pipe;
     DevBuf pipe_colptr;
     PinVec<int32_t> pipe_status; PinVec<double> pipe_resid;
+    bool have_weights = false;          // diagonal cost weights (sls_set_weights)
+    std::vector<double> h_wx, h_wu;
+    DevBuf d_wx, d_wu;
     std::vector<int32_t> h_Akmax, h_Akmin;   // largest / smallest row index (0-based) stored in each column of A
 };
 
@@ -204,6 +207,7 @@ extern "C" void sls_destroy(sls_handle* h) {
     for (PipeCtx* x : h->pipe) { x->release(); delete x; }
     h->pipe.clear();
     h->pipe_colptr.release(); h->pipe_status.release(); h->pipe_resid.release();
+    h->d_wx.release(); h->d_wu.release();
     for (int i = 0; i < SLS_PIPE_MAX; i++) h->pipe_in[i].destroy();
     h->pipe_done.destroy();
     rt::stream_destroy(h->in_stream);
@@ -283,6 +287,17 @@ extern "C" int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
     if (m) return fail(h, -2, (std::string("sls_set_plant: B2: ") + m).c_str());
     SLS_ARG(A_nzval || A_colptr[Nx] == 1, "sls_set_plant: A nzval is NULL");
     SLS_ARG(B2_nzval || B2_colptr[Nu] == 1, "sls_set_plant: B2 nzval is NULL");
+    std::vector<double> As, Bs;                                // similarity-scaled values when cost weights are set
+    if (h->have_weights) {
+        if ((int64_t)h->h_wx.size() != Nx || (int64_t)h->h_wu.size() != Nu)
+            return fail(h, -1, "sls_set_plant: the cost weights were set for other dimensions (call sls_set_weights again)");
+        As.resize(A_colptr[Nx] - 1); Bs.resize(B2_colptr[Nu] - 1);
+        for (int64_t c = 0; c < Nx; c++)
+            for (int64_t e = A_colptr[c] - 1; e < A_colptr[c + 1] - 1; e++) As[e] = A_nzval[e] * h->h_wx[A_rowval[e] - 1] / h->h_wx[c];
+        for (int64_t c = 0; c < Nu; c++)
+            for (int64_t e = B2_colptr[c] - 1; e < B2_colptr[c + 1] - 1; e++) Bs[e] = B2_nzval[e] * h->h_wx[B2_rowval[e] - 1] / h->h_wu[c];
+        A_nzval = As.data(); B2_nzval = Bs.data();
+    }
     h->ev[0].record(h->stream);
     SLS_CK(upload_csc(h, h->A, Nx, A_colptr, A_rowval, A_nzval));
     SLS_CK(upload_csc(h, h->B2, Nu, B2_colptr, B2_rowval, B2_nzval));
@@ -306,6 +321,26 @@ extern "C" int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
     }
     if (h->have_supports && (h->Nx != Nx || h->Nu != Nu)) { h->have_supports = false; }
     h->Nx = Nx; h->Nu = Nu; h->have_plant = true; h->plan.valid = false; h->solved = false;
+    return 0;
+}
+
+// Diagonal cost weights: cost = sum_t ||wx .* x_t||^2 + ||wu .* u_t||^2, i.e. C1 = [diag(wx); 0], D12 = [0; diag(wu)]
+// (GeneralizedPlant.jl:101-103; synthesis.jl:50,76-77).  Handled by similarity scaling (sls_scatter.cu: sls_unscale_kernel).
+extern "C" int sls_set_weights(sls_handle* h, int64_t Nx, int64_t Nu, const double* wx, const double* wu) {
+    if (!h) return -1;
+    SLS_CK(rt::set_device(h->device));
+    h->have_plant = false; h->plan.valid = false; h->solved = false;   // the plant values on the device depend on the weights
+    if (!wx && !wu) { h->have_weights = false; return 0; }
+    SLS_ARG(Nx >= 1 && Nu >= 0, "sls_set_weights: bad dimensions");
+    h->h_wx.assign(Nx, 1.0); h->h_wu.assign(std::max<int64_t>(Nu, 1), 1.0);
+    if (wx) for (int64_t i = 0; i < Nx; i++) { if (!(wx[i] > 0) || !std::isfinite(wx[i])) return fail(h, -3, "sls_set_weights: weights must be positive and finite"); h->h_wx[i] = wx[i]; }
+    if (wu) for (int64_t i = 0; i < Nu; i++) { if (!(wu[i] > 0) || !std::isfinite(wu[i])) return fail(h, -3, "sls_set_weights: weights must be positive and finite"); h->h_wu[i] = wu[i]; }
+    h->h_wu.resize(Nu);
+    SLS_CK(h->d_wx.ensure(Nx * sizeof(double))); SLS_CK(h->d_wu.ensure(std::max<int64_t>(Nu, 1) * sizeof(double)));
+    SLS_CK(rt::h2d(h->d_wx.p, h->h_wx.data(), Nx * sizeof(double), h->stream));
+    SLS_CK(rt::h2d(h->d_wu.p, h->h_wu.data(), Nu * sizeof(double), h->stream));
+    SLS_CK(rt::sync(h->stream));
+    h->have_weights = true;
     return 0;
 }
 
@@ -826,6 +861,11 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
             SLS_CK(sls_launch_solve(c.N, a, h->sm_count, h->max_smem, &warps, h->stream));
             launches++;
         }
+        if (h->have_weights) {                                  // back-scaling needs kernel 3's rowval as well
+            SLS_CK(rt::stream_wait(h->stream, h->chunk_ev[15]));
+            SLS_CK(sls_launch_unscale(v, cb[ch], cb[ch + 1], reinterpret_cast<const int64_t* const*>(h->out_ptrs.as<void*>()),
+                                      reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T), h->d_wx.as<double>(), h->d_wu.as<double>(), h->stream));
+        }
         if (ho) {
             h->chunk_ev[ch].record(h->stream);
             SLS_CK(rt::stream_wait(h->copy_stream, h->chunk_ev[ch]));
@@ -1121,6 +1161,11 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
             launches++;
         }
         if (e) break;
+        if (h->have_weights) {
+            PIPE_CK(rt::stream_wait(h->stream, x.ev_scat));
+            PIPE_CK(sls_launch_unscale(v, 0, p.ncols, reinterpret_cast<const int64_t* const*>(x.out_ptrs.as<void*>()),
+                                       reinterpret_cast<double* const*>(x.out_ptrs.as<void*>() + 2 * T), h->d_wx.as<double>(), h->d_wu.as<double>(), h->stream));
+        }
         x.ev_solved.record(h->stream);
         // device -> host, in the order the data becomes final: colptr, rowval, then nzval / status / residual
         PIPE_CK(rt::stream_wait(h->copy_stream, x.ev_plan));
@@ -1201,6 +1246,7 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     const int64_t Nx = h->Nx, Nu = h->Nu, T = h->T;
     for (int64_t s = 0; s < nscen; s++)
         if (dist_col[s] < 1 || dist_col[s] > Nx || dist_time[s] < 1) return fail(h, -3, "sls_simulate: scenario out of range");
+    if (h->have_weights) return fail(h, -1, "sls_simulate: not available with cost weights (the plant on the device is the scaled one)");
     if (nscen == 0) return 0;
     const Plan& p = h->plan;
     DevBuf dcol, dtime, dnw, dnu, dxn, dun, dxo, duo, dovf, dW, dWu, dnent, dtapcnt, dpkoff, dpkcnt, dpkrow, dpkval;

@@ -120,3 +120,31 @@ int sls_kgather64(int64_t* dst, const int64_t* src, size_t pitch, int count, sls
     SLS_LAUNCH(kp, (count + 127) / 128, 128, 0, stream, dst, src, pitch, count);
     return rt::last_error();
 }
+
+// Diagonal cost weights (sls_set_weights): the weighted problem  min sum (wx.x)^2 + (wu.u)^2  is the unweighted one for
+// the similarity-scaled plant  A^ = Wx A Wx^-1,  B2^ = Wx B2 Wu^-1  (uploaded by sls_set_plant) with
+//     Phi_x[t][i,j] = (wx_j / wx_i) Phi^_x[t][i,j],     Phi_u[t][l,j] = (wx_j / wu_l) Phi^_u[t][l,j].
+// This pass applies the back-scaling to the stored values of the planned columns [c_begin, c_end): one warp per column.
+__global__ void __launch_bounds__(256)
+sls_unscale_kernel(SlsPlanView P, int c_begin, int c_end, const int64_t* const* rowval, double* const* nzval,
+                   const double* wx, const double* wu) {
+    const int c = c_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= c_end) return;
+    const int lane = sls_lane();
+    const int64_t j = P.cols[c];
+    const double wj = wx[j];
+    for (int tt = 0; tt < 2 * P.T; tt++) {
+        const int64_t* cp = P.colptr + (int64_t)tt * (P.Nx + 1);
+        const int64_t e0 = cp[j] - 1, e1 = cp[j + 1] - 1;
+        const int64_t* rv = rowval[tt]; double* nz = nzval[tt];
+        const double* w = (tt < P.T) ? wx : wu;
+        for (int64_t e = e0 + lane; e < e1; e += 32) nz[e] *= wj / w[rv[e] - 1];
+    }
+}
+int sls_launch_unscale(const SlsPlanView& P, int c_begin, int c_end, const int64_t* const* rowval, double* const* nzval,
+                       const double* wx, const double* wu, sls_stream_t stream) {
+    if (c_end <= c_begin) return 0;
+    auto kp = &sls_unscale_kernel;
+    SLS_LAUNCH(kp, (c_end - c_begin + 7) / 8, 256, 0, stream, P, c_begin, c_end, rowval, nzval, wx, wu);
+    return rt::last_error();
+}

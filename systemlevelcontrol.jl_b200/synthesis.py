@@ -59,16 +59,15 @@ def _as_julia(M, dtype):
 
 class Plant:
     """`Plant(A, B₁, B₂)`: state-feedback generalized plant with the LQR-style defaults of the
-    3-argument constructor — C₁ = [I;0], D₁₂ = [0;I], D₁₁ = 0, C₂ = I (GeneralizedPlant.jl:105-110).
+    3-argument constructor — C₁ = [I;0], D₁₂ = [0;I], D₁₁ = 0, C₂ = I (GeneralizedPlant.jl:105-110) — or the
+    6-argument `Plant(A, B₁, B₂, C₁, D₁₁, D₁₂)` (GeneralizedPlant.jl:101-103; D₁₁ = 0 gives zeros of the right size).
     Dimension checks follow validate_GeneralizedPlant (GeneralizedPlant.jl:291-311): a mismatch raises
     ValueError (the reference throws ErrorException)."""
 
-    def __init__(self, A, B1, B2):
+    def __init__(self, A, B1, B2, C1=None, D11=None, D12=None):
         self.A = sp.csc_matrix(A, dtype=np.float64)
         self.B1 = sp.csc_matrix(B1, dtype=np.float64)
         self.B2 = sp.csc_matrix(B2, dtype=np.float64)
-        for M in (self.A, self.B1, self.B2):
-            M.sort_indices()
         if self.A.shape[0] != self.A.shape[1]:
             raise ValueError("A must be a square matrix")
         if self.B1.shape[0] != self.A.shape[0] or self.B2.shape[0] != self.A.shape[0]:
@@ -76,14 +75,82 @@ class Plant:
         self.Nx = self.A.shape[0]
         self.Nw = self.B1.shape[1]
         self.Nu = self.B2.shape[1]
-        self.Nz = self.Nx + self.Nu
+        if (C1 is None) != (D12 is None):
+            raise ValueError("C1 and D12 must be given together")
+        if C1 is None:
+            CD = sp.identity(self.Nx + self.Nu, format="csc", dtype=np.float64)
+            C1, D12 = CD[:, :self.Nx], CD[:, self.Nx:]
+        self.C1 = sp.csc_matrix(C1, dtype=np.float64)
+        self.D12 = sp.csc_matrix(D12, dtype=np.float64)
+        self.Nz = self.C1.shape[0]
+        if self.C1.shape[1] != self.Nx or self.D12.shape != (self.Nz, self.Nu):
+            raise ValueError("C1 must be Nz x Nx and D12 must be Nz x Nu")
+        if D11 is None or (np.isscalar(D11) and D11 == 0):
+            self.D11 = sp.csc_matrix((self.Nz, self.Nw), dtype=np.float64)
+        else:
+            self.D11 = sp.csc_matrix(D11, dtype=np.float64)
+            if self.D11.shape != (self.Nz, self.Nw):
+                raise ValueError("D11 must be Nz x Nw")
+        for M in (self.A, self.B1, self.B2, self.C1, self.D11, self.D12):
+            M.sort_indices()
         self.Ny = self.Nx
         self.feedback = "StateFeedback"
+
+    def diagonal_cost(self):
+        """(wx, wu, why): the diagonal weights when [C₁ D₁₂] = blockdiag(diag(wx), diag(wu)) with positive entries,
+        D₁₁ = 0 and B₁ is diagonal with a nonzero diagonal — the cost family libslsb200 solves (sls_set_weights);
+        wx = wu = None for the identity.  Otherwise (None, None, reason)."""
+        Nx, Nu = self.Nx, self.Nu
+        if self.B1.shape != (Nx, Nx):
+            return None, None, "B1 is not square (Nw != Nx)"
+        B1 = self.B1.tocoo()
+        if (B1.row != B1.col).any() and abs(B1.data[B1.row != B1.col]).max() > 0:
+            return None, None, "B1 is not diagonal: R = B1~[ii_x,:] couples the columns of a group in the cost"
+        if (self.B1.diagonal() == 0).any():
+            return None, None, "B1 has a zero on its diagonal: the cost of that column vanishes"
+        if self.D11.nnz and abs(self.D11.data).max() > 0:
+            return None, None, "D11 != 0 adds a linear term to the cost"
+        if self.Nz != Nx + Nu:
+            return None, None, "Nz != Nx + Nu"
+        wx = self.C1[:Nx, :].diagonal(); wu = self.D12[Nx:, :].diagonal()
+        Cd = sp.vstack([sp.diags(wx), sp.csc_matrix((Nu, Nx))]).tocsc()
+        Dd = sp.vstack([sp.csc_matrix((Nx, Nu)), sp.diags(wu)]).tocsc()
+        if abs(self.C1 - Cd).nnz and abs(self.C1 - Cd).max() > 0 or abs(self.D12 - Dd).nnz and abs(self.D12 - Dd).max() > 0:
+            return None, None, "[C1 D12] is not diagonal"
+        if (wx <= 0).any() or (wu <= 0).any():
+            return None, None, "a diagonal cost weight is not positive"
+        if (wx == 1).all() and (wu == 1).all():
+            return None, None, None
+        return np.ascontiguousarray(wx, dtype=np.float64), np.ascontiguousarray(wu, dtype=np.float64), None
 
     def _b1_is_identity(self):
         if self.B1.shape != (self.Nx, self.Nx):
             return False
         return (abs(self.B1 - sp.identity(self.Nx, format="csc")).nnz == 0)
+
+
+def _groups_decouple(P, Sx, Su, groups):
+    """A column group cⱼ with q > 1 shares sₓ = the union of its columns' index sets (reduction.jl:14), so every column
+    gets the union's constraint rows.  With a diagonal B₁ the cost is separable, and the group problem equals the
+    single-column problems exactly when the extra rows are empty for every member column j: everything A and B₂ reach
+    from column j's own supports already lies inside j's own sₓ.  Checked here on the patterns (host, integer work)."""
+    pA = (P.A != 0).astype(np.int64).tocsc()
+    pB = (P.B2 != 0).astype(np.int64).tocsc()
+    own = ((sp.csc_matrix(Sx[-1]) != 0).astype(np.int64) @ pA).tocsc()       # column j: its own s_x
+    reach = None
+    for M, pat in ((Sx, pA), (Su, pB)):
+        for St in M:
+            Rm = (pat @ (sp.csc_matrix(St) != 0).astype(np.int64)).tocsc()
+            reach = Rm if reach is None else reach + Rm
+    reach = reach.tocsc()
+    for g in groups:
+        if len(g) < 2:
+            continue
+        for j in g:
+            rows = reach.indices[reach.indptr[j]:reach.indptr[j + 1]]
+            if not np.isin(rows, own.indices[own.indptr[j]:own.indptr[j + 1]]).all():
+                return False
+    return True
 
 
 class Synthesizer:
@@ -116,6 +183,12 @@ class Synthesizer:
         self.api.check(self.h, rc)
 
     # -- inputs ---------------------------------------------------------------------------------
+    def set_weights(self, wx, wu, Nx, Nu):
+        """Diagonal cost weights (sls_set_weights); call before set_plant.  (None, None) clears them."""
+        wx = None if wx is None else np.ascontiguousarray(wx, dtype=np.float64)
+        wu = None if wu is None else np.ascontiguousarray(wu, dtype=np.float64)
+        self._ck(self.api.sls_set_weights(self.h, Nx, Nu, ptr(wx, f64p), ptr(wu, f64p)))
+
     def set_plant(self, A, B2):
         A = _as_julia(A, np.float64)
         B2 = _as_julia(B2, np.float64)
@@ -345,20 +418,26 @@ def SLS_H2(P, S, I=None, *, device: int = 0, return_info: bool = False, api=None
     Like the reference, a plant that is not state-feedback returns None (synthesis.jl:13 falls through)."""
     if not _check_plant(P):
         return None
-    if not P._b1_is_identity():
-        raise NotImplementedError("libslsb200 covers plants built as Plant(A, I, B2) (cost = squared Frobenius norm of Φ); "
-                                  "general B1 / C1 / D12 weights are SURVEY §8f-3")
+    wx, wu, why = P.diagonal_cost()
+    if why is not None:
+        raise NotImplementedError("libslsb200 covers diagonal cost weights [C1 D12] = blockdiag(diag(wx), diag(wu)) > 0 with "
+                                  f"D11 = 0 and a diagonal B1 (SURVEY §8f-3); this plant: {why}")
     Sx, Su = S
     cols = None
     if I is not None:
-        cols = []
-        for g in I:
-            g = np.atleast_1d(np.asarray(g))
-            if g.size != 1:
-                raise NotImplementedError("column groups with more than one column (q > 1) are SURVEY §8f-3")
-            cols.append(int(g[0]))
+        groups = [[int(c) for c in np.atleast_1d(np.asarray(g))] for g in I]
+        cols = [c for g in groups for c in g]
+        if any(len(g) != 1 for g in groups):
+            if len(set(cols)) != len(cols):
+                raise ValueError("a column appears in more than one group")
+            if not _groups_decouple(P, Sx, Su, groups):
+                raise NotImplementedError("a column group's union index set adds non-empty constraint rows to a member column "
+                                          "(supports not closed under the plant's pattern): coupled group problems are not "
+                                          "implemented (SURVEY §8f-3)")
     syn = Synthesizer(device=device, api=api)
     try:
+        if wx is not None:
+            syn.set_weights(wx, wu, P.Nx, P.Nu)
         syn.set_plant(P.A, P.B2)
         if cols is None and not return_info:
             out = syn.synthesize(Sx, Su)              # the default 𝓘 = 1..Nx: one pipelined call

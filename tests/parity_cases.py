@@ -271,3 +271,47 @@ def check_pipelined(api, plant, S, chunks, pass_nzval=True):
         else:
             os.environ["SLS_PIPE_CHUNKS"] = old
         syn.close()
+
+
+def check_weighted_cost(api, cols=(3, 14, 39)):
+    """6-argument Plant with diagonal [C1 D12] (+ a diagonal B1 and a q = 2 group) through SLS_H2 -> sls_set_weights,
+    against the oracle's general restatement of synthesis.jl:42-43,50,76-77."""
+    Nx, d, T = 40, 6, 20
+    A, B1, B2 = O.chain_plant(Nx)
+    S = O.make_supports(A, B2, d, T, 1.5)
+    rng = np.random.default_rng(0)
+    Nu = B2.shape[1]
+    wx, wu = rng.uniform(0.5, 2, Nx), rng.uniform(0.5, 2, Nu)
+    C1 = sp.vstack([sp.diags(wx), sp.csc_matrix((Nu, Nx))]).tocsc()
+    D12 = sp.vstack([sp.csc_matrix((Nx, Nu)), sp.diags(wu)]).tocsc()
+    B1d = sp.diags(np.linspace(0.5, 2, Nx)).tocsc()
+    cols = list(cols)
+    groups = [cols[:2], cols[2:]]
+    Ox, Ou = O.SLS_H2_general(O.Plant(A, B1d, B2, C1, 0, D12), S, I=groups)
+    Gx, Gu = slc_b200.SLS_H2(slc_b200.Plant(A, B1d, B2, C1, 0, D12), S, I=groups, api=api)
+    worst = 0.0
+    for G, H in zip(Gx + Gu, Ox + Ou):
+        assert np.array_equal(G.indptr, H.indptr) and np.array_equal(G.indices, H.indices)
+        nb = np.linalg.norm(H.data)
+        if nb > 0:
+            worst = max(worst, np.linalg.norm(G.data - H.data) / nb)
+    assert worst < PHI_RTOL, worst
+    # all columns, one-shot pipelined path with weights == three-call path with weights
+    syn = slc_b200.Synthesizer(api=api)
+    try:
+        syn.set_weights(wx, wu, Nx, Nu)
+        syn.set_plant(A, B2)
+        syn.set_supports(*S)
+        syn.plan(None)
+        ref = syn.solve()
+        out = syn.synthesize(*S)
+        for fam in ("x", "u"):
+            for t in range(T):
+                assert np.array_equal(out[fam]["nzval"][t], ref[fam]["nzval"][t])
+        # clearing the weights needs the plant again
+        syn.set_weights(None, None, Nx, Nu)
+        with pytest.raises(_capi.SlsError):
+            syn.set_supports(*S)
+    finally:
+        syn.close()
+    return worst

@@ -45,10 +45,49 @@ def test_non_state_feedback_returns_none_like_reference():
 
 
 def test_unsupported_shapes_raise():
+    """Cost shapes outside the diagonal family and coupled column groups are refused loudly."""
     A, B1, B2 = O.chain_plant(12)
-    P = Plant(A, 2.0 * B1, B2)
+    Nx, Nu = 12, B2.shape[1]
+    B1c = sp.csc_matrix(B1 + sp.diags([0.1 * np.ones(Nx - 1)], [1]))          # R = B1~[ii_x,:] would couple group columns
     with pytest.raises(NotImplementedError):
-        slc_b200.SLS_H2(P, [[], []])
+        slc_b200.SLS_H2(Plant(A, B1c, B2), [[], []])
+    C1 = sp.vstack([sp.identity(Nx) + sp.diags([0.1 * np.ones(Nx - 1)], [1]), sp.csc_matrix((Nu, Nx))])
+    D12 = sp.vstack([sp.csc_matrix((Nx, Nu)), sp.identity(Nu)])
+    with pytest.raises(NotImplementedError):
+        slc_b200.SLS_H2(Plant(A, B1, B2, C1, 0, D12), [[], []])
+    D11 = sp.csc_matrix(np.ones((Nx + Nu, Nx)))
+    with pytest.raises(NotImplementedError):
+        slc_b200.SLS_H2(Plant(A, B1, B2, sp.vstack([sp.identity(Nx), sp.csc_matrix((Nu, Nx))]), D11, D12), [[], []])
+    # supports not closed under the plant's pattern: a group's union adds non-empty rows to a member -> refused
     P = Plant(A, B1, B2)
+    wide = sp.csc_matrix(O._pat_power(O._pat(A), 3) != 0)
     with pytest.raises(NotImplementedError):
-        slc_b200.SLS_H2(P, [[sp.identity(12, format="csc")], [sp.csc_matrix((B2.shape[1], 12))]], I=[[0, 1]])
+        slc_b200.SLS_H2(P, [[wide, sp.identity(12, format="csc", dtype=bool)], [sp.csc_matrix((Nu, 12), dtype=bool)] * 2], I=[[0, 1]])
+
+
+def test_diagonal_cost_classification():
+    A, B1, B2 = O.chain_plant(12)
+    Nx, Nu = 12, B2.shape[1]
+    assert Plant(A, B1, B2).diagonal_cost() == (None, None, None)
+    assert Plant(A, 2.0 * B1, B2).diagonal_cost() == (None, None, None)       # diagonal B1: same minimiser
+    wx, wu = np.linspace(0.5, 2, Nx), np.linspace(1, 3, Nu)
+    C1 = sp.vstack([sp.diags(wx), sp.csc_matrix((Nu, Nx))]); D12 = sp.vstack([sp.csc_matrix((Nx, Nu)), sp.diags(wu)])
+    gx, gu, why = Plant(A, B1, B2, C1, 0, D12).diagonal_cost()
+    assert why is None and np.array_equal(gx, wx) and np.array_equal(gu, wu)
+    P6 = Plant(A, B1, B2, C1, 0, D12)
+    assert (P6.Nz, P6.D11.shape) == (Nx + Nu, (Nx + Nu, Nx))
+    with pytest.raises(ValueError):
+        Plant(A, B1, B2, C1, 0, sp.csc_matrix((Nx + Nu + 1, Nu)))
+
+
+def test_group_decoupling_check():
+    from slc_b200.synthesis import _groups_decouple
+    A, B1, B2, S = (*O.chain_plant(30), None)
+    S = O.make_supports(A, B2, 4, 10, 1.5)
+    P = Plant(A, B1, B2)
+    assert _groups_decouple(P, S[0], S[1], [[0, 1, 2], [10, 25]])             # README-style supports are closed
+    wide = sp.csc_matrix(O._pat_power(O._pat(A), 3) != 0)                     # a wide tap before a narrow last tap is not
+    Sx = [wide, sp.identity(30, format="csc", dtype=bool)]
+    Su = [sp.csc_matrix((B2.shape[1], 30), dtype=bool)] * 2
+    assert not _groups_decouple(P, Sx, Su, [[3, 4]])
+    assert _groups_decouple(P, Sx, Su, [[3], [4]])                            # single-column groups never couple

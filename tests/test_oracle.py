@@ -87,3 +87,42 @@ def test_grid_infeasible_actuation_is_detected():
     S = O.make_supports(A, B2, 3, 10, 1.5)
     _, _, infos = O.SLS_H2(P, S, I=[40, 41], return_info=True)
     assert infos[40]["residual"] < 1e-12 and infos[41]["residual"] > 1e-3
+
+
+def _weighted_case():
+    Nx, d, T = 40, 6, 20
+    A, B1, B2 = O.chain_plant(Nx)
+    S = O.make_supports(A, B2, d, T, 1.5)
+    rng = np.random.default_rng(0)
+    wx, wu = rng.uniform(0.5, 2, Nx), rng.uniform(0.5, 2, B2.shape[1])
+    Nu = B2.shape[1]
+    C1 = sp.vstack([sp.diags(wx), sp.csc_matrix((Nu, Nx))]).tocsc()
+    D12 = sp.vstack([sp.csc_matrix((Nx, Nu)), sp.diags(wu)]).tocsc()
+    return A, B1, B2, S, wx, wu, C1, D12
+
+
+def test_general_cost_oracle_reduces_to_the_default():
+    """synthesis.jl:42-43,50,76-77 restated in full (L = [C1~ D12~], R = B1~[ii_x,:], D = D11~, groups) equals the
+    min-norm oracle for the 3-argument Plant, for single columns and for a q = 2 group (separable cost)."""
+    A, B1, B2, S, *_ = _weighted_case()
+    P = O.Plant(A, B1, B2)
+    Px, Pu = O.SLS_H2(P, S, I=[3, 14, 39])
+    for groups in ([[3], [14], [39]], [[3, 14], [39]]):
+        Gx, Gu = O.SLS_H2_general(P, S, I=groups)
+        assert max(abs(a - b).max() for a, b in zip(Px + Pu, Gx + Gu)) < 1e-10
+
+
+def test_diagonal_weights_are_a_similarity_scaling():
+    """The identity libslsb200's weighted path rests on: the weighted minimiser is Wx^-1 Phi^ Wx / Wu^-1 Phi^ Wx of the
+    unweighted problem for (Wx A Wx^-1, Wx B2 Wu^-1); a diagonal B1 does not change it."""
+    A, B1, B2, S, wx, wu, C1, D12 = _weighted_case()
+    cols = [3, 14, 39]
+    Wx, Wu = O.SLS_H2_general(O.Plant(A, B1, B2, C1, 0, D12), S, I=[[c] for c in cols])
+    Ah = (sp.diags(wx) @ A @ sp.diags(1 / wx)).tocsc(); Bh = (sp.diags(wx) @ B2 @ sp.diags(1 / wu)).tocsc()
+    Sx_, Su_ = O.SLS_H2(O.Plant(Ah, B1, Bh), S, I=cols)
+    for t in range(len(S[0])):
+        assert abs(np.diag(1 / wx) @ Sx_[t].toarray() @ np.diag(wx) - Wx[t].toarray()).max() < 1e-10
+        assert abs(np.diag(1 / wu) @ Su_[t].toarray() @ np.diag(wx) - Wu[t].toarray()).max() < 1e-10
+    B1d = sp.diags(np.linspace(0.5, 2, 40)).tocsc()
+    Gx, Gu = O.SLS_H2_general(O.Plant(A, B1d, B2, C1, 0, D12), S, I=[[3, 14], [39]])
+    assert max(abs(a - b).max() for a, b in zip(Gx + Gu, Wx + Wu)) < 1e-10

@@ -265,3 +265,8 @@ def test_pipelined_one_shot_config3_100k_bit_for_bit(cuda_api):
                 assert np.array_equal(np.concatenate([h0[fam]["rowval"][t], h1[fam]["rowval"][t]]), ref[fam]["rowval"][t])
     finally:
         syn.close()
+
+
+def test_weighted_cost_and_column_groups_vs_general_oracle(cuda_api):
+    """6-argument Plant with diagonal cost weights, diagonal B1, q = 2 group."""
+    assert pc.check_weighted_cost(cuda_api, cols=(3, 14, 39, 0, 20, 27)) < 1e-10
