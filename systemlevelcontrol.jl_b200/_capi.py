@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libslsb200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 5
 STATUS_OK, STATUS_RESIDUAL, STATUS_RANK_SKIPPED, STATUS_NO_IMPULSE = 0, 1, 2, 4
 
 i64p = C.POINTER(C.c_int64)
