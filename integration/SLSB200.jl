@@ -78,6 +78,54 @@ function synthesize(A::SparseMatrixCSC{Float64,Int64}, B₂::SparseMatrixCSC{Flo
     end
 end
 
+"""
+    synthesize_pipelined(A, B₂, 𝓢ₓ, 𝓢ᵤ; first_col=1, ncols=0, wx=nothing, wu=nothing, device=0)
+
+One call for the default 𝓘 = 1:Nx (or a contiguous shard `first_col : first_col+ncols-1`): `sls_synthesize` overlaps the
+host→device copy of the supports, kernels 1-3 and the device→host copy of Φ column chunk by column chunk.  Because the
+stored pattern of Φ[t] is a subset of 𝓢[t]'s, outputs are allocated at nnz(𝓢[t]) and `resize!`d to the returned counts.
+`wx`/`wu` are optional diagonal cost weights (`C₁ = [Diagonal(wx); 0]`, `D₁₂ = [0; Diagonal(wu)]`, sls_set_weights).
+"""
+function synthesize_pipelined(A::SparseMatrixCSC{Float64,Int64}, B₂::SparseMatrixCSC{Float64,Int64},
+                              𝓢ₓ::Vector{SparseMatrixCSC{Bool,Int64}}, 𝓢ᵤ::Vector{SparseMatrixCSC{Bool,Int64}};
+                              first_col::Integer=1, ncols::Integer=0, wx=nothing, wu=nothing, device::Integer=0)
+    Nx, Nu, T = size(A, 1), size(B₂, 2), length(𝓢ₓ)
+    nc = ncols <= 0 ? Nx : ncols
+    h = Handle(device=device)
+    GC.@preserve A B₂ 𝓢ₓ 𝓢ᵤ wx wu begin
+        if wx !== nothing || wu !== nothing
+            check(h.ptr, ccall((:sls_set_weights, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
+                  h.ptr, Nx, Nu, wx === nothing ? C_NULL : wx, wu === nothing ? C_NULL : wu))
+        end
+        check(h.ptr, ccall((:sls_set_plant, LIB), Cint,
+              (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+              h.ptr, Nx, Nu, A.colptr, A.rowval, A.nzval, B₂.colptr, B₂.rowval, B₂.nzval))
+        ptrs(f, S) = [pointer(f(M)) for M in S]
+        xcp, xrv, xnz = ptrs(M -> M.colptr, 𝓢ₓ), ptrs(M -> M.rowval, 𝓢ₓ), [Ptr{UInt8}(pointer(M.nzval)) for M in 𝓢ₓ]
+        ucp, urv, unz = ptrs(M -> M.colptr, 𝓢ᵤ), ptrs(M -> M.rowval, 𝓢ᵤ), [Ptr{UInt8}(pointer(M.nzval)) for M in 𝓢ᵤ]
+        capx, capu = Int64[nnz(M) for M in 𝓢ₓ], Int64[nnz(M) for M in 𝓢ᵤ]
+        mk(cap, nrow) = [SparseMatrixCSC{Float64,Int64}(nrow, Nx, ones(Int64, Nx + 1), Vector{Int64}(undef, cap[t]), Vector{Float64}(undef, cap[t])) for t in 1:T]
+        Φₓ, Φᵤ = mk(capx, Nx), mk(capu, Nu)
+        nnzx, nnzu = zeros(Int64, T), zeros(Int64, T)
+        status, resid = zeros(Int32, nc), zeros(Float64, nc)
+        GC.@preserve Φₓ Φᵤ begin
+            check(h.ptr, ccall((:sls_synthesize, LIB), Cint,
+                  (Ptr{Cvoid}, Int64, Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{UInt8}}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{UInt8}},
+                   Int64, Int64, Ptr{Int64}, Ptr{Int64},
+                   Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{Float64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{Float64}},
+                   Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}),
+                  h.ptr, T, xcp, xrv, xnz, ucp, urv, unz, first_col, ncols, capx, capu,
+                  ptrs(M -> M.colptr, Φₓ), ptrs(M -> M.rowval, Φₓ), ptrs(M -> M.nzval, Φₓ),
+                  ptrs(M -> M.colptr, Φᵤ), ptrs(M -> M.rowval, Φᵤ), ptrs(M -> M.nzval, Φᵤ), nnzx, nnzu, status, resid))
+        end
+        for t in 1:T
+            resize!(Φₓ[t].rowval, nnzx[t]); resize!(Φₓ[t].nzval, nnzx[t])
+            resize!(Φᵤ[t].rowval, nnzu[t]); resize!(Φᵤ[t].nzval, nnzu[t])
+        end
+        return Φₓ, Φᵤ, status, resid
+    end
+end
+
 end # module
 
 # --- drop-in replacement of SLS_𝓗₂ in src/synthesis.jl (signature and return shape unchanged) -----------------
@@ -85,9 +133,11 @@ end # module
 #     if P isa GeneralizedPlant{T,StateFeedback} where {T}
 #         𝓘 = (𝓘 === nothing) ? [[i] for i in 1:P.Nx] : 𝓘;                      # :15
 #         𝓢ₓ,𝓢ᵤ = 𝓢;  T = length(𝓢ₓ)                                           # :19-20
-#         all(length(c) == 1 for c in 𝓘) || error("libslsb200: column groups must be single columns")
-#         cols = Int64[c[1] for c in 𝓘]
-#         Φₓ,Φᵤ,status,resid = SLSB200.synthesize(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ, cols)
+#         # q > 1 groups: with a diagonal B₁ the cost is separable and the group problem equals its columns' problems
+#         # when the supports are closed under the plant's pattern (checked on the host; see synthesis.py::_groups_decouple)
+#         cols = Int64[c for g in 𝓘 for c in g]
+#         Φₓ,Φᵤ,status,resid = (𝓘 === nothing) ? SLSB200.synthesize_pipelined(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ) :
+#                                                  SLSB200.synthesize(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ, cols)
 #         # optional: dropzeros!.(Φₓ); dropzeros!.(Φᵤ) reproduces the zero-dropping of `Φ̃ += …` (:67)
 #         Φ = [Φₓ Φᵤ]                                                           # T×2 Matrix{SparseMatrixCSC}
 #         return eachcol(Φ)                                                      # :27

@@ -500,13 +500,52 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
         for (int rr = 0; rr < RPL; rr++) { const int i = lane + 32 * rr; if (i < N) xnext[i] = 0.0; }
         double resmax = 0.0;
+        // History double buffer (size classes up to N = 32): -Z_{k-1} and yh_{k-1} of the NEXT tap are loaded into
+        // registers one full iteration ahead (the matrix registers of the forward pass are dead here), so the L2/HBM
+        // latency of the history hides behind a whole tap instead of heading its serial chain.
+        constexpr bool PRELOAD = (NB <= 4);
+        constexpr int NZB = PRELOAD ? NB * (NB + 1) / 2 : 1;
+        double zn[NZB][2], yn[RPL];
+        auto load_hist = [&](int kk, double (&z)[NZB][2], double (&yv)[RPL]) {
+            const double* hk = zhist + (size_t)kk * TRI;
+            int idx = 0;
+#pragma unroll
+            for (int bi = 0; bi < NB; bi++) {
+                const int r = 8 * bi + g;
+#pragma unroll
+                for (int bj = 0; bj <= bi; bj++) {
+                    const int c0 = 8 * bj + 2 * q;
+                    double z0 = 0.0, z1 = 0.0;
+                    if (kk >= 1) {
+                        if (bj < bi) {
+                            if (r < n) { z0 = hk[rowoff[bi] + c0]; z1 = hk[rowoff[bi] + c0 + 1]; }
+                        } else {
+                            if (r < n && c0 < n) z0 = (c0 <= r) ? hk[rowoff[bi] + c0] : hk[c0 * (c0 + 1) / 2 + r];
+                            if (r < n && c0 + 1 < n) z1 = (c0 + 1 <= r) ? hk[rowoff[bi] + c0 + 1] : hk[(c0 + 1) * (c0 + 2) / 2 + r];
+                        }
+                    }
+                    z[idx][0] = z0; z[idx][1] = z1; idx++;
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < RPL; rr++) { const int i = lane + 32 * rr; yv[rr] = (i < n) ? yhist[(size_t)kk * N + i] : 0.0; }
+        };
+        if (PRELOAD) load_hist(T - 1, zn, yn);
         for (int k = T; k >= 1; k--) {
             const mask_t mk = mxs[k - 1];
             const uint32_t* muk = mus + (size_t)(k - 1) * wu;
+            double zc[NZB][2], yc[RPL];
+            if (PRELOAD) {
+#pragma unroll
+                for (int i = 0; i < NZB; i++) { zc[i][0] = zn[i][0]; zc[i][1] = zn[i][1]; }
+#pragma unroll
+                for (int rr = 0; rr < RPL; rr++) yc[rr] = yn[rr];
+                if (k >= 2) load_hist(k - 2, zn, yn);
+            }
 #ifndef SLS_EMU
             // the next iteration's history (-Z_{k-2}, yh_{k-2}) is fetched towards L1 now: its loads sit at the head
             // of a serial chain and would otherwise pay L2/HBM latency every tap
-            if (k >= 3) {
+            if (!PRELOAD && k >= 3) {
                 const char* hz = reinterpret_cast<const char*>(zhist + (size_t)(k - 2) * TRI);
                 for (int o = lane * 128; o < (int)(n * (n + 1) / 2 * sizeof(double)); o += 32 * 128)
                     asm volatile("prefetch.global.L1 [%0];" :: "l"(hz + o));
@@ -539,7 +578,8 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
             for (int rr = 0; rr < RPL; rr++) {
                 const int i = lane + 32 * rr;
-                if (i < N) rhs_s[i] = (i < n) ? (yhist[(size_t)(k - 1) * N + i] + (sls_mbit(mk, i) ? tx[i] : 0.0)) : 0.0;
+                const double yprev_k = PRELOAD ? yc[rr] : ((i < n) ? yhist[(size_t)(k - 1) * N + i] : 0.0);
+                if (i < N) rhs_s[i] = (i < n) ? (yprev_k + (sls_mbit(mk, i) ? tx[i] : 0.0)) : 0.0;
             }
             __syncwarp();
             // lambda_{k-1} = Z_{k-1} rhs  (history read back in accumulator layout; symmetric mat-vec) -> gbuf
@@ -554,6 +594,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 double racc[NB], cacc[NB][2];
 #pragma unroll
                 for (int b = 0; b < NB; b++) { racc[b] = 0.0; cacc[b][0] = 0.0; cacc[b][1] = 0.0; }
+                int zi = 0;
 #pragma unroll
                 for (int bi = 0; bi < NB; bi++) {
                     const int r = 8 * bi + g;
@@ -563,14 +604,18 @@ sls_solve_kernel(SlsSolveArgs a) {
                         const int c0 = 8 * bj + 2 * q;
                         const double2 vc = *reinterpret_cast<const double2*>(rhs_s + c0);
                         double z0 = 0.0, z1 = 0.0;
-                        if (bj < bi) {
+                        if (PRELOAD) {
+                            z0 = zc[PRELOAD ? zi : 0][0]; z1 = zc[PRELOAD ? zi : 0][1]; zi++;
+                        } else if (bj < bi) {
                             if (r < n) { z0 = hk[rowoff[bi] + c0]; z1 = hk[rowoff[bi] + c0 + 1]; }
-                            cacc[bj][0] = fma(z0, vr, cacc[bj][0]);
-                            cacc[bj][1] = fma(z1, vr, cacc[bj][1]);
                         } else {
                             // diagonal block: full 8x8 from the packed lower triangle by symmetric addressing
                             if (r < n && c0 < n) z0 = (c0 <= r) ? hk[rowoff[bi] + c0] : hk[c0 * (c0 + 1) / 2 + r];
                             if (r < n && c0 + 1 < n) z1 = (c0 + 1 <= r) ? hk[rowoff[bi] + c0 + 1] : hk[(c0 + 1) * (c0 + 2) / 2 + r];
+                        }
+                        if (bj < bi) {
+                            cacc[bj][0] = fma(z0, vr, cacc[bj][0]);
+                            cacc[bj][1] = fma(z1, vr, cacc[bj][1]);
                         }
                         racc[bi] = fma(z0, vc.x, racc[bi]);
                         racc[bi] = fma(z1, vc.y, racc[bi]);
