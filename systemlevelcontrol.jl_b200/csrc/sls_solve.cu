@@ -506,8 +506,10 @@ sls_solve_kernel(SlsSolveArgs a) {
         constexpr bool PRELOAD = (NB <= 4);
         constexpr int NZB = PRELOAD ? NB * (NB + 1) / 2 : 1;
         double zn[NZB][2], yn[RPL];
-        auto load_hist = [&](int kk, double (&z)[NZB][2], double (&yv)[RPL]) {
-            const double* hk = zhist + (size_t)kk * TRI;
+        // element offsets of the lane's accumulator-layout entries inside a tap's packed lower triangle (-1: none);
+        // the diagonal blocks are completed by symmetric addressing.  Computed once per column.
+        int zoff[NZB][2];
+        if (PRELOAD) {
             int idx = 0;
 #pragma unroll
             for (int bi = 0; bi < NB; bi++) {
@@ -515,17 +517,23 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
                 for (int bj = 0; bj <= bi; bj++) {
                     const int c0 = 8 * bj + 2 * q;
-                    double z0 = 0.0, z1 = 0.0;
-                    if (kk >= 1) {
-                        if (bj < bi) {
-                            if (r < n) { z0 = hk[rowoff[bi] + c0]; z1 = hk[rowoff[bi] + c0 + 1]; }
-                        } else {
-                            if (r < n && c0 < n) z0 = (c0 <= r) ? hk[rowoff[bi] + c0] : hk[c0 * (c0 + 1) / 2 + r];
-                            if (r < n && c0 + 1 < n) z1 = (c0 + 1 <= r) ? hk[rowoff[bi] + c0 + 1] : hk[(c0 + 1) * (c0 + 2) / 2 + r];
-                        }
+                    int o0 = -1, o1 = -1;
+                    if (bj < bi) {
+                        if (r < n) { o0 = rowoff[bi] + c0; o1 = o0 + 1; }
+                    } else {
+                        if (r < n && c0 < n) o0 = (c0 <= r) ? rowoff[bi] + c0 : c0 * (c0 + 1) / 2 + r;
+                        if (r < n && c0 + 1 < n) o1 = (c0 + 1 <= r) ? rowoff[bi] + c0 + 1 : (c0 + 1) * (c0 + 2) / 2 + r;
                     }
-                    z[idx][0] = z0; z[idx][1] = z1; idx++;
+                    zoff[PRELOAD ? idx : 0][0] = o0; zoff[PRELOAD ? idx : 0][1] = o1; idx++;
                 }
+            }
+        }
+        auto load_hist = [&](int kk, double (&z)[NZB][2], double (&yv)[RPL]) {
+            const double* hk = zhist + (size_t)kk * TRI;
+#pragma unroll
+            for (int i = 0; i < NZB; i++) {
+                z[i][0] = (kk >= 1 && zoff[i][0] >= 0) ? hk[zoff[i][0]] : 0.0;
+                z[i][1] = (kk >= 1 && zoff[i][1] >= 0) ? hk[zoff[i][1]] : 0.0;
             }
 #pragma unroll
             for (int rr = 0; rr < RPL; rr++) { const int i = lane + 32 * rr; yv[rr] = (i < n) ? yhist[(size_t)kk * N + i] : 0.0; }
