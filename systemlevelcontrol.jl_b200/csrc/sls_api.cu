@@ -141,6 +141,7 @@ struct sls_handle {
     std::vector<PipeCtx*> pipe;
     DevBuf pipe_colptr;
     PinVec<int32_t> pipe_status; PinVec<double> pipe_resid;
+    PinVec<int64_t> t_cp[2], t_rv[2]; PinVec<double> t_nz[2]; std::vector<int64_t> t_fill;   // transposes of A, B2 (set_plant)
     bool have_weights = false;          // diagonal cost weights (sls_set_weights)
     std::vector<double> h_wx, h_wu;
     DevBuf d_wx, d_wu;
@@ -208,6 +209,7 @@ extern "C" void sls_destroy(sls_handle* h) {
     h->pipe.clear();
     h->pipe_colptr.release(); h->pipe_status.release(); h->pipe_resid.release();
     h->d_wx.release(); h->d_wu.release();
+    for (int i = 0; i < 2; i++) { h->t_cp[i].release(); h->t_rv[i].release(); h->t_nz[i].release(); }
     for (int i = 0; i < SLS_PIPE_MAX; i++) h->pipe_in[i].destroy();
     h->pipe_done.destroy();
     rt::stream_destroy(h->in_stream);
@@ -247,20 +249,23 @@ static const char* check_csc(int64_t nrow, int64_t ncol, const int64_t* cp, cons
 }
 
 // CSC of the transpose (== CSR of M), 1-based like the input
-static void transpose_csc(int64_t nrow, int64_t ncol, const int64_t* cp, const int64_t* rv, const double* nz,
-                          std::vector<int64_t>& tcp, std::vector<int64_t>& trv, std::vector<double>& tnz) {
+// (into pinned scratch owned by the handle: the upload that follows is then truly asynchronous and needs no
+// intermediate synchronisation; `fill` is reusable host scratch)
+static int transpose_csc(int64_t nrow, int64_t ncol, const int64_t* cp, const int64_t* rv, const double* nz,
+                         PinVec<int64_t>& tcp, PinVec<int64_t>& trv, PinVec<double>& tnz, std::vector<int64_t>& fill) {
     const int64_t nnz = cp[ncol] - 1;
-    tcp.assign(nrow + 1, 0); trv.resize(nnz); tnz.resize(nnz);
-    std::vector<int64_t> cnt(nrow, 0);
-    for (int64_t e = 0; e < nnz; e++) cnt[rv[e] - 1]++;
+    int e_ = tcp.resize(nrow + 1); if (!e_) e_ = trv.resize(std::max<int64_t>(nnz, 1)); if (!e_) e_ = tnz.resize(std::max<int64_t>(nnz, 1));
+    if (e_) return e_;
+    fill.assign(nrow + 1, 0);
+    for (int64_t e = 0; e < nnz; e++) fill[rv[e]]++;          // counts at index row (1-based) -> shifted prefix below
     tcp[0] = 1;
-    for (int64_t r = 0; r < nrow; r++) tcp[r + 1] = tcp[r] + cnt[r];
-    std::vector<int64_t> fill(tcp.begin(), tcp.end() - 1);
+    for (int64_t r = 0; r < nrow; r++) { tcp[r + 1] = tcp[r] + fill[r + 1]; fill[r] = tcp[r]; }
     for (int64_t c = 0; c < ncol; c++)
         for (int64_t e = cp[c] - 1; e < cp[c + 1] - 1; e++) {
             const int64_t dst = fill[rv[e] - 1]++ - 1;
             trv[dst] = c + 1; tnz[dst] = nz[e];
         }
+    return 0;
 }
 
 static int upload_csc(sls_handle* h, DevCsc& d, int64_t ncol, const int64_t* cp, const int64_t* rv, const double* nz) {
@@ -301,15 +306,11 @@ extern "C" int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
     h->ev[0].record(h->stream);
     SLS_CK(upload_csc(h, h->A, Nx, A_colptr, A_rowval, A_nzval));
     SLS_CK(upload_csc(h, h->B2, Nu, B2_colptr, B2_rowval, B2_nzval));
-    std::vector<int64_t> tcp, trv; std::vector<double> tnz;
-    transpose_csc(Nx, Nx, A_colptr, A_rowval, A_nzval, tcp, trv, tnz);
-    SLS_CK(upload_csc(h, h->Ar, Nx, tcp.data(), trv.data(), tnz.data()));
-    SLS_CK(rt::sync(h->stream));                              // tcp/trv/tnz are reused below
-    transpose_csc(Nx, Nu, B2_colptr, B2_rowval, B2_nzval, tcp, trv, tnz);
-    SLS_CK(upload_csc(h, h->B2r, Nx, tcp.data(), trv.data(), tnz.data()));
+    SLS_CK(transpose_csc(Nx, Nx, A_colptr, A_rowval, A_nzval, h->t_cp[0], h->t_rv[0], h->t_nz[0], h->t_fill));
+    SLS_CK(upload_csc(h, h->Ar, Nx, h->t_cp[0].data(), h->t_rv[0].data(), h->t_nz[0].data()));
+    SLS_CK(transpose_csc(Nx, Nu, B2_colptr, B2_rowval, B2_nzval, h->t_cp[1], h->t_rv[1], h->t_nz[1], h->t_fill));
+    SLS_CK(upload_csc(h, h->B2r, Nx, h->t_cp[1].data(), h->t_rv[1].data(), h->t_nz[1].data()));
     h->ev[1].record(h->stream);
-    SLS_CK(rt::sync(h->stream));
-    h->tm.h2d_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);
     int mc = 0;
     for (int64_t c = 0; c < Nx; c++) mc = std::max<int>(mc, (int)(A_colptr[c + 1] - A_colptr[c]));
     h->maxcolA = mc;
@@ -319,6 +320,8 @@ extern "C" int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
         h->h_Akmax[c] = any ? (int32_t)(A_rowval[A_colptr[c + 1] - 2] - 1) : (int32_t)c;
         h->h_Akmin[c] = any ? (int32_t)(A_rowval[A_colptr[c] - 1] - 1) : (int32_t)c;
     }
+    SLS_CK(rt::sync(h->stream));                              // As/Bs and the caller's arrays must outlive the copies
+    h->tm.h2d_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);
     if (h->have_supports && (h->Nx != Nx || h->Nu != Nu)) { h->have_supports = false; }
     h->Nx = Nx; h->Nu = Nu; h->have_plant = true; h->plan.valid = false; h->solved = false;
     return 0;
