@@ -88,6 +88,8 @@ struct Plan {
     std::vector<SolveClass> classes;
     int64_t tot_packed = 0;
     double alg_flops = 0, alg_bytes = 0;
+    bool stats_valid = false;           // alg_flops / alg_bytes are computed on demand (plan_stats)
+    int identity_cols = 0;              // h_cols currently holds 0..identity_cols-1 (the cols == NULL plan)
     void release() {
         DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists};
         for (DevBuf* b : all) b->release();
@@ -126,13 +128,14 @@ struct sls_handle {
     int64_t Nx = 0, Nu = 0, T = 0;
     bool have_plant = false, have_supports = false, solved = false;
     DevCsc A, B2, Ar, B2r;
-    int maxcolA = 0;
+    int maxcolA = 0, maxcolB2 = 0;
     DevSupports Sx, Su;
     Plan plan;
     DevBuf xw, hist, status, resid, out_rowval, out_nzval, out_ptrs;
     rt::Event ev[8];
     rt::Event marks[2];
     sls_timing tm{};
+    bool tm_from_plan = true;           // alg_flops / alg_bytes of tm come from h->plan (lazily) rather than from sls_synthesize
     // pipelined one-shot path
     sls_stream_t in_stream{}, scat_stream{}, out2_stream{};
     rt::Event pipe_done2;
@@ -314,6 +317,9 @@ extern "C" int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
     int mc = 0;
     for (int64_t c = 0; c < Nx; c++) mc = std::max<int>(mc, (int)(A_colptr[c + 1] - A_colptr[c]));
     h->maxcolA = mc;
+    mc = 0;
+    for (int64_t c = 0; c < Nu; c++) mc = std::max<int>(mc, (int)(B2_colptr[c + 1] - B2_colptr[c]));
+    h->maxcolB2 = mc;
     h->h_Akmax.assign(Nx, 0); h->h_Akmin.assign(Nx, 0);
     for (int64_t c = 0; c < Nx; c++) {
         const bool any = A_colptr[c + 1] > A_colptr[c];
@@ -558,8 +564,10 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     if (!cols) ncols = Nx;
     p.ncols = (int)ncols;
     SLS_CK(p.h_cols.resize(std::max<int64_t>(ncols, 1)));
-    if (!cols) { for (int64_t i = 0; i < ncols; i++) p.h_cols[i] = (int32_t)i; }
-    else {
+    if (!cols) {
+        if (p.identity_cols != ncols) { for (int64_t i = 0; i < ncols; i++) p.h_cols[i] = (int32_t)i; p.identity_cols = (int)ncols; }
+    } else {
+        p.identity_cols = 0;
         std::vector<uint8_t> seen(unique_cols ? Nx : 0, 0);
         for (int64_t i = 0; i < ncols; i++) {
             const int64_t j = cols[i] - 1;
@@ -569,7 +577,7 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
         }
     }
     p.cols_sorted = true;
-    for (int64_t i = 1; i < ncols; i++) if (p.h_cols[i] <= p.h_cols[i - 1]) { p.cols_sorted = false; break; }
+    if (cols) for (int64_t i = 1; i < ncols; i++) if (p.h_cols[i] <= p.h_cols[i - 1]) { p.cols_sorted = false; break; }
     // candidate-list capacity of kernel 1 (power of two, >= 32)
     int64_t cand = (int64_t)h->maxcolA * std::max(h->Sx.maxlen_last, h->Su.maxlen_last);
     int cap = 32; while (cap < cand) cap <<= 1;
@@ -657,19 +665,25 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     for (int64_t tt = 0; tt < 2 * T; tt++) { p.nnz_tap[tt] -= 1; p.out_off[tt + 1] = p.out_off[tt] + p.nnz_tap[tt]; }
     p.tot_packed = tot[p.ncols];
     if (p.tot_packed != p.out_off[2 * T]) return fail(h, -5, "plan: internal count mismatch");
-    // SURVEY §8d algorithmic work, and the size classes of kernel 2
-    p.alg_flops = 0; p.alg_bytes = 0;
-    for (int i = 0; i < p.ncols; i++) {
-        const double n = p.h_n[i], m = p.h_m[i], v_ = (double)(tot[i + 1] - tot[i]);
-        p.alg_flops += n * n * v_ + (7.0 / 3.0) * (double)T * n * n * n;
-        p.alg_bytes += v_ * 25.0 + 2.0 * T * 24.0 + 16.0 * ((double)lA[i] + n + (double)lB[i] + m);
-    }
-    for (SolveClass& c : p.classes) {
-        c.nnzcap = 0;
-        for (int k = 0; k < c.count; k++) c.nnzcap = std::max(c.nnzcap, p.h_lnnz[p.h_lists[c.list_off + k]]);
-    }
+    // local-nnz capacity of each size class of kernel 2: nnz(A[sx,sx]) + nnz(B2[sx,su]) <= n*maxcol(A) + m*maxcol(B2)
+    // (a bound instead of the exact class maximum keeps a 100k-entry host loop off the critical path)
+    for (SolveClass& c : p.classes)
+        c.nnzcap = (int)std::min<int64_t>((int64_t)c.N * h->maxcolA + (int64_t)c.mcap * h->maxcolB2, (int64_t)c.N * (c.N + c.mcap));
+    p.stats_valid = false;
     p.valid = true;
     return 0;
+}
+
+// SURVEY §8d algorithmic work of a plan (reported by sls_get_timing; not needed to run the kernels)
+static void plan_stats(Plan& p, int64_t T) {
+    if (p.stats_valid) return;
+    p.alg_flops = 0; p.alg_bytes = 0;
+    for (int i = 0; i < p.ncols; i++) {
+        const double n = p.h_n[i], m = p.h_m[i], v_ = (double)(p.h_tot[i + 1] - p.h_tot[i]);
+        p.alg_flops += n * n * v_ + (7.0 / 3.0) * (double)T * n * n * n;
+        p.alg_bytes += v_ * 25.0 + 2.0 * T * 24.0 + 16.0 * ((double)p.h_lA[i] + n + (double)p.h_lB[i] + m);
+    }
+    p.stats_valid = true;
 }
 
 extern "C" int sls_plan(sls_handle* h, const int64_t* cols, int64_t ncols,
@@ -684,8 +698,7 @@ extern "C" int sls_plan(sls_handle* h, const int64_t* cols, int64_t ncols,
     SLS_CK(rt::sync(h->stream));
     h->tm.gather_ms = rt::elapsed_ms(h->ev[2], h->ev[3]);
     h->tm.gather_launches = 3;
-    h->tm.ncols = h->plan.ncols; h->tm.nnz_out = h->plan.tot_packed;
-    h->tm.alg_flops = h->plan.alg_flops; h->tm.alg_bytes = h->plan.alg_bytes;
+    h->tm.ncols = h->plan.ncols; h->tm.nnz_out = h->plan.tot_packed; h->tm_from_plan = true;
     const int64_t T = h->T;
     for (int64_t t = 0; t < T; t++) {
         if (nnz_x) nnz_x[t] = h->plan.nnz_tap[t];
@@ -1199,7 +1212,7 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
         PIPE_CK(obatch.flush(vstream));
         x.ev_out.record(vstream);
         for (int64_t tt = 0; tt < 2 * T; tt++) base[tt] += p.nnz_tap[tt];
-        nnz_total += p.tot_packed; flops += p.alg_flops; bytes += p.alg_bytes;
+        nnz_total += p.tot_packed;
     }
 #undef PIPE_CK
     if (e) feed_stop.store(true);
@@ -1231,7 +1244,9 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
     h->tm = sls_timing{};
     h->tm.solve_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);       // whole pipelined call (copies, kernels 1-3) on the device clock
     h->tm.solve_launches = launches; h->tm.gather_launches = 3 * K; h->tm.scatter_launches = 2 * K;
+    for (int c = 0; c < K; c++) { plan_stats(h->pipe[c]->plan, T); flops += h->pipe[c]->plan.alg_flops; bytes += h->pipe[c]->plan.alg_bytes; }
     h->tm.ncols = ncols; h->tm.nnz_out = nnz_total; h->tm.alg_flops = flops; h->tm.alg_bytes = bytes;
+    h->tm_from_plan = false;
     // the support columns of the range (+halo) stay on the device; a later sls_plan of other columns needs
     // sls_set_supports.  The outputs live in per-chunk buffers, so the
     // device-resident accessors (sls_device_output, sls_simulate) need a sls_plan + sls_solve_device first
@@ -1357,6 +1372,11 @@ extern "C" int sls_device_status(sls_handle* h, const int32_t** d_status, const 
 
 extern "C" int sls_get_timing(const sls_handle* h, sls_timing* out) {
     if (!h || !out) return -1;
+    sls_handle* hm = const_cast<sls_handle*>(h);
+    if (hm->tm_from_plan && hm->plan.valid) {
+        plan_stats(hm->plan, hm->T);
+        hm->tm.alg_flops = hm->plan.alg_flops; hm->tm.alg_bytes = hm->plan.alg_bytes;
+    }
     *out = h->tm;
     return 0;
 }
