@@ -262,6 +262,14 @@ def check_pipelined(api, plant, S, chunks, pass_nzval=True):
         with pytest.raises(_capi.SlsError) as ei:
             syn.synthesize(*S, out=small)
         assert ei.value.code == -4
+        # a broken colptr in a later column chunk is reported by the feeder thread as a layout error (-2), not a crash
+        os.environ["SLS_PIPE_CHUNKS"] = "3"
+        Sx_bad = [slc_b200.JuliaCSC.from_scipy(sp.csc_matrix(M), np.bool_) for M in S[0]]
+        cp = Sx_bad[1].colptr.copy(); j = (3 * syn.Nx) // 4; cp[j] = cp[j + 1] + 1
+        Sx_bad[1] = slc_b200.JuliaCSC(Sx_bad[1].m, Sx_bad[1].n, cp, Sx_bad[1].rowval, Sx_bad[1].nzval)
+        with pytest.raises(_capi.SlsError) as ei:
+            syn.synthesize(Sx_bad, S[1])
+        assert ei.value.code == -2
         # the handle is still usable afterwards
         out = syn.synthesize(*S)
         assert np.array_equal(out["x"]["nzval"][0], ref["x"]["nzval"][0])
