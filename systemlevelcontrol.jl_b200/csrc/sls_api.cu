@@ -89,6 +89,7 @@ struct Plan {
     int64_t tot_packed = 0;
     double alg_flops = 0, alg_bytes = 0;
     bool stats_valid = false;           // alg_flops / alg_bytes are computed on demand (plan_stats)
+    int64_t col_lo = 0, col_hi = 0;     // planned columns lie in [col_lo, col_hi)
     int identity_cols = 0;              // h_cols currently holds 0..identity_cols-1 (the cols == NULL plan)
     void release() {
         DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists};
@@ -445,8 +446,8 @@ static int make_both_families(sls_handle* h, int64_t T, const std::vector<int>& 
     a.xcolptr = dcpx.as<int64_t>(); a.ucolptr = dcpu.as<int64_t>();
     a.overflow = dovf.as<int>();
     MS_CK(sls_launch_supports(a, false, h->stream));
-    MS_CK(sls_launch_scan(dcpx.as<int64_t>(), Nx + 1, nsx, dtot.as<int64_t>(), 1, h->stream));
-    MS_CK(sls_launch_scan(dcpu.as<int64_t>(), Nx + 1, nsu, dtot.as<int64_t>(), 1, h->stream));
+    MS_CK(sls_launch_scan(dcpx.as<int64_t>(), Nx + 1, nsx, dtot.as<int64_t>(), 1, 0, Nx + 1, h->stream));
+    MS_CK(sls_launch_scan(dcpu.as<int64_t>(), Nx + 1, nsu, dtot.as<int64_t>(), 1, 0, Nx + 1, h->stream));
     std::vector<int64_t> lastx(nsx), lastu(nsu), offx(nsx + 1, 0), offu(nsu + 1, 0);
     int ovf = 0;
     MS_CK(rt::d2h_strided(lastx.data(), dcpx.as<int64_t>() + Nx, 8, (size_t)(Nx + 1) * 8, (size_t)nsx, h->stream));
@@ -564,6 +565,12 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     if (!cols) ncols = Nx;
     p.ncols = (int)ncols;
     SLS_CK(p.h_cols.resize(std::max<int64_t>(ncols, 1)));
+    p.col_lo = 0; p.col_hi = cols ? 0 : ncols;
+    if (cols && ncols > 0) {
+        int64_t lo = cols[0], hi = cols[0];
+        for (int64_t i = 1; i < ncols; i++) { lo = std::min(lo, cols[i]); hi = std::max(hi, cols[i]); }
+        p.col_lo = std::max<int64_t>(lo - 1, 0); p.col_hi = std::min<int64_t>(hi, Nx);    // 1-based in, 0-based half-open out
+    }
     if (!cols) {
         if (p.identity_cols != ncols) { for (int64_t i = 0; i < ncols; i++) p.h_cols[i] = (int32_t)i; p.identity_cols = (int)ncols; }
     } else {
@@ -615,13 +622,14 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_CK(p.pre.ensure((size_t)nc1 * 2 * T * sizeof(uint32_t)));
     SLS_CK(p.tot.ensure((size_t)(p.ncols + 1) * sizeof(int64_t)));
     SLS_CK(p.colptr.ensure((size_t)2 * T * (Nx + 1) * sizeof(int64_t)));
-    SLS_CK(rt::zero(p.colptr.p, (size_t)2 * T * (Nx + 1) * sizeof(int64_t), h->stream));
+    // counts are written for the planned columns only: zero (and later scan) just the window that holds them
+    SLS_CK(rt::zero2d(p.colptr.as<int64_t>() + p.col_lo, (size_t)(Nx + 1) * sizeof(int64_t), (size_t)(p.col_hi - p.col_lo) * sizeof(int64_t), (size_t)(2 * T), h->stream));
     SLS_CK(rt::zero(p.tot.p, (size_t)(p.ncols + 1) * sizeof(int64_t), h->stream));
     const SlsPlanView v = plan_view(h, p);
     const size_t fill_smem = (size_t)4 * sls_gather_fill_words(cap, p.nstride, p.mstride, p.wx, p.wu, (int)T) * sizeof(int32_t);
     if (fill_smem > (size_t)h->max_smem) return fail(h, -4, "plan: index sets do not fit shared memory");
     SLS_CK(sls_launch_gather_fill(h->A.view(), h->B2.view(), h->Sx.view(), h->Su.view(), v, cap, h->stream));
-    SLS_CK(sls_launch_scan(v.colptr, Nx + 1, (int)(2 * T), v.tot, p.ncols + 1, h->stream));
+    SLS_CK(sls_launch_scan(v.colptr, Nx + 1, (int)(2 * T), v.tot, p.ncols + 1, p.col_lo, p.col_hi, h->stream));
     // sizes back to the host
     SLS_CK(p.h_lnnz.resize(nc1)); SLS_CK(p.h_lA.resize(nc1)); SLS_CK(p.h_lB.resize(nc1));
     SLS_CK(p.h_tot.resize(p.ncols + 1)); SLS_CK(p.h_last.resize(2 * T));

@@ -217,18 +217,22 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
 // (length len = Nx+1); block narr scans tot (length totlen = ncols+1) into 0-based packed offsets.
 #define SCAN_THREADS 1024
 #define SCAN_ITEMS 8
+// Only the window [lo, hi) of a colptr array can hold non-zero counts (the planned columns): it is scanned, the
+// entries before it are set to 1 and the entries from hi on to 1 + total, so the serial part of the scan does not
+// grow with Nx when one GPU plans a shard of a larger plant (weak scaling).  Nothing outside [lo, hi) is read.
 __global__ void __launch_bounds__(SCAN_THREADS)
-sls_scan_kernel(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen) {
+sls_scan_kernel(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, int64_t lo, int64_t hi) {
     __shared__ int64_t wsum[SCAN_THREADS / 32];
     __shared__ int64_t carry_s, tile_total_s;
     const int b = blockIdx.x;
     int64_t* arr = (b < narr) ? colptr + (int64_t)b * len : tot;
-    const int64_t L = (b < narr) ? len : totlen;
+    const int64_t T0 = (b < narr) ? lo : 0;
+    const int64_t L = (b < narr) ? hi : totlen;
     const int64_t add = (b < narr) ? 1 : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int64_t tile = 0; tile < L; tile += (int64_t)SCAN_THREADS * SCAN_ITEMS) {
+    for (int64_t tile = T0; tile < L; tile += (int64_t)SCAN_THREADS * SCAN_ITEMS) {
         const int64_t i0 = tile + (int64_t)tid * SCAN_ITEMS;
         int64_t v[SCAN_ITEMS];
         int64_t sum = 0;
@@ -255,6 +259,15 @@ sls_scan_kernel(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t to
         if (tid == 0) carry_s += tile_total_s;
         __syncthreads();
     }
+    if (b < narr && tid == 0 && hi < len) arr[hi] = carry_s + 1;     // the value of every entry from hi on (sls_colptr_fill_kernel)
+}
+
+// entries outside the scanned window: 1 before it, arr[hi] (= 1 + total, written by the scan) after it
+__global__ void sls_colptr_fill_kernel(int64_t* colptr, int64_t len, int64_t lo, int64_t hi) {
+    int64_t* arr = colptr + (int64_t)blockIdx.y * len;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < lo) arr[i] = 1;
+    else if (i > hi && i < len) arr[i] = arr[hi];
 }
 
 // Dense local blocks of one planned column, for sls_local_problem (test / inspection of kernel 1 and
@@ -315,9 +328,16 @@ int sls_launch_gather_fill(const SlsCsc& A, const SlsCsc& B2, const SlsSupports&
     return rt::last_error();
 }
 
-int sls_launch_scan(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, sls_stream_t stream) {
+int sls_launch_scan(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, int64_t lo, int64_t hi, sls_stream_t stream) {
     auto kp = &sls_scan_kernel;
-    SLS_LAUNCH(kp, narr + 1, SCAN_THREADS, 0, stream, colptr, len, narr, tot, totlen);
+    if (lo < 0) lo = 0;
+    if (hi > len || hi < lo) hi = len;
+    SLS_LAUNCH(kp, narr + 1, SCAN_THREADS, 0, stream, colptr, len, narr, tot, totlen, lo, hi);
+    if (narr > 0 && (lo > 0 || hi + 1 < len)) {
+        auto kf = &sls_colptr_fill_kernel;
+        dim3 grid((unsigned)((len + 255) / 256), narr, 1);
+        SLS_LAUNCH(kf, grid, 256, 0, stream, colptr, len, lo, hi);
+    }
     return rt::last_error();
 }
 

@@ -18,6 +18,10 @@ inline int h2d(void* d, const void* h, size_t n, sls_stream_t) { memcpy(d, h, n)
 inline int d2h(void* h, const void* d, size_t n, sls_stream_t) { memcpy(h, d, n); return 0; }
 inline int d2d(void* d, const void* s, size_t n, sls_stream_t) { memcpy(d, s, n); return 0; }
 inline int zero(void* d, size_t n, sls_stream_t) { memset(d, 0, n); return 0; }
+inline int zero2d(void* d, size_t pitch, size_t width, size_t height, sls_stream_t) {
+    for (size_t i = 0; i < height; i++) memset((char*)d + i * pitch, 0, width);
+    return 0;
+}
 inline int d2h_strided(void* h, const void* d, size_t elem, size_t pitch, size_t count, sls_stream_t) {
     for (size_t i = 0; i < count; i++) memcpy((char*)h + i * elem, (const char*)d + i * pitch, elem);
     return 0;
@@ -64,6 +68,9 @@ inline int h2d(void* d, const void* h, size_t n, sls_stream_t s) { return n ? (i
 inline int d2h(void* h, const void* d, size_t n, sls_stream_t s) { return n ? (int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) : 0; }
 inline int d2d(void* d, const void* s_, size_t n, sls_stream_t s) { return n ? (int)cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s) : 0; }
 inline int zero(void* d, size_t n, sls_stream_t s) { return n ? (int)cudaMemsetAsync(d, 0, n, s) : 0; }
+inline int zero2d(void* d, size_t pitch, size_t width, size_t height, sls_stream_t s) {
+    return (width && height) ? (int)cudaMemset2DAsync(d, pitch, 0, width, height, s) : 0;
+}
 inline int d2h_strided(void* h, const void* d, size_t elem, size_t pitch, size_t count, sls_stream_t s) {
     return count ? (int)cudaMemcpy2DAsync(h, elem, d, pitch, elem, count, cudaMemcpyDeviceToHost, s) : 0;
 }
