@@ -192,12 +192,23 @@ sls_solve_kernel(SlsSolveArgs a) {
                 const bool act = i < n;
                 int cntA = 0, cntB = 0;
                 int64_t ea0 = 0, ea1 = 0, eb0 = 0, eb1 = 0;
+                // the local index of a row's first 8 entries found by the counting pass is kept (one byte each,
+                // 0xff = outside the index set) so that the filling pass does not repeat the binary searches
+                uint64_t fa = ~0ull, fb = ~0ull;
                 if (act) {
                     const int64_t gr = sx[i];
                     ea0 = a.Ar.colptr[gr] - 1; ea1 = a.Ar.colptr[gr + 1] - 1;
                     eb0 = a.B2r.colptr[gr] - 1; eb1 = a.B2r.colptr[gr + 1] - 1;
-                    for (int64_t e = ea0; e < ea1; e++) cntA += (sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1)) >= 0);
-                    for (int64_t e = eb0; e < eb1; e++) cntB += (sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1)) >= 0);
+                    for (int64_t e = ea0; e < ea1; e++) {
+                        const int l = sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
+                        cntA += (l >= 0);
+                        if (e - ea0 < 8) fa = (fa & ~(0xffull << (8 * (e - ea0)))) | ((uint64_t)(l & 0xff) << (8 * (e - ea0)));
+                    }
+                    for (int64_t e = eb0; e < eb1; e++) {
+                        const int l = sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1));
+                        cntB += (l >= 0);
+                        if (e - eb0 < 8) fb = (fb & ~(0xffull << (8 * (e - eb0)))) | ((uint64_t)(l & 0xff) << (8 * (e - eb0)));
+                    }
                 }
                 int incl = cntA + cntB;
 #pragma unroll
@@ -207,14 +218,18 @@ sls_solve_kernel(SlsSolveArgs a) {
                     rptr[i] = (uint16_t)excl; rsplit[i] = (uint16_t)(excl + cntA);
                     int o = excl;
                     for (int64_t e = ea0; e < ea1; e++) {
-                        const int l = sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
+                        int l;
+                        if (e - ea0 < 8) { l = (int)((fa >> (8 * (e - ea0))) & 0xff); if (l == 0xff) l = -1; }
+                        else l = sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
                         if (l >= 0) {
                             colr[o] = (uint16_t)l; valr[o] = a.Ar.nzval[e]; o++;
                             nzA |= 1ull << ((i >> 3) * NB + (l >> 3));
                         }
                     }
                     for (int64_t e = eb0; e < eb1; e++) {
-                        const int l = sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1));
+                        int l;
+                        if (e - eb0 < 8) { l = (int)((fb >> (8 * (e - eb0))) & 0xff); if (l == 0xff) l = -1; }
+                        else l = sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1));
                         if (l >= 0) { colr[o] = (uint16_t)(n + l); valr[o] = a.B2r.nzval[e]; o++; }
                     }
                 }
@@ -231,11 +246,16 @@ sls_solve_kernel(SlsSolveArgs a) {
                 const int p = p0 + lane;
                 int cnt = 0;
                 int64_t e0 = 0, e1 = 0;
+                uint64_t fc = ~0ull;
                 const SlsCsc& M = (p < n) ? a.A : a.B2;
                 if (p < n + m) {
                     const int64_t gc = (p < n) ? sx[p] : su[p - n];
                     e0 = M.colptr[gc] - 1; e1 = M.colptr[gc + 1] - 1;
-                    for (int64_t e = e0; e < e1; e++) cnt += (sls_find_cold(sx, n, (int32_t)(M.rowval[e] - 1)) >= 0);
+                    for (int64_t e = e0; e < e1; e++) {
+                        const int r = sls_find_cold(sx, n, (int32_t)(M.rowval[e] - 1));
+                        cnt += (r >= 0);
+                        if (e - e0 < 8) fc = (fc & ~(0xffull << (8 * (e - e0)))) | ((uint64_t)(r & 0xff) << (8 * (e - e0)));
+                    }
                 }
                 int incl = cnt;
 #pragma unroll
@@ -244,7 +264,9 @@ sls_solve_kernel(SlsSolveArgs a) {
                     int o = carry + incl - cnt;
                     cptr[p] = (uint16_t)o;
                     for (int64_t e = e0; e < e1; e++) {
-                        const int r = sls_find_cold(sx, n, (int32_t)(M.rowval[e] - 1));
+                        int r;
+                        if (e - e0 < 8) { r = (int)((fc >> (8 * (e - e0))) & 0xff); if (r == 0xff) r = -1; }
+                        else r = sls_find_cold(sx, n, (int32_t)(M.rowval[e] - 1));
                         if (r >= 0) { rowc[o] = (uint16_t)r; valc[o] = M.nzval[e]; o++; }
                     }
                 }
