@@ -84,7 +84,7 @@ struct SlsSolveLayout {
         SLS_SEC(oRptr, 2 * (N + 2));
         SLS_SEC(oRsplit, 2 * (N + 2));
         SLS_SEC(oTx, 8 * (N + mcap));
-        SLS_SEC(oUc, 8 * mcap);
+        SLS_SEC(oUc, 8 * (N + mcap));                       // [x_k | u_k]: one vector for the residual's gathers
         SLS_SEC(oValR, 8 * nnzcap);
         SLS_SEC(oValC, 8 * nnzcap);
         SLS_SEC(oSu, 4 * mcap);
@@ -517,10 +517,10 @@ sls_solve_kernel(SlsSolveArgs a) {
 
         // ------------------------------------------------------------------ back substitution, k = T..1
         // lam_s holds lambda_k (zero beyond n) at the top of every iteration
-        double* xnext = xa;   // x_{k+1}
-        double* xcur = xb;    // x_k
+        double* const xcur = ucur; // [x_k | u_k] (shared: the residual gathers both through the local CSR, whose B~ columns are n + l)
+        double xnext_r[RPL];       // x_{k+1}[i] of the lane's own rows stays in registers
 #pragma unroll
-        for (int rr = 0; rr < RPL; rr++) { const int i = lane + 32 * rr; if (i < N) xnext[i] = 0.0; }
+        for (int rr = 0; rr < RPL; rr++) xnext_r[rr] = 0.0;
         double resmax = 0.0;
         // History double buffer (size classes up to N = 32): -Z_{k-1} and yh_{k-1} of the NEXT tap are loaded into
         // registers one full iteration ahead (the matrix registers of the forward pass are dead here), so the L2/HBM
@@ -600,7 +600,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                     const uint32_t word = muk[l0 >> 5];
                     const bool on = (l < m) && ((word >> lane) & 1u);
                     const double u = on ? -tx[n + l] : 0.0;
-                    if (l < m) ucur[l] = u;
+                    if (l < m) ucur[n + l] = u;
                     if (on) a.out_nzval[T + k - 1][obase[T + k - 1] + rank0 + __popc(word & ((1u << lane) - 1u))] = u;
                     rank0 += __popc(word);
                 }
@@ -676,13 +676,16 @@ sls_solve_kernel(SlsSolveArgs a) {
             }
             __syncwarp();
             // gbuf = -lambda_{k-1} (history stores -Z);  x_k = mx_k o (lambda_{k-1} - A~^T lambda_k)
+            double xk_r[RPL];
 #pragma unroll
             for (int rr = 0; rr < RPL; rr++) {
                 const int i = lane + 32 * rr;
                 const bool on = (i < n) && sls_mbit(mk, i);
                 const double lam_prev = (i < n) ? -gbuf[i] : 0.0;
                 const double x = on ? (lam_prev - tx[i]) : 0.0;
-                if (i < N) { xcur[i] = x; lam_s[i] = lam_prev; }
+                xk_r[rr] = x;
+                if (i < n) xcur[i] = x;
+                if (i < N) lam_s[i] = lam_prev;
                 if (on) a.out_nzval[k - 1][obase[k - 1] + sls_mrank(mk, i)] = x;
             }
             __syncwarp();
@@ -691,21 +694,21 @@ sls_solve_kernel(SlsSolveArgs a) {
             for (int rr = 0; rr < RPL; rr++) {
                 const int i = lane + 32 * rr;
                 if (i < n) {
-                    double r = -xnext[i];
-                    const int r0 = rptr[i], r1 = rsplit[i], r2 = rptr[i + 1];
-                    for (int e = r0; e < r1; e++) r = fma(valr[e], xcur[colr[e]], r);
-                    for (int e = r1; e < r2; e++) r = fma(valr[e], ucur[colr[e] - n], r);
+                    double r = -xnext_r[rr];
+                    const int r0 = rptr[i], r2 = rptr[i + 1];
+                    for (int e = r0; e < r2; e++) r = fma(valr[e], xcur[colr[e]], r);
                     resmax = fmax(resmax, fabs(r));
                 }
             }
-            double* tswap = xnext; xnext = xcur; xcur = tswap;
+#pragma unroll
+            for (int rr = 0; rr < RPL; rr++) xnext_r[rr] = xk_r[rr];
         }
         __syncwarp();
         // block 0: x_1 = e
 #pragma unroll
         for (int rr = 0; rr < RPL; rr++) {
             const int i = lane + 32 * rr;
-            if (i < n) resmax = fmax(resmax, fabs(((i == jl) ? 1.0 : 0.0) - xnext[i]));
+            if (i < n) resmax = fmax(resmax, fabs(((i == jl) ? 1.0 : 0.0) - xnext_r[rr]));
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) resmax = fmax(resmax, __shfl_xor_sync(SLS_FULL, resmax, d));
