@@ -169,8 +169,11 @@ sls_solve_kernel(SlsSolveArgs a) {
         const int n = P.n[c], m = P.m[c], jl = P.jloc[c];
         __syncwarp();
         // ------------------------------------------------------------------ metadata -> shared
+#pragma unroll 1
         for (int i = lane; i < n; i += 32) sx[i] = P.sx[(size_t)c * P.nstride + i];
+#pragma unroll 1
         for (int l = lane; l < m; l += 32) su[l] = P.su[(size_t)c * P.mstride + l];
+#pragma unroll 1
         for (int t = lane; t < T; t += 32) {
             const uint32_t* w = P.maskx + ((size_t)c * T + t) * P.wx;
             mask_t v = (mask_t)w[0];
@@ -178,8 +181,11 @@ sls_solve_kernel(SlsSolveArgs a) {
             mxs[t] = v;
         }
         if (lane == 0) mxs[T] = (mask_t)0;
+#pragma unroll 1
         for (int t = lane; t < T * wu; t += 32) mus[t] = P.masku[(size_t)c * T * wu + t];
+#pragma unroll 1
         for (int t = lane; t < 2 * T; t += 32) obase[t] = P.colptr[(int64_t)t * (P.Nx + 1) + P.cols[c]] - 1;
+#pragma unroll 1
         for (int e = lane; e < N * N; e += 32) Am[e] = 0.0;
         __syncwarp();
         // ------------------------------------------------------------------ local CSR of C~ = [A~ B~]
@@ -199,11 +205,13 @@ sls_solve_kernel(SlsSolveArgs a) {
                     const int64_t gr = sx[i];
                     ea0 = a.Ar.colptr[gr] - 1; ea1 = a.Ar.colptr[gr + 1] - 1;
                     eb0 = a.B2r.colptr[gr] - 1; eb1 = a.B2r.colptr[gr + 1] - 1;
+#pragma unroll 1
                     for (int64_t e = ea0; e < ea1; e++) {
                         const int l = sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
                         cntA += (l >= 0);
                         if (e - ea0 < 8) fa = (fa & ~(0xffull << (8 * (e - ea0)))) | ((uint64_t)(l & 0xff) << (8 * (e - ea0)));
                     }
+#pragma unroll 1
                     for (int64_t e = eb0; e < eb1; e++) {
                         const int l = sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1));
                         cntB += (l >= 0);
@@ -217,6 +225,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 if (act) {
                     rptr[i] = (uint16_t)excl; rsplit[i] = (uint16_t)(excl + cntA);
                     int o = excl;
+#pragma unroll 1
                     for (int64_t e = ea0; e < ea1; e++) {
                         int l;
                         if (e - ea0 < 8) { l = (int)((fa >> (8 * (e - ea0))) & 0xff); if (l == 0xff) l = -1; }
@@ -226,6 +235,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                             nzA |= 1ull << ((i >> 3) * NB + (l >> 3));
                         }
                     }
+#pragma unroll 1
                     for (int64_t e = eb0; e < eb1; e++) {
                         int l;
                         if (e - eb0 < 8) { l = (int)((fb >> (8 * (e - eb0))) & 0xff); if (l == 0xff) l = -1; }
@@ -242,6 +252,7 @@ sls_solve_kernel(SlsSolveArgs a) {
         // ------------------------------------------------------------------ local CSC of C~ (columns 0..n+m)
         {
             int carry = 0;
+#pragma unroll 1
             for (int p0 = 0; p0 < n + m; p0 += 32) {
                 const int p = p0 + lane;
                 int cnt = 0;
@@ -251,6 +262,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 if (p < n + m) {
                     const int64_t gc = (p < n) ? sx[p] : su[p - n];
                     e0 = M.colptr[gc] - 1; e1 = M.colptr[gc + 1] - 1;
+#pragma unroll 1
                     for (int64_t e = e0; e < e1; e++) {
                         const int r = sls_find_cold(sx, n, (int32_t)(M.rowval[e] - 1));
                         cnt += (r >= 0);
@@ -263,6 +275,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 if (p < n + m) {
                     int o = carry + incl - cnt;
                     cptr[p] = (uint16_t)o;
+#pragma unroll 1
                     for (int64_t e = e0; e < e1; e++) {
                         int r;
                         if (e - e0 < 8) { r = (int)((fc >> (8 * (e - e0))) & 0xff); if (r == 0xff) r = -1; }
@@ -334,6 +347,7 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
             for (int w = 0; w < 4; w++) if (w < wu) same = same && (muk[w] == mu_prev[w]);
             if (!same) {
+#pragma unroll 1
                 for (int e = lane; e < N * N; e += 32) Dp[e] = 0.0;
                 __syncwarp();
                 nonempty = 0ull;
@@ -344,17 +358,20 @@ sls_solve_kernel(SlsSolveArgs a) {
                     if (i < n) {
                         const int r0 = rptr[i], r1 = rsplit[i], r2 = rptr[i + 1];
                         if (sls_mbit(mk1, i)) { dref = 1.0; Dp[sls_blk(NB, i, i)] = 1.0; }
+#pragma unroll 1
                         for (int e = r0; e < r1; e++) {
                             const int l = colr[e]; const double v = valr[e];
                             const bool on = sls_mbit(mk, l);
                             Am[sls_blk(NB, i, l)] = on ? v : 0.0;
                             if (on) dref = fma(v, v, dref);
                         }
+#pragma unroll 1
                         for (int e = r1; e < r2; e++) {
                             const int l = colr[e] - n;
                             if (!sls_bit(muk, l)) continue;
                             const double v = valr[e];
                             dref = fma(v, v, dref);
+#pragma unroll 1
                             for (int e2 = cptr[n + l]; e2 < cptr[n + l + 1]; e2++) Dp[sls_blk(NB, i, rowc[e2])] += v * valc[e2];
                         }
                     }
@@ -373,6 +390,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 double acc = 0.0;
                 if (i < n) {
                     const int r0 = rptr[i], r1 = rsplit[i];
+#pragma unroll 1
                     for (int e = r0; e < r1; e++) acc = fma(valr[e], gbuf[colr[e]], acc);
                 }
                 if (i < N) { ycur[i] = acc; yhist[(size_t)k * N + i] = acc; }
@@ -577,6 +595,7 @@ sls_solve_kernel(SlsSolveArgs a) {
             // of a serial chain and would otherwise pay L2/HBM latency every tap
             if (!PRELOAD && k >= 3) {
                 const char* hz = reinterpret_cast<const char*>(zhist + (size_t)(k - 2) * TRI);
+#pragma unroll 1
                 for (int o = lane * 128; o < (int)(n * (n + 1) / 2 * sizeof(double)); o += 32 * 128)
                     asm volatile("prefetch.global.L1 [%0];" :: "l"(hz + o));
                 if (lane == 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(yhist + (size_t)(k - 2) * N));
@@ -585,9 +604,11 @@ sls_solve_kernel(SlsSolveArgs a) {
 #endif
             __syncwarp();
             // t = C~^T lambda_k
+#pragma unroll 1
             for (int p = lane; p < n + m; p += 32) {
                 double acc = 0.0;
                 const int e0 = cptr[p], e1 = cptr[p + 1];
+#pragma unroll 1
                 for (int e = e0; e < e1; e++) acc = fma(valc[e], lam_s[rowc[e]], acc);
                 tx[p] = acc;
             }
@@ -595,6 +616,7 @@ sls_solve_kernel(SlsSolveArgs a) {
             // u_k = -mu_k o t_u  -> packed result
             {
                 int rank0 = 0;
+#pragma unroll 1
                 for (int l0 = 0; l0 < m; l0 += 32) {
                     const int l = l0 + lane;
                     const uint32_t word = muk[l0 >> 5];
@@ -696,6 +718,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 if (i < n) {
                     double r = -xnext_r[rr];
                     const int r0 = rptr[i], r2 = rptr[i + 1];
+#pragma unroll 1
                     for (int e = r0; e < r2; e++) r = fma(valr[e], xcur[colr[e]], r);
                     resmax = fmax(resmax, fabs(r));
                 }
