@@ -26,22 +26,29 @@ __device__ int sls_warp_index_set(const SlsCsc& A, const SlsSupports& S, int T, 
     const int64_t* scp = S.colptr + (int64_t)(T - 1) * (Nx + 1);
     const int64_t base = S.tap_off[T - 1];
     int C = 0;
+#pragma unroll 1
     for (int64_t e = a0; e < a1; e++) {
         if (A.nzval[e] == 0.0) continue;                      // `A .≠ 0` drops stored zeros
         const int64_t k = A.rowval[e] - 1;
         const int64_t s0 = base + scp[k] - 1, s1 = base + scp[k + 1] - 1;
         const int len = (int)(s1 - s0);
         if (C + len > cap) return -1;
+#pragma unroll 1
         for (int i = lane; i < len; i += 32) buf[C + i] = (int32_t)(S.rowval[s0 + i] - 1);
         C += len;
     }
     int P = 32;
+#pragma unroll 1
     while (P < C) P <<= 1;
     if (P > cap) P = cap;                                     // cap >= 32 and a power of two
+#pragma unroll 1
     for (int i = C + lane; i < P; i += 32) buf[i] = INT_MAX;
     __syncwarp();
+#pragma unroll 1
     for (int k = 2; k <= P; k <<= 1) {
+#pragma unroll 1
         for (int jj = k >> 1; jj > 0; jj >>= 1) {
+#pragma unroll 1
             for (int i = lane; i < P; i += 32) {
                 const int ixj = i ^ jj;
                 if (ixj > i) {
@@ -54,6 +61,7 @@ __device__ int sls_warp_index_set(const SlsCsc& A, const SlsSupports& S, int T, 
         }
     }
     int n = 0, prev_last = -1;
+#pragma unroll 1
     for (int b0 = 0; b0 < P; b0 += 32) {
         const int v = buf[b0 + lane];
         int pv = __shfl_up_sync(SLS_FULL, v, 1);
@@ -116,6 +124,7 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
     const int64_t j = P.cols[c];
 
     // segment table first: these loads overlap with the index-set work below
+#pragma unroll 1
     for (int tt = lane; tt < 2 * T; tt += 32) {
         const SlsSupports& S = (tt < T) ? Sx : Su;
         const int t = (tt < T) ? tt : tt - T;
@@ -123,12 +132,15 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
         const int64_t s0 = S.tap_off[t] + cp[j] - 1, s1 = S.tap_off[t] + cp[j + 1] - 1;
         seg0[tt] = s0; cnt[tt] = (int)(s1 - s0);
     }
+#pragma unroll 1
     for (int w = lane; w < T * nmw; w += 32) mw[w] = 0u;
 
     const int n = sls_warp_index_set(A, Sx, T, Nx, j, buf, cap);
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) { sx[i] = buf[i]; P.sx[(size_t)c * P.nstride + i] = buf[i]; }
     __syncwarp();
     const int m = sls_warp_index_set(A, Su, T, Nx, j, buf, cap);
+#pragma unroll 1
     for (int i = lane; i < m; i += 32) { su[i] = buf[i]; P.su[(size_t)c * P.mstride + i] = buf[i]; }
     __syncwarp();
     if (lane == 0) { P.n[c] = n; P.m[c] = m; P.jloc[c] = sls_find(sx, n, (int32_t)j); }
@@ -136,6 +148,7 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
     // prefix sums of the 2T segment lengths
     {
         int carry = 0;
+#pragma unroll 1
         for (int t0 = 0; t0 < 2 * T; t0 += 32) {
             const int tt = t0 + lane;
             const int v = (tt < 2 * T) ? cnt[tt] : 0;
@@ -149,8 +162,10 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
     }
     __syncwarp();
     const int total = pfx[2 * T];
+#pragma unroll 1
     for (int f = lane; f < total; f += 32) {
         int lo = 0, hi = 2 * T;                               // largest tt with pfx[tt] <= f
+#pragma unroll 1
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pfx[mid] <= f) lo = mid; else hi = mid; }
         const int tt = lo;
         const bool isu = tt >= T;
@@ -163,21 +178,25 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
     }
     __syncwarp();
     // per-tap counts, masks to global, colptr counts
+#pragma unroll 1
     for (int tt = lane; tt < 2 * T; tt += 32) {
         const bool isu = tt >= T;
         const int t = isu ? tt - T : tt;
         const uint32_t* w = mw + t * nmw + (isu ? P.wx : 0);
         const int nwd = isu ? P.wu : P.wx;
         int k = 0;
+#pragma unroll 1
         for (int q = 0; q < nwd; q++) k += __popc(w[q]);
         cnt[tt] = k;
         P.colptr[(int64_t)tt * (Nx + 1) + j] = k;
         uint32_t* dst = isu ? P.masku + ((size_t)c * T + t) * P.wu : P.maskx + ((size_t)c * T + t) * P.wx;
+#pragma unroll 1
         for (int q = 0; q < nwd; q++) dst[q] = w[q];
     }
     __syncwarp();
     // offsets of the (x_t, u_t) segments inside the column's packed result: order x_0 u_0 x_1 u_1 ...
     uint32_t run = 0;
+#pragma unroll 1
     for (int t0 = 0; t0 < T; t0 += 32) {
         const int t = t0 + lane;
         const int cx = (t < T) ? cnt[t] : 0, cu = (t < T) ? cnt[T + t] : 0;
@@ -193,13 +212,17 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
     }
     // local nnz: A[sx,sx] by columns, B2[sx,su] by columns, and the full column lengths of B2[:,su]
     int cntA = 0, cntB = 0, cntBfull = 0;
+#pragma unroll 1
     for (int l = lane; l < n; l += 32) {
         const int64_t e0 = A.colptr[sx[l]] - 1, e1 = A.colptr[sx[l] + 1] - 1;
+#pragma unroll 1
         for (int64_t e = e0; e < e1; e++) cntA += (sls_find(sx, n, (int32_t)(A.rowval[e] - 1)) >= 0);
     }
+#pragma unroll 1
     for (int l = lane; l < m; l += 32) {
         const int64_t e0 = B2.colptr[su[l]] - 1, e1 = B2.colptr[su[l] + 1] - 1;
         cntBfull += (int)(e1 - e0);
+#pragma unroll 1
         for (int64_t e = e0; e < e1; e++) cntB += (sls_find(sx, n, (int32_t)(B2.rowval[e] - 1)) >= 0);
     }
     cntA = __reduce_add_sync(SLS_FULL, cntA);
@@ -279,25 +302,33 @@ __global__ void sls_local_dense_kernel(SlsCsc A, SlsCsc B2, SlsPlanView P, int c
     const int32_t* sx = P.sx + (size_t)c * P.nstride;
     const int32_t* su = P.su + (size_t)c * P.mstride;
     const int tid = threadIdx.x, nt = blockDim.x;
+#pragma unroll 1
     for (int i = tid; i < n * n; i += nt) At[i] = 0.0;
+#pragma unroll 1
     for (int i = tid; i < n * m; i += nt) B2t[i] = 0.0;
     __syncthreads();
+#pragma unroll 1
     for (int l = tid; l < n; l += nt) {
+#pragma unroll 1
         for (int64_t e = A.colptr[sx[l]] - 1; e < A.colptr[sx[l] + 1] - 1; e++) {
             const int r = sls_find(sx, n, (int32_t)(A.rowval[e] - 1));
             if (r >= 0) At[(size_t)l * n + r] = A.nzval[e];
         }
     }
+#pragma unroll 1
     for (int l = tid; l < m; l += nt) {
+#pragma unroll 1
         for (int64_t e = B2.colptr[su[l]] - 1; e < B2.colptr[su[l] + 1] - 1; e++) {
             const int r = sls_find(sx, n, (int32_t)(B2.rowval[e] - 1));
             if (r >= 0) B2t[(size_t)l * n + r] = B2.nzval[e];
         }
     }
+#pragma unroll 1
     for (int i = tid; i < P.T * n; i += nt) {
         const int t = i / n, r = i % n;
         Mx[i] = (P.maskx[((size_t)c * P.T + t) * P.wx + (r >> 5)] >> (r & 31)) & 1u;
     }
+#pragma unroll 1
     for (int i = tid; i < P.T * m; i += nt) {
         const int t = i / m, r = i % m;
         Mu[i] = (P.masku[((size_t)c * P.T + t) * P.wu + (r >> 5)] >> (r & 31)) & 1u;

@@ -31,12 +31,14 @@ __host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, in
 // append the rows of column gc of every tap in [tt0, tt1) to buf[cnt..]; returns new count or -1 on overflow
 __device__ int sls_sim_append(const SlsSimArgs& a, int tt0, int tt1, int64_t gc, int32_t* buf, int cnt, int cap) {
     const int lane = sls_lane();
+#pragma unroll 1
     for (int tt = tt0; tt < tt1; tt++) {
         const int64_t* cp = a.colptr + (int64_t)tt * (a.Nx + 1);
         const int64_t e0 = cp[gc] - 1, e1 = cp[gc + 1] - 1;
         const int len = (int)(e1 - e0);
         if (cnt + len > cap) return -1;
         const int64_t* rv = a.rowval[tt];
+#pragma unroll 1
         for (int i = lane; i < len; i += 32) buf[cnt + i] = (int32_t)(rv[e0 + i] - 1);
         cnt += len;
     }
@@ -47,12 +49,17 @@ __device__ int sls_sim_append(const SlsSimArgs& a, int tt0, int tt1, int64_t gc,
 __device__ int sls_sim_sort_unique(int32_t* buf, int cnt, int cap) {
     const int lane = sls_lane();
     int P = 32;
+#pragma unroll 1
     while (P < cnt) P <<= 1;
     if (P > cap) P = cap;
+#pragma unroll 1
     for (int i = cnt + lane; i < P; i += 32) buf[i] = INT_MAX;
     __syncwarp();
+#pragma unroll 1
     for (int k = 2; k <= P; k <<= 1)
+#pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
             for (int i = lane; i < P; i += 32) {
                 const int ixj = i ^ j;
                 if (ixj > i) {
@@ -64,6 +71,7 @@ __device__ int sls_sim_sort_unique(int32_t* buf, int cnt, int cap) {
             __syncwarp();
         }
     int n = 0, prev_last = -1;
+#pragma unroll 1
     for (int b0 = 0; b0 < P; b0 += 32) {
         const int v = buf[b0 + lane];
         int pv = __shfl_up_sync(SLS_FULL, v, 1);
@@ -91,10 +99,12 @@ __device__ int sls_sim_window(const SlsSimArgs& a, int64_t j, int32_t* buf, int3
     __syncwarp();
     int n1 = sls_sim_sort_unique(buf, cnt, cap);
     if (n1 > tmpcap) return -1;
+#pragma unroll 1
     for (int i = lane; i < n1; i += 32) tmp[i] = buf[i];
     __syncwarp();
     // level 2: add the rows of Phi_x[:, c] for every c of level 1
     int n = n1;
+#pragma unroll 1
     for (int k = 0; k < n1; k++) {
         cnt = sls_sim_append(a, 0, T, tmp[k], buf, n, cap);
         if (cnt < 0) return -1;
@@ -105,13 +115,16 @@ __device__ int sls_sim_window(const SlsSimArgs& a, int64_t j, int32_t* buf, int3
     {
         const int nw = n;
         cnt = nw;
+#pragma unroll 1
         for (int k0 = 0; k0 < nw; k0 += 32) {
             // sequential over window columns to keep the append deterministic and bounded
+#pragma unroll 1
             for (int kk = k0; kk < min(k0 + 32, nw); kk++) {
                 const int64_t gc = buf[kk];
                 const int64_t e0 = a.A.colptr[gc] - 1, e1 = a.A.colptr[gc + 1] - 1;
                 const int len = (int)(e1 - e0);
                 if (cnt + len > cap) return -1;
+#pragma unroll 1
                 for (int i = lane; i < len; i += 32) buf[cnt + i] = (int32_t)(a.A.rowval[e0 + i] - 1);
                 cnt += len;
             }
@@ -126,6 +139,7 @@ __device__ int sls_sim_window(const SlsSimArgs& a, int64_t j, int32_t* buf, int3
 __device__ int sls_sim_uwindow(const SlsSimArgs& a, const int32_t* W, int nw, int32_t* buf, int cap) {
     const int T = a.T;
     int n = 0;
+#pragma unroll 1
     for (int k = 0; k < nw; k++) {
         const int cnt = sls_sim_append(a, T, 2 * T, W[k], buf, n, cap);
         if (cnt < 0) return -1;
@@ -150,12 +164,15 @@ sls_sim_size_kernel(SlsSimArgs a, int32_t* nw_out, int32_t* nu_out, int cap, int
     __syncwarp();
     int nu = -1;
     if (nw >= 0) {
+#pragma unroll 1
         for (int i = lane; i < nw; i += 32) tmp[i] = buf[i];
         __syncwarp();
         nu = sls_sim_uwindow(a, tmp, nw, ub, cap);
     }
     if (Wg && nw >= 0 && nu >= 0 && nw <= wcap && nu <= ucap) {           // second call: store the windows (exact strides)
+#pragma unroll 1
         for (int i = lane; i < nw; i += 32) Wg[(size_t)s * wcap + i] = tmp[i];
+#pragma unroll 1
         for (int i = lane; i < nu; i += 32) Wug[(size_t)s * ucap + i] = ub[i];
     }
     if (lane == 0) { nw_out[s] = nw; nu_out[s] = nu; }
@@ -177,22 +194,27 @@ sls_sim_pack_kernel(SlsSimArgs a, int wcap, int ucap, int64_t* nent, uint32_t* t
     int32_t* Wu = W + wcap;
     const int nw = a.nw[s], nu = a.nu[s];
     if (nw < 0 || nu < 0 || nw > wcap || nu > ucap) return;
+#pragma unroll 1
     for (int i = lane; i < nw; i += 32) W[i] = a.Wg[(size_t)s * wcap + i];
+#pragma unroll 1
     for (int i = lane; i < nu; i += 32) Wu[i] = a.Wug[(size_t)s * ucap + i];
     __syncwarp();
     int64_t run = 0;
     const int64_t base = FILL ? pk_off[s] : 0;
+#pragma unroll 1
     for (int tt = 0; tt < 2 * T; tt++) {
         const bool isu = tt >= T;
         const int64_t* cp = a.colptr + (int64_t)tt * (a.Nx + 1);
         const int64_t* rv = a.rowval[tt]; const double* nz = a.nzval[tt];
         const int32_t* Wr = isu ? Wu : W; const int nr = isu ? nu : nw;
         uint32_t tapn = 0;
+#pragma unroll 1
         for (int cl = 0; cl < nw; cl++) {
             int cnt = 0;
             if (tt != 0) {                                     // Phi_x[1] is never used by the recursion
                 const int64_t gc = W[cl];
                 const int64_t e0 = cp[gc] - 1, e1 = cp[gc + 1] - 1;
+#pragma unroll 1
                 for (int64_t eb = e0; eb < e1; eb += 32) {
                     const int64_t e = eb + lane;
                     int lr = -1;
@@ -237,28 +259,38 @@ sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
     const int64_t pkbase = a.pk_off[s];
     if (lane == 0) {
         uint32_t run = 0;
+#pragma unroll 1
         for (int tt = 0; tt < 2 * T; tt++) { tapoff[tt] = run; run += a.pk_tapcnt[(size_t)s * 2 * T + tt]; }
         tapoff[2 * T] = run;
     }
     // ---- windows (computed by the window pass)
     const int nw = a.nw[s], nu = a.nu[s];
     if (nw < 0 || nu < 0 || nw > wcap || nu > ucap) { if (lane == 0) atomicOr(a.overflow, 1); return; }
+#pragma unroll 1
     for (int i = lane; i < nw; i += 32) W[i] = a.Wg[(size_t)s * wcap + i];
+#pragma unroll 1
     for (int i = lane; i < nu; i += 32) Wu[i] = a.Wug[(size_t)s * ucap + i];
+#pragma unroll 1
     for (int i = lane; i < T * wcap; i += 32) what[i] = 0.0;
+#pragma unroll 1
     for (int i = lane; i < wcap; i += 32) { x[i] = 0.0; xn[i] = 0.0; beta[i] = 0.0; }
+#pragma unroll 1
     for (int i = lane; i < ucap; i += 32) u[i] = 0.0;
     __syncwarp();
     const int jl = sls_find(W, nw, (int32_t)j);
     double* xnorm = a.xnorm ? a.xnorm + (size_t)s * a.steps : nullptr;
     double* unorm = a.unorm ? a.unorm + (size_t)s * a.steps : nullptr;
     // everything is exactly zero up to and including t = ts (x(ts) = 0); norms of those steps stay 0 (pre-zeroed)
+#pragma unroll 1
     for (int64_t t = (ts < 1 ? 1 : ts); t <= a.steps - 1; t++) {
         // beta(t+1), u(t) from what(t+1-tau)
+#pragma unroll 1
         for (int i = lane; i < nw; i += 32) beta[i] = 0.0;
+#pragma unroll 1
         for (int i = lane; i < nu; i += 32) u[i] = 0.0;
         __syncwarp();
         const int taumax = (int)(t < T ? t : T);
+#pragma unroll 1
         for (int tau = 1; tau <= taumax; tau++) {
             const int64_t src = t + 1 - tau;
             if (src <= ts) break;                              // what(s) = 0 exactly for s <= ts
@@ -270,13 +302,16 @@ sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
                 double* acc = fam ? u : beta;
                 int64_t ptr = pkbase + tapoff[tt];
                 const uint16_t* cnts = a.pk_cnt + ((size_t)s * 2 * T + tt) * wcap;
+#pragma unroll 1
                 for (int cl0 = 0; cl0 < nw; cl0 += 32) {
                     const int mycnt = (cl0 + lane < nw) ? (int)cnts[cl0 + lane] : 0;
                     const int kmax = (nw - cl0 < 32) ? (nw - cl0) : 32;
+#pragma unroll 1
                     for (int k = 0; k < kmax; k++) {
                         const int len = __shfl_sync(SLS_FULL, mycnt, k);
                         const double wc = wv[cl0 + k];
                         if (len != 0 && wc != 0.0) {
+#pragma unroll 1
                             for (int i = lane; i < len; i += 32) {
                                 const int lr = a.pk_row[ptr + i];
                                 acc[lr] = fma(a.pk_val[ptr + i], wc, acc[lr]);
@@ -291,14 +326,18 @@ sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
         __syncwarp();
         // x(t+1) = A x(t) + w(t) + B2 u(t) on the window rows
         double un = 0.0, xnn = 0.0;
+#pragma unroll 1
         for (int i = lane; i < nu; i += 32) un = fma(u[i], u[i], un);
+#pragma unroll 1
         for (int lr = lane; lr < nw; lr += 32) {
             const int64_t gr = W[lr];
             double acc = (t == ts && lr == jl) ? 1.0 : 0.0;
+#pragma unroll 1
             for (int64_t e = a.Ar.colptr[gr] - 1; e < a.Ar.colptr[gr + 1] - 1; e++) {
                 const int lc = sls_find(W, nw, (int32_t)(a.Ar.rowval[e] - 1));
                 if (lc >= 0) acc = fma(a.Ar.nzval[e], x[lc], acc);
             }
+#pragma unroll 1
             for (int64_t e = a.B2r.colptr[gr] - 1; e < a.B2r.colptr[gr + 1] - 1; e++) {
                 const int lc = sls_find(Wu, nu, (int32_t)(a.B2r.rowval[e] - 1));
                 if (lc >= 0) acc = fma(a.B2r.nzval[e], u[lc], acc);
@@ -316,6 +355,7 @@ sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
         __syncwarp();
         // what(t+1) = x(t+1) - beta(t+1);  x <- x(t+1)
         double* wn = what + (size_t)((t + 1) % T) * wcap;
+#pragma unroll 1
         for (int lr = lane; lr < nw; lr += 32) {
             const double xv = xn[lr];
             wn[lr] = xv - beta[lr];

@@ -18,12 +18,17 @@
 __device__ int sls_supp_sort_unique(int32_t* buf, int cnt, int cap) {
     const int lane = sls_lane();
     int P = 32;
+#pragma unroll 1
     while (P < cnt) P <<= 1;
     if (P > cap) P = cap;
+#pragma unroll 1
     for (int i = cnt + lane; i < P; i += 32) buf[i] = INT_MAX;
     __syncwarp();
+#pragma unroll 1
     for (int k = 2; k <= P; k <<= 1)
+#pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
             for (int i = lane; i < P; i += 32) {
                 const int ixj = i ^ j;
                 if (ixj > i) {
@@ -35,6 +40,7 @@ __device__ int sls_supp_sort_unique(int32_t* buf, int cnt, int cap) {
             __syncwarp();
         }
     int n = 0, prev_last = -1;
+#pragma unroll 1
     for (int b0 = 0; b0 < P; b0 += 32) {
         const int v = buf[b0 + lane];
         int pv = __shfl_up_sync(SLS_FULL, v, 1);
@@ -56,6 +62,7 @@ __device__ int sls_supp_sort_unique(int32_t* buf, int cnt, int cap) {
 __device__ int sls_supp_expand(const SlsCsc& M, const int32_t* src, int ns, int32_t* dst, int cap) {
     const int lane = sls_lane();
     int cnt = 0;
+#pragma unroll 1
     for (int k0 = 0; k0 < ns; k0 += 32) {
         const int k = k0 + lane;
         int64_t e0 = 0;
@@ -67,6 +74,7 @@ __device__ int sls_supp_expand(const SlsCsc& M, const int32_t* src, int ns, int3
         const int total = __shfl_sync(SLS_FULL, incl, 31);
         if (cnt + total > cap) return -1;
         const int base = cnt + incl - len;
+#pragma unroll 1
         for (int i = 0; i < len; i++)
             dst[base + i] = (M.nzval[e0 + i] != 0.0) ? (int32_t)(M.rowval[e0 + i] - 1) : INT_MAX;   // `.≠ 0` drops stored zeros
         cnt += total;
@@ -88,6 +96,7 @@ sls_supp_kernel(SlsSuppArgs a) {
     if (lane == 0) cur[0] = (int32_t)j;
     __syncwarp();
     int n = 1;
+#pragma unroll 1
     for (int s = 0; s <= a.nlev; s++) {
         const int xs = a.ex_slot[s], us = a.eu_slot[s];
         if (xs >= 0) {
@@ -95,6 +104,7 @@ sls_supp_kernel(SlsSuppArgs a) {
             if (!FILL) { if (lane == 0) cp[j] = n; }
             else {
                 int64_t* dst = a.xrow + a.xoff[xs] + cp[j] - 1;
+#pragma unroll 1
                 for (int i = lane; i < n; i += 32) dst[i] = (int64_t)cur[i] + 1;
             }
         }
@@ -105,6 +115,7 @@ sls_supp_kernel(SlsSuppArgs a) {
             if (!FILL) { if (lane == 0) cp[j] = m; }
             else {
                 int64_t* dst = a.urow + a.uoff[us] + cp[j] - 1;
+#pragma unroll 1
                 for (int i = lane; i < m; i += 32) dst[i] = (int64_t)ub[i] + 1;
             }
             __syncwarp();
