@@ -43,16 +43,17 @@ __device__ __forceinline__ void sls_dmma(double& c0, double& c1, double a, doubl
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 #endif
 }
-// 1/x for x > 0 to ~1 ulp: hardware seed (rcp.approx.ftz.f64, >= 20 good bits) + 2 Newton steps
+// 1/x for x > 0 to 1 ulp: hardware seed (rcp.approx.ftz.f64) + one cubic correction
 __device__ __forceinline__ double sls_rcp(double x) {
 #ifdef SLS_EMU
     return 1.0 / x;
 #else
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    y = fma(y, fma(-x, y, 1.0), y);
-    y = fma(y, fma(-x, y, 1.0), y);
-    return y;
+    // the seed is good to 2^-19.9 (measured): with e = 1 - x*y,  1/x = y (1 + e + e^2 + O(e^3)),  e^3 < 2^-59.
+    // Three dependent FMAs instead of two Newton steps (four); 1 ulp worst case (scratch/rcp/rcp_test.cu).
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
 #endif
 }
 // acc += X * W^T for two 8x8 blocks in accumulator layout
@@ -442,12 +443,14 @@ sls_solve_kernel(SlsSolveArgs a) {
                 double d0 = S[p][p][0], d1 = S[p][p][1];
                 uint32_t kb = 0u;
                 const uint32_t actp = (uint32_t)(nonempty >> (8 * p)) & 0xffu;   // non-empty rows of D_k in this block
+                // rows beyond n are never touched; an empty row inside the block (threshold +inf) takes the skip path of
+                // the arithmetic below (pinv = 0 on an all-zero row and column), so no per-pivot branch is needed
+                const int npair = (actp == 0u) ? 0 : ((min(8, n - 8 * p) + 1) >> 1);
 #pragma unroll 1
-                for (int rp = 0; rp < 4; rp++) {
+                for (int rp = 0; rp < npair; rp++) {
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
                         const int r = 2 * rp + e;
-                        if (!((actp >> r) & 1u)) continue;   // empty constraint row: its row/column of S_k is exactly zero
                         const double src = e ? d1 : d0;
                         const double dv = __shfl_sync(SLS_FULL, src, 4 * r + rp);
                         const double cg = __shfl_sync(SLS_FULL, src, (lane & ~3) | rp);
