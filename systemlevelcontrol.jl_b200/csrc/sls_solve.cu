@@ -51,7 +51,7 @@ __device__ __forceinline__ double sls_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     // the seed is good to 2^-19.9 (measured): with e = 1 - x*y,  1/x = y (1 + e + e^2 + O(e^3)),  e^3 < 2^-59.
-    // Three dependent FMAs instead of two Newton steps (four); 1 ulp worst case (scratch/rcp/rcp_test.cu).
+    // Three dependent FMAs instead of two Newton steps (four); 1 ulp worst case (tools/rcp_test.cu).
     const double e = fma(-x, y, 1.0);
     return fma(y, fma(e, e, e), y);
 #endif
