@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <thread>
 #include <atomic>
 
@@ -136,6 +137,7 @@ struct sls_handle {
     rt::Event ev[8];
     rt::Event marks[2];
     sls_timing tm{};
+    int pipe_chunks = 0;                // chunks of the last sls_synthesize (their plans hold its statistics)
     bool tm_from_plan = true;           // alg_flops / alg_bytes of tm come from h->plan (lazily) rather than from sls_synthesize
     // pipelined one-shot path
     sls_stream_t in_stream{}, scat_stream{}, out2_stream{};
@@ -560,6 +562,9 @@ static SlsPlanView plan_view(const sls_handle* h, const Plan& p) {
 static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols, bool unique_cols) {
     const int64_t Nx = h->Nx, T = h->T;
     p.valid = false;
+    static const bool trace = getenv("SLS_PLAN_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = trace ? now() : 0; double t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
     SLS_ARG(h->have_plant && h->have_supports, "plan: plant and supports must be set first");
     SLS_ARG(ncols >= 0 && ncols < (int64_t)1 << 31, "plan: bad ncols");
     if (!cols) ncols = Nx;
@@ -593,7 +598,14 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_CK(p.cols.ensure(nc1 * sizeof(int32_t)));
     SLS_CK(p.n.ensure(nc1 * sizeof(int32_t)));
     SLS_CK(p.m.ensure(nc1 * sizeof(int32_t)));
-    SLS_CK(sls_kcopy(p.cols.p, p.h_cols.data(), (size_t)p.ncols * sizeof(int32_t), h->stream));
+    {
+        // a contiguous ascending list (the all-columns plan, a shard, a pipeline chunk) is generated on the device
+        bool contiguous = p.ncols > 0;
+        const int32_t first = p.ncols > 0 ? p.h_cols[0] : 0;
+        if (cols) for (int i = 1; i < p.ncols && contiguous; i++) contiguous = (p.h_cols[i] == first + i);
+        if (contiguous) SLS_CK(sls_launch_iota(p.cols.as<int32_t>(), first, p.ncols, h->stream));
+        else SLS_CK(sls_kcopy(p.cols.p, p.h_cols.data(), (size_t)p.ncols * sizeof(int32_t), h->stream));
+    }
     if ((size_t)cap * 4 * sizeof(int32_t) + 4096 > (size_t)h->max_smem)
         return fail(h, -4, "plan: candidate index list of a column does not fit shared memory");
     SLS_CK(sls_launch_gather_count(h->A.view(), h->Sx.view(), h->Su.view(), (int)T, Nx, p.cols.as<int32_t>(), p.ncols,
@@ -602,7 +614,9 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     p.h_n[0] = 0; p.h_m[0] = 0;
     SLS_CK(sls_kcopy(p.h_n.data(), p.n.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
     SLS_CK(sls_kcopy(p.h_m.data(), p.m.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    if (trace) t1 = now();
     SLS_CK(rt::sync(h->stream));
+    if (trace) t2 = now();
     int nmax = 0, mmax = 0;
     for (int i = 0; i < p.ncols; i++) {
         if (p.h_n[i] < 0 || p.h_m[i] < 0) return fail(h, -4, "plan: candidate index list overflow in kernel 1");
@@ -628,6 +642,7 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     const SlsPlanView v = plan_view(h, p);
     const size_t fill_smem = (size_t)4 * sls_gather_fill_words(cap, p.nstride, p.mstride, p.wx, p.wu, (int)T) * sizeof(int32_t);
     if (fill_smem > (size_t)h->max_smem) return fail(h, -4, "plan: index sets do not fit shared memory");
+    if (trace) t3 = now();
     SLS_CK(sls_launch_gather_fill(h->A.view(), h->B2.view(), h->Sx.view(), h->Su.view(), v, cap, h->stream));
     SLS_CK(sls_launch_scan(v.colptr, Nx + 1, (int)(2 * T), v.tot, p.ncols + 1, p.col_lo, p.col_hi, h->stream));
     // sizes back to the host
@@ -635,11 +650,11 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_CK(p.h_tot.resize(p.ncols + 1)); SLS_CK(p.h_last.resize(2 * T));
     PinVec<int32_t>& lA = p.h_lA; PinVec<int32_t>& lB = p.h_lB; PinVec<int64_t>& tot = p.h_tot;
     p.nnz_tap.assign(2 * T, 0);
-    SLS_CK(sls_kcopy(p.h_lnnz.data(), p.lnnz.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
-    SLS_CK(sls_kcopy(lA.data(), p.lnnzA.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
-    SLS_CK(sls_kcopy(lB.data(), p.lnnzB.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
-    SLS_CK(sls_kcopy(tot.data(), p.tot.p, (size_t)(p.ncols + 1) * sizeof(int64_t), h->stream));
+    // only the totals cross the bus here; the per-column arrays (lnnz, lA, lB, tot) are statistics and are fetched by
+    // plan_stats when somebody asks for them
+    SLS_CK(sls_kcopy(tot.data() + p.ncols, p.tot.as<int64_t>() + p.ncols, sizeof(int64_t), h->stream));
     SLS_CK(sls_kgather64(p.h_last.data(), v.colptr + Nx, (size_t)(Nx + 1), (int)(2 * T), h->stream));
+    (void)lA; (void)lB;
     // size classes of kernel 2 (by n, known since the count pass): binned on the host while kernel 1b runs
     p.classes.clear();
     SLS_CK(p.h_lists.resize(nc1));
@@ -667,7 +682,9 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
         SLS_CK(p.lists.ensure(nc1 * sizeof(int32_t)));
         SLS_CK(sls_kcopy(p.lists.p, p.h_lists.data(), off * sizeof(int32_t), h->stream));
     }
+    if (trace) t4 = now();
     SLS_CK(rt::sync(h->stream));
+    if (trace) t5 = now();
     for (int64_t tt = 0; tt < 2 * T; tt++) p.nnz_tap[tt] = p.h_last[tt];
     p.out_off.assign(2 * T + 1, 0);
     for (int64_t tt = 0; tt < 2 * T; tt++) { p.nnz_tap[tt] -= 1; p.out_off[tt + 1] = p.out_off[tt] + p.nnz_tap[tt]; }
@@ -678,14 +695,23 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     for (SolveClass& c : p.classes)
         c.nnzcap = (int)std::min<int64_t>((int64_t)c.N * h->maxcolA + (int64_t)c.mcap * h->maxcolB2, (int64_t)c.N * (c.N + c.mcap));
     p.stats_valid = false;
+    if (trace) fprintf(stderr, "[plan] to-sync1 %.3f  sync1 %.3f  host->fill %.3f  fill..sync2 %.3f  sync2 %.3f  tail %.3f  total %.3f ms\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, now() - t5, now() - t0);
     p.valid = true;
     return 0;
 }
 
 // SURVEY §8d algorithmic work of a plan (reported by sls_get_timing; not needed to run the kernels)
-static void plan_stats(Plan& p, int64_t T) {
+static void plan_stats(sls_handle* h, Plan& p, int64_t T) {
     if (p.stats_valid) return;
     p.alg_flops = 0; p.alg_bytes = 0;
+    if (p.ncols > 0) {
+        int e = sls_kcopy(p.h_lnnz.data(), p.lnnz.p, (size_t)p.ncols * sizeof(int32_t), h->stream);
+        if (!e) e = sls_kcopy(p.h_lA.data(), p.lnnzA.p, (size_t)p.ncols * sizeof(int32_t), h->stream);
+        if (!e) e = sls_kcopy(p.h_lB.data(), p.lnnzB.p, (size_t)p.ncols * sizeof(int32_t), h->stream);
+        if (!e) e = sls_kcopy(p.h_tot.data(), p.tot.p, (size_t)(p.ncols + 1) * sizeof(int64_t), h->stream);
+        if (!e) e = rt::sync(h->stream);
+        if (e) return;
+    }
     for (int i = 0; i < p.ncols; i++) {
         const double n = p.h_n[i], m = p.h_m[i], v_ = (double)(p.h_tot[i + 1] - p.h_tot[i]);
         p.alg_flops += n * n * v_ + (7.0 / 3.0) * (double)T * n * n * n;
@@ -1252,7 +1278,7 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
     h->tm = sls_timing{};
     h->tm.solve_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);       // whole pipelined call (copies, kernels 1-3) on the device clock
     h->tm.solve_launches = launches; h->tm.gather_launches = 3 * K; h->tm.scatter_launches = 2 * K;
-    for (int c = 0; c < K; c++) { plan_stats(h->pipe[c]->plan, T); flops += h->pipe[c]->plan.alg_flops; bytes += h->pipe[c]->plan.alg_bytes; }
+    h->pipe_chunks = K;                                        // alg_flops / alg_bytes: summed over the chunks' plans on demand (sls_get_timing)
     h->tm.ncols = ncols; h->tm.nnz_out = nnz_total; h->tm.alg_flops = flops; h->tm.alg_bytes = bytes;
     h->tm_from_plan = false;
     // the support columns of the range (+halo) stay on the device; a later sls_plan of other columns needs
@@ -1382,8 +1408,15 @@ extern "C" int sls_get_timing(const sls_handle* h, sls_timing* out) {
     if (!h || !out) return -1;
     sls_handle* hm = const_cast<sls_handle*>(h);
     if (hm->tm_from_plan && hm->plan.valid) {
-        plan_stats(hm->plan, hm->T);
+        plan_stats(hm, hm->plan, hm->T);
         hm->tm.alg_flops = hm->plan.alg_flops; hm->tm.alg_bytes = hm->plan.alg_bytes;
+    } else if (!hm->tm_from_plan && hm->pipe_chunks > 0) {
+        double flops = 0, bytes = 0;
+        for (int c = 0; c < hm->pipe_chunks && c < (int)hm->pipe.size(); c++) {
+            plan_stats(hm, hm->pipe[c]->plan, hm->T);
+            flops += hm->pipe[c]->plan.alg_flops; bytes += hm->pipe[c]->plan.alg_bytes;
+        }
+        hm->tm.alg_flops = flops; hm->tm.alg_bytes = bytes;
     }
     *out = h->tm;
     return 0;

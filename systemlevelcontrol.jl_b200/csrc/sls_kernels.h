@@ -51,6 +51,7 @@ struct SlsScatterArgs {
 int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream);
 int sls_launch_unscale(const SlsPlanView& P, int c_begin, int c_end, const int64_t* const* rowval, double* const* nzval,
                        const double* wx, const double* wu, sls_stream_t stream);
+int sls_launch_iota(int32_t* dst, int32_t first, int n, sls_stream_t stream);
 int sls_kcopy(void* dst, const void* src, size_t bytes, sls_stream_t stream);   // either side may be pinned host memory
 int sls_kgather64(int64_t* dst, const int64_t* src, size_t pitch, int count, sls_stream_t stream);
 int sls_launch_colptr_rebase(int64_t* dst, const int64_t* src, const int64_t* base, int64_t len, int narr, int64_t j0, int64_t j1,

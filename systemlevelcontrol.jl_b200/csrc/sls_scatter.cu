@@ -101,12 +101,25 @@ int sls_launch_colptr_rebase(int64_t* dst, const int64_t* src, const int64_t* ba
 __global__ void sls_kcopy_kernel(uint32_t* dst, const uint32_t* src, size_t nwords) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
+// 16-byte variant: SM-initiated PCIe reads are latency-bound per request, so wide requests matter when src is host memory
+__global__ void sls_kcopy16_kernel(uint4* dst, const uint4* src, size_t nvec) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
 int sls_kcopy(void* dst, const void* src, size_t bytes, sls_stream_t stream) {
     if (!bytes) return 0;
-    const size_t nwords = (bytes + 3) / 4;
-    const int grid = (int)((nwords + 255) / 256 < 296 ? (nwords + 255) / 256 : 296);
-    auto kp = &sls_kcopy_kernel;
-    SLS_LAUNCH(kp, grid, 256, 0, stream, reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const uint32_t*>(src), nwords);
+    const size_t nvec = ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) ? bytes / 16 : 0;
+    if (nvec) {
+        const int grid = (int)((nvec + 255) / 256 < 296 ? (nvec + 255) / 256 : 296);
+        auto kp = &sls_kcopy16_kernel;
+        SLS_LAUNCH(kp, grid, 256, 0, stream, reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), nvec);
+    }
+    const size_t done = nvec * 16;
+    if (done < bytes) {
+        const size_t nwords = (bytes - done + 3) / 4;
+        const int grid = (int)((nwords + 255) / 256 < 296 ? (nwords + 255) / 256 : 296);
+        auto kp = &sls_kcopy_kernel;
+        SLS_LAUNCH(kp, grid, 256, 0, stream, reinterpret_cast<uint32_t*>((char*)dst + done), reinterpret_cast<const uint32_t*>((const char*)src + done), nwords);
+    }
     return rt::last_error();
 }
 // dst[i] = src[i * pitch], i < count  (the last colptr entry of every tap)
@@ -146,5 +159,17 @@ int sls_launch_unscale(const SlsPlanView& P, int c_begin, int c_end, const int64
     if (c_end <= c_begin) return 0;
     auto kp = &sls_unscale_kernel;
     SLS_LAUNCH(kp, (c_end - c_begin + 7) / 8, 256, 0, stream, P, c_begin, c_end, rowval, nzval, wx, wu);
+    return rt::last_error();
+}
+
+// dst[i] = first + i  (the column list of a plan over all columns / a contiguous range: nothing to copy from the host)
+__global__ void sls_iota_kernel(int32_t* dst, int32_t first, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = first + i;
+}
+int sls_launch_iota(int32_t* dst, int32_t first, int n, sls_stream_t stream) {
+    if (n <= 0) return 0;
+    auto kp = &sls_iota_kernel;
+    SLS_LAUNCH(kp, (n + 255) / 256, 256, 0, stream, dst, first, n);
     return rt::last_error();
 }

@@ -224,5 +224,6 @@ template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; 
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 using std::max; using std::min; using std::sqrt;
 
+struct uint4 { unsigned int x, y, z, w; };
 struct double2 { double x, y; };
 inline double2 make_double2(double a, double b) { return double2{a, b}; }
