@@ -44,6 +44,17 @@ def _worker(rank, world, port, q):
     c0, c1 = int(ranges[rank]), int(ranges[rank + 1])
     Sx, Su = W.chain_supports(Nx, 9, 29, 1.5, max(0, c0 - 1), min(Nx, c1 + 1))     # slab + halo only
     Phix, Phiu = slc_b200.SLS_H2(slc_b200.Plant(A, B1, B2), [Sx, Su], I=[[j] for j in range(c0, c1)], api=api)
+    # the same shard through the one-shot pipelined entry point (sls_synthesize with a column range), what bench.py's
+    # e2e leg runs per rank: must equal the three-call result bit for bit
+    os.environ["SLS_PIPE_CHUNKS"] = "2"
+    syn = slc_b200.Synthesizer(api=api)
+    syn.set_plant(A, B2)
+    out = syn.synthesize(Sx, Su, col_range=(c0, c1))
+    Px, Pu = syn.outputs_to_scipy(out)
+    syn.close()
+    for t in range(len(Phix)):
+        for F, G in ((Px[t], Phix[t]), (Pu[t], Phiu[t])):
+            assert np.array_equal(F.indptr, G.indptr) and np.array_equal(F.indices, G.indices) and np.array_equal(F.data, G.data)
     gathered = [None] * world
     dist.all_gather_object(gathered, (Phix, Phiu))
     if rank == 0:
