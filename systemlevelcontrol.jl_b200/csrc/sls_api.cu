@@ -140,8 +140,7 @@ struct sls_handle {
     int pipe_chunks = 0;                // chunks of the last sls_synthesize (their plans hold its statistics)
     bool tm_from_plan = true;           // alg_flops / alg_bytes of tm come from h->plan (lazily) rather than from sls_synthesize
     // pipelined one-shot path
-    sls_stream_t in_stream{}, scat_stream{}, out2_stream{}, side_stream{};   // side: the minor size classes of kernel 2
-    rt::Event side_ev, side_go;
+    sls_stream_t in_stream{}, scat_stream{}, out2_stream{};
     rt::Event pipe_done2;
     rt::Event pipe_in[SLS_PIPE_MAX];
     rt::Event pipe_done;
@@ -191,9 +190,6 @@ extern "C" int sls_create(const sls_options* opts, sls_handle** out) {
     if (!e) e = rt::stream_create(&h->in_stream);
     if (!e) e = rt::stream_create(&h->scat_stream);
     if (!e) e = rt::stream_create(&h->out2_stream);
-    if (!e) e = rt::stream_create(&h->side_stream);
-    if (!e) e = h->side_ev.create();
-    if (!e) e = h->side_go.create();
     if (!e) e = h->pipe_done2.create();
     for (int i = 0; i < SLS_PIPE_MAX && !e; i++) e = h->pipe_in[i].create();
     if (!e) e = h->pipe_done.create();
@@ -215,7 +211,6 @@ extern "C" void sls_destroy(sls_handle* h) {
     rt::sync(h->in_stream);
     rt::sync(h->scat_stream);
     rt::sync(h->out2_stream);
-    rt::sync(h->side_stream);
     for (PipeCtx* x : h->pipe) { x->release(); delete x; }
     h->pipe.clear();
     h->pipe_colptr.release(); h->pipe_status.release(); h->pipe_resid.release();
@@ -226,8 +221,6 @@ extern "C" void sls_destroy(sls_handle* h) {
     rt::stream_destroy(h->in_stream);
     rt::stream_destroy(h->scat_stream);
     rt::stream_destroy(h->out2_stream);
-    rt::stream_destroy(h->side_stream);
-    h->side_ev.destroy(); h->side_go.destroy();
     h->pipe_done2.destroy();
     h->A.release(); h->B2.release(); h->Ar.release(); h->B2r.release();
     h->Sx.release(); h->Su.release(); h->plan.release();
@@ -820,57 +813,6 @@ extern "C" int sls_local_problem(sls_handle* h, int64_t k, double* At, double* B
 }
 
 // ---- solve (kernels 2 + 3) ------------------------------------------------------------------
-// Kernel 2 over the size classes of a plan (planned-column positions [c_lo, c_hi)).  The class with the most columns runs
-// on the main stream; the minor classes (the few edge columns of a chain: 2 blocks, 0.14 ms of an otherwise idle GPU)
-// run beside it on the side stream, each class in its own region of the history buffer.
-static int launch_solve_classes(sls_handle* h, Plan& p, const SlsPlanView& v, int c_lo, int c_hi, double* const* out_nzval,
-                                int32_t* status, double* resid, int64_t* launches) {
-    const int64_t T = h->T;
-    const int nk = (int)p.classes.size();
-    std::vector<size_t> hoff(nk + 1, 0);
-    int major = 0;
-    for (int k = 0; k < nk; k++) {
-        const SolveClass& c = p.classes[k];
-        const int maxw = sls_solve_max_resident_warps(c.N, c.mcap, c.nnzcap, (int)T, p.wu, h->sm_count, h->max_smem);
-        if (maxw <= 0) return fail(h, -4, "sls_solve: local problem does not fit shared memory");
-        const int64_t warps = std::min<int64_t>(maxw, ((int64_t)c.count + 3) / 4 * 4);
-        hoff[k + 1] = hoff[k] + (size_t)warps * sls_solve_hist_doubles(c.N, (int)T);
-        if (c.count > p.classes[major].count) major = k;
-    }
-    SLS_CK(h->hist.ensure(std::max<size_t>(hoff[nk], 1) * sizeof(double)));
-    bool side_used = false;
-    int side_warps = 0;                                        // the major class leaves these resident slots to the minor ones
-    for (int pass = 0; pass < 2; pass++) {                      // minor classes first: they are in flight when the major one starts
-        for (int k = 0; k < nk; k++) {
-            if ((pass == 0) == (k == major)) continue;
-            const SolveClass& c = p.classes[k];
-            const int32_t* lb = p.h_lists.data() + c.list_off;
-            const int lo = (int)(std::lower_bound(lb, lb + c.count, c_lo) - lb);
-            const int hi = (int)(std::lower_bound(lb, lb + c.count, c_hi) - lb);
-            if (hi <= lo) continue;
-            SlsSolveArgs a{};
-            a.A = h->A.view(); a.B2 = h->B2.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();
-            a.P = v; a.list = p.lists.as<int32_t>() + c.list_off + lo; a.count = hi - lo;
-            a.mcap = c.mcap; a.nnzcap = c.nnzcap;
-            a.out_nzval = out_nzval; a.hist = h->hist.as<double>() + hoff[k];
-            a.hist_stride = sls_solve_hist_doubles(c.N, (int)T);
-            a.status = status; a.resid = resid;
-            a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
-            int warps = (k == major) ? side_warps : 0;
-            sls_stream_t st = h->stream;
-            if (k != major) {
-                if (!side_used) { h->side_go.record(h->stream); SLS_CK(rt::stream_wait(h->side_stream, h->side_go)); side_used = true; }
-                st = h->side_stream;
-            }
-            SLS_CK(sls_launch_solve(c.N, a, h->sm_count, h->max_smem, &warps, st));
-            if (k != major) side_warps += warps;
-            (*launches)++;
-        }
-    }
-    if (side_used) { h->side_ev.record(h->side_stream); SLS_CK(rt::stream_wait(h->stream, h->side_ev)); }
-    return 0;
-}
-
 namespace {
 struct HostOut {
     int64_t* const* cps[2]; int64_t* const* rvs[2]; double* const* nzs[2];
@@ -920,7 +862,16 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         }
         SLS_CK(rt::sync(h->stream));
     }
+    // history slots: sized for the most demanding class
+    size_t hist_bytes = 8;
     const SlsPlanView v = plan_view(h, p);
+    for (const SolveClass& c : p.classes) {
+        const int maxw = sls_solve_max_resident_warps(c.N, c.mcap, c.nnzcap, (int)T, p.wu, h->sm_count, h->max_smem);
+        if (maxw <= 0) return fail(h, -4, "sls_solve: local problem does not fit shared memory");
+        const int64_t warps = std::min<int64_t>(maxw, ((int64_t)c.count + 3) / 4 * 4);
+        hist_bytes = std::max(hist_bytes, (size_t)warps * sls_solve_hist_doubles(c.N, (int)T) * sizeof(double));
+    }
+    SLS_CK(h->hist.ensure(hist_bytes));
     h->ev[4].record(h->stream);
     if (ho) {                                                  // colptr arrays are final since sls_plan
         SLS_CK(rt::stream_wait(h->copy_stream, h->ev[4]));
@@ -943,8 +894,23 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         if (p.ncols) scatters++;
     }
     for (int ch = 0; ch < nchunk; ch++) {
-        SLS_CK(launch_solve_classes(h, p, v, cb[ch], cb[ch + 1], reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T),
-                                    h->status.as<int32_t>(), h->resid.as<double>(), &launches));
+        for (const SolveClass& c : p.classes) {
+            const int32_t* lb = p.h_lists.data() + c.list_off;
+            const int lo = (int)(std::lower_bound(lb, lb + c.count, cb[ch]) - lb);
+            const int hi = (int)(std::lower_bound(lb, lb + c.count, cb[ch + 1]) - lb);
+            if (hi <= lo) continue;
+            SlsSolveArgs a{};
+            a.A = h->A.view(); a.B2 = h->B2.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();
+            a.P = v; a.list = p.lists.as<int32_t>() + c.list_off + lo; a.count = hi - lo;
+            a.mcap = c.mcap; a.nnzcap = c.nnzcap;
+            a.out_nzval = reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T); a.hist = h->hist.as<double>();
+            a.hist_stride = sls_solve_hist_doubles(c.N, (int)T);
+            a.status = h->status.as<int32_t>(); a.resid = h->resid.as<double>();
+            a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
+            int warps = 0;
+            SLS_CK(sls_launch_solve(c.N, a, h->sm_count, h->max_smem, &warps, h->stream));
+            launches++;
+        }
         if (h->have_weights) {                                  // back-scaling needs kernel 3's rowval as well
             SLS_CK(rt::stream_wait(h->stream, h->chunk_ev[15]));
             SLS_CK(sls_launch_unscale(v, cb[ch], cb[ch + 1], reinterpret_cast<const int64_t* const*>(h->out_ptrs.as<void*>()),
@@ -1086,7 +1052,7 @@ static int pipe_enqueue_slice(sls_handle* h, PipeSupp& f, int64_t T, int64_t nco
 }
 
 static void pipe_drain(sls_handle* h) {
-    rt::sync(h->in_stream); rt::sync(h->stream); rt::sync(h->scat_stream); rt::sync(h->copy_stream); rt::sync(h->out2_stream); rt::sync(h->side_stream);
+    rt::sync(h->in_stream); rt::sync(h->stream); rt::sync(h->scat_stream); rt::sync(h->copy_stream); rt::sync(h->out2_stream);
 }
 
 extern "C" int sls_synthesize(sls_handle* h, int64_t T,
@@ -1209,6 +1175,15 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
         PIPE_CK(sls_kcopy(x.out_ptrs.p, x.h_ptrs.data(), (size_t)4 * T * sizeof(void*), h->stream));
         PIPE_CK(sls_kcopy(x.base.p, x.h_base.data(), (size_t)2 * T * sizeof(int64_t), h->stream));
         const SlsPlanView v = plan_view(h, p);
+        size_t hist_bytes = 8;
+        for (const SolveClass& cl : p.classes) {
+            const int maxw = sls_solve_max_resident_warps(cl.N, cl.mcap, cl.nnzcap, (int)T, p.wu, h->sm_count, h->max_smem);
+            if (maxw <= 0) { e = fail(h, -4, "sls_synthesize: local problem does not fit shared memory"); break; }
+            const int64_t warps = std::min<int64_t>(maxw, ((int64_t)cl.count + 3) / 4 * 4);
+            hist_bytes = std::max(hist_bytes, (size_t)warps * sls_solve_hist_doubles(cl.N, (int)T) * sizeof(double));
+        }
+        if (e) break;
+        PIPE_CK(h->hist.ensure(hist_bytes));
         // the caller's colptr = the chunk's colptr + entries of the earlier chunks (columns c0+1..c1; chunk 0 also writes [0])
         const int64_t j0 = (c == 0) ? 0 : c0 + 1, j1 = (c == K - 1) ? Nx : c1;   // columns outside the range are empty
         PIPE_CK(sls_launch_colptr_rebase(h->pipe_colptr.as<int64_t>(), p.colptr.as<int64_t>(), x.base.as<int64_t>(), Nx + 1, (int)(2 * T), j0, j1, h->stream));
@@ -1222,8 +1197,19 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
             PIPE_CK(sls_launch_scatter(sa, h->scat_stream));
         }
         x.ev_scat.record(h->scat_stream);
-        e = launch_solve_classes(h, p, v, 0, p.ncols, reinterpret_cast<double* const*>(x.out_ptrs.as<void*>() + 2 * T),
-                                 x.status.as<int32_t>(), x.resid.as<double>(), &launches);
+        for (const SolveClass& cl : p.classes) {
+            SlsSolveArgs a{};
+            a.A = h->A.view(); a.B2 = h->B2.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();
+            a.P = v; a.list = p.lists.as<int32_t>() + cl.list_off; a.count = cl.count;
+            a.mcap = cl.mcap; a.nnzcap = cl.nnzcap;
+            a.out_nzval = reinterpret_cast<double* const*>(x.out_ptrs.as<void*>() + 2 * T); a.hist = h->hist.as<double>();
+            a.hist_stride = sls_solve_hist_doubles(cl.N, (int)T);
+            a.status = x.status.as<int32_t>(); a.resid = x.resid.as<double>();
+            a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
+            int warps = 0;
+            PIPE_CK(sls_launch_solve(cl.N, a, h->sm_count, h->max_smem, &warps, h->stream));
+            launches++;
+        }
         if (e) break;
         if (h->have_weights) {
             PIPE_CK(rt::stream_wait(h->stream, x.ev_scat));

@@ -36,7 +36,7 @@ int sls_solve_class_N(int k);
 // shared memory (bytes per warp) and history doubles per warp for class N
 size_t sls_solve_smem_per_warp(int N, int mcap, int nnzcap, int T, int wu);
 int64_t sls_solve_hist_doubles(int N, int T);
-// launches one class; *warps_launched: in = resident warps to leave free for kernels running beside it, out = warps launched
+// launches one class; *slots_io: in = available history slots (warps), out = warps launched
 int sls_launch_solve(int N, const SlsSolveArgs& a, int sm_count, int max_smem, int* warps_launched,
                      sls_stream_t stream);
 int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem);

@@ -778,10 +778,7 @@ static int launch_class(const SlsSolveArgs& a, int sm_count, int max_smem, int* 
     if (maxw <= 0) return -5;
     auto kp = &sls_solve_kernel<NB>;
     int blocks = (a.count + WPB - 1) / WPB;
-    // *warps_launched on entry: resident warps to leave free for kernels of other size classes running beside this one
-    int room = (maxw - *warps_launched) / WPB;
-    if (room < maxw / WPB / 2) room = maxw / WPB / 2;
-    if (blocks > room) blocks = room;
+    if (blocks > maxw / WPB) blocks = maxw / WPB;
     if (blocks < 1) blocks = 1;
     *warps_launched = blocks * WPB;
     SLS_LAUNCH(kp, blocks, WPB * 32, per_block, stream, a);
@@ -801,8 +798,8 @@ int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int
 
 int sls_launch_solve(int N, const SlsSolveArgs& a, int sm_count, int max_smem, int* warps_launched,
                      sls_stream_t stream) {
-    if (*warps_launched < 0) *warps_launched = 0;
-    if (a.count == 0) { *warps_launched = 0; return 0; }
+    *warps_launched = 0;
+    if (a.count == 0) return 0;
     switch (N / 8) {
 #define X(nb) case nb: return launch_class<nb>(a, sm_count, max_smem, warps_launched, stream);
         SLS_FOR_CLASSES(X)
