@@ -162,18 +162,22 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
     }
     __syncwarp();
     const int total = pfx[2 * T];
+    // an index set that is a run of consecutive rows (banded plants) maps a row to its local index by subtraction
+    const bool runx = n > 0 && sx[n - 1] - sx[0] == n - 1, runu = m > 0 && su[m - 1] - su[0] == m - 1;
+    int tt = 0;                                               // a lane's entries f = lane, lane+32, ... move forward through the taps
 #pragma unroll 1
     for (int f = lane; f < total; f += 32) {
-        int lo = 0, hi = 2 * T;                               // largest tt with pfx[tt] <= f
 #pragma unroll 1
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pfx[mid] <= f) lo = mid; else hi = mid; }
-        const int tt = lo;
+        while (pfx[tt + 1] <= f) tt++;                        // largest tt with pfx[tt] <= f  (pfx[2T] = total > f)
         const bool isu = tt >= T;
         const int t = isu ? tt - T : tt;
         const SlsSupports& S = isu ? Su : Sx;
         const int64_t e = seg0[tt] + (f - pfx[tt]);
         const bool on = S.nzval ? (S.nzval[e] != 0) : true;   // `𝓢[t][s,cⱼ] .≠ 1` fixes the entry (synthesis.jl:58-59)
-        const int idx = isu ? sls_find(su, m, (int32_t)(S.rowval[e] - 1)) : sls_find(sx, n, (int32_t)(S.rowval[e] - 1));
+        const int32_t row = (int32_t)(S.rowval[e] - 1);
+        int idx;
+        if (isu) { if (runu) { idx = row - su[0]; if (idx < 0 || idx >= m) idx = -1; } else idx = sls_find(su, m, row); }
+        else { if (runx) { idx = row - sx[0]; if (idx < 0 || idx >= n) idx = -1; } else idx = sls_find(sx, n, row); }
         if (on && idx >= 0) atomicOr(&mw[t * nmw + (isu ? P.wx : 0) + (idx >> 5)], 1u << (idx & 31));
     }
     __syncwarp();
