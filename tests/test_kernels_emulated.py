@@ -51,3 +51,14 @@ def test_emu_pipelined_one_shot_equals_three_call(emu_api):
 
 def test_emu_weighted_cost_and_groups(emu_api):
     pc.check_weighted_cost(emu_api, cols=(3, 39, 14))
+
+
+def test_emu_pipelined_ring_plant_long_range_coupling(emu_api):
+    """A ring (A[0,Nx-1], A[Nx-1,0] != 0): the first column chunk reaches the last support columns and vice versa, so the
+    copy-in / plan dependency logic of sls_synthesize degenerates to waiting for every upload; results must not change."""
+    import scipy.sparse as sp
+    Nx = 24
+    A, B1, B2 = O.chain_plant(Nx)
+    A = sp.lil_matrix(A); A[0, Nx - 1] = -0.2; A[Nx - 1, 0] = 0.2; A = sp.csc_matrix(A)
+    S = O.make_supports(A, B2, 3, 8, 1.5)
+    pc.check_pipelined(emu_api, (A, B1, B2), S, chunks=[4])
