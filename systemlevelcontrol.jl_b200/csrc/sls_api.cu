@@ -77,7 +77,7 @@ struct SolveClass { int N, count, mcap, nnzcap; size_t list_off; };
 struct Plan {
     bool valid = false;
     int ncols = 0, nstride = 1, mstride = 1, wx = 1, wu = 1, nmax = 0, mmax = 0, cap = 32;
-    DevBuf cols, n, m, sx, su, maskx, masku, jloc, lnnz, lnnzA, lnnzB, pre, tot, colptr, lists;
+    DevBuf cols, n, m, sx, su, maskx, masku, jloc, lnnz, lnnzA, lnnzB, pre, tot, colptr, lists, keepx, keepu;
     PinVec<int32_t> h_cols, h_lists;    // pinned: read by kernel copies (sls_kcopy)
     bool cols_sorted = true;            // planned columns strictly ascending => a planned-index range is a CSC column range
     PinVec<int32_t> h_status; PinVec<double> h_resid;
@@ -93,7 +93,7 @@ struct Plan {
     int64_t col_lo = 0, col_hi = 0;     // planned columns lie in [col_lo, col_hi)
     int identity_cols = 0;              // h_cols currently holds 0..identity_cols-1 (the cols == NULL plan)
     void release() {
-        DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists};
+        DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists, &keepx, &keepu};
         for (DevBuf* b : all) b->release();
         h_seg.release(); h_status.release(); h_resid.release(); h_cols.release(); h_lists.release();
         h_n.release(); h_m.release(); h_lnnz.release(); h_lA.release(); h_lB.release(); h_tot.release(); h_last.release();
@@ -608,8 +608,12 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     }
     if ((size_t)cap * 4 * sizeof(int32_t) + 4096 > (size_t)h->max_smem)
         return fail(h, -4, "plan: candidate index list of a column does not fit shared memory");
+    // kernel 1a leaves the index sets for kernel 1b (row stride cap) unless that would take more than 1 GB
+    const bool keep = (size_t)nc1 * cap * 2 * sizeof(int32_t) <= ((size_t)1 << 30);
+    if (keep) { SLS_CK(p.keepx.ensure((size_t)nc1 * cap * sizeof(int32_t))); SLS_CK(p.keepu.ensure((size_t)nc1 * cap * sizeof(int32_t))); }
     SLS_CK(sls_launch_gather_count(h->A.view(), h->Sx.view(), h->Su.view(), (int)T, Nx, p.cols.as<int32_t>(), p.ncols,
-                                   p.n.as<int32_t>(), p.m.as<int32_t>(), cap, h->stream));
+                                   p.n.as<int32_t>(), p.m.as<int32_t>(), cap, keep ? p.keepx.as<int32_t>() : nullptr,
+                                   keep ? p.keepu.as<int32_t>() : nullptr, h->stream));
     SLS_CK(p.h_n.resize(nc1)); SLS_CK(p.h_m.resize(nc1));
     p.h_n[0] = 0; p.h_m[0] = 0;
     SLS_CK(sls_kcopy(p.h_n.data(), p.n.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
@@ -643,7 +647,8 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     const size_t fill_smem = (size_t)4 * sls_gather_fill_words(cap, p.nstride, p.mstride, p.wx, p.wu, (int)T) * sizeof(int32_t);
     if (fill_smem > (size_t)h->max_smem) return fail(h, -4, "plan: index sets do not fit shared memory");
     if (trace) t3 = now();
-    SLS_CK(sls_launch_gather_fill(h->A.view(), h->B2.view(), h->Sx.view(), h->Su.view(), v, cap, h->stream));
+    SLS_CK(sls_launch_gather_fill(h->A.view(), h->B2.view(), h->Sx.view(), h->Su.view(), v, cap, keep ? p.keepx.as<int32_t>() : nullptr,
+                                  keep ? p.keepu.as<int32_t>() : nullptr, h->stream));
     SLS_CK(sls_launch_scan(v.colptr, Nx + 1, (int)(2 * T), v.tot, p.ncols + 1, p.col_lo, p.col_hi, h->stream));
     // sizes back to the host
     SLS_CK(p.h_lnnz.resize(nc1)); SLS_CK(p.h_lA.resize(nc1)); SLS_CK(p.h_lB.resize(nc1));

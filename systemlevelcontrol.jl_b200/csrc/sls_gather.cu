@@ -80,16 +80,24 @@ __device__ int sls_warp_index_set(const SlsCsc& A, const SlsSupports& S, int T, 
 // kernel 1a: sizes only (n, m) so that the host can size the strided metadata exactly.
 __global__ void __launch_bounds__(GATHER_WPB * 32)
 sls_gather_count_kernel(SlsCsc A, SlsSupports Sx, SlsSupports Su, int T, int64_t Nx,
-                        const int32_t* __restrict__ cols, int ncols, int32_t* n_out, int32_t* m_out, int cap) {
+                        const int32_t* __restrict__ cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
+                        int32_t* keep_x, int32_t* keep_u) {
     SLS_DYN_SMEM(smem);
     const int warp = threadIdx.x >> 5, lane = sls_lane();
     const int c = blockIdx.x * GATHER_WPB + warp;
     if (c >= ncols) return;
     int32_t* buf = reinterpret_cast<int32_t*>(smem) + (size_t)warp * cap;
     const int64_t j = cols[c];
+    // the index sets are kept (row stride cap) so that kernel 1b does not gather and sort them a second time
     const int n = sls_warp_index_set(A, Sx, T, Nx, j, buf, cap);
+    if (keep_x)
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) keep_x[(size_t)c * cap + i] = buf[i];
     __syncwarp();
     const int m = sls_warp_index_set(A, Su, T, Nx, j, buf, cap);
+    if (keep_u)
+#pragma unroll 1
+        for (int i = lane; i < m; i += 32) keep_u[(size_t)c * cap + i] = buf[i];
     if (lane == 0) { n_out[c] = n; m_out[c] = m; }
 }
 
@@ -104,7 +112,8 @@ __host__ __device__ int sls_gather_fill_words(int cap, int nstride, int mstride,
 // (segment table + prefix sums in shared memory), so all their loads are independent and in flight together
 // instead of 2T dependent colptr -> rowval round trips.
 __global__ void __launch_bounds__(GATHER_WPB * 32)
-sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsPlanView P, int cap) {
+sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsPlanView P, int cap,
+                       const int32_t* __restrict__ keep_x, const int32_t* __restrict__ keep_u) {
     SLS_DYN_SMEM(smem);
     const int warp = threadIdx.x >> 5, lane = sls_lane();
     const int c = blockIdx.x * GATHER_WPB + warp;
@@ -135,14 +144,24 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
 #pragma unroll 1
     for (int w = lane; w < T * nmw; w += 32) mw[w] = 0u;
 
-    const int n = sls_warp_index_set(A, Sx, T, Nx, j, buf, cap);
+    int n, m;
+    if (keep_x && keep_u) {                                   // index sets left by kernel 1a (P.n / P.m hold their sizes)
+        n = P.n[c]; m = P.m[c];
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) { sx[i] = buf[i]; P.sx[(size_t)c * P.nstride + i] = buf[i]; }
-    __syncwarp();
-    const int m = sls_warp_index_set(A, Su, T, Nx, j, buf, cap);
+        for (int i = lane; i < n; i += 32) { const int32_t r = keep_x[(size_t)c * cap + i]; sx[i] = r; P.sx[(size_t)c * P.nstride + i] = r; }
 #pragma unroll 1
-    for (int i = lane; i < m; i += 32) { su[i] = buf[i]; P.su[(size_t)c * P.mstride + i] = buf[i]; }
-    __syncwarp();
+        for (int i = lane; i < m; i += 32) { const int32_t r = keep_u[(size_t)c * cap + i]; su[i] = r; P.su[(size_t)c * P.mstride + i] = r; }
+        __syncwarp();
+    } else {
+        n = sls_warp_index_set(A, Sx, T, Nx, j, buf, cap);
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) { sx[i] = buf[i]; P.sx[(size_t)c * P.nstride + i] = buf[i]; }
+        __syncwarp();
+        m = sls_warp_index_set(A, Su, T, Nx, j, buf, cap);
+#pragma unroll 1
+        for (int i = lane; i < m; i += 32) { su[i] = buf[i]; P.su[(size_t)c * P.mstride + i] = buf[i]; }
+        __syncwarp();
+    }
     if (lane == 0) { P.n[c] = n; P.m[c] = m; P.jloc[c] = sls_find(sx, n, (int32_t)j); }
 
     // prefix sums of the 2T segment lengths
@@ -342,24 +361,24 @@ __global__ void sls_local_dense_kernel(SlsCsc A, SlsCsc B2, SlsPlanView P, int c
 // ---- host launchers -------------------------------------------------------------------------
 int sls_launch_gather_count(const SlsCsc& A, const SlsSupports& Sx, const SlsSupports& Su, int T, int64_t Nx,
                             const int32_t* cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
-                            sls_stream_t stream) {
+                            int32_t* keep_x, int32_t* keep_u, sls_stream_t stream) {
     if (ncols == 0) return 0;
     const int grid = (ncols + GATHER_WPB - 1) / GATHER_WPB;
     const size_t smem = (size_t)GATHER_WPB * cap * sizeof(int32_t);
     auto kp = &sls_gather_count_kernel;
     if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
-    SLS_LAUNCH(kp, grid, GATHER_WPB * 32, smem, stream, A, Sx, Su, T, Nx, cols, ncols, n_out, m_out, cap);
+    SLS_LAUNCH(kp, grid, GATHER_WPB * 32, smem, stream, A, Sx, Su, T, Nx, cols, ncols, n_out, m_out, cap, keep_x, keep_u);
     return rt::last_error();
 }
 
 int sls_launch_gather_fill(const SlsCsc& A, const SlsCsc& B2, const SlsSupports& Sx, const SlsSupports& Su,
-                           const SlsPlanView& P, int cap, sls_stream_t stream) {
+                           const SlsPlanView& P, int cap, const int32_t* keep_x, const int32_t* keep_u, sls_stream_t stream) {
     if (P.ncols == 0) return 0;
     const int grid = (P.ncols + GATHER_WPB - 1) / GATHER_WPB;
     const size_t smem = (size_t)GATHER_WPB * sls_gather_fill_words(cap, P.nstride, P.mstride, P.wx, P.wu, P.T) * sizeof(int32_t);
     auto kp = &sls_gather_fill_kernel;
     if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
-    SLS_LAUNCH(kp, grid, GATHER_WPB * 32, smem, stream, A, B2, Sx, Su, P, cap);
+    SLS_LAUNCH(kp, grid, GATHER_WPB * 32, smem, stream, A, B2, Sx, Su, P, cap, keep_x, keep_u);
     return rt::last_error();
 }
 

@@ -5,10 +5,10 @@
 // ---- kernel 1 (sls_gather.cu) ----
 int sls_launch_gather_count(const SlsCsc& A, const SlsSupports& Sx, const SlsSupports& Su, int T, int64_t Nx,
                             const int32_t* cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
-                            sls_stream_t stream);
+                            int32_t* keep_x, int32_t* keep_u, sls_stream_t stream);   // keep_*: [ncols][cap] index sets for kernel 1b, or null
 __host__ __device__ int sls_gather_fill_words(int cap, int nstride, int mstride, int wx, int wu, int T);
 int sls_launch_gather_fill(const SlsCsc& A, const SlsCsc& B2, const SlsSupports& Sx, const SlsSupports& Su,
-                           const SlsPlanView& P, int cap, sls_stream_t stream);
+                           const SlsPlanView& P, int cap, const int32_t* keep_x, const int32_t* keep_u, sls_stream_t stream);
 // scans the window [lo, hi) of every colptr array (counts outside it are known to be zero and are not read)
 int sls_launch_scan(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, int64_t lo, int64_t hi, sls_stream_t stream);
 int sls_launch_local_dense(const SlsCsc& A, const SlsCsc& B2, const SlsPlanView& P, int c,
