@@ -622,9 +622,21 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_CK(rt::sync(h->stream));
     if (trace) t2 = now();
     int nmax = 0, mmax = 0;
-    for (int i = 0; i < p.ncols; i++) {
-        if (p.h_n[i] < 0 || p.h_m[i] < 0) return fail(h, -4, "plan: candidate index list overflow in kernel 1");
-        nmax = std::max(nmax, p.h_n[i]); mmax = std::max(mmax, p.h_m[i]);
+    // one pass over the sizes: maxima, overflow check and the histogram of kernel 2's size classes (class = ceil(n/8) - 1;
+    // everything beyond the last class lands in a catch-all bin and is rejected by sls_solve)
+    const int nk_ = sls_solve_class_count();
+    int cls_count[16] = {0};
+    {
+        int bad = 0;
+        const int32_t* hn = p.h_n.data(); const int32_t* hm = p.h_m.data();
+        for (int i = 0; i < p.ncols; i++) {
+            const int n_ = hn[i], m_ = hm[i];
+            bad |= (n_ | m_);
+            nmax = std::max(nmax, n_); mmax = std::max(mmax, m_);
+            int k = n_ > 0 ? (n_ - 1) >> 3 : 0;
+            cls_count[k < nk_ ? k : nk_]++;
+        }
+        if (bad < 0) return fail(h, -4, "plan: candidate index list overflow in kernel 1");
     }
     p.nmax = nmax; p.mmax = mmax;
     p.nstride = std::max(nmax, 1); p.mstride = std::max(mmax, 1);
@@ -663,27 +675,24 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     // size classes of kernel 2 (by n, known since the count pass): binned on the host while kernel 1b runs
     p.classes.clear();
     SLS_CK(p.h_lists.resize(nc1));
-    std::fill(p.h_lists.data(), p.h_lists.data() + nc1, 0);
     {
         size_t off = 0;
-        const int nk = sls_solve_class_count();
+        const int nk = nk_;
         std::vector<SolveClass> cls(nk);
-        std::vector<int> cls_of_n(p.nmax + 2, -1);
-        for (int n = 0; n <= p.nmax; n++) {
-            const int N = sls_solve_class_of(n);
-            for (int k = 0; k < nk; k++) if (sls_solve_class_N(k) == N) cls_of_n[n] = k;
+        int fillpos[17], mcapk[17] = {0};
+        for (int k = 0; k < nk; k++) { cls[k] = SolveClass{sls_solve_class_N(k), cls_count[k], 0, 0, off}; fillpos[k] = (int)off; off += cls_count[k]; }
+        fillpos[nk] = -1;
+        {
+            const int32_t* hn = p.h_n.data(); const int32_t* hm = p.h_m.data(); int32_t* hl = p.h_lists.data();
+            for (int i = 0; i < p.ncols; i++) {
+                const int n_ = hn[i];
+                int k = n_ > 0 ? (n_ - 1) >> 3 : 0;
+                if (k >= nk) continue;                         // larger than the largest class: reported by sls_solve (nmax check)
+                hl[fillpos[k]++] = i;
+                mcapk[k] = std::max(mcapk[k], hm[i]);
+            }
         }
-        for (int k = 0; k < nk; k++) cls[k] = SolveClass{sls_solve_class_N(k), 0, 0, 0, 0};
-        for (int i = 0; i < p.ncols; i++) { const int k = cls_of_n[p.h_n[i]]; if (k >= 0) cls[k].count++; }
-        for (int k = 0; k < nk; k++) { cls[k].list_off = off; off += cls[k].count; cls[k].count = 0; }
-        for (int i = 0; i < p.ncols; i++) {
-            const int k = cls_of_n[p.h_n[i]];
-            if (k < 0) continue;
-            SolveClass& c = cls[k];
-            p.h_lists[c.list_off + c.count++] = i;
-            c.mcap = std::max(c.mcap, p.h_m[i]);
-        }
-        for (int k = 0; k < nk; k++) if (cls[k].count) p.classes.push_back(cls[k]);
+        for (int k = 0; k < nk; k++) { cls[k].mcap = mcapk[k]; if (cls[k].count) p.classes.push_back(cls[k]); }
         SLS_CK(p.lists.ensure(nc1 * sizeof(int32_t)));
         SLS_CK(sls_kcopy(p.lists.p, p.h_lists.data(), off * sizeof(int32_t), h->stream));
     }
