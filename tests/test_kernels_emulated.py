@@ -62,3 +62,8 @@ def test_emu_pipelined_ring_plant_long_range_coupling(emu_api):
     A = sp.lil_matrix(A); A[0, Nx - 1] = -0.2; A[Nx - 1, 0] = 0.2; A = sp.csc_matrix(A)
     S = O.make_supports(A, B2, 3, 8, 1.5)
     pc.check_pipelined(emu_api, (A, B1, B2), S, chunks=[4])
+
+
+def test_emu_random_banded_plants_vs_oracle(emu_api):
+    worst, nclean, nflag = pc.check_random_banded(emu_api, seeds=(0, 5), cols=(0, 5, 24, 47))
+    assert nclean >= 3 and nflag >= 2 and worst < 1e-10

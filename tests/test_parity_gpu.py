@@ -270,3 +270,11 @@ def test_pipelined_one_shot_config3_100k_bit_for_bit(cuda_api):
 def test_weighted_cost_and_column_groups_vs_general_oracle(cuda_api):
     """6-argument Plant with diagonal cost weights, diagonal B1, q = 2 group."""
     assert pc.check_weighted_cost(cuda_api, cols=(3, 14, 39, 0, 20, 27)) < 1e-10
+
+
+def test_random_banded_plants_vs_oracle(cuda_api):
+    """Pentadiagonal random plants with two-state actuators and random gains (not a chain, not a grid): the accuracy /
+    flagging contract on well-conditioned, ill-conditioned and infeasible columns (parity_cases.check_random_banded)."""
+    worst, nclean, nflag = pc.check_random_banded(cuda_api, seeds=(0, 1, 2, 3, 4, 5))
+    assert nclean >= 10 and nflag >= 8, (nclean, nflag)
+    assert worst < 1e-9, worst
