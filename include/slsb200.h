@@ -42,7 +42,7 @@ typedef struct sls_options {
     int32_t device;      /* CUDA device ordinal                                                        */
     int32_t flags;       /* reserved, 0                                                                */
     double  rank_tol;    /* pivot <= rank_tol * diag(D_k) => constraint row treated as redundant; 0 -> 1e-10 */
-    double  feas_tol;    /* max-abs achievability residual above which SLS_STATUS_RESIDUAL is set; 0 -> 1e-12 */
+    double  feas_tol;    /* max-abs achievability residual above which SLS_STATUS_RESIDUAL is set; 0 -> 1e-13 */
 } sls_options;
 
 typedef struct sls_timing {      /* device times (CUDA events on the handle's stream) of the last plan+solve */

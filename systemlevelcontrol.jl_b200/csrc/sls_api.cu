@@ -181,9 +181,9 @@ extern "C" int sls_create(const sls_options* opts, sls_handle** out) {
     if (!h) return fail(nullptr, -2, "sls_create: out of host memory");
     if (opts) h->opt = *opts;
     if (h->opt.rank_tol <= 0) h->opt.rank_tol = 1e-10;
-    // 1e-12: the normal-equations solve is accurate to ~2e-16 cond(G)^2 and the residual tracks that error (error <~ 1e3 x
+    // 1e-13: the normal-equations solve is accurate to ~2e-16 cond(G)^2 and the residual tracks that error (error <~ 1e3 x
     // residual, tests/parity_cases.py::check_random_banded), so this flags every column whose Phi may miss the 1e-9 bar
-    if (h->opt.feas_tol <= 0) h->opt.feas_tol = 1e-12;
+    if (h->opt.feas_tol <= 0) h->opt.feas_tol = 1e-13;
     h->device = h->opt.device;
     if (h->device < 0 || h->device >= ndev) { delete h; return fail(nullptr, -1, "sls_create: device ordinal out of range"); }
     int e = rt::set_device(h->device);

@@ -275,6 +275,6 @@ def test_weighted_cost_and_column_groups_vs_general_oracle(cuda_api):
 def test_random_banded_plants_vs_oracle(cuda_api):
     """Pentadiagonal random plants with two-state actuators and random gains (not a chain, not a grid): the accuracy /
     flagging contract on well-conditioned, ill-conditioned and infeasible columns (parity_cases.check_random_banded)."""
-    worst, nclean, nflag = pc.check_random_banded(cuda_api, seeds=(0, 1, 2, 3, 4, 5))
-    assert nclean >= 10 and nflag >= 8, (nclean, nflag)
-    assert worst < 1e-9, worst
+    worst, nclean, nflag = pc.check_random_banded(cuda_api, seeds=tuple(range(12)))
+    assert nclean >= 15 and nflag >= 15, (nclean, nflag)
+    assert worst < 1e-10, worst                               # measured: 1.4e-11 over 16 seeds
