@@ -908,6 +908,14 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         SLS_CK(sls_launch_scatter(s, h->copy_stream));
         h->chunk_ev[15].record(h->copy_stream);
         if (p.ncols) scatters++;
+        // rowval is final now (it does not depend on kernel 2): its device->host copies start at once, whole taps, so the
+        // D2H engine works from the first millisecond of kernel 2 and only the values trail the solve chunks
+        if (ho)
+            for (int64_t tt = 0; tt < 2 * T; tt++) {
+                const int x = tt >= T; const int64_t t = x ? tt - T : tt;
+                if (ho->rvs[x] && ho->rvs[x][t] && p.nnz_tap[tt])
+                    SLS_CK(rt::d2h(ho->rvs[x][t], h->out_rowval.as<int64_t>() + p.out_off[tt], (size_t)p.nnz_tap[tt] * sizeof(int64_t), h->copy_stream));
+            }
     }
     for (int ch = 0; ch < nchunk; ch++) {
         for (const SolveClass& c : p.classes) {
@@ -940,8 +948,6 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
                 int64_t o0 = 0, o1 = p.nnz_tap[tt];
                 if (nchunk > 1) { o0 = p.h_seg[(size_t)ch * 2 * T + tt] - 1; o1 = p.h_seg[(size_t)(ch + 1) * 2 * T + tt] - 1; }
                 if (o1 <= o0) continue;
-                if (ho->rvs[x] && ho->rvs[x][t])
-                    SLS_CK(rt::d2h(ho->rvs[x][t] + o0, h->out_rowval.as<int64_t>() + p.out_off[tt] + o0, (o1 - o0) * sizeof(int64_t), h->copy_stream));
                 if (ho->nzs[x] && ho->nzs[x][t])
                     SLS_CK(rt::d2h(ho->nzs[x][t] + o0, h->out_nzval.as<double>() + p.out_off[tt] + o0, (o1 - o0) * sizeof(double), h->copy_stream));
             }
