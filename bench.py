@@ -37,8 +37,9 @@ sys.path.insert(0, ROOT)
 NX_PER_GPU = 100_000
 D, T, ALPHA = 9, 29, 1.5
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
-# (profiles/r01_step_kernels_ncu_raw.txt): kernel 2 N=24 class; kernel 1b + kernel 3
-NCU_TRAFFIC = {("chain", 100_000, "solve"): 9.86e9, ("chain", 100_000, "gather_scatter"): 0.747e9 + 0.577e9}
+# (profiles/r01_solve_final_ncu_summary.txt: kernel 2, N=24 class, 3.35 GB read + 6.13 GB written — the factor history;
+#  profiles/r01_gather_fill_ncu_summary.txt: kernel 1b 0.67 + 0.10 GB; kernel 3 0.577 GB from profiles/r01_step_kernels_ncu_raw.txt)
+NCU_TRAFFIC = {("chain", 100_000, "solve"): 9.48e9, ("chain", 100_000, "gather_scatter"): 0.770e9 + 0.577e9}
 METRIC = "Phi synthesis throughput, localized H2 state feedback (chain Nx=100k/GPU, d=9, T=29)"
 UNIT = "columns/s"
 
