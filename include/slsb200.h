@@ -21,12 +21,13 @@
 #define SLSB200_H
 
 #include <stdint.h>
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define SLS_ABI_VERSION 5
+#define SLS_ABI_VERSION 6
 
 /* per-column status bits written by sls_solve* (improves on the reference, which ignores the
  * solver's termination status: src/synthesis.jl:62-65) */
@@ -57,6 +58,10 @@ typedef struct sls_timing {      /* device times (CUDA events on the handle's st
     double  alg_bytes;           /* B_col summed over columns                              */
     float sim_ms;                /* sls_simulate: device time of the simulation kernel                  */
     int32_t sim_window, sim_uwindow;   /* largest state / input window over the scenarios             */
+    float gather_gpu_ms;         /* kernel 1 launches alone (gather_ms also holds the host round trips between them) */
+    float sim_pack_ms;           /* sls_simulate: window + pack passes before the simulation kernel     */
+    int64_t refined;             /* columns of the last solve that took >= 1 refinement sweep of kernel 2 */
+    double  sim_bytes;           /* sls_simulate: packed Phi bytes the recursion consumed (sum over scenarios and steps) */
 } sls_timing;
 
 int         sls_abi_version(void);
@@ -147,6 +152,28 @@ int sls_synthesize(sls_handle* h, int64_t T,
                    int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
                    int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
                    int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid);
+
+/* Shard form of sls_synthesize — the shape of one `@distributed` chunk (src/synthesis.jl:16,23-27) without any array that
+ * grows with the total Nx.  The supports are given as a column WINDOW [win_first, win_first + win_ncols) (1-based) that
+ * must cover the range and its halo (the rows of nz(A[:,j]) for j in the range): every colptr array has win_ncols + 1
+ * entries whose values are 1-based offsets into the rowval / nzval pointers beside it (Julia: `pointer(𝓢[t].colptr,
+ * win_first)` with the full rowval, or the fields of the slice `𝓢[t][:, win]`).  The outputs are the column SLAB
+ * Φ[t][:, first_col : first_col+ncols-1]: colptr arrays of ncols + 1 entries starting at 1, rowval (global rows) and
+ * nzval sized by cap_x / cap_u (NULL = nnz of the window).  Everything else is as in sls_synthesize.  Per-GPU bytes over
+ * PCIe then depend on the shard, not on Nx. */
+int sls_synthesize_window(sls_handle* h, int64_t T, int64_t win_first, int64_t win_ncols,
+                          const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
+                          const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval,
+                          int64_t first_col, int64_t ncols, const int64_t* cap_x, const int64_t* cap_u,
+                          int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
+                          int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
+                          int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid);
+
+/* Page-lock (cudaHostRegister) / release a caller-owned host range: the copy pipelines of sls_solve and sls_synthesize*
+ * only overlap with the kernels when the host buffers are page-locked; pageable buffers are correct but serialise.
+ * Ranges still registered are released by sls_destroy. */
+int sls_host_register(sls_handle* h, void* p, size_t bytes);
+int sls_host_unregister(sls_handle* h, void* p);
 
 /* Device-resident variants: run kernels 1-3 without any host<->device payload copy (inputs must
  * already be set).  sls_solve_device leaves Φ in handle-owned device buffers; sls_device_output

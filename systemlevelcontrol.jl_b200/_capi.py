@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libslsb200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 STATUS_OK, STATUS_RESIDUAL, STATUS_RANK_SKIPPED, STATUS_NO_IMPULSE = 0, 1, 2, 4
 
 i64p = C.POINTER(C.c_int64)
@@ -35,7 +35,8 @@ class SlsTiming(C.Structure):
                 ("solve_launches", C.c_int64), ("gather_launches", C.c_int64), ("scatter_launches", C.c_int64),
                 ("ncols", C.c_int64), ("nnz_out", C.c_int64),
                 ("alg_flops", C.c_double), ("alg_bytes", C.c_double),
-                ("sim_ms", C.c_float), ("sim_window", C.c_int32), ("sim_uwindow", C.c_int32)]
+                ("sim_ms", C.c_float), ("sim_window", C.c_int32), ("sim_uwindow", C.c_int32),
+                ("gather_gpu_ms", C.c_float), ("sim_pack_ms", C.c_float), ("refined", C.c_int64), ("sim_bytes", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -62,6 +63,13 @@ SIGNATURES = {
                                  C.POINTER(i64p), C.POINTER(i64p), C.POINTER(u8p), C.c_int64, C.c_int64, i64p, i64p,
                                  C.POINTER(i64p), C.POINTER(i64p), C.POINTER(f64p),
                                  C.POINTER(i64p), C.POINTER(i64p), C.POINTER(f64p), i64p, i64p, i32p, f64p]),
+    "sls_synthesize_window": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                        C.POINTER(i64p), C.POINTER(i64p), C.POINTER(u8p),
+                                        C.POINTER(i64p), C.POINTER(i64p), C.POINTER(u8p), C.c_int64, C.c_int64, i64p, i64p,
+                                        C.POINTER(i64p), C.POINTER(i64p), C.POINTER(f64p),
+                                        C.POINTER(i64p), C.POINTER(i64p), C.POINTER(f64p), i64p, i64p, i32p, f64p]),
+    "sls_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sls_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sls_device_output": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), i64p]),
     "sls_device_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),

@@ -90,6 +90,7 @@ struct Plan {
     int64_t tot_packed = 0;
     double alg_flops = 0, alg_bytes = 0;
     bool stats_valid = false;           // alg_flops / alg_bytes are computed on demand (plan_stats)
+    float gpu_ms = 0;                   // device time of kernels 1a + 1b + scan (without the host round trips between them)
     int64_t col_lo = 0, col_hi = 0;     // planned columns lie in [col_lo, col_hi)
     int identity_cols = 0;              // h_cols currently holds 0..identity_cols-1 (the cols == NULL plan)
     void release() {
@@ -152,6 +153,10 @@ struct sls_handle {
     std::vector<double> h_wx, h_wu;
     DevBuf d_wx, d_wu;
     std::vector<int32_t> h_Akmax, h_Akmin;   // largest / smallest row index (0-based) stored in each column of A
+    int64_t supp_lo = 0, supp_hi = 0;        // support columns [supp_lo, supp_hi) (0-based) are valid on the device
+    DevBuf d_flag; PinVec<int32_t> h_flag;   // set by sls_validate_supports_kernel (malformed support rows)
+    rt::Event gev[4];                        // around kernel 1a and kernels 1b + scan (gather_gpu_ms)
+    std::vector<void*> registered;           // host ranges page-locked through sls_host_register
 };
 
 static thread_local std::string g_create_err;
@@ -198,6 +203,11 @@ extern "C" int sls_create(const sls_options* opts, sls_handle** out) {
     for (int i = 0; i < 16 && !e; i++) e = h->chunk_ev[i].create();
     for (int i = 0; i < 8 && !e; i++) e = h->ev[i].create();
     for (int i = 0; i < 2 && !e; i++) e = h->marks[i].create();
+    for (int i = 0; i < 4 && !e; i++) e = h->gev[i].create();
+    if (!e) e = h->d_flag.ensure(sizeof(int32_t));
+    if (!e) e = h->h_flag.resize(1);
+    if (!e) e = rt::zero(h->d_flag.p, sizeof(int32_t), h->stream);
+    if (!e) e = rt::sync(h->stream);
     if (e) { delete h; return fail(nullptr, e, "sls_create: CUDA initialisation failed"); }
     h->sm_count = rt::sm_count(h->device);
     h->max_smem = rt::max_smem_optin(h->device);
@@ -216,7 +226,10 @@ extern "C" void sls_destroy(sls_handle* h) {
     for (PipeCtx* x : h->pipe) { x->release(); delete x; }
     h->pipe.clear();
     h->pipe_colptr.release(); h->pipe_status.release(); h->pipe_resid.release();
-    h->d_wx.release(); h->d_wu.release();
+    h->d_wx.release(); h->d_wu.release(); h->d_flag.release(); h->h_flag.release();
+    for (void* q : h->registered) rt::host_unregister(q);
+    h->registered.clear();
+    for (int i = 0; i < 4; i++) h->gev[i].destroy();
     for (int i = 0; i < 2; i++) { h->t_cp[i].release(); h->t_rv[i].release(); h->t_nz[i].release(); }
     for (int i = 0; i < SLS_PIPE_MAX; i++) h->pipe_in[i].destroy();
     h->pipe_done.destroy();
@@ -300,6 +313,8 @@ extern "C" int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
     if (m) return fail(h, -2, (std::string("sls_set_plant: B2: ") + m).c_str());
     SLS_ARG(A_nzval || A_colptr[Nx] == 1, "sls_set_plant: A nzval is NULL");
     SLS_ARG(B2_nzval || B2_colptr[Nu] == 1, "sls_set_plant: B2 nzval is NULL");
+    for (int64_t e = 0; e < A_colptr[Nx] - 1; e++) if (!std::isfinite(A_nzval[e])) return fail(h, -3, "sls_set_plant: A holds a non-finite value");
+    for (int64_t e = 0; e < B2_colptr[Nu] - 1; e++) if (!std::isfinite(B2_nzval[e])) return fail(h, -3, "sls_set_plant: B2 holds a non-finite value");
     std::vector<double> As, Bs;                                // similarity-scaled values when cost weights are set
     if (h->have_weights) {
         if ((int64_t)h->h_wx.size() != Nx || (int64_t)h->h_wu.size() != Nu)
@@ -406,14 +421,20 @@ extern "C" int sls_set_supports(sls_handle* h, int64_t T,
     SLS_CK(rt::set_device(h->device));
     h->have_supports = false; h->plan.valid = false; h->solved = false;
     h->ev[0].record(h->stream);
+    SLS_CK(rt::zero(h->d_flag.p, sizeof(int32_t), h->stream));
     int e = upload_supports(h, h->Sx, T, h->Nx, h->Nx, Sx_colptr, Sx_rowval, Sx_nzval, "Sx");
     if (e) return e;
     e = upload_supports(h, h->Su, T, h->Nu, h->Nx, Su_colptr, Su_rowval, Su_nzval, "Su");
     if (e) return e;
     h->ev[1].record(h->stream);
+    // row indices are checked on the device (range, strictly ascending): ~0.1 ms per 100 MB instead of a host pass
+    SLS_CK(sls_launch_validate_supports(h->Sx.view(), (int)T, h->Nx, h->Nx, 0, h->Nx, h->d_flag.as<int32_t>(), h->stream));
+    SLS_CK(sls_launch_validate_supports(h->Su.view(), (int)T, h->Nx, h->Nu, 0, h->Nx, h->d_flag.as<int32_t>(), h->stream));
+    SLS_CK(sls_kcopy(h->h_flag.data(), h->d_flag.p, sizeof(int32_t), h->stream));
     SLS_CK(rt::sync(h->stream));
+    if (h->h_flag[0]) return fail(h, -2, "sls_set_supports: rowval out of range or not strictly ascending inside a column");
     h->tm.h2d_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);
-    h->T = T; h->have_supports = true;
+    h->T = T; h->have_supports = true; h->supp_lo = 0; h->supp_hi = h->Nx;
     return 0;
 }
 
@@ -517,18 +538,20 @@ extern "C" int sls_make_supports(sls_handle* h, int64_t d, int64_t T, double alp
         nlev = std::max(nlev, std::max(kx[t - 1], ku[t - 1]));
     }
     h->ev[0].record(h->stream);
+    SLS_CK(rt::zero(h->d_flag.p, sizeof(int32_t), h->stream));
     int e = make_both_families(h, T, kx, ku, nlev, nnz_x, nnz_u);
     if (e) return e;
     h->ev[1].record(h->stream);
     SLS_CK(rt::sync(h->stream));
     h->tm.h2d_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);
-    h->T = T; h->have_supports = true;
+    h->T = T; h->have_supports = true; h->supp_lo = 0; h->supp_hi = h->Nx;
     return 0;
 }
 
 extern "C" int sls_get_supports(sls_handle* h, int which, int64_t t, int64_t* colptr, int64_t* rowval, uint8_t* nzval) {
     if (!h) return -1;
     SLS_ARG(h->have_supports, "sls_get_supports: no supports on the device");
+    SLS_ARG(h->supp_lo == 0 && h->supp_hi == h->Nx, "sls_get_supports: only a column window of the supports is on the device (after sls_synthesize); call sls_set_supports");
     SLS_ARG((which == 0 || which == 1) && t >= 0 && t < h->T, "sls_get_supports: bad tap");
     SLS_CK(rt::set_device(h->device));
     const DevSupports& d = which ? h->Su : h->Sx;
@@ -590,6 +613,15 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
             p.h_cols[i] = (int32_t)j;
         }
     }
+    // every support column kernel 1 reads (the rows of nz(A[:,j])) must be on the device: after sls_synthesize of a
+    // column range only that range and its halo are
+    if (h->supp_lo > 0 || h->supp_hi < Nx)
+        for (int64_t i = 0; i < ncols; i++) {
+            const int64_t j = p.h_cols[i];
+            if (h->h_Akmin[j] < h->supp_lo || h->h_Akmax[j] >= h->supp_hi || j < h->supp_lo || j >= h->supp_hi)
+                return fail(h, -3, "plan: a column needs support columns that are not on the device (only the window of the last "
+                                   "sls_synthesize is): call sls_set_supports");
+        }
     p.cols_sorted = true;
     if (cols) for (int64_t i = 1; i < ncols; i++) if (p.h_cols[i] <= p.h_cols[i - 1]) { p.cols_sorted = false; break; }
     // candidate-list capacity of kernel 1 (power of two, >= 32)
@@ -613,9 +645,12 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     // kernel 1a leaves the index sets for kernel 1b (row stride cap) unless that would take more than 1 GB
     const bool keep = (size_t)nc1 * cap * 2 * sizeof(int32_t) <= ((size_t)1 << 30);
     if (keep) { SLS_CK(p.keepx.ensure((size_t)nc1 * cap * sizeof(int32_t))); SLS_CK(p.keepu.ensure((size_t)nc1 * cap * sizeof(int32_t))); }
+    h->gev[0].record(h->stream);
     SLS_CK(sls_launch_gather_count(h->A.view(), h->Sx.view(), h->Su.view(), (int)T, Nx, p.cols.as<int32_t>(), p.ncols,
                                    p.n.as<int32_t>(), p.m.as<int32_t>(), cap, keep ? p.keepx.as<int32_t>() : nullptr,
-                                   keep ? p.keepu.as<int32_t>() : nullptr, h->stream));
+                                   keep ? p.keepu.as<int32_t>() : nullptr, h->d_flag.as<int32_t>(), h->stream));
+    h->gev[1].record(h->stream);
+    SLS_CK(sls_kcopy(h->h_flag.data(), h->d_flag.p, sizeof(int32_t), h->stream));
     SLS_CK(p.h_n.resize(nc1)); SLS_CK(p.h_m.resize(nc1));
     p.h_n[0] = 0; p.h_m[0] = 0;
     SLS_CK(sls_kcopy(p.h_n.data(), p.n.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
@@ -623,6 +658,7 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     if (trace) t1 = now();
     SLS_CK(rt::sync(h->stream));
     if (trace) t2 = now();
+    if (h->h_flag[0]) return fail(h, -2, "plan: support rowval out of range or not strictly ascending inside a column");
     int nmax = 0, mmax = 0;
     // one pass over the sizes: maxima, overflow check and the histogram of kernel 2's size classes (class = ceil(n/8) - 1;
     // everything beyond the last class lands in a catch-all bin and is rejected by sls_solve)
@@ -661,9 +697,11 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     const size_t fill_smem = (size_t)4 * sls_gather_fill_words(cap, p.nstride, p.mstride, p.wx, p.wu, (int)T) * sizeof(int32_t);
     if (fill_smem > (size_t)h->max_smem) return fail(h, -4, "plan: index sets do not fit shared memory");
     if (trace) t3 = now();
+    h->gev[2].record(h->stream);
     SLS_CK(sls_launch_gather_fill(h->A.view(), h->B2.view(), h->Sx.view(), h->Su.view(), v, cap, keep ? p.keepx.as<int32_t>() : nullptr,
                                   keep ? p.keepu.as<int32_t>() : nullptr, h->stream));
     SLS_CK(sls_launch_scan(v.colptr, Nx + 1, (int)(2 * T), v.tot, p.ncols + 1, p.col_lo, p.col_hi, h->stream));
+    h->gev[3].record(h->stream);
     // sizes back to the host
     SLS_CK(p.h_lnnz.resize(nc1)); SLS_CK(p.h_lA.resize(nc1)); SLS_CK(p.h_lB.resize(nc1));
     SLS_CK(p.h_tot.resize(p.ncols + 1)); SLS_CK(p.h_last.resize(2 * T));
@@ -711,6 +749,7 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     for (SolveClass& c : p.classes)
         c.nnzcap = (int)std::min<int64_t>((int64_t)c.N * h->maxcolA + (int64_t)c.mcap * h->maxcolB2, (int64_t)c.N * (c.N + c.mcap));
     p.stats_valid = false;
+    p.gpu_ms = rt::elapsed_ms(h->gev[0], h->gev[1]) + rt::elapsed_ms(h->gev[2], h->gev[3]);
     if (trace) fprintf(stderr, "[plan] to-sync1 %.3f  sync1 %.3f  host->fill %.3f  fill..sync2 %.3f  sync2 %.3f  tail %.3f  total %.3f ms\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, now() - t5, now() - t0);
     p.valid = true;
     return 0;
@@ -747,6 +786,7 @@ extern "C" int sls_plan(sls_handle* h, const int64_t* cols, int64_t ncols,
     h->ev[3].record(h->stream);
     SLS_CK(rt::sync(h->stream));
     h->tm.gather_ms = rt::elapsed_ms(h->ev[2], h->ev[3]);
+    h->tm.gather_gpu_ms = h->plan.gpu_ms;
     h->tm.gather_launches = 3;
     h->tm.ncols = h->plan.ncols; h->tm.nnz_out = h->plan.tot_packed; h->tm_from_plan = true;
     const int64_t T = h->T;
@@ -768,8 +808,17 @@ extern "C" int sls_reduce(sls_handle* h, const int64_t* cj, int64_t q,
     SLS_ARG(cj && q >= 1, "sls_reduce: empty column group");
     SLS_ARG(n_sx && n_su, "sls_reduce: n_sx / n_su is NULL");
     SLS_CK(rt::set_device(h->device));
+    // unique(findnz(M[:,cj])[1]) only sees first occurrences: a column repeated in cj adds nothing (reduction.jl:14)
+    std::vector<int64_t> cju;
+    {
+        std::vector<uint8_t> seen(h->Nx, 0);
+        for (int64_t i = 0; i < q; i++) {
+            if (cj[i] < 1 || cj[i] > h->Nx) return fail(h, -3, "sls_reduce: column index out of range (1-based, 1..Nx)");
+            if (!seen[cj[i] - 1]) { seen[cj[i] - 1] = 1; cju.push_back(cj[i]); }
+        }
+    }
     Plan p;
-    int e = build_plan(h, p, cj, q, false);
+    int e = build_plan(h, p, cju.data(), (int64_t)cju.size(), false);
     if (e) { p.release(); return e; }
     std::vector<int32_t> sx((size_t)p.ncols * p.nstride), su((size_t)p.ncols * p.mstride);
     e = rt::d2h(sx.data(), p.sx.p, sx.size() * sizeof(int32_t), h->stream);
@@ -1011,50 +1060,58 @@ struct PipeSupp {
 };
 }
 
-static int pipe_prepare(sls_handle* h, PipeSupp& f, int64_t T, int64_t ncol) {
+// The caller passes a column WINDOW of every support tap: colptr arrays of wn + 1 entries for the columns [w0, w0 + wn)
+// whose values are 1-based offsets into the rowval / nzval pointers given beside them (a full matrix is the window
+// w0 = 0, wn = Nx; a view `pointer(S.colptr, w0 + 1)` into a full matrix and a slice `S[:, w0+1:w0+wn]` both qualify).
+// On the device the taps' window slices lie back to back; tap_off[t] is shifted so that kernels keep indexing
+// rowval[tap_off[t] + colptr[t][j] - 1] with the caller's colptr values.
+static int pipe_prepare(sls_handle* h, PipeSupp& f, int64_t T, int64_t Nx, int64_t w0, int64_t wn) {
     DevSupports& d = *f.d;
-    std::vector<int64_t> off(T + 1, 0);
+    std::vector<int64_t> slot(T + 1, 0), off(T + 1, 0);
     bool any_nz = false, all_nz = true;
     for (int64_t t = 0; t < T; t++) {
         if (!f.cps[t]) return fail(h, -2, (std::string("sls_synthesize: ") + f.name + ": colptr is NULL").c_str());
-        if (f.cps[t][0] != 1 || f.cps[t][ncol] < 1) return fail(h, -2, (std::string("sls_synthesize: ") + f.name + ": colptr[1] must be 1 (Julia 1-based CSC)").c_str());
-        if (f.cps[t][ncol] > 1 && !(f.rvs && f.rvs[t])) return fail(h, -2, (std::string("sls_synthesize: ") + f.name + ": rowval is NULL").c_str());
-        off[t + 1] = off[t] + f.cps[t][ncol] - 1;
+        if (f.cps[t][0] < 1 || f.cps[t][wn] < f.cps[t][0] || (w0 == 0 && wn == Nx && f.cps[t][0] != 1))
+            return fail(h, -2, (std::string("sls_synthesize: ") + f.name + ": colptr[1] must be 1 (Julia 1-based CSC)").c_str());
+        if (f.cps[t][wn] > f.cps[t][0] && !(f.rvs && f.rvs[t])) return fail(h, -2, (std::string("sls_synthesize: ") + f.name + ": rowval is NULL").c_str());
+        slot[t + 1] = slot[t] + f.cps[t][wn] - f.cps[t][0];
+        off[t] = slot[t] - (f.cps[t][0] - 1);
         if (f.nzs && f.nzs[t]) any_nz = true; else all_nz = false;
     }
+    off[T] = slot[T];
     if (any_nz && !all_nz) return fail(h, -2, "sls_synthesize: nzval must be given for every tap or for none");
-    d.nnz = off[T]; d.has_nzval = any_nz;
-    SLS_CK(d.colptr.ensure(T * (ncol + 1) * sizeof(int64_t)));
+    d.nnz = slot[T]; d.has_nzval = any_nz;
+    SLS_CK(d.colptr.ensure(T * (Nx + 1) * sizeof(int64_t)));
     SLS_CK(d.rowval.ensure(std::max<int64_t>(d.nnz, 1) * sizeof(int64_t)));
     SLS_CK(d.tap_off.ensure((T + 1) * sizeof(int64_t)));
     if (any_nz) SLS_CK(d.nzval.ensure(std::max<int64_t>(d.nnz, 1)));
     d.h_tap_off = off;
     int ml = 0;
     const int64_t* cl = f.cps[T - 1];
-    for (int64_t c = 0; c < ncol; c++) ml = std::max<int>(ml, (int)std::min<int64_t>(std::max<int64_t>(cl[c + 1] - cl[c], 0), 1 << 30));
+    for (int64_t c = 0; c < wn; c++) ml = std::max<int>(ml, (int)std::min<int64_t>(std::max<int64_t>(cl[c + 1] - cl[c], 0), 1 << 30));
     d.maxlen_last = ml;
     SLS_CK(rt::h2d(d.tap_off.p, d.h_tap_off.data(), (T + 1) * sizeof(int64_t), h->in_stream));   // pageable: before the big copies
     for (int64_t t = 0; t < T; t++)
-        SLS_CK(rt::h2d(d.colptr.as<int64_t>() + t * (ncol + 1), f.cps[t], (ncol + 1) * sizeof(int64_t), h->in_stream));
+        SLS_CK(rt::h2d(d.colptr.as<int64_t>() + t * (Nx + 1) + w0, f.cps[t], (wn + 1) * sizeof(int64_t), h->in_stream));
     // the Bool values are 1/9 of the bytes but would be half of the slice copies (each copy costs ~10 us of driver
     // time): they go up whole, once per tap, ahead of the column chunks
     if (any_nz)
         for (int64_t t = 0; t < T; t++)
-            SLS_CK(rt::h2d(d.nzval.as<uint8_t>() + off[t], f.nzs[t], (size_t)(off[t + 1] - off[t]), h->in_stream));
+            SLS_CK(rt::h2d(d.nzval.as<uint8_t>() + slot[t], f.nzs[t] + (f.cps[t][0] - 1), (size_t)(slot[t + 1] - slot[t]), h->in_stream));
     return 0;
 }
 
 // validates and enqueues the support columns [c0, c1) of every tap of one family
 // (runs on the feeder thread: errors are returned as a message, never through the handle)
-static int pipe_enqueue_slice(sls_handle* h, PipeSupp& f, int64_t T, int64_t ncol, int64_t c0, int64_t c1, CopyBatch& cbatch,
+static int pipe_enqueue_slice(sls_handle* h, PipeSupp& f, int64_t T, int64_t w0, int64_t wn, int64_t c0, int64_t c1, CopyBatch& cbatch,
                               std::string& msg) {
     DevSupports& d = *f.d;
     const bool rows = (h->opt.flags & 1) != 0;
     for (int64_t t = 0; t < T; t++) {
-        const int64_t* cp = f.cps[t];
+        const int64_t* cp = f.cps[t] - w0;                      // indexed by the global column
         for (int64_t c = c0; c < c1; c++)
             if (cp[c + 1] < cp[c]) { msg = std::string("sls_synthesize: ") + f.name + ": colptr is not monotone"; return -2; }
-        if (cp[c0] < 1 || cp[c1] > cp[ncol]) { msg = std::string("sls_synthesize: ") + f.name + ": colptr is not monotone"; return -2; }
+        if (cp[c0] < cp[w0] || cp[c1] > cp[w0 + wn]) { msg = std::string("sls_synthesize: ") + f.name + ": colptr is not monotone"; return -2; }
         const int64_t s0 = cp[c0] - 1, s1 = cp[c1] - 1;
         if (rows)
             for (int64_t c = c0; c < c1; c++) {
@@ -1077,21 +1134,25 @@ static void pipe_drain(sls_handle* h) {
     rt::sync(h->in_stream); rt::sync(h->stream); rt::sync(h->scat_stream); rt::sync(h->copy_stream); rt::sync(h->out2_stream);
 }
 
-extern "C" int sls_synthesize(sls_handle* h, int64_t T,
-                              const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
-                              const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval,
-                              int64_t first_col, int64_t ncols, const int64_t* cap_x, const int64_t* cap_u,
-                              int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
-                              int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
-                              int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid) {
+// `slab`: the supports are a column window [w0, w0 + wn) and the outputs are the column slab of the range
+// (colptr arrays of ncols + 1 entries starting at 1) — sls_synthesize_window; otherwise full-width arrays.
+static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int64_t wn,
+                           const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
+                           const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval,
+                           int64_t first_col, int64_t ncols, const int64_t* cap_x, const int64_t* cap_u,
+                           int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
+                           int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
+                           int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid) {
     if (!h) return -1;
     SLS_ARG(h->have_plant, "sls_synthesize: call sls_set_plant first");
     SLS_ARG(T >= 1 && T < 4096, "sls_synthesize: bad T");
     SLS_ARG(Sx_colptr && Sx_rowval && Su_colptr && Su_rowval, "sls_synthesize: NULL array of pointers");
     SLS_CK(rt::set_device(h->device));
     const int64_t Nx = h->Nx, Nu = h->Nu;
+    if (!slab) { w0 = 0; wn = Nx; }
     if (ncols <= 0) { first_col = 1; ncols = Nx; }
     SLS_ARG(first_col >= 1 && first_col + ncols - 1 <= Nx, "sls_synthesize: column range out of 1..Nx");
+    SLS_ARG(w0 >= 0 && wn >= 1 && w0 + wn <= Nx, "sls_synthesize_window: support window out of 1..Nx");
     const int64_t r0 = first_col - 1, r1 = r0 + ncols;          // 0-based half-open column range
     h->have_supports = false; h->plan.valid = false; h->solved = false;
     // chunk count: every chunk costs ~230 slice copies of ~10 us driver/engine time each way, against the pipeline's
@@ -1110,6 +1171,8 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
         ub[c + 1] = std::max(ub[c], hi);
     }
     for (int c = 1; c <= K; c++) ub[c] = std::max(ub[c], ub[c - 1]);
+    if (ub[0] < w0 || ub[K] > w0 + wn)
+        return fail(h, -3, "sls_synthesize_window: the support window must cover the column range and its halo (the rows of nz(A[:,j]))");
     while ((int)h->pipe.size() < K) {
         PipeCtx* x = new (std::nothrow) PipeCtx();
         if (!x) return fail(h, -2, "sls_synthesize: out of host memory");
@@ -1120,8 +1183,9 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
     h->ev[0].record(h->stream);
     SLS_CK(rt::stream_wait(h->in_stream, h->ev[0]));            // earlier work on the main stream may still read the supports
     PipeSupp fam[2] = {{&h->Sx, Sx_colptr, Sx_rowval, Sx_nzval, Nx, "Sx"}, {&h->Su, Su_colptr, Su_rowval, Su_nzval, Nu, "Su"}};
-    for (int f = 0; f < 2; f++) { int e = pipe_prepare(h, fam[f], T, Nx); if (e) { pipe_drain(h); return e; } }
-    h->T = T;
+    SLS_CK(rt::zero(h->d_flag.p, sizeof(int32_t), h->in_stream));
+    for (int f = 0; f < 2; f++) { int e = pipe_prepare(h, fam[f], T, Nx, w0, wn); if (e) { pipe_drain(h); return e; } }
+    h->T = T; h->supp_lo = ub[0]; h->supp_hi = ub[K];
     SLS_CK(h->pipe_colptr.ensure((size_t)2 * T * (Nx + 1) * sizeof(int64_t)));
     SLS_CK(h->pipe_status.resize(ncols)); SLS_CK(h->pipe_resid.resize(ncols));
     // Feeder thread: validates and enqueues the support slices of every chunk on the copy-in stream as fast as the
@@ -1135,8 +1199,12 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
         CopyBatch cbatch;
         for (int c = 0; c < K && !feed_stop.load(); c++) {
             int e = 0;
-            for (int f = 0; f < 2 && !e; f++) e = pipe_enqueue_slice(h, fam[f], T, Nx, ub[c], ub[c + 1], cbatch, feed_msg);
+            for (int f = 0; f < 2 && !e; f++) e = pipe_enqueue_slice(h, fam[f], T, w0, wn, ub[c], ub[c + 1], cbatch, feed_msg);
             if (!e) { e = cbatch.flush(h->in_stream); if (e) feed_msg = "sls_synthesize: host to device copy"; }
+            // row indices of the slice are checked on the device behind its copies; kernel 1a indexes nothing once the flag is set
+            if (!e) e = sls_launch_validate_supports(h->Sx.view(), (int)T, Nx, Nx, ub[c], ub[c + 1], h->d_flag.as<int32_t>(), h->in_stream);
+            if (!e) e = sls_launch_validate_supports(h->Su.view(), (int)T, Nx, Nu, ub[c], ub[c + 1], h->d_flag.as<int32_t>(), h->in_stream);
+            if (e && feed_msg.empty()) feed_msg = "sls_synthesize: support validation launch";
             if (e) { feed_err.store(e); return; }
             h->pipe_in[c].record(h->in_stream);
             fed.store(c + 1, std::memory_order_release);
@@ -1177,7 +1245,7 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
         for (int64_t tt = 0; tt < 2 * T && !e; tt++) {
             const int x_ = tt >= T; const int64_t t = x_ ? tt - T : tt;
             const int64_t* capv = x_ ? cap_u : cap_x;
-            const int64_t cap = capv ? capv[t] : (fam[x_].cps[t][Nx] - 1);
+            const int64_t cap = capv ? capv[t] : (fam[x_].cps[t][wn] - fam[x_].cps[t][0]);
             if (base[tt] + p.nnz_tap[tt] > cap) e = fail(h, -4, "sls_synthesize: output capacity of a tap is too small");
         }
         if (e) break;
@@ -1207,7 +1275,7 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
         if (e) break;
         PIPE_CK(h->hist.ensure(hist_bytes));
         // the caller's colptr = the chunk's colptr + entries of the earlier chunks (columns c0+1..c1; chunk 0 also writes [0])
-        const int64_t j0 = (c == 0) ? 0 : c0 + 1, j1 = (c == K - 1) ? Nx : c1;   // columns outside the range are empty
+        const int64_t j0 = (c == 0) ? (slab ? r0 : 0) : c0 + 1, j1 = (c == K - 1) ? (slab ? r1 : Nx) : c1;   // columns outside the range are empty
         PIPE_CK(sls_launch_colptr_rebase(h->pipe_colptr.as<int64_t>(), p.colptr.as<int64_t>(), x.base.as<int64_t>(), Nx + 1, (int)(2 * T), j0, j1, h->stream));
         x.ev_plan.record(h->stream);
         // kernel 3 beside kernel 2
@@ -1245,7 +1313,10 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
             for (int64_t tt = 0; tt < 2 * T; tt++) {
                 const int x_ = tt >= T; const int64_t t = x_ ? tt - T : tt;
                 int64_t* const* hc = x_ ? Pu_colptr : Px_colptr;
-                if (hc && hc[t]) obatch.add(hc[t], h->pipe_colptr.as<int64_t>() + tt * (Nx + 1), (size_t)(Nx + 1) * sizeof(int64_t));
+                if (!(hc && hc[t])) continue;
+                // slab form: only the range's ncols + 1 entries (they start at 1: nothing is stored before column r0)
+                if (slab) obatch.add(hc[t], h->pipe_colptr.as<int64_t>() + tt * (Nx + 1) + r0, (size_t)(ncols + 1) * sizeof(int64_t));
+                else obatch.add(hc[t], h->pipe_colptr.as<int64_t>() + tt * (Nx + 1), (size_t)(Nx + 1) * sizeof(int64_t));
             }
             PIPE_CK(obatch.flush(h->copy_stream));
         }
@@ -1281,8 +1352,10 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
     SLS_CK(rt::stream_wait(h->stream, h->pipe_done2));
     SLS_CK(rt::stream_wait(h->stream, h->pipe_in[K - 1]));
     h->ev[1].record(h->stream);
+    SLS_CK(sls_kcopy(h->h_flag.data(), h->d_flag.p, sizeof(int32_t), h->stream));
     SLS_CK(rt::sync(h->stream));
     SLS_CK(rt::sync(h->scat_stream));
+    if (h->h_flag[0]) { h->have_supports = false; return fail(h, -2, "sls_synthesize: support rowval out of range or not strictly ascending inside a column"); }
     if (status) memcpy(status, h->pipe_status.data(), (size_t)ncols * sizeof(int32_t));
     if (resid) memcpy(resid, h->pipe_resid.data(), (size_t)ncols * sizeof(double));
     for (int64_t t = 0; t < T; t++) {
@@ -1307,6 +1380,53 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
     // sls_set_supports.  The outputs live in per-chunk buffers, so the
     // device-resident accessors (sls_device_output, sls_simulate) need a sls_plan + sls_solve_device first
     h->plan.valid = false; h->solved = false;
+    return 0;
+}
+
+extern "C" int sls_synthesize(sls_handle* h, int64_t T,
+                              const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
+                              const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval,
+                              int64_t first_col, int64_t ncols, const int64_t* cap_x, const int64_t* cap_u,
+                              int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
+                              int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
+                              int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid) {
+    return synthesize_impl(h, T, false, 0, 0, Sx_colptr, Sx_rowval, Sx_nzval, Su_colptr, Su_rowval, Su_nzval, first_col, ncols, cap_x, cap_u,
+                           Px_colptr, Px_rowval, Px_nzval, Pu_colptr, Pu_rowval, Pu_nzval, nnz_x, nnz_u, status, resid);
+}
+
+extern "C" int sls_synthesize_window(sls_handle* h, int64_t T, int64_t win_first, int64_t win_ncols,
+                                     const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
+                                     const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval,
+                                     int64_t first_col, int64_t ncols, const int64_t* cap_x, const int64_t* cap_u,
+                                     int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
+                                     int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
+                                     int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid) {
+    if (!h) return -1;
+    SLS_ARG(ncols >= 1, "sls_synthesize_window: ncols must be >= 1");
+    return synthesize_impl(h, T, true, win_first - 1, win_ncols, Sx_colptr, Sx_rowval, Sx_nzval, Su_colptr, Su_rowval, Su_nzval, first_col, ncols,
+                           cap_x, cap_u, Px_colptr, Px_rowval, Px_nzval, Pu_colptr, Pu_rowval, Pu_nzval, nnz_x, nnz_u, status, resid);
+}
+
+// Page-locks a caller-owned host range so that copies to / from it are truly asynchronous (the D2H / H2D pipelines of
+// sls_solve and sls_synthesize serialise on pageable memory).  Julia: call on the `Vector`s behind 𝓢[t].rowval / Φ[t].nzval
+// once, under GC.@preserve; ranges still registered are released by sls_destroy.
+extern "C" int sls_host_register(sls_handle* h, void* p, size_t bytes) {
+    if (!h) return -1;
+    SLS_ARG(p && bytes > 0, "sls_host_register: empty range");
+    SLS_CK(rt::set_device(h->device));
+    int e = rt::host_register(p, bytes);
+    if (e) { rt::last_error(); return fail(h, e, "sls_host_register"); }
+    h->registered.push_back(p);
+    return 0;
+}
+
+extern "C" int sls_host_unregister(sls_handle* h, void* p) {
+    if (!h) return -1;
+    auto it = std::find(h->registered.begin(), h->registered.end(), p);
+    SLS_ARG(it != h->registered.end(), "sls_host_unregister: range was not registered through this handle");
+    h->registered.erase(it);
+    int e = rt::host_unregister(p);
+    if (e) { rt::last_error(); return fail(h, e, "sls_host_unregister"); }
     return 0;
 }
 

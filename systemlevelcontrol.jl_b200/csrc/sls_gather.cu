@@ -81,11 +81,12 @@ __device__ int sls_warp_index_set(const SlsCsc& A, const SlsSupports& S, int T, 
 __global__ void __launch_bounds__(GATHER_WPB * 32)
 sls_gather_count_kernel(SlsCsc A, SlsSupports Sx, SlsSupports Su, int T, int64_t Nx,
                         const int32_t* __restrict__ cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
-                        int32_t* keep_x, int32_t* keep_u) {
+                        int32_t* keep_x, int32_t* keep_u, const int32_t* __restrict__ bad_supports) {
     SLS_DYN_SMEM(smem);
     const int warp = threadIdx.x >> 5, lane = sls_lane();
     const int c = blockIdx.x * GATHER_WPB + warp;
     if (c >= ncols) return;
+    if (bad_supports && *bad_supports) return;               // malformed support rows (sls_validate_supports_kernel): index nothing
     int32_t* buf = reinterpret_cast<int32_t*>(smem) + (size_t)warp * cap;
     const int64_t j = cols[c];
     // the index sets are kept (row stride cap) so that kernel 1b does not gather and sort them a second time
@@ -358,16 +359,46 @@ __global__ void sls_local_dense_kernel(SlsCsc A, SlsCsc B2, SlsPlanView P, int c
     }
 }
 
+// Layout check of the uploaded support columns [c0, c1) of every tap: row indices within 1..nrow and strictly ascending
+// inside a column (the binary searches and the run-of-consecutive-rows shortcut of kernel 1 rely on it; out-of-range
+// rows would index A / B2 out of bounds).  One thread per (tap, column); sets *flag on the first violation.
+__global__ void __launch_bounds__(256)
+sls_validate_supports_kernel(SlsSupports S, int64_t Nx, int64_t nrow, int64_t c0, int64_t c1, int32_t* flag) {
+    const int t = blockIdx.y;
+    const int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    const int64_t* cp = S.colptr + (int64_t)t * (Nx + 1);
+    const int64_t e0 = S.tap_off[t] + cp[c] - 1, e1 = S.tap_off[t] + cp[c + 1] - 1;
+    int64_t prev = 0;
+    bool bad = false;
+#pragma unroll 1
+    for (int64_t e = e0; e < e1; e++) {
+        const int64_t r = S.rowval[e];
+        bad |= (r <= prev) | (r > nrow);
+        prev = r;
+    }
+    if (bad) *flag = 1;
+}
+
+int sls_launch_validate_supports(const SlsSupports& S, int T, int64_t Nx, int64_t nrow, int64_t c0, int64_t c1, int32_t* flag,
+                                 sls_stream_t stream) {
+    if (c1 <= c0 || T <= 0) return 0;
+    dim3 grid((unsigned)((c1 - c0 + 255) / 256), T, 1);
+    auto kp = &sls_validate_supports_kernel;
+    SLS_LAUNCH(kp, grid, 256, 0, stream, S, Nx, nrow, c0, c1, flag);
+    return rt::last_error();
+}
+
 // ---- host launchers -------------------------------------------------------------------------
 int sls_launch_gather_count(const SlsCsc& A, const SlsSupports& Sx, const SlsSupports& Su, int T, int64_t Nx,
                             const int32_t* cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
-                            int32_t* keep_x, int32_t* keep_u, sls_stream_t stream) {
+                            int32_t* keep_x, int32_t* keep_u, const int32_t* bad_supports, sls_stream_t stream) {
     if (ncols == 0) return 0;
     const int grid = (ncols + GATHER_WPB - 1) / GATHER_WPB;
     const size_t smem = (size_t)GATHER_WPB * cap * sizeof(int32_t);
     auto kp = &sls_gather_count_kernel;
     if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
-    SLS_LAUNCH(kp, grid, GATHER_WPB * 32, smem, stream, A, Sx, Su, T, Nx, cols, ncols, n_out, m_out, cap, keep_x, keep_u);
+    SLS_LAUNCH(kp, grid, GATHER_WPB * 32, smem, stream, A, Sx, Su, T, Nx, cols, ncols, n_out, m_out, cap, keep_x, keep_u, bad_supports);
     return rt::last_error();
 }
 

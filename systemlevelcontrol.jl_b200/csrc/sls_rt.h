@@ -32,6 +32,8 @@ inline int copy_batch(void** dsts, void** srcs, size_t* sizes, size_t n, sls_str
 }
 inline int host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
 inline void host_free(void* p) { free(p); }
+inline int host_register(void*, size_t) { return 0; }
+inline int host_unregister(void*) { return 0; }
 inline int sync(sls_stream_t) { return 0; }
 inline int last_error() { return 0; }
 inline const char* err_str(int) { return "emu"; }
@@ -84,6 +86,8 @@ inline int copy_batch(void** dsts, void** srcs, size_t* sizes, size_t n, sls_str
 }
 inline int host_alloc(void** p, size_t n) { return (int)cudaMallocHost(p, n ? n : 1); }
 inline void host_free(void* p) { if (p) cudaFreeHost(p); }
+inline int host_register(void* p, size_t n) { return (int)cudaHostRegister(p, n, cudaHostRegisterPortable); }
+inline int host_unregister(void* p) { return (int)cudaHostUnregister(p); }
 inline int sync(sls_stream_t s) { return (int)cudaStreamSynchronize(s); }
 inline int last_error() { return (int)cudaGetLastError(); }
 inline const char* err_str(int e) { return cudaGetErrorString((cudaError_t)e); }

@@ -56,6 +56,8 @@ __device__ __forceinline__ double sls_rcp(double x) {
     return fma(y, fma(e, e, e), y);
 #endif
 }
+// max that keeps a NaN from either side (fmax would drop it: a NaN residual must end as SLS_STATUS_RESIDUAL)
+__device__ __forceinline__ double sls_nanmax(double a, double b) { return (b > a || b != b) ? b : a; }
 // acc += X * W^T for two 8x8 blocks in accumulator layout
 __device__ __forceinline__ void sls_mma_xwt(double (&acc)[2], const double (&x)[2], const double (&w)[2]) {
     sls_dmma(acc[0], acc[1], x[0], w[0]);
@@ -723,7 +725,8 @@ sls_solve_kernel(SlsSolveArgs a) {
                     const int r0 = rptr[i], r2 = rptr[i + 1];
 #pragma unroll 1
                     for (int e = r0; e < r2; e++) r = fma(valr[e], xcur[colr[e]], r);
-                    resmax = fmax(resmax, fabs(r));
+                    const double ar = fabs(r);
+                    resmax = sls_nanmax(resmax, ar);
                 }
             }
 #pragma unroll
@@ -734,10 +737,10 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
         for (int rr = 0; rr < RPL; rr++) {
             const int i = lane + 32 * rr;
-            if (i < n) resmax = fmax(resmax, fabs(((i == jl) ? 1.0 : 0.0) - xnext_r[rr]));
+            if (i < n) { const double ar = fabs(((i == jl) ? 1.0 : 0.0) - xnext_r[rr]); resmax = sls_nanmax(resmax, ar); }
         }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) resmax = fmax(resmax, __shfl_xor_sync(SLS_FULL, resmax, d));
+        for (int d = 16; d > 0; d >>= 1) resmax = sls_nanmax(resmax, __shfl_xor_sync(SLS_FULL, resmax, d));
         if (!(resmax <= a.feas_tol)) status |= SLS_ST_RESIDUAL;
         if (lane == 0) { a.status[c] = status; a.resid[c] = resmax; }
     }

@@ -363,6 +363,59 @@ class Synthesizer:
                                          ptr(nnz_x, i64p), ptr(nnz_u, i64p), ptr(out["status"], i32p), ptr(out["resid"], f64p)))
         return nnz_x, nnz_u
 
+    def synthesize_window(self, Sx, Su, win, col_range, out=None, pass_nzval=True, pinned=False, values_only=False):
+        """Shard form (sls_synthesize_window): `win` = (w0, w1) 0-based half-open support window that covers the column
+        range `col_range` = (c0, c1) and its halo.  Sx / Su are either full-width JuliaCSC matrices (their colptr is passed
+        as a view starting at w0 — the `pointer(S.colptr, w0+1)` form) or window slices with w1-w0 columns.  Outputs are
+        the column slab: colptr arrays of c1-c0+1 entries.  values_only: NULL rowval outputs (the caller aliases
+        S[t].rowval when the returned counts equal nnz(S[t][:, range]))."""
+        w0, w1 = int(win[0]), int(win[1])
+        c0, c1 = int(col_range[0]), int(col_range[1])
+        Sx = [_as_julia(M, np.bool_) for M in Sx]
+        Su = [_as_julia(M, np.bool_) for M in Su]
+        self.T = T = len(Sx)
+
+        def cp_view(M):
+            if M.n == w1 - w0:
+                return M.colptr
+            assert M.n == self.Nx, "supports must be full-width or exactly the window"
+            return M.colptr[w0:w1 + 1]
+        cps = [[cp_view(M) for M in S] for S in (Sx, Su)]
+        if out is None:
+            self.nnz_x = np.array([int(cp[c1 - w0] - cp[c0 - w0]) for cp in cps[0]], np.int64)
+            self.nnz_u = np.array([int(cp[c1 - w0] - cp[c0 - w0]) for cp in cps[1]], np.int64)
+            self.ncols = c1 - c0
+            Nx_keep = self.Nx
+            try:
+                self.Nx = c1 - c0                        # slab colptr arrays: ncols + 1 entries
+                out = self.alloc_outputs(pinned=pinned)
+            finally:
+                self.Nx = Nx_keep
+        cap_x = np.array([a.size for a in out["x"]["nzval"]], np.int64)
+        cap_u = np.array([a.size for a in out["u"]["nzval"]], np.int64)
+        args = []
+        for S, cp in ((Sx, cps[0]), (Su, cps[1])):
+            args.append(ptr_array(cp, i64p))
+            args.append(ptr_array([M.rowval for M in S], i64p))
+            args.append(ptr_array([M.nzval for M in S], u8p) if pass_nzval else None)
+        oargs = []
+        for name in ("x", "u"):
+            oargs.append(ptr_array(out[name]["colptr"], i64p))
+            oargs.append(None if values_only else ptr_array(out[name]["rowval"], i64p))
+            oargs.append(ptr_array(out[name]["nzval"], f64p))
+        nnz_x = np.zeros(T, np.int64); nnz_u = np.zeros(T, np.int64)
+        self._ck(self.api.sls_synthesize_window(self.h, T, w0 + 1, w1 - w0, *args, c0 + 1, c1 - c0, ptr(cap_x, i64p), ptr(cap_u, i64p),
+                                                *oargs, ptr(nnz_x, i64p), ptr(nnz_u, i64p), ptr(out["status"], i32p), ptr(out["resid"], f64p)))
+        self.nnz_x, self.nnz_u, self.ncols = nnz_x, nnz_u, c1 - c0
+        return out, nnz_x, nnz_u
+
+    def host_register(self, arr):
+        """Page-lock a caller-owned numpy array (sls_host_register)."""
+        self._ck(self.api.sls_host_register(self.h, C.c_void_p(arr.ctypes.data), arr.nbytes))
+
+    def host_unregister(self, arr):
+        self._ck(self.api.sls_host_unregister(self.h, C.c_void_p(arr.ctypes.data)))
+
     def solve_device(self):
         self._ck(self.api.sls_solve_device(self.h))
 

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cmath>
 #include <vector>
+#include <mutex>
 #include <functional>
 #include <algorithm>
 #include <chrono>
@@ -83,8 +84,12 @@ inline void trampoline() {
     b->fibers[b->cur].done = true;
     swapcontext(&b->fibers[b->cur].ctx, &b->sched);
 }
+// the emulator's state is global: launches from different host threads (the feeder thread of sls_synthesize launches
+// the support validation kernels) are serialised
+inline std::mutex& launch_mutex() { static std::mutex m; return m; }
 template <class F>
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& f) {
+    std::lock_guard<std::mutex> lock(launch_mutex());
     const size_t STACK = 256 * 1024;
     int nt = block.x * block.y * block.z;
     gdim() = grid; bdim() = block;

@@ -281,6 +281,93 @@ def check_pipelined(api, plant, S, chunks, pass_nzval=True):
         syn.close()
 
 
+def check_window(api, plant, S, ranges, halo=1, chunks=(1, 3)):
+    """sls_synthesize_window (support window in, column slab out) == the three-call path on the same columns, bit for
+    bit — for both ways of passing a window (a colptr view into the full matrices; rebased slices), and with the
+    rowval outputs left out.  Also: the handle then refuses plans that reach outside the uploaded window, a window that
+    does not cover the halo is an argument error, malformed support rows are caught by the device-side check."""
+    import os
+    A, B1, B2 = plant
+    Nx = A.shape[0]
+    syn = slc_b200.Synthesizer(api=api)
+    old = os.environ.get("SLS_PIPE_CHUNKS")
+    try:
+        syn.set_plant(A, B2)
+        Sxj = [slc_b200.JuliaCSC.from_scipy(sp.csc_matrix(M), np.bool_) for M in S[0]]
+        Suj = [slc_b200.JuliaCSC.from_scipy(sp.csc_matrix(M), np.bool_) for M in S[1]]
+        T = len(Sxj)
+        for (c0, c1) in ranges:
+            w0, w1 = max(0, c0 - halo), min(Nx, c1 + halo)
+            syn.set_supports(*S)
+            syn.plan(np.arange(c0, c1))
+            ref = syn.solve()
+            for K in chunks:
+                os.environ["SLS_PIPE_CHUNKS"] = str(K)
+                for form in ("view", "slice", "values_only"):
+                    if form == "slice":
+                        def sl(M):
+                            lo, hi = int(M.colptr[w0] - 1), int(M.colptr[w1] - 1)
+                            return slc_b200.JuliaCSC(M.m, w1 - w0, np.ascontiguousarray(M.colptr[w0:w1 + 1] - lo),
+                                                     np.ascontiguousarray(M.rowval[lo:hi]), np.ascontiguousarray(M.nzval[lo:hi]))
+                        X, U = [sl(M) for M in Sxj], [sl(M) for M in Suj]
+                    else:
+                        X, U = Sxj, Suj
+                    out, nnz_x, nnz_u = syn.synthesize_window(X, U, (w0, w1), (c0, c1), values_only=(form == "values_only"))
+                    for fam, nnz in (("x", nnz_x), ("u", nnz_u)):
+                        for t in range(T):
+                            full_cp = ref[fam]["colptr"][t]
+                            lo, hi = int(full_cp[c0] - 1), int(full_cp[c1] - 1)
+                            assert nnz[t] == hi - lo
+                            assert np.array_equal(out[fam]["colptr"][t], full_cp[c0:c1 + 1] - lo), (form, K, fam, t)
+                            assert np.array_equal(out[fam]["nzval"][t][:hi - lo], ref[fam]["nzval"][t][lo:hi]), (form, K, fam, t)
+                            if form != "values_only":
+                                assert np.array_equal(out[fam]["rowval"][t][:hi - lo], ref[fam]["rowval"][t][lo:hi]), (form, K, fam, t)
+                    assert np.array_equal(out["status"][:c1 - c0], ref["status"][:c1 - c0])
+                    assert np.array_equal(out["resid"][:c1 - c0], ref["resid"][:c1 - c0])
+        # the window of the last call is all the device holds: planning a column outside it is refused, not garbage
+        c0, c1 = ranges[-1]
+        far = 0 if c0 > halo + 1 else Nx - 1
+        if not (max(0, c0 - halo) <= far < min(Nx, c1 + halo)):
+            with pytest.raises(_capi.SlsError) as ei:
+                syn.plan([far])
+            assert ei.value.code == -3
+        # a window without the halo
+        if c0 > 0:
+            with pytest.raises(_capi.SlsError) as ei:
+                syn.synthesize_window(Sxj, Suj, (c0, min(Nx, c1 + halo)), (c0, c1))
+            assert ei.value.code == -3
+        # malformed rows (descending inside a column) are caught on the device, in both paths
+        bad = [slc_b200.JuliaCSC(M.m, M.n, M.colptr, M.rowval.copy(), M.nzval) for M in Sxj]
+        M = bad[T - 1]; e = int(M.colptr[c0] - 1)
+        assert M.colptr[c0 + 1] - M.colptr[c0] >= 2
+        M.rowval[e], M.rowval[e + 1] = M.rowval[e + 1], M.rowval[e]
+        with pytest.raises(_capi.SlsError) as ei:
+            syn.synthesize_window(bad, Suj, (max(0, c0 - halo), min(Nx, c1 + halo)), (c0, c1))
+        assert ei.value.code == -2
+        with pytest.raises(_capi.SlsError) as ei:
+            syn.set_supports(bad, Suj)
+        assert ei.value.code == -2
+        M.rowval[e] = Nx + 5                                    # out of range
+        with pytest.raises(_capi.SlsError) as ei:
+            syn.set_supports(bad, Suj)
+        assert ei.value.code == -2
+        # the handle is still usable
+        syn.set_supports(*S)
+        syn.plan(np.arange(c0, c1))
+        again = syn.solve()
+        assert np.array_equal(again["x"]["nzval"][T - 1], ref["x"]["nzval"][T - 1])
+        # duplicates in a reduction group are first occurrences (reduction.jl:14), not an error
+        a = syn.reduce([c0, c0 + 1, c0])
+        b = syn.reduce([c0, c0 + 1])
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    finally:
+        if old is None:
+            os.environ.pop("SLS_PIPE_CHUNKS", None)
+        else:
+            os.environ["SLS_PIPE_CHUNKS"] = old
+        syn.close()
+
+
 def check_weighted_cost(api, cols=(3, 14, 39)):
     """6-argument Plant with diagonal [C1 D12] (+ a diagonal B1 and a q = 2 group) through SLS_H2 -> sls_set_weights,
     against the oracle's general restatement of synthesis.jl:42-43,50,76-77."""

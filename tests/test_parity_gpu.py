@@ -267,6 +267,12 @@ def test_pipelined_one_shot_config3_100k_bit_for_bit(cuda_api):
         syn.close()
 
 
+def test_window_shard_form(cuda_api):
+    """sls_synthesize_window: support window in, column slab out (the per-GPU shape; no array grows with Nx)."""
+    A, B1, B2, S = pc.chain(600)
+    pc.check_window(cuda_api, (A, B1, B2), S, ranges=[(0, 200), (199, 417), (417, 600)], chunks=(1, 4))
+
+
 def test_weighted_cost_and_column_groups_vs_general_oracle(cuda_api):
     """6-argument Plant with diagonal cost weights, diagonal B1, q = 2 group."""
     assert pc.check_weighted_cost(cuda_api, cols=(3, 14, 39, 0, 20, 27)) < 1e-10
