@@ -159,9 +159,15 @@ int sls_synthesize(sls_handle* h, int64_t T,
  * entries whose values are 1-based offsets into the rowval / nzval pointers beside it (Julia: `pointer(𝓢[t].colptr,
  * win_first)` with the full rowval, or the fields of the slice `𝓢[t][:, win]`).  The outputs are the column SLAB
  * Φ[t][:, first_col : first_col+ncols-1]: colptr arrays of ncols + 1 entries starting at 1, rowval (global rows) and
- * nzval sized by cap_x / cap_u (NULL = nnz of the window).  Everything else is as in sls_synthesize.  Per-GPU bytes over
- * PCIe then depend on the shard, not on Nx. */
-int sls_synthesize_window(sls_handle* h, int64_t T, int64_t win_first, int64_t win_ncols,
+ * nzval sized by cap_x / cap_u (NULL = nnz of the window).  Everything else is as in sls_synthesize.
+ * Sub-plant shards: when the handle's plant is itself the sub-plant P[pw, pw] of a larger plant (a rank that owns the
+ * columns pw ⊇ range ∪ every s_x of the range sets A[pw,pw], B2[pw,uw] with sls_set_plant), the supports may keep the
+ * row numbers of the large plant: row_off_x / row_off_u (>= 0) are subtracted from every support row on the device
+ * (local row = stored row - row_off; a row that falls outside 1..Nx / 1..Nu of the handle's plant is a layout error)
+ * and added to every output row, so the slabs of all ranks concatenate into the global Φ[t] without a host pass over
+ * rowval.  Column numbers (win_first, first_col) are those of the handle's plant.  Per-GPU host work, device memory and
+ * bytes over PCIe then depend on the shard only, not on the global Nx. */
+int sls_synthesize_window(sls_handle* h, int64_t T, int64_t win_first, int64_t win_ncols, int64_t row_off_x, int64_t row_off_u,
                           const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
                           const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval,
                           int64_t first_col, int64_t ncols, const int64_t* cap_x, const int64_t* cap_u,

@@ -63,7 +63,7 @@ SIGNATURES = {
                                  C.POINTER(i64p), C.POINTER(i64p), C.POINTER(u8p), C.c_int64, C.c_int64, i64p, i64p,
                                  C.POINTER(i64p), C.POINTER(i64p), C.POINTER(f64p),
                                  C.POINTER(i64p), C.POINTER(i64p), C.POINTER(f64p), i64p, i64p, i32p, f64p]),
-    "sls_synthesize_window": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+    "sls_synthesize_window": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                         C.POINTER(i64p), C.POINTER(i64p), C.POINTER(u8p),
                                         C.POINTER(i64p), C.POINTER(i64p), C.POINTER(u8p), C.c_int64, C.c_int64, i64p, i64p,
                                         C.POINTER(i64p), C.POINTER(i64p), C.POINTER(f64p),

@@ -63,11 +63,12 @@ struct DevSupports {            // T Bool CSC matrices, taps concatenated
     DevBuf colptr, rowval, nzval, tap_off;
     bool has_nzval = false;
     int64_t nnz = 0;
+    int64_t row_off = 0;        // stored row - row_off = plant row (sls_synthesize_window on a sub-plant)
     int maxlen_last = 0;        // longest column of the last tap (bounds kernel 1's candidate list)
     std::vector<int64_t> h_tap_off;   // host copy of tap_off (sls_get_supports)
     SlsSupports view() const {
         return SlsSupports{colptr.as<int64_t>(), rowval.as<int64_t>(), has_nzval ? nzval.as<uint8_t>() : nullptr,
-                           tap_off.as<int64_t>()};
+                           tap_off.as<int64_t>(), row_off};
     }
     void release() { colptr.release(); rowval.release(); nzval.release(); tap_off.release(); }
 };
@@ -420,6 +421,7 @@ extern "C" int sls_set_supports(sls_handle* h, int64_t T,
     SLS_ARG(Sx_colptr && Sx_rowval && Su_colptr && Su_rowval, "sls_set_supports: NULL array of pointers");
     SLS_CK(rt::set_device(h->device));
     h->have_supports = false; h->plan.valid = false; h->solved = false;
+    h->Sx.row_off = h->Su.row_off = 0;
     h->ev[0].record(h->stream);
     SLS_CK(rt::zero(h->d_flag.p, sizeof(int32_t), h->stream));
     int e = upload_supports(h, h->Sx, T, h->Nx, h->Nx, Sx_colptr, Sx_rowval, Sx_nzval, "Sx");
@@ -483,6 +485,7 @@ static int make_both_families(sls_handle* h, int64_t T, const std::vector<int>& 
     for (int k = 0; k < nsx; k++) offx[k + 1] = offx[k] + lastx[k] - 1;
     for (int k = 0; k < nsu; k++) offu[k + 1] = offu[k] + lastu[k] - 1;
     DevSupports& X = h->Sx; DevSupports& U = h->Su;
+    X.row_off = U.row_off = 0;
     X.nnz = offx[nsx]; U.nnz = offu[nsu]; X.has_nzval = U.has_nzval = false;
     MS_CK(X.rowval.ensure(std::max<int64_t>(X.nnz, 1) * 8));
     MS_CK(U.rowval.ensure(std::max<int64_t>(U.nnz, 1) * 8));
@@ -953,6 +956,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         SlsScatterArgs s{};
         s.P = v; s.c_begin = 0; s.c_end = p.ncols;
         s.rowval = reinterpret_cast<int64_t* const*>(h->out_ptrs.as<void*>());
+        s.row_off_x = h->Sx.row_off; s.row_off_u = h->Su.row_off;
         h->ev[5].record(h->copy_stream);
         SLS_CK(sls_launch_scatter(s, h->copy_stream));
         h->chunk_ev[15].record(h->copy_stream);
@@ -987,7 +991,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         if (h->have_weights) {                                  // back-scaling needs kernel 3's rowval as well
             SLS_CK(rt::stream_wait(h->stream, h->chunk_ev[15]));
             SLS_CK(sls_launch_unscale(v, cb[ch], cb[ch + 1], reinterpret_cast<const int64_t* const*>(h->out_ptrs.as<void*>()),
-                                      reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T), h->d_wx.as<double>(), h->d_wu.as<double>(), h->stream));
+                                      reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T), h->d_wx.as<double>(), h->d_wu.as<double>(), h->Sx.row_off, h->Su.row_off, h->stream));
         }
         if (ho) {
             h->chunk_ev[ch].record(h->stream);
@@ -1117,7 +1121,7 @@ static int pipe_enqueue_slice(sls_handle* h, PipeSupp& f, int64_t T, int64_t w0,
             for (int64_t c = c0; c < c1; c++) {
                 int64_t prev = 0;
                 for (int64_t e = cp[c] - 1; e < cp[c + 1] - 1; e++) {
-                    if (f.rvs[t][e] < 1 || f.rvs[t][e] > f.nrow || f.rvs[t][e] <= prev) {
+                    if (f.rvs[t][e] - d.row_off < 1 || f.rvs[t][e] - d.row_off > f.nrow || f.rvs[t][e] <= prev) {
                         msg = std::string("sls_synthesize: ") + f.name + ": rowval out of range or not strictly ascending"; return -2;
                     }
                     prev = f.rvs[t][e];
@@ -1136,7 +1140,7 @@ static void pipe_drain(sls_handle* h) {
 
 // `slab`: the supports are a column window [w0, w0 + wn) and the outputs are the column slab of the range
 // (colptr arrays of ncols + 1 entries starting at 1) — sls_synthesize_window; otherwise full-width arrays.
-static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int64_t wn,
+static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int64_t wn, int64_t row_off_x, int64_t row_off_u,
                            const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
                            const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval,
                            int64_t first_col, int64_t ncols, const int64_t* cap_x, const int64_t* cap_u,
@@ -1184,6 +1188,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
     SLS_CK(rt::stream_wait(h->in_stream, h->ev[0]));            // earlier work on the main stream may still read the supports
     PipeSupp fam[2] = {{&h->Sx, Sx_colptr, Sx_rowval, Sx_nzval, Nx, "Sx"}, {&h->Su, Su_colptr, Su_rowval, Su_nzval, Nu, "Su"}};
     SLS_CK(rt::zero(h->d_flag.p, sizeof(int32_t), h->in_stream));
+    h->Sx.row_off = row_off_x; h->Su.row_off = row_off_u;
     for (int f = 0; f < 2; f++) { int e = pipe_prepare(h, fam[f], T, Nx, w0, wn); if (e) { pipe_drain(h); return e; } }
     h->T = T; h->supp_lo = ub[0]; h->supp_hi = ub[K];
     SLS_CK(h->pipe_colptr.ensure((size_t)2 * T * (Nx + 1) * sizeof(int64_t)));
@@ -1284,6 +1289,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
             SlsScatterArgs sa{};
             sa.P = v; sa.c_begin = 0; sa.c_end = p.ncols;
             sa.rowval = reinterpret_cast<int64_t* const*>(x.out_ptrs.as<void*>());
+            sa.row_off_x = h->Sx.row_off; sa.row_off_u = h->Su.row_off;
             PIPE_CK(sls_launch_scatter(sa, h->scat_stream));
         }
         x.ev_scat.record(h->scat_stream);
@@ -1304,7 +1310,8 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
         if (h->have_weights) {
             PIPE_CK(rt::stream_wait(h->stream, x.ev_scat));
             PIPE_CK(sls_launch_unscale(v, 0, p.ncols, reinterpret_cast<const int64_t* const*>(x.out_ptrs.as<void*>()),
-                                       reinterpret_cast<double* const*>(x.out_ptrs.as<void*>() + 2 * T), h->d_wx.as<double>(), h->d_wu.as<double>(), h->stream));
+                                       reinterpret_cast<double* const*>(x.out_ptrs.as<void*>() + 2 * T), h->d_wx.as<double>(), h->d_wu.as<double>(),
+                                       h->Sx.row_off, h->Su.row_off, h->stream));
         }
         x.ev_solved.record(h->stream);
         // device -> host, in the order the data becomes final: colptr, rowval, then nzval / status / residual
@@ -1390,11 +1397,11 @@ extern "C" int sls_synthesize(sls_handle* h, int64_t T,
                               int64_t* const* Px_colptr, int64_t* const* Px_rowval, double* const* Px_nzval,
                               int64_t* const* Pu_colptr, int64_t* const* Pu_rowval, double* const* Pu_nzval,
                               int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid) {
-    return synthesize_impl(h, T, false, 0, 0, Sx_colptr, Sx_rowval, Sx_nzval, Su_colptr, Su_rowval, Su_nzval, first_col, ncols, cap_x, cap_u,
+    return synthesize_impl(h, T, false, 0, 0, 0, 0, Sx_colptr, Sx_rowval, Sx_nzval, Su_colptr, Su_rowval, Su_nzval, first_col, ncols, cap_x, cap_u,
                            Px_colptr, Px_rowval, Px_nzval, Pu_colptr, Pu_rowval, Pu_nzval, nnz_x, nnz_u, status, resid);
 }
 
-extern "C" int sls_synthesize_window(sls_handle* h, int64_t T, int64_t win_first, int64_t win_ncols,
+extern "C" int sls_synthesize_window(sls_handle* h, int64_t T, int64_t win_first, int64_t win_ncols, int64_t row_off_x, int64_t row_off_u,
                                      const int64_t* const* Sx_colptr, const int64_t* const* Sx_rowval, const uint8_t* const* Sx_nzval,
                                      const int64_t* const* Su_colptr, const int64_t* const* Su_rowval, const uint8_t* const* Su_nzval,
                                      int64_t first_col, int64_t ncols, const int64_t* cap_x, const int64_t* cap_u,
@@ -1403,7 +1410,7 @@ extern "C" int sls_synthesize_window(sls_handle* h, int64_t T, int64_t win_first
                                      int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid) {
     if (!h) return -1;
     SLS_ARG(ncols >= 1, "sls_synthesize_window: ncols must be >= 1");
-    return synthesize_impl(h, T, true, win_first - 1, win_ncols, Sx_colptr, Sx_rowval, Sx_nzval, Su_colptr, Su_rowval, Su_nzval, first_col, ncols,
+    return synthesize_impl(h, T, true, win_first - 1, win_ncols, row_off_x, row_off_u, Sx_colptr, Sx_rowval, Sx_nzval, Su_colptr, Su_rowval, Su_nzval, first_col, ncols,
                            cap_x, cap_u, Px_colptr, Px_rowval, Px_nzval, Pu_colptr, Pu_rowval, Pu_nzval, nnz_x, nnz_u, status, resid);
 }
 
@@ -1447,6 +1454,7 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     int e = 0;
     auto cleanup = [&]() { DevBuf* all[] = {&dcol, &dtime, &dnw, &dnu, &dxn, &dun, &dxo, &duo, &dovf, &dW, &dWu, &dnent, &dtapcnt, &dpkoff, &dpkcnt, &dpkrow, &dpkval}; for (DevBuf* b : all) b->release(); };
 #define SIM_CK(expr) do { e = (expr); if (e) { cleanup(); return fail(h, e, #expr); } } while (0)
+    h->ev[2].record(h->stream);
     SIM_CK(dcol.ensure(nscen * 8)); SIM_CK(dtime.ensure(nscen * 8));
     SIM_CK(dnw.ensure(nscen * 4)); SIM_CK(dnu.ensure(nscen * 4)); SIM_CK(dovf.ensure(4));
     SIM_CK(rt::h2d(dcol.p, dist_col, nscen * 8, h->stream));
@@ -1481,10 +1489,21 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     if (wcap > 65535 || ucap > 65535) { cleanup(); return fail(h, -4, "sls_simulate: window too large"); }
     SIM_CK(dnent.ensure(nscen * 8)); SIM_CK(dtapcnt.ensure((size_t)nscen * 2 * T * 4)); SIM_CK(dpkoff.ensure(nscen * 8));
     SIM_CK(sls_launch_sim_pack(a, false, wcap, ucap, dnent.as<int64_t>(), dtapcnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, h->stream));
+    double sim_bytes = 0;
     {
         std::vector<int64_t> nent(nscen), off(nscen);
+        std::vector<uint32_t> tapcnt((size_t)nscen * 2 * T);
         SIM_CK(rt::d2h(nent.data(), dnent.p, nscen * 8, h->stream));
+        SIM_CK(rt::d2h(tapcnt.data(), dtapcnt.p, tapcnt.size() * 4, h->stream));
         SIM_CK(rt::sync(h->stream));
+        // packed entries (8 B value + 2 B local row) the recursion multiplies: tap tau of scenario s is applied at every
+        // step t with t_s + tau <= t <= steps - 1 (what(t+1-tau) is exactly zero before that)
+        for (int64_t s = 0; s < nscen; s++)
+            for (int64_t tau = 1; tau <= T; tau++) {
+                const double reps = (double)std::max<int64_t>(0, steps - std::max<int64_t>(dist_time[s], 1) - tau);
+                const double ent = (tau <= T - 1 ? (double)tapcnt[(size_t)s * 2 * T + tau] : 0.0) + (double)tapcnt[(size_t)s * 2 * T + T + tau - 1];
+                sim_bytes += reps * ent * 10.0;
+            }
         int64_t run = 0;
         for (int64_t s = 0; s < nscen; s++) { off[s] = run; run += nent[s]; }
         SIM_CK(rt::h2d(dpkoff.p, off.data(), nscen * 8, h->stream));
@@ -1519,6 +1538,8 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     SIM_CK(rt::sync(h->stream));
 #undef SIM_CK
     h->tm.sim_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);
+    h->tm.sim_pack_ms = rt::elapsed_ms(h->ev[2], h->ev[0]);
+    h->tm.sim_bytes = sim_bytes;
     h->tm.sim_window = wmax; h->tm.sim_uwindow = umax;
     cleanup();
     if (ovf) return fail(h, -4, "sls_simulate: window scratch overflow");

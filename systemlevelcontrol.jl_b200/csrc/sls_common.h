@@ -22,6 +22,8 @@ struct SlsSupports {            // T Bool CSC matrices, concatenated
     const int64_t* rowval;      // all taps back to back
     const uint8_t* nzval;       // same indexing as rowval, or nullptr (= all true)
     const int64_t* tap_off;     // T+1 offsets of each tap inside rowval
+    int64_t row_off;            // stored row - row_off = row of the handle's plant (0 unless the plant is a sub-plant window
+                                // and the supports keep their global row numbers: sls_synthesize_window)
 };
 
 struct SlsPlanView {            // per planned column c (0 <= c < ncols), written by kernel 1

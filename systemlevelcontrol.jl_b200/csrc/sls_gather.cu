@@ -34,7 +34,7 @@ __device__ int sls_warp_index_set(const SlsCsc& A, const SlsSupports& S, int T, 
         const int len = (int)(s1 - s0);
         if (C + len > cap) return -1;
 #pragma unroll 1
-        for (int i = lane; i < len; i += 32) buf[C + i] = (int32_t)(S.rowval[s0 + i] - 1);
+        for (int i = lane; i < len; i += 32) buf[C + i] = (int32_t)(S.rowval[s0 + i] - 1 - S.row_off);
         C += len;
     }
     int P = 32;
@@ -194,7 +194,7 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
         const SlsSupports& S = isu ? Su : Sx;
         const int64_t e = seg0[tt] + (f - pfx[tt]);
         const bool on = S.nzval ? (S.nzval[e] != 0) : true;   // `𝓢[t][s,cⱼ] .≠ 1` fixes the entry (synthesis.jl:58-59)
-        const int32_t row = (int32_t)(S.rowval[e] - 1);
+        const int32_t row = (int32_t)(S.rowval[e] - 1 - S.row_off);
         int idx;
         if (isu) { if (runu) { idx = row - su[0]; if (idx < 0 || idx >= m) idx = -1; } else idx = sls_find(su, m, row); }
         else { if (runx) { idx = row - sx[0]; if (idx < 0 || idx >= n) idx = -1; } else idx = sls_find(sx, n, row); }
@@ -373,7 +373,7 @@ sls_validate_supports_kernel(SlsSupports S, int64_t Nx, int64_t nrow, int64_t c0
     bool bad = false;
 #pragma unroll 1
     for (int64_t e = e0; e < e1; e++) {
-        const int64_t r = S.rowval[e];
+        const int64_t r = S.rowval[e] - S.row_off;
         bad |= (r <= prev) | (r > nrow);
         prev = r;
     }

@@ -50,10 +50,11 @@ struct SlsScatterArgs {
     int c_begin, c_end;      // planned-column range handled by this launch
     // destination arrays: per tap tt in [0,2T): base pointers (device arrays of pointers)
     int64_t* const* rowval;  // [2T] -> int64 rowval buffers (1-based out)
+    int64_t row_off_x, row_off_u;   // added to the stored rows (global numbering of a sub-plant window's outputs)
 };
 int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream);
 int sls_launch_unscale(const SlsPlanView& P, int c_begin, int c_end, const int64_t* const* rowval, double* const* nzval,
-                       const double* wx, const double* wu, sls_stream_t stream);
+                       const double* wx, const double* wu, int64_t row_off_x, int64_t row_off_u, sls_stream_t stream);
 int sls_launch_iota(int32_t* dst, int32_t first, int n, sls_stream_t stream);
 int sls_kcopy(void* dst, const void* src, size_t bytes, sls_stream_t stream);   // either side may be pinned host memory
 int sls_kgather64(int64_t* dst, const int64_t* src, size_t pitch, int count, sls_stream_t stream);

@@ -63,7 +63,7 @@ sls_scatter_kernel(SlsScatterArgs a) {
         const uint32_t* mw = mbase + ((size_t)cc * T + t) * nw;
         const int li = sls_select_bit(mw, nw, r);
         const int32_t grow = isu ? P.su[(size_t)cc * P.mstride + li] : P.sx[(size_t)cc * P.nstride + li];
-        rowval[dst] = (int64_t)grow + 1;
+        rowval[dst] = (int64_t)grow + 1 + (isu ? a.row_off_u : a.row_off_x);
     }
 }
 
@@ -140,7 +140,7 @@ int sls_kgather64(int64_t* dst, const int64_t* src, size_t pitch, int count, sls
 // This pass applies the back-scaling to the stored values of the planned columns [c_begin, c_end): one warp per column.
 __global__ void __launch_bounds__(256)
 sls_unscale_kernel(SlsPlanView P, int c_begin, int c_end, const int64_t* const* rowval, double* const* nzval,
-                   const double* wx, const double* wu) {
+                   const double* wx, const double* wu, int64_t row_off_x, int64_t row_off_u) {
     const int c = c_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
     if (c >= c_end) return;
     const int lane = sls_lane();
@@ -151,14 +151,15 @@ sls_unscale_kernel(SlsPlanView P, int c_begin, int c_end, const int64_t* const* 
         const int64_t e0 = cp[j] - 1, e1 = cp[j + 1] - 1;
         const int64_t* rv = rowval[tt]; double* nz = nzval[tt];
         const double* w = (tt < P.T) ? wx : wu;
-        for (int64_t e = e0 + lane; e < e1; e += 32) nz[e] *= wj / w[rv[e] - 1];
+        const int64_t ro = (tt < P.T) ? row_off_x : row_off_u;
+        for (int64_t e = e0 + lane; e < e1; e += 32) nz[e] *= wj / w[rv[e] - 1 - ro];
     }
 }
 int sls_launch_unscale(const SlsPlanView& P, int c_begin, int c_end, const int64_t* const* rowval, double* const* nzval,
-                       const double* wx, const double* wu, sls_stream_t stream) {
+                       const double* wx, const double* wu, int64_t row_off_x, int64_t row_off_u, sls_stream_t stream) {
     if (c_end <= c_begin) return 0;
     auto kp = &sls_unscale_kernel;
-    SLS_LAUNCH(kp, (c_end - c_begin + 7) / 8, 256, 0, stream, P, c_begin, c_end, rowval, nzval, wx, wu);
+    SLS_LAUNCH(kp, (c_end - c_begin + 7) / 8, 256, 0, stream, P, c_begin, c_end, rowval, nzval, wx, wu, row_off_x, row_off_u);
     return rt::last_error();
 }
 

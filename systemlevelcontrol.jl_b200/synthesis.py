@@ -304,6 +304,13 @@ class Synthesizer:
         self._ck(self.api.sls_solve(self.h, *args, ptr(out["status"], i32p), ptr(out["resid"], f64p)))
         return out
 
+    def solve_status(self):
+        """sls_solve with every CSC output left out (NULL): runs kernels 2+3 and returns (status, resid) only."""
+        status = np.zeros(max(self.ncols, 1), np.int32)
+        resid = np.zeros(max(self.ncols, 1), np.float64)
+        self._ck(self.api.sls_solve(self.h, None, None, None, None, None, None, ptr(status, i32p), ptr(resid, f64p)))
+        return status[:self.ncols], resid[:self.ncols]
+
     def synthesize(self, Sx, Su, pass_nzval=True, out=None, pinned=False, col_range=None):
         """One-shot pipelined `set_supports + plan(all columns) + solve` (sls_synthesize): H2D of the next column
         chunk, kernels 1-3 and D2H of the previous chunk overlap.  Output taps are allocated at the support's size
@@ -363,12 +370,15 @@ class Synthesizer:
                                          ptr(nnz_x, i64p), ptr(nnz_u, i64p), ptr(out["status"], i32p), ptr(out["resid"], f64p)))
         return nnz_x, nnz_u
 
-    def synthesize_window(self, Sx, Su, win, col_range, out=None, pass_nzval=True, pinned=False, values_only=False):
+    def synthesize_window(self, Sx, Su, win, col_range, out=None, pass_nzval=True, pinned=False, values_only=False,
+                          row_off=(0, 0)):
         """Shard form (sls_synthesize_window): `win` = (w0, w1) 0-based half-open support window that covers the column
         range `col_range` = (c0, c1) and its halo.  Sx / Su are either full-width JuliaCSC matrices (their colptr is passed
         as a view starting at w0 — the `pointer(S.colptr, w0+1)` form) or window slices with w1-w0 columns.  Outputs are
         the column slab: colptr arrays of c1-c0+1 entries.  values_only: NULL rowval outputs (the caller aliases
-        S[t].rowval when the returned counts equal nnz(S[t][:, range]))."""
+        S[t].rowval when the returned counts equal nnz(S[t][:, range])).  row_off = (x, u): the supports' rows are numbered
+        in a larger plant of which the handle's plant is the window starting at those offsets (win / col_range stay in
+        the handle's own column numbering); output rows come back in the larger plant's numbering."""
         w0, w1 = int(win[0]), int(win[1])
         c0, c1 = int(col_range[0]), int(col_range[1])
         Sx = [_as_julia(M, np.bool_) for M in Sx]
@@ -404,7 +414,7 @@ class Synthesizer:
             oargs.append(None if values_only else ptr_array(out[name]["rowval"], i64p))
             oargs.append(ptr_array(out[name]["nzval"], f64p))
         nnz_x = np.zeros(T, np.int64); nnz_u = np.zeros(T, np.int64)
-        self._ck(self.api.sls_synthesize_window(self.h, T, w0 + 1, w1 - w0, *args, c0 + 1, c1 - c0, ptr(cap_x, i64p), ptr(cap_u, i64p),
+        self._ck(self.api.sls_synthesize_window(self.h, T, w0 + 1, w1 - w0, int(row_off[0]), int(row_off[1]), *args, c0 + 1, c1 - c0, ptr(cap_x, i64p), ptr(cap_u, i64p),
                                                 *oargs, ptr(nnz_x, i64p), ptr(nnz_u, i64p), ptr(out["status"], i32p), ptr(out["resid"], f64p)))
         self.nnz_x, self.nnz_u, self.ncols = nnz_x, nnz_u, c1 - c0
         return out, nnz_x, nnz_u

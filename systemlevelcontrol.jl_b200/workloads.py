@@ -24,17 +24,22 @@ def chain_plant(Nx: int, off: float = 0.2):
     return A, B1, B2
 
 
-def _band_csc(Nx, nrows, radius, col_lo, col_hi, row_map=None, row_ok=None):
+def _band_csc(Nx, nrows, radius, col_lo, col_hi, row_map=None, row_ok=None, window=False):
     """CSC (Julia layout) whose column j in [col_lo,col_hi) holds the states within `radius` of j (optionally
-    filtered by row_ok(state) and renamed by row_map(state)); other columns are empty."""
+    filtered by row_ok(state) and renamed by row_map(state)); other columns are empty.  window=True returns only the
+    columns [col_lo, col_hi) (a matrix with col_hi - col_lo columns — the slice S[:, col_lo+1:col_hi] in Julia)."""
     j = np.arange(col_lo, col_hi, dtype=np.int64)
     offs = np.arange(-radius, radius + 1, dtype=np.int64)
     rows = j[:, None] + offs[None, :]
     valid = (rows >= 0) & (rows < Nx)
     if row_ok is not None:
         valid &= row_ok(rows)
-    cnt = np.zeros(Nx, np.int64)
-    cnt[col_lo:col_hi] = valid.sum(axis=1)
+    if window:
+        cnt = valid.sum(axis=1).astype(np.int64)
+        Nx = col_hi - col_lo
+    else:
+        cnt = np.zeros(Nx, np.int64)
+        cnt[col_lo:col_hi] = valid.sum(axis=1)
     colptr = np.empty(Nx + 1, np.int64)
     colptr[0] = 1
     np.cumsum(cnt, out=colptr[1:])
@@ -46,9 +51,10 @@ def _band_csc(Nx, nrows, radius, col_lo, col_hi, row_map=None, row_ok=None):
     return JuliaCSC(nrows, Nx, colptr, rowval, np.ones(rowval.size, np.uint8))
 
 
-def chain_supports(Nx: int, d: int, T: int, alpha: float, col_lo: int = 0, col_hi: int | None = None):
+def chain_supports(Nx: int, d: int, T: int, alpha: float, col_lo: int = 0, col_hi: int | None = None, window: bool = False):
     """(Sx, Su): two length-T lists of JuliaCSC Bool matrices for the chain plant; only columns
-    [col_lo, col_hi) are populated (a rank's column slab plus the halo it needs)."""
+    [col_lo, col_hi) are populated (a rank's column slab plus the halo it needs).  window=True: the matrices hold just
+    those columns (col_hi - col_lo columns, rows still numbered in the Nx-state plant)."""
     col_hi = Nx if col_hi is None else col_hi
     Nu = int(((np.arange(Nx) % 6) < 2).sum())
     Sx, Su = [], []
@@ -57,10 +63,10 @@ def chain_supports(Nx: int, d: int, T: int, alpha: float, col_lo: int = 0, col_h
         k = int(np.floor(alpha * (t - 1)))
         kx, ku = min(d, k), min(d + 1, k)
         if ("x", kx) not in cache:
-            cache[("x", kx)] = _band_csc(Nx, Nx, kx, col_lo, col_hi)
+            cache[("x", kx)] = _band_csc(Nx, Nx, kx, col_lo, col_hi, window=window)
         if ("u", ku) not in cache:
             cache[("u", ku)] = _band_csc(Nx, Nu, ku, col_lo, col_hi, row_map=lambda s: 2 * (s // 6) + (s % 6),
-                                         row_ok=lambda s: (s % 6) < 2)
+                                         row_ok=lambda s: (s % 6) < 2, window=window)
         Sx.append(cache[("x", kx)])
         Su.append(cache[("u", ku)])
     return Sx, Su

@@ -27,7 +27,7 @@ def restrict_cols(taps, cols, ncol):
     return out
 
 
-def check_golden(api, name, plant, cols=None, rtol=PHI_RTOL):
+def check_golden(api, name, plant, cols=None, rtol=PHI_RTOL, floor=0.0):
     g = load_golden(name)
     A, B1, B2 = plant
     S = O.make_supports(A, B2, int(g["d"]), int(g["T"]), float(g["alpha"]))
@@ -39,8 +39,8 @@ def check_golden(api, name, plant, cols=None, rtol=PHI_RTOL):
     tx, tu = golden_taps(g, "x"), golden_taps(g, "u")
     if cols is not None:
         tx, tu = restrict_cols(tx, use, A.shape[0]), restrict_cols(tu, use, A.shape[0])
-    wx = assert_phi_matches(Phix, tx, "Phix", rtol)
-    wu = assert_phi_matches(Phiu, tu, "Phiu", rtol)
+    wx = assert_phi_matches(Phix, tx, "Phix", rtol, floor)
+    wu = assert_phi_matches(Phiu, tu, "Phiu", rtol, floor)
     # n, m per column are integer outputs of kernel 1: exact
     pos = {int(c): i for i, c in enumerate(gcols)}
     idx = [pos[int(c)] for c in use]
@@ -92,7 +92,7 @@ def check_local_blocks(api, A, B1, B2, S, cols):
         syn.close()
 
 
-def check_against_oracle(api, A, B1, B2, S, cols, rtol=PHI_RTOL):
+def check_against_oracle(api, A, B1, B2, S, cols, rtol=PHI_RTOL, floor=0.0):
     """Φ columns from the library vs the oracle's exact minimiser on the same columns."""
     Po = O.Plant(A, B1, B2)
     Ox, Ou, infos = O.SLS_H2(Po, S, I=cols, return_info=True)
@@ -100,7 +100,7 @@ def check_against_oracle(api, A, B1, B2, S, cols, rtol=PHI_RTOL):
     worst = 0.0
     for name, G, H in (("Phix", Phix, Ox), ("Phiu", Phiu, Ou)):
         taps = [(np.asarray(M.indptr, np.int64), np.asarray(M.indices, np.int64), M.data) for M in H]
-        worst = max(worst, assert_phi_matches(G, taps, name, rtol))
+        worst = max(worst, assert_phi_matches(G, taps, name, rtol, floor))
     return worst, info, infos
 
 
@@ -281,7 +281,7 @@ def check_pipelined(api, plant, S, chunks, pass_nzval=True):
         syn.close()
 
 
-def check_window(api, plant, S, ranges, halo=1, chunks=(1, 3)):
+def check_window(api, plant, S, ranges, halo=1, chunks=(1, 3), sub_reach=None):
     """sls_synthesize_window (support window in, column slab out) == the three-call path on the same columns, bit for
     bit — for both ways of passing a window (a colptr view into the full matrices; rebased slices), and with the
     rowval outputs left out.  Also: the handle then refuses plans that reach outside the uploaded window, a window that
@@ -324,8 +324,52 @@ def check_window(api, plant, S, ranges, halo=1, chunks=(1, 3)):
                                 assert np.array_equal(out[fam]["rowval"][t][:hi - lo], ref[fam]["rowval"][t][lo:hi]), (form, K, fam, t)
                     assert np.array_equal(out["status"][:c1 - c0], ref["status"][:c1 - c0])
                     assert np.array_equal(out["resid"][:c1 - c0], ref["resid"][:c1 - c0])
+        # sub-plant shard: the handle holds P[pw, pw] only, the supports keep the large plant's row numbers
+        if sub_reach is not None:
+            sub = slc_b200.Synthesizer(api=api)
+            try:
+                for (c0, c1) in ranges:
+                    p0, p1 = max(0, c0 - sub_reach), min(Nx, c1 + sub_reach)
+                    ucols = np.unique(sp.csc_matrix(B2)[p0:p1, :].nonzero()[1])
+                    assert ucols.size == 0 or np.array_equal(ucols, np.arange(ucols[0], ucols[-1] + 1))
+                    u0 = int(ucols[0]) if ucols.size else 0
+                    sub.set_plant(sp.csc_matrix(A)[p0:p1, :][:, p0:p1], sp.csc_matrix(B2)[p0:p1, :][:, ucols])
+                    w0, w1 = max(0, c0 - halo), min(Nx, c1 + halo)
+
+                    def sl(M):
+                        lo, hi = int(M.colptr[w0] - 1), int(M.colptr[w1] - 1)
+                        return slc_b200.JuliaCSC(M.m, w1 - w0, np.ascontiguousarray(M.colptr[w0:w1 + 1] - lo),
+                                                 np.ascontiguousarray(M.rowval[lo:hi]), np.ascontiguousarray(M.nzval[lo:hi]))
+                    syn.set_supports(*S)
+                    syn.plan(np.arange(c0, c1))
+                    ref = syn.solve()
+                    out, nnz_x, nnz_u = sub.synthesize_window([sl(M) for M in Sxj], [sl(M) for M in Suj], (w0 - p0, w1 - p0),
+                                                              (c0 - p0, c1 - p0), row_off=(p0, u0))
+                    for fam, nnz in (("x", nnz_x), ("u", nnz_u)):
+                        for t in range(T):
+                            full_cp = ref[fam]["colptr"][t]
+                            lo, hi = int(full_cp[c0] - 1), int(full_cp[c1] - 1)
+                            assert nnz[t] == hi - lo
+                            assert np.array_equal(out[fam]["colptr"][t], full_cp[c0:c1 + 1] - lo), ("sub", fam, t)
+                            assert np.array_equal(out[fam]["rowval"][t][:hi - lo], ref[fam]["rowval"][t][lo:hi]), ("sub", fam, t)
+                            assert np.array_equal(out[fam]["nzval"][t][:hi - lo], ref[fam]["nzval"][t][lo:hi]), ("sub", fam, t)
+                    assert np.array_equal(out["resid"][:c1 - c0], ref["resid"][:c1 - c0])
+                # a sub-plant that is too small for the supports is a layout error (rows fall outside the handle's plant)
+                c0, c1 = ranges[len(ranges) // 2]
+                p0, p1 = max(0, c0 - halo), min(Nx, c1 + halo)
+                w0, w1 = p0, p1                                 # (sl() slices the supports to [w0, w1))
+                if p0 > 0:
+                    ucols = np.unique(sp.csc_matrix(B2)[p0:p1, :].nonzero()[1])
+                    sub.set_plant(sp.csc_matrix(A)[p0:p1, :][:, p0:p1], sp.csc_matrix(B2)[p0:p1, :][:, ucols])
+                    with pytest.raises(_capi.SlsError) as ei:
+                        sub.synthesize_window([sl(M) for M in Sxj], [sl(M) for M in Suj], (0, p1 - p0), (c0 - p0, c1 - p0),
+                                              row_off=(p0, int(ucols[0])))
+                    assert ei.value.code == -2
+            finally:
+                sub.close()
         # the window of the last call is all the device holds: planning a column outside it is refused, not garbage
         c0, c1 = ranges[-1]
+        syn.synthesize_window(Sxj, Suj, (max(0, c0 - halo), min(Nx, c1 + halo)), (c0, c1))
         far = 0 if c0 > halo + 1 else Nx - 1
         if not (max(0, c0 - halo) <= far < min(Nx, c1 + halo)):
             with pytest.raises(_capi.SlsError) as ei:

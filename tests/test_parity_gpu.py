@@ -10,6 +10,7 @@ import parity_cases as pc
 import slc_b200
 from slc_b200 import _capi
 from oracle import sls_oracle as O
+from conftest import PHI_FLOOR
 
 pytestmark = pytest.mark.gpu
 
@@ -41,13 +42,13 @@ def test_jitter_chain_vs_golden(cuda_api):
 
 
 def test_grid_9x9_vs_golden(cuda_api):
-    worst, _ = pc.check_golden(cuda_api, "grid_9x9_full_d2_T8", O.grid_plant(9, 9, actuation="full"))
+    worst, _ = pc.check_golden(cuda_api, "grid_9x9_full_d2_T8", O.grid_plant(9, 9, actuation="full"), floor=PHI_FLOOR)
     assert worst < 1e-10
 
 
 def test_grid_13x13_wide_solver_vs_golden(cuda_api):
     """n up to 61, m up to 85: the 64-bit-mask / N=64 size classes of kernel 2 (BASELINE config #4 shapes)."""
-    worst, info = pc.check_golden(cuda_api, "grid_13x13_full_d4_T20_subset", O.grid_plant(13, 13, actuation="full"))
+    worst, info = pc.check_golden(cuda_api, "grid_13x13_full_d4_T20_subset", O.grid_plant(13, 13, actuation="full"), floor=PHI_FLOOR)
     assert info["n"].max() == 61 and info["m"].max() == 85
     assert worst < 1e-9
 
@@ -73,8 +74,55 @@ def test_config4_grid_properties(cuda_api):
         assert np.array_equal(Phix[t].indices, S[0][t].indices) and np.array_equal(Phiu[t].indices, S[1][t].indices)
     assert r < 1e-12
     cols = [0, 59, 1830, 1831, 3599]
-    worst, _, _ = pc.check_against_oracle(cuda_api, A, B1, B2, S, cols)
+    worst, _, _ = pc.check_against_oracle(cuda_api, A, B1, B2, S, cols, floor=PHI_FLOOR)
     assert worst < 1e-9
+
+
+def test_config4_grid_300x300_full_size(cuda_api):
+    """BASELINE config #4 at its stated size (Nx = 90 000, d = 4, T = 20, B2 = I): invariants on all 90 000 columns
+    (no residual flag, pattern == support pattern bit-exact, global achievability, translation invariance of interior
+    columns bit for bit) and oracle parity on 6 columns (corner, edge, near-edge, interior)."""
+    from slc_b200 import workloads as W
+    nr = nc = 300
+    Nx = nr * nc
+    A, B1, B2 = W.grid_plant(nr, nc)
+    Sx, Su = W.grid_supports(nr, nc, 4, 20, 1.5)
+    syn = slc_b200.Synthesizer(api=cuda_api)
+    try:
+        syn.set_plant(A, B2); syn.set_supports(Sx, Su)
+        _, _, n, m = syn.plan(None)
+        out = syn.solve()
+        assert n.max() == 61 and m.max() == 85
+        assert not (out["status"][:Nx] & _capi.STATUS_RESIDUAL).any() and out["resid"][:Nx].max() < 1e-12
+        Phix, Phiu = syn.outputs_to_scipy(out)
+    finally:
+        syn.close()
+    for t in range(20):
+        assert np.array_equal(out["x"]["colptr"][t], Sx[t].colptr) and np.array_equal(out["x"]["rowval"][t], Sx[t].rowval)
+        assert np.array_equal(out["u"]["colptr"][t], Su[t].colptr) and np.array_equal(out["u"]["rowval"][t], Su[t].rowval)
+    I = sp.identity(Nx, format="csc")
+    r = abs(Phix[0] - I).max()
+    for t in range(20):
+        nxt = Phix[t + 1] if t + 1 < 20 else sp.csc_matrix((Nx, Nx))
+        R = nxt - A @ Phix[t] - B2 @ Phiu[t]
+        r = max(r, abs(R).max() if R.nnz else 0.0)
+    assert r < 1e-12
+    # interior columns are translates of each other: identical values, bit for bit
+    j0 = 150 * nc + 150
+    for t in (0, 1, 3, 19):
+        M = Phix[t]
+        a = M.data[M.indptr[j0]:M.indptr[j0 + 1]]
+        for j in (j0 + 1, j0 + nc, 40 * nc + 77, 250 * nc + 13):
+            assert np.array_equal(a, M.data[M.indptr[j]:M.indptr[j + 1]])
+    # oracle on a few columns of the full-size problem (the oracle's gather is Θ(1) per column once the product is hoisted)
+    S = [[M.to_scipy().astype(bool) for M in Sx], [M.to_scipy().astype(bool) for M in Su]]
+    cols = [0, nc - 1, 3 * nc + 2, j0, j0 + 7 * nc + 5, Nx - 1]
+    Ox, Ou = O.SLS_H2(O.Plant(A, B1, B2), S, I=cols)
+    for t in range(20):
+        for G, H in ((Phix[t], Ox[t]), (Phiu[t], Ou[t])):
+            nmax = max(np.linalg.norm(M_[:, cols].toarray()) for M_ in (Ox if G is Phix[t] else Ou))
+            a = G[:, cols].toarray(); b = H[:, cols].toarray()
+            assert np.linalg.norm(a - b) <= 1e-9 * np.linalg.norm(b) + PHI_FLOOR * nmax
 
 
 def test_error_paths(cuda_api):
@@ -270,7 +318,7 @@ def test_pipelined_one_shot_config3_100k_bit_for_bit(cuda_api):
 def test_window_shard_form(cuda_api):
     """sls_synthesize_window: support window in, column slab out (the per-GPU shape; no array grows with Nx)."""
     A, B1, B2, S = pc.chain(600)
-    pc.check_window(cuda_api, (A, B1, B2), S, ranges=[(0, 200), (199, 417), (417, 600)], chunks=(1, 4))
+    pc.check_window(cuda_api, (A, B1, B2), S, ranges=[(0, 200), (199, 417), (417, 600)], chunks=(1, 4), sub_reach=11)
 
 
 def test_weighted_cost_and_column_groups_vs_general_oracle(cuda_api):
