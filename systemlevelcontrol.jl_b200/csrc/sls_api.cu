@@ -205,9 +205,9 @@ extern "C" int sls_create(const sls_options* opts, sls_handle** out) {
     for (int i = 0; i < 8 && !e; i++) e = h->ev[i].create();
     for (int i = 0; i < 2 && !e; i++) e = h->marks[i].create();
     for (int i = 0; i < 4 && !e; i++) e = h->gev[i].create();
-    if (!e) e = h->d_flag.ensure(sizeof(int32_t));
-    if (!e) e = h->h_flag.resize(1);
-    if (!e) e = rt::zero(h->d_flag.p, sizeof(int32_t), h->stream);
+    if (!e) e = h->d_flag.ensure(2 * sizeof(int32_t));          // [0] malformed-supports flag, [1] refined-columns counter
+    if (!e) e = h->h_flag.resize(2);
+    if (!e) e = rt::zero(h->d_flag.p, 2 * sizeof(int32_t), h->stream);
     if (!e) e = rt::sync(h->stream);
     if (e) { delete h; return fail(nullptr, e, "sls_create: CUDA initialisation failed"); }
     h->sm_count = rt::sm_count(h->device);
@@ -940,6 +940,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         hist_bytes = std::max(hist_bytes, (size_t)warps * sls_solve_hist_doubles(c.N, (int)T) * sizeof(double));
     }
     SLS_CK(h->hist.ensure(hist_bytes));
+    SLS_CK(rt::zero(h->d_flag.as<int32_t>() + 1, sizeof(int32_t), h->stream));
     h->ev[4].record(h->stream);
     if (ho) {                                                  // colptr arrays are final since sls_plan
         SLS_CK(rt::stream_wait(h->copy_stream, h->ev[4]));
@@ -984,6 +985,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
             a.hist_stride = sls_solve_hist_doubles(c.N, (int)T);
             a.status = h->status.as<int32_t>(); a.resid = h->resid.as<double>();
             a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
+            a.refine_tol = h->opt.feas_tol; a.max_refine = (h->opt.flags & 4) ? 0 : 3; a.refined = h->d_flag.as<int32_t>() + 1;
             int warps = 0;
             SLS_CK(sls_launch_solve(c.N, a, h->sm_count, h->max_smem, &warps, h->stream));
             launches++;
@@ -1008,7 +1010,9 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
     }
     SLS_CK(rt::stream_wait(h->stream, h->chunk_ev[15]));       // join: rowval scatter done
     h->ev[6].record(h->stream);
+    SLS_CK(sls_kcopy(h->h_flag.data() + 1, h->d_flag.as<int32_t>() + 1, sizeof(int32_t), h->stream));
     SLS_CK(rt::sync(h->stream));
+    h->tm.refined = h->h_flag[1];
     if (ho) {
         // per-column outcomes go through pinned staging: the caller's arrays may be pageable, and a pageable
         // cudaMemcpyAsync would block the host in the middle of the pipeline
@@ -1184,6 +1188,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
         if (e) { x->release(); delete x; return fail(h, e, "sls_synthesize: event creation"); }
         h->pipe.push_back(x);
     }
+    SLS_CK(rt::zero(h->d_flag.as<int32_t>() + 1, sizeof(int32_t), h->stream));
     h->ev[0].record(h->stream);
     SLS_CK(rt::stream_wait(h->in_stream, h->ev[0]));            // earlier work on the main stream may still read the supports
     PipeSupp fam[2] = {{&h->Sx, Sx_colptr, Sx_rowval, Sx_nzval, Nx, "Sx"}, {&h->Su, Su_colptr, Su_rowval, Su_nzval, Nu, "Su"}};
@@ -1302,6 +1307,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
             a.hist_stride = sls_solve_hist_doubles(cl.N, (int)T);
             a.status = x.status.as<int32_t>(); a.resid = x.resid.as<double>();
             a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
+            a.refine_tol = h->opt.feas_tol; a.max_refine = (h->opt.flags & 4) ? 0 : 3; a.refined = h->d_flag.as<int32_t>() + 1;
             int warps = 0;
             PIPE_CK(sls_launch_solve(cl.N, a, h->sm_count, h->max_smem, &warps, h->stream));
             launches++;
@@ -1359,7 +1365,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
     SLS_CK(rt::stream_wait(h->stream, h->pipe_done2));
     SLS_CK(rt::stream_wait(h->stream, h->pipe_in[K - 1]));
     h->ev[1].record(h->stream);
-    SLS_CK(sls_kcopy(h->h_flag.data(), h->d_flag.p, sizeof(int32_t), h->stream));
+    SLS_CK(sls_kcopy(h->h_flag.data(), h->d_flag.p, 2 * sizeof(int32_t), h->stream));
     SLS_CK(rt::sync(h->stream));
     SLS_CK(rt::sync(h->scat_stream));
     if (h->h_flag[0]) { h->have_supports = false; return fail(h, -2, "sls_synthesize: support rowval out of range or not strictly ascending inside a column"); }
@@ -1382,6 +1388,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
     h->tm.solve_launches = launches; h->tm.gather_launches = 3 * K; h->tm.scatter_launches = 2 * K;
     h->pipe_chunks = K;                                        // alg_flops / alg_bytes: summed over the chunks' plans on demand (sls_get_timing)
     h->tm.ncols = ncols; h->tm.nnz_out = nnz_total; h->tm.alg_flops = flops; h->tm.alg_bytes = bytes;
+    h->tm.refined = h->h_flag[1];
     h->tm_from_plan = false;
     // the support columns of the range (+halo) stay on the device; a later sls_plan of other columns needs
     // sls_set_supports.  The outputs live in per-chunk buffers, so the

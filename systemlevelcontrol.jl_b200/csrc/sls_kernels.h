@@ -31,6 +31,9 @@ struct SlsSolveArgs {
     int32_t* status;         // per planned column
     double* resid;           // per planned column: max-abs achievability residual
     double rank_tol, feas_tol;
+    double refine_tol;       // residual above which a column takes a refinement sweep on the stored factors
+    int max_refine;          // at most this many sweeps (0 = never)
+    int32_t* refined;        // counter of columns that took >= 1 sweep (may be null)
 };
 // size classes (template instantiations) available for the local state dimension n
 int sls_solve_class_of(int n);                 // smallest instantiated N >= n, or -1

@@ -505,9 +505,10 @@ sls_solve_kernel(SlsSolveArgs a) {
                 S[p][p][0] = d0; S[p][p][1] = d1;
             }
             if (keep != nonempty) status |= SLS_ST_RANK_SKIPPED;
-            // (8) history: packed lower triangle (row-major) of -Z_k, k = 1..T-1 (Z_0 is diag(mx_1), Z_T is used at once)
-            if (k < T) {
-                double* hk = zhist + (size_t)k * TRI;
+            // (8) history: packed lower triangle (row-major) of -Z_k, k = 1..T-1 (Z_0 is diag(mx_1)); -Z_T, which the back
+            //     substitution uses straight from the registers, goes to slot 0 for the refinement sweeps
+            {
+                double* hk = zhist + (size_t)(k < T ? k : 0) * TRI;
 #pragma unroll
                 for (int bi = 0; bi < NB; bi++)
 #pragma unroll
@@ -542,9 +543,17 @@ sls_solve_kernel(SlsSolveArgs a) {
         // lam_s holds lambda_k (zero beyond n) at the top of every iteration
         double* const xcur = ucur; // [x_k | u_k] (shared: the residual gathers both through the local CSR, whose B~ columns are n + l)
         double xnext_r[RPL];       // x_{k+1}[i] of the lane's own rows stays in registers
+        double resmax = 0.0, resprev = SLS_INF;
+        // Refinement (cold path): the recursion works on the normal equations G G^T, so lambda — and with it v = G^T lambda —
+        // carries an error ~eps cond(G)^2.  The residual rho = h - G v of the COMPUTED v is accurate to eps ||G|| ||v||, and
+        // v += G^T dlambda with (G G^T) dlambda = rho (stored factors: one forward sweep over the -Z_k history, one more back
+        // substitution) brings the error down to ~eps cond(G) (Bjorck's corrected normal equations).  Taken only by columns
+        // whose residual exceeds refine_tol (none on the BASELINE chain / grid configs).
+#pragma unroll 1
+        for (int pass = 0;; pass++) {
 #pragma unroll
         for (int rr = 0; rr < RPL; rr++) xnext_r[rr] = 0.0;
-        double resmax = 0.0;
+        resmax = 0.0;
         // History double buffer (size classes up to N = 32): -Z_{k-1} and yh_{k-1} of the NEXT tap are loaded into
         // registers one full iteration ahead (the matrix registers of the forward pass are dead here), so the L2/HBM
         // latency of the history hides behind a whole tap instead of heading its serial chain.
@@ -626,9 +635,13 @@ sls_solve_kernel(SlsSolveArgs a) {
                     const int l = l0 + lane;
                     const uint32_t word = muk[l0 >> 5];
                     const bool on = (l < m) && ((word >> lane) & 1u);
-                    const double u = on ? -tx[n + l] : 0.0;
+                    double u = on ? -tx[n + l] : 0.0;
+                    if (on) {
+                        double* dst = a.out_nzval[T + k - 1] + (obase[T + k - 1] + rank0 + __popc(word & ((1u << lane) - 1u)));
+                        if (pass) u += *dst;                    // refinement: u_k += du_k
+                        *dst = u;
+                    }
                     if (l < m) ucur[n + l] = u;
-                    if (on) a.out_nzval[T + k - 1][obase[T + k - 1] + rank0 + __popc(word & ((1u << lane) - 1u))] = u;
                     rank0 += __popc(word);
                 }
             }
@@ -709,11 +722,15 @@ sls_solve_kernel(SlsSolveArgs a) {
                 const int i = lane + 32 * rr;
                 const bool on = (i < n) && sls_mbit(mk, i);
                 const double lam_prev = (i < n) ? -gbuf[i] : 0.0;
-                const double x = on ? (lam_prev - tx[i]) : 0.0;
+                double x = on ? (lam_prev - tx[i]) : 0.0;
+                if (on) {
+                    double* dst = a.out_nzval[k - 1] + (obase[k - 1] + sls_mrank(mk, i));
+                    if (pass) x += *dst;                        // refinement: x_k += dx_k
+                    *dst = x;
+                }
                 xk_r[rr] = x;
                 if (i < n) xcur[i] = x;
                 if (i < N) lam_s[i] = lam_prev;
-                if (on) a.out_nzval[k - 1][obase[k - 1] + sls_mrank(mk, i)] = x;
             }
             __syncwarp();
             // residual of constraint block k: A~ x_k + B~ u_k - x_{k+1}
@@ -741,6 +758,156 @@ sls_solve_kernel(SlsSolveArgs a) {
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) resmax = sls_nanmax(resmax, __shfl_xor_sync(SLS_FULL, resmax, d));
+        // stop: accurate enough, out of sweeps, no longer contracting (infeasible column, or cond(G)^2 eps >~ 1), or NaN
+        // (a residual above 1e-2 of the unit impulse is an infeasible localisation, not a conditioning problem: no sweep)
+        if (!(resmax > a.refine_tol) || pass >= a.max_refine || !(resmax < 0.5 * resprev) || !(resmax <= 1e-2)) break;
+        resprev = resmax;
+        if (pass == 0 && lane == 0 && a.refined) atomicAdd(a.refined, 1);
+        __syncwarp();
+        // ---- (R1) rho_k = h_k - (G v)_k of the stored solution -> yhist[k]   (rho_0 = e - x_1, rho_k = A~ x_k + B~ u_k - x_{k+1})
+#pragma unroll
+        for (int rr = 0; rr < RPL; rr++) xnext_r[rr] = 0.0;
+#pragma unroll 1
+        for (int k = T; k >= 1; k--) {
+            const mask_t mk = mxs[k - 1];
+            const uint32_t* muk = mus + (size_t)(k - 1) * wu;
+            int rank0 = 0;
+#pragma unroll 1
+            for (int l0 = 0; l0 < m; l0 += 32) {
+                const int l = l0 + lane;
+                const uint32_t word = muk[l0 >> 5];
+                const bool on = (l < m) && ((word >> lane) & 1u);
+                if (l < m) ucur[n + l] = on ? a.out_nzval[T + k - 1][obase[T + k - 1] + rank0 + __popc(word & ((1u << lane) - 1u))] : 0.0;
+                rank0 += __popc(word);
+            }
+            double xk_r[RPL];
+#pragma unroll
+            for (int rr = 0; rr < RPL; rr++) {
+                const int i = lane + 32 * rr;
+                const bool on = (i < n) && sls_mbit(mk, i);
+                const double x = on ? a.out_nzval[k - 1][obase[k - 1] + sls_mrank(mk, i)] : 0.0;
+                xk_r[rr] = x;
+                if (i < n) xcur[i] = x;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < RPL; rr++) {
+                const int i = lane + 32 * rr;
+                if (i < N) {
+                    double r = 0.0;
+                    if (i < n) {
+                        r = -xnext_r[rr];
+                        const int r0 = rptr[i], r2 = rptr[i + 1];
+#pragma unroll 1
+                        for (int e = r0; e < r2; e++) r = fma(valr[e], xcur[colr[e]], r);
+                    }
+                    yhist[(size_t)k * N + i] = r;
+                }
+                xnext_r[rr] = xk_r[rr];
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int rr = 0; rr < RPL; rr++) {
+            const int i = lane + 32 * rr;
+            if (i < N) { const double r = (i < n) ? (((i == jl) ? 1.0 : 0.0) - xnext_r[rr]) : 0.0; yhist[i] = r; rhs_s[i] = r; }
+        }
+        __syncwarp();
+        // ---- (R2) forward sweep with the stored factors: yh_0 = rho_0, yh_k = rho_k + A~ (mx_k o Z_{k-1} yh_{k-1}) -> yhist[k]
+        //      rhs_s holds yh_{k-1} at the top of every iteration
+#pragma unroll 1
+        for (int k = 1; k <= T + 1; k++) {
+            // gbuf = (-Z_{k-1}) rhs_s  (k-1 = 0: Z_0 = diag(mx_1); k-1 = T: slot 0)
+            if (k == 1) {
+#pragma unroll
+                for (int rr = 0; rr < RPL; rr++) {
+                    const int i = lane + 32 * rr;
+                    if (i < N) gbuf[i] = (i < n && sls_mbit(mxs[0], i)) ? -rhs_s[i] : 0.0;
+                }
+            } else {
+                const double* hk = zhist + (size_t)(k - 1 < T ? k - 1 : 0) * TRI;
+                double racc[NB], cacc[NB][2];
+#pragma unroll
+                for (int b = 0; b < NB; b++) { racc[b] = 0.0; cacc[b][0] = 0.0; cacc[b][1] = 0.0; }
+#pragma unroll
+                for (int bi = 0; bi < NB; bi++) {
+                    const int r = 8 * bi + g;
+                    const double vr = rhs_s[r];
+#pragma unroll
+                    for (int bj = 0; bj <= bi; bj++) {
+                        const int c0 = 8 * bj + 2 * q;
+                        const double2 vc = *reinterpret_cast<const double2*>(rhs_s + c0);
+                        double z0 = 0.0, z1 = 0.0;
+                        if (bj < bi) {
+                            if (r < n) { z0 = hk[rowoff[bi] + c0]; z1 = hk[rowoff[bi] + c0 + 1]; }
+                        } else {
+                            if (r < n && c0 < n) z0 = (c0 <= r) ? hk[rowoff[bi] + c0] : hk[c0 * (c0 + 1) / 2 + r];
+                            if (r < n && c0 + 1 < n) z1 = (c0 + 1 <= r) ? hk[rowoff[bi] + c0 + 1] : hk[(c0 + 1) * (c0 + 2) / 2 + r];
+                        }
+                        if (bj < bi) { cacc[bj][0] = fma(z0, vr, cacc[bj][0]); cacc[bj][1] = fma(z1, vr, cacc[bj][1]); }
+                        racc[bi] = fma(z0, vc.x, racc[bi]);
+                        racc[bi] = fma(z1, vc.y, racc[bi]);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    racc[b] += __shfl_xor_sync(SLS_FULL, racc[b], 1);
+                    racc[b] += __shfl_xor_sync(SLS_FULL, racc[b], 2);
+                    if (b < NB - 1) {
+#pragma unroll
+                        for (int d = 4; d < 32; d <<= 1) {
+                            cacc[b][0] += __shfl_xor_sync(SLS_FULL, cacc[b][0], d);
+                            cacc[b][1] += __shfl_xor_sync(SLS_FULL, cacc[b][1], d);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (q == 0) {
+#pragma unroll
+                    for (int b = 0; b < NB; b++) gbuf[8 * b + g] = racc[b];
+                }
+                __syncwarp();
+                if (g == 0) {
+#pragma unroll
+                    for (int b = 0; b < NB - 1; b++) { gbuf[8 * b + 2 * q] += cacc[b][0]; gbuf[8 * b + 2 * q + 1] += cacc[b][1]; }
+                }
+            }
+            __syncwarp();
+            if (k == T + 1) {                                   // lambda_T = Z_T yh_T
+#pragma unroll
+                for (int rr = 0; rr < RPL; rr++) {
+                    const int i = lane + 32 * rr;
+                    if (i < N) lam_s[i] = (i < n) ? -gbuf[i] : 0.0;
+                }
+                break;
+            }
+            // g = mx_k o (Z_{k-1} yh_{k-1}) = -(mx_k o gbuf);  yh_k = rho_k + A~ g
+            const mask_t mk = mxs[k - 1];
+#pragma unroll
+            for (int rr = 0; rr < RPL; rr++) {
+                const int i = lane + 32 * rr;
+                if (i < N) xa[i] = (i < n && sls_mbit(mk, i)) ? -gbuf[i] : 0.0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < RPL; rr++) {
+                const int i = lane + 32 * rr;
+                if (i < N) {
+                    double acc = 0.0;
+                    if (i < n) {
+                        acc = yhist[(size_t)k * N + i];
+                        const int r0 = rptr[i], r1 = rsplit[i];
+#pragma unroll 1
+                        for (int e = r0; e < r1; e++) acc = fma(valr[e], xa[colr[e]], acc);
+                    }
+                    yhist[(size_t)k * N + i] = acc;
+                    rhs_s[i] = acc;
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        }   // refinement loop
         if (!(resmax <= a.feas_tol)) status |= SLS_ST_RESIDUAL;
         if (lane == 0) { a.status[c] = status; a.resid[c] = resmax; }
     }

@@ -71,4 +71,4 @@ def test_emu_pipelined_ring_plant_long_range_coupling(emu_api):
 
 def test_emu_random_banded_plants_vs_oracle(emu_api):
     worst, nclean, nflag = pc.check_random_banded(emu_api, seeds=(0, 5), cols=(0, 5, 24, 47))
-    assert nclean >= 3 and nflag >= 2 and worst < 1e-10
+    assert nclean >= 6 and nflag >= 1 and worst < 1e-9

@@ -330,5 +330,5 @@ def test_random_banded_plants_vs_oracle(cuda_api):
     """Pentadiagonal random plants with two-state actuators and random gains (not a chain, not a grid): the accuracy /
     flagging contract on well-conditioned, ill-conditioned and infeasible columns (parity_cases.check_random_banded)."""
     worst, nclean, nflag = pc.check_random_banded(cuda_api, seeds=tuple(range(12)))
-    assert nclean >= 15 and nflag >= 15, (nclean, nflag)
-    assert worst < 1e-10, worst                               # measured: 1.4e-11 over 16 seeds
+    assert nclean >= 30 and nflag >= 8, (nclean, nflag)       # flagged = infeasible or cond(G) >= 1e6 only
+    assert worst < 1e-9, worst
