@@ -1,6 +1,6 @@
 # SLSB200.jl — the binding a SystemLevelControl.jl maintainer adds to route `SLS_𝓗₂` through libslsb200.
 # Written against Julia 1.8 / SystemLevelControl v1.1.0-DEV; NOT executed in this repository's environment
-# (no Julia in the image).  Every `ccall` targets a symbol declared in include/slsb200.h; the Python binding
+# (no Julia in the image; ABI v6).  Every `ccall` targets a symbol declared in include/slsb200.h; the Python binding
 # (systemlevelcontrol.jl_b200/_capi.py) drives the same symbols and is what the tests exercise.
 #
 # Replaces: src/synthesis.jl:23-27 (the @distributed loop) and src/synthesis.jl:34-72 (_SLS_𝓗₂).
@@ -46,10 +46,14 @@ end
 """
 function synthesize(A::SparseMatrixCSC{Float64,Int64}, B₂::SparseMatrixCSC{Float64,Int64},
                     𝓢ₓ::Vector{SparseMatrixCSC{Bool,Int64}}, 𝓢ᵤ::Vector{SparseMatrixCSC{Bool,Int64}},
-                    cols::Union{Nothing,Vector{Int64}}; device::Integer=0)
+                    cols::Union{Nothing,Vector{Int64}}; wx=nothing, wu=nothing, device::Integer=0)
     Nx, Nu, T = size(A, 1), size(B₂, 2), length(𝓢ₓ)
     h = Handle(device=device)
-    GC.@preserve A B₂ 𝓢ₓ 𝓢ᵤ cols begin
+    GC.@preserve A B₂ 𝓢ₓ 𝓢ᵤ cols wx wu begin
+        if wx !== nothing || wu !== nothing        # before sls_set_plant: the device holds the similarity-scaled plant
+            check(h.ptr, ccall((:sls_set_weights, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
+                  h.ptr, Nx, Nu, wx === nothing ? C_NULL : wx, wu === nothing ? C_NULL : wu))
+        end
         check(h.ptr, ccall((:sls_set_plant, LIB), Cint,
               (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
               h.ptr, Nx, Nu, A.colptr, A.rowval, A.nzval, B₂.colptr, B₂.rowval, B₂.nzval))
@@ -126,26 +130,137 @@ function synthesize_pipelined(A::SparseMatrixCSC{Float64,Int64}, B₂::SparseMat
     end
 end
 
+
+"""
+    register!(h, arrays...) / unregister!(h, arrays...)
+
+Page-lock ordinary Julia `Vector`s in place (`sls_host_register`): the copy pipelines of `sls_solve` / `sls_synthesize*`
+only overlap with the kernels on page-locked memory.  Measured on config #3 (bench.py `e2e_pageable` / `e2e_registered`):
+92.6 ms per call with pageable vectors, 34.7 ms once they are registered (registering 1.75 GB costs ~240 ms, once).
+"""
+register!(h::Handle, arrays...) = foreach(a -> isempty(a) || check(h.ptr, ccall((:sls_host_register, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), h.ptr, pointer(a), sizeof(a))), arrays)
+unregister!(h::Handle, arrays...) = foreach(a -> isempty(a) || check(h.ptr, ccall((:sls_host_unregister, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, pointer(a))), arrays)
+
+"""
+    synthesize_shard(h, A, B₂, 𝓢ₓ, 𝓢ᵤ, cols::UnitRange; halo=cols, values_only=true) -> (Φₓ, Φᵤ, status, resid)
+
+One GPU's share of the `@distributed` loop (src/synthesis.jl:16,23-27) through `sls_synthesize_window`: only the support
+columns `halo ⊇ cols ∪ {rows of nz(A[:,j]), j ∈ cols}` are uploaded (a `pointer(𝓢[t].colptr, first(halo))` view, no copy)
+and the column SLAB Φ[t][:, cols] comes back (colptr of length(cols)+1 entries).  `values_only = true` is the documented
+fast path: the stored pattern of Φ[t] is the mask pattern, a subset of 𝓢[t]'s; when the returned count equals
+nnz(𝓢[t][:, cols]) the pattern IS 𝓢[t]'s, and the slab aliases a `view`-free copy of that rowval segment made on the host
+only when needed (no 0.53 GB of Int64 row indices over PCIe at config #3: 27.6 ms instead of 35.6 ms).  Otherwise the
+call is repeated with rowval outputs.
+"""
+function synthesize_shard(h::Handle, A::SparseMatrixCSC{Float64,Int64}, B₂::SparseMatrixCSC{Float64,Int64},
+                          𝓢ₓ::Vector{SparseMatrixCSC{Bool,Int64}}, 𝓢ᵤ::Vector{SparseMatrixCSC{Bool,Int64}},
+                          cols::UnitRange{Int}; halo::UnitRange{Int}=cols, values_only::Bool=true)
+    Nx, Nu, T = size(A, 1), size(B₂, 2), length(𝓢ₓ)
+    nc, w1, wn = length(cols), first(halo), length(halo)
+    GC.@preserve A B₂ 𝓢ₓ 𝓢ᵤ begin
+        check(h.ptr, ccall((:sls_set_plant, LIB), Cint,
+              (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+              h.ptr, Nx, Nu, A.colptr, A.rowval, A.nzval, B₂.colptr, B₂.rowval, B₂.nzval))
+        xcp = [pointer(M.colptr, w1) for M in 𝓢ₓ]; ucp = [pointer(M.colptr, w1) for M in 𝓢ᵤ]     # window views
+        xrv = [pointer(M.rowval) for M in 𝓢ₓ];     urv = [pointer(M.rowval) for M in 𝓢ᵤ]
+        xnz = [Ptr{UInt8}(pointer(M.nzval)) for M in 𝓢ₓ]; unz = [Ptr{UInt8}(pointer(M.nzval)) for M in 𝓢ᵤ]
+        seg(M) = M.colptr[first(cols)]:(M.colptr[last(cols) + 1] - 1)
+        capx, capu = Int64[length(seg(M)) for M in 𝓢ₓ], Int64[length(seg(M)) for M in 𝓢ᵤ]
+        cp() = [Vector{Int64}(undef, nc + 1) for _ in 1:T]
+        xc, uc = cp(), cp()
+        xv, uv = [Vector{Float64}(undef, capx[t]) for t in 1:T], [Vector{Float64}(undef, capu[t]) for t in 1:T]
+        xr = values_only ? nothing : [Vector{Int64}(undef, capx[t]) for t in 1:T]
+        ur = values_only ? nothing : [Vector{Int64}(undef, capu[t]) for t in 1:T]
+        nnzx, nnzu = zeros(Int64, T), zeros(Int64, T)
+        status, resid = zeros(Int32, nc), zeros(Float64, nc)
+        p(v) = v === nothing ? C_NULL : [pointer(a) for a in v]
+        GC.@preserve xc uc xv uv xr ur begin
+            check(h.ptr, ccall((:sls_synthesize_window, LIB), Cint,
+                  (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64,
+                   Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{UInt8}}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{UInt8}},
+                   Int64, Int64, Ptr{Int64}, Ptr{Int64},
+                   Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{Float64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{Float64}},
+                   Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}),
+                  h.ptr, T, w1, wn, 0, 0, xcp, xrv, xnz, ucp, urv, unz, first(cols), nc, capx, capu,
+                  p(xc), p(xr), p(xv), p(uc), p(ur), p(uv), nnzx, nnzu, status, resid))
+        end
+        if values_only
+            # pattern == support pattern?  (a stored `false` in 𝓢[t], or a support row outside s_x, shrinks the count)
+            all(nnzx .== capx) && all(nnzu .== capu) ||
+                return synthesize_shard(h, A, B₂, 𝓢ₓ, 𝓢ᵤ, cols; halo=halo, values_only=false)
+            xr = [𝓢ₓ[t].rowval[seg(𝓢ₓ[t])] for t in 1:T]
+            ur = [𝓢ᵤ[t].rowval[seg(𝓢ᵤ[t])] for t in 1:T]
+        end
+        Φₓ = [SparseMatrixCSC{Float64,Int64}(Nx, nc, xc[t], resize!(xr[t], nnzx[t]), resize!(xv[t], nnzx[t])) for t in 1:T]
+        Φᵤ = [SparseMatrixCSC{Float64,Int64}(Nu, nc, uc[t], resize!(ur[t], nnzu[t]), resize!(uv[t], nnzu[t])) for t in 1:T]
+        return Φₓ, Φᵤ, status, resid          # column slabs: hcat the ranks' slabs (or write them into one colptr-offset Φ[t])
+    end
+end
+
+"""
+    diagonal_cost(P) -> (wx, wu)  or error(...)
+
+The cost family libslsb200 solves on the device (the Python mirror's `Plant.diagonal_cost`): `[C₁ D₁₂]` = blockdiag(
+Diagonal(wx), Diagonal(wu)) > 0, `D₁₁ = 0`, diagonal `B₁` without zeros (a diagonal B₁ rescales each column's cost and does
+not change Φ).  Anything else would silently give a Φ that differs from the reference's, so it is refused here.
+"""
+function diagonal_cost(P)
+    Nx, Nu = P.Nx, P.Nu
+    size(P.B₁) == (Nx, Nx) && isdiag(P.B₁) && all(!iszero, diag(P.B₁)) ||
+        error("libslsb200: B₁ must be diagonal without zeros (R = B̃₁[iiₓ,:] otherwise couples the columns of a group)")
+    iszero(P.D₁₁) || error("libslsb200: D₁₁ ≠ 0 adds a linear term to the cost (not implemented on the device)")
+    L = [P.C₁ P.D₁₂]
+    size(L) == (Nx + Nu, Nx + Nu) && isdiag(L) && all(>(0), diag(L)) ||
+        error("libslsb200: [C₁ D₁₂] must be diagonal with positive entries (general cost: SURVEY §8f-3)")
+    w = diag(L)
+    all(==(1.0), w) ? (nothing, nothing) : (Vector{Float64}(w[1:Nx]), Vector{Float64}(w[Nx+1:end]))
+end
+
+"""
+    groups_decouple(P, 𝓢ₓ, 𝓢ᵤ, 𝓘) -> Bool
+
+Pattern check behind q > 1 groups (mirror of synthesis.py::_groups_decouple): every row that A or B₂ reaches from a member
+column's own supports already lies inside that column's own s_x, so the group's union index set only adds empty rows.
+"""
+function groups_decouple(P, 𝓢ₓ, 𝓢ᵤ, 𝓘)
+    pA, pB = P.A .≠ 0, P.B₂ .≠ 0
+    own = (𝓢ₓ[end] * pA) .≠ 0
+    reach = reduce((a, b) -> a .| b, [((pA * (S .≠ 0)) .≠ 0) for S in 𝓢ₓ]) .| reduce((a, b) -> a .| b, [((pB * (S .≠ 0)) .≠ 0) for S in 𝓢ᵤ])
+    all(g -> length(g) < 2 || all(j -> issubset(findnz(reach[:, j])[1], findnz(own[:, j])[1]), g), 𝓘)
+end
+
 end # module
 
 # --- drop-in replacement of SLS_𝓗₂ in src/synthesis.jl (signature and return shape unchanged) -----------------
 # function SLS_𝓗₂(P::AbstractGeneralizedPlant, 𝓢::AbstractVector; 𝓘=nothing)
 #     if P isa GeneralizedPlant{T,StateFeedback} where {T}
-#         𝓘 = (𝓘 === nothing) ? [[i] for i in 1:P.Nx] : 𝓘;                      # :15
+#         default = 𝓘 === nothing                                               # captured BEFORE the reassignment below
+#         𝓘 = default ? [[i] for i in 1:P.Nx] : 𝓘;                             # :15
 #         𝓢ₓ,𝓢ᵤ = 𝓢;  T = length(𝓢ₓ)                                           # :19-20
-#         # q > 1 groups: with a diagonal B₁ the cost is separable and the group problem equals its columns' problems
-#         # when the supports are closed under the plant's pattern (checked on the host; see synthesis.py::_groups_decouple)
+#         wx, wu = SLSB200.diagonal_cost(P)                                     # error(...) for costs the device does not solve
+#         # q > 1 groups: with a diagonal B₁ the cost is separable, and the group problem equals its columns' problems only
+#         # when the union index set adds just EMPTY constraint rows to every member column (supports closed under the
+#         # plant's pattern): check it on the patterns as synthesis.py::_groups_decouple does, else error(...)
+#         all(g -> length(g) == 1, 𝓘) || SLSB200.groups_decouple(P, 𝓢ₓ, 𝓢ᵤ, 𝓘) ||
+#             error("libslsb200: coupled column groups are not implemented on the device (SURVEY §8f-3)")
 #         cols = Int64[c for g in 𝓘 for c in g]
-#         Φₓ,Φᵤ,status,resid = (𝓘 === nothing) ? SLSB200.synthesize_pipelined(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ) :
-#                                                  SLSB200.synthesize(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ, cols)
+#         Φₓ,Φᵤ,status,resid = default ? SLSB200.synthesize_pipelined(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ; wx=wx, wu=wu) :
+#                                        SLSB200.synthesize(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ, cols; wx=wx, wu=wu)
+#         any(!iszero, status .& 1) && @warn "SLS_𝓗₂: $(count(!iszero, status .& 1)) column(s) infeasible / not converged (status bit 0)"
 #         # optional: dropzeros!.(Φₓ); dropzeros!.(Φᵤ) reproduces the zero-dropping of `Φ̃ += …` (:67)
 #         Φ = [Φₓ Φᵤ]                                                           # T×2 Matrix{SparseMatrixCSC}
 #         return eachcol(Φ)                                                      # :27
 #     end
 # end
 #
-# Multi-GPU with `julia -p N` (one worker per GPU, the @distributed shape of :23-27): each worker calls
-# SLSB200.synthesize(...; device = myid()-2) on its slice of 𝓘; the (+) reduction concatenates disjoint columns.
+# Multi-GPU with `julia -p N` (one worker per GPU, the @distributed shape of :23-27): worker r owns a contiguous column
+# range and calls SLSB200.synthesize_shard(h, A, B₂, 𝓢ₓ, 𝓢ᵤ, cols; halo = (first(cols)-1):(last(cols)+1) ∩ 1:Nx) with its own
+# handle (device = myid()-2); the slabs concatenate by column (`hcat`), which is all the (+) reduction of disjoint columns
+# does.  To keep host work and PCIe bytes independent of the global Nx, a worker may pass the sub-plant A[pw,pw], B₂[pw,uw]
+# (pw ⊇ every s_x of its columns) and the global supports with row_off_x = first(pw)-1, row_off_u = first(uw)-1
+# (sls_synthesize_window's last two integer arguments before the arrays; bench.py does exactly this at N > 1).
 #
 # sparsity_dim_reduction(P, cⱼ, 𝓢) (src/reduction.jl:11-27) maps to sls_reduce:
 #   ccall((:sls_reduce, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ref{Int64}, Ptr{Int64}, Int64, Ref{Int64}, Ptr{UInt8}),

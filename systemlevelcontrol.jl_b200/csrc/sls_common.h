@@ -52,5 +52,50 @@ __device__ __forceinline__ int sls_find(const int32_t* s, int n, int key) {
 
 __device__ __forceinline__ int sls_lane() { return threadIdx.x & 31; }
 
+// In-place ascending sort + unique of buf[0..cnt) by one warp (bitonic network in shared memory, padded with INT_MAX to
+// the next power of two <= cap; cap >= 32 is a power of two and cnt <= cap).  Returns the number of distinct values
+// (INT_MAX entries are padding and are dropped).  Shared by kernel 1 (index sets), the support generator and the
+// simulation windows.
+__device__ __forceinline__ int sls_warp_sort_unique(int32_t* buf, int cnt, int cap) {
+    const int lane = sls_lane();
+    int P = 32;
+#pragma unroll 1
+    while (P < cnt) P <<= 1;
+    if (P > cap) P = cap;
+#pragma unroll 1
+    for (int i = cnt + lane; i < P; i += 32) buf[i] = 0x7fffffff;
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 2; k <= P; k <<= 1)
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
+            for (int i = lane; i < P; i += 32) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int x = buf[i], y = buf[ixj];
+                    const bool asc = (i & k) == 0;
+                    if ((x > y) == asc) { buf[i] = y; buf[ixj] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    int n = 0, prev_last = -1;
+#pragma unroll 1
+    for (int b0 = 0; b0 < P; b0 += 32) {
+        const int v = buf[b0 + lane];
+        int pv = __shfl_up_sync(SLS_FULL, v, 1);
+        if (lane == 0) pv = prev_last;
+        const bool keep = (v != 0x7fffffff) && (v != pv);
+        const unsigned bal = __ballot_sync(SLS_FULL, keep);
+        __syncwarp();
+        if (keep) buf[n + __popc(bal & ((1u << lane) - 1u))] = v;
+        n += __popc(bal);
+        prev_last = __shfl_sync(SLS_FULL, v, 31);
+        __syncwarp();
+    }
+    return n;
+}
+
 // out-of-line copy for cold code (per-column setup of kernel 2): keeps the hot loops' code footprint small
 static __device__ __noinline__ int sls_find_cold(const int32_t* s, int n, int key) { return sls_find(s, n, key); }

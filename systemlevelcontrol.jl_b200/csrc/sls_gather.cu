@@ -37,44 +37,8 @@ __device__ int sls_warp_index_set(const SlsCsc& A, const SlsSupports& S, int T, 
         for (int i = lane; i < len; i += 32) buf[C + i] = (int32_t)(S.rowval[s0 + i] - 1 - S.row_off);
         C += len;
     }
-    int P = 32;
-#pragma unroll 1
-    while (P < C) P <<= 1;
-    if (P > cap) P = cap;                                     // cap >= 32 and a power of two
-#pragma unroll 1
-    for (int i = C + lane; i < P; i += 32) buf[i] = INT_MAX;
     __syncwarp();
-#pragma unroll 1
-    for (int k = 2; k <= P; k <<= 1) {
-#pragma unroll 1
-        for (int jj = k >> 1; jj > 0; jj >>= 1) {
-#pragma unroll 1
-            for (int i = lane; i < P; i += 32) {
-                const int ixj = i ^ jj;
-                if (ixj > i) {
-                    const int a = buf[i], b = buf[ixj];
-                    const bool asc = (i & k) == 0;
-                    if ((a > b) == asc) { buf[i] = b; buf[ixj] = a; }
-                }
-            }
-            __syncwarp();
-        }
-    }
-    int n = 0, prev_last = -1;
-#pragma unroll 1
-    for (int b0 = 0; b0 < P; b0 += 32) {
-        const int v = buf[b0 + lane];
-        int pv = __shfl_up_sync(SLS_FULL, v, 1);
-        if (lane == 0) pv = prev_last;
-        const bool keep = (v != INT_MAX) && (v != pv);
-        const unsigned bal = __ballot_sync(SLS_FULL, keep);
-        __syncwarp();
-        if (keep) buf[n + __popc(bal & ((1u << lane) - 1u))] = v;
-        n += __popc(bal);
-        prev_last = __shfl_sync(SLS_FULL, v, 31);
-    }
-    __syncwarp();
-    return n;
+    return sls_warp_sort_unique(buf, C, cap);
 }
 
 // kernel 1a: sizes only (n, m) so that the host can size the strided metadata exactly.

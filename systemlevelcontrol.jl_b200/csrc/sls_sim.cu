@@ -45,48 +45,6 @@ __device__ int sls_sim_append(const SlsSimArgs& a, int tt0, int tt1, int64_t gc,
     return cnt;
 }
 
-// in-place sort + unique of buf[0..cnt) (warp-cooperative bitonic sort, cnt <= cap, cap a power of two)
-__device__ int sls_sim_sort_unique(int32_t* buf, int cnt, int cap) {
-    const int lane = sls_lane();
-    int P = 32;
-#pragma unroll 1
-    while (P < cnt) P <<= 1;
-    if (P > cap) P = cap;
-#pragma unroll 1
-    for (int i = cnt + lane; i < P; i += 32) buf[i] = INT_MAX;
-    __syncwarp();
-#pragma unroll 1
-    for (int k = 2; k <= P; k <<= 1)
-#pragma unroll 1
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 1
-            for (int i = lane; i < P; i += 32) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const int x = buf[i], y = buf[ixj];
-                    const bool asc = (i & k) == 0;
-                    if ((x > y) == asc) { buf[i] = y; buf[ixj] = x; }
-                }
-            }
-            __syncwarp();
-        }
-    int n = 0, prev_last = -1;
-#pragma unroll 1
-    for (int b0 = 0; b0 < P; b0 += 32) {
-        const int v = buf[b0 + lane];
-        int pv = __shfl_up_sync(SLS_FULL, v, 1);
-        if (lane == 0) pv = prev_last;
-        const bool keep = (v != INT_MAX) && (v != pv);
-        const unsigned bal = __ballot_sync(SLS_FULL, keep);
-        __syncwarp();
-        if (keep) buf[n + __popc(bal & ((1u << lane) - 1u))] = v;
-        n += __popc(bal);
-        prev_last = __shfl_sync(SLS_FULL, v, 31);
-        __syncwarp();
-    }
-    return n;
-}
-
 // window of scenario column j: returns |W| (rows in buf[0..|W|)), or -1 on overflow.  `tmp` holds a copy of level 1.
 __device__ int sls_sim_window(const SlsSimArgs& a, int64_t j, int32_t* buf, int32_t* tmp, int cap, int tmpcap) {
     const int lane = sls_lane();
@@ -97,7 +55,7 @@ __device__ int sls_sim_window(const SlsSimArgs& a, int64_t j, int32_t* buf, int3
     int cnt = sls_sim_append(a, 0, T, j, buf, 1, cap);
     if (cnt < 0) return -1;
     __syncwarp();
-    int n1 = sls_sim_sort_unique(buf, cnt, cap);
+    int n1 = sls_warp_sort_unique(buf, cnt, cap);
     if (n1 > tmpcap) return -1;
 #pragma unroll 1
     for (int i = lane; i < n1; i += 32) tmp[i] = buf[i];
@@ -109,7 +67,7 @@ __device__ int sls_sim_window(const SlsSimArgs& a, int64_t j, int32_t* buf, int3
         cnt = sls_sim_append(a, 0, T, tmp[k], buf, n, cap);
         if (cnt < 0) return -1;
         __syncwarp();
-        n = sls_sim_sort_unique(buf, cnt, cap);
+        n = sls_warp_sort_unique(buf, cnt, cap);
     }
     // one hop of A (x(t+1) = A x(t) reaches the neighbours of the support): rows r with A[r, c] != 0, c in W
     {
@@ -130,7 +88,7 @@ __device__ int sls_sim_window(const SlsSimArgs& a, int64_t j, int32_t* buf, int3
             }
             __syncwarp();
         }
-        n = sls_sim_sort_unique(buf, cnt, cap);
+        n = sls_warp_sort_unique(buf, cnt, cap);
     }
     return n;
 }
@@ -144,7 +102,7 @@ __device__ int sls_sim_uwindow(const SlsSimArgs& a, const int32_t* W, int nw, in
         const int cnt = sls_sim_append(a, T, 2 * T, W[k], buf, n, cap);
         if (cnt < 0) return -1;
         __syncwarp();
-        n = sls_sim_sort_unique(buf, cnt, cap);
+        n = sls_warp_sort_unique(buf, cnt, cap);
     }
     return n;
 }

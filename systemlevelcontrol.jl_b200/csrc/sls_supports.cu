@@ -15,47 +15,6 @@
 
 #define SUPP_WPB 4
 
-__device__ int sls_supp_sort_unique(int32_t* buf, int cnt, int cap) {
-    const int lane = sls_lane();
-    int P = 32;
-#pragma unroll 1
-    while (P < cnt) P <<= 1;
-    if (P > cap) P = cap;
-#pragma unroll 1
-    for (int i = cnt + lane; i < P; i += 32) buf[i] = INT_MAX;
-    __syncwarp();
-#pragma unroll 1
-    for (int k = 2; k <= P; k <<= 1)
-#pragma unroll 1
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 1
-            for (int i = lane; i < P; i += 32) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const int x = buf[i], y = buf[ixj];
-                    const bool asc = (i & k) == 0;
-                    if ((x > y) == asc) { buf[i] = y; buf[ixj] = x; }
-                }
-            }
-            __syncwarp();
-        }
-    int n = 0, prev_last = -1;
-#pragma unroll 1
-    for (int b0 = 0; b0 < P; b0 += 32) {
-        const int v = buf[b0 + lane];
-        int pv = __shfl_up_sync(SLS_FULL, v, 1);
-        if (lane == 0) pv = prev_last;
-        const bool keep = (v != INT_MAX) && (v != pv);
-        const unsigned bal = __ballot_sync(SLS_FULL, keep);
-        __syncwarp();
-        if (keep) buf[n + __popc(bal & ((1u << lane) - 1u))] = v;
-        n += __popc(bal);
-        prev_last = __shfl_sync(SLS_FULL, v, 31);
-        __syncwarp();
-    }
-    return n;
-}
-
 // dst = sorted unique union over c in src[0..ns) of the stored-nonzero rows of M[:,c]; returns size or -1 (overflow).
 // One lane per source column: the colptr loads of 32 columns are in flight together, then every lane copies its own
 // rows to the offset a warp scan gives it.
@@ -80,7 +39,7 @@ __device__ int sls_supp_expand(const SlsCsc& M, const int32_t* src, int ns, int3
         cnt += total;
     }
     __syncwarp();
-    return sls_supp_sort_unique(dst, cnt, cap);
+    return sls_warp_sort_unique(dst, cnt, cap);
 }
 
 template <bool FILL>
