@@ -32,8 +32,8 @@ extern "C" {
 /* per-column status bits written by sls_solve* (improves on the reference, which ignores the
  * solver's termination status: src/synthesis.jl:62-65) */
 #define SLS_STATUS_OK            0
-#define SLS_STATUS_RESIDUAL      1   /* achievability residual above feas_tol: infeasible, or ill-conditioned
-                                        (cond(G) >~ 1e4: the per-tap error of Φ is up to ~1e3 x resid)      */
+#define SLS_STATUS_RESIDUAL      1   /* achievability residual above feas_tol after the refinement sweeps: infeasible
+                                        localisation, rank-deficient beyond rank_tol, or cond(G) >~ 1e6   */
 #define SLS_STATUS_RANK_SKIPPED  2   /* informational: >=1 redundant constraint row was eliminated      */
 #define SLS_STATUS_NO_IMPULSE    4   /* column j is not in its own s_x (Ĩ is a zero column) => Φ = 0    */
 
@@ -45,7 +45,8 @@ typedef struct sls_options {
                             bit 1: sls_solve copies the outputs back after kernel 2 instead of chunk by chunk;
                             bit 2: no refinement sweeps in kernel 2 (columns whose residual exceeds feas_tol are only flagged) */
     double  rank_tol;    /* pivot <= rank_tol * diag(D_k) => constraint row treated as redundant; 0 -> 1e-10 */
-    double  feas_tol;    /* max-abs achievability residual above which SLS_STATUS_RESIDUAL is set; 0 -> 1e-13 */
+    double  feas_tol;    /* max-abs achievability residual above which SLS_STATUS_RESIDUAL is set; 0 -> 1e-12.  Columns above
+                            feas_tol / 10 first take up to 3 refinement sweeps on the stored factors (flags bit 2: none) */
 } sls_options;
 
 typedef struct sls_timing {      /* device times (CUDA events on the handle's stream) of the last plan+solve */

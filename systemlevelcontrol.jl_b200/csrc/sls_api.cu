@@ -187,9 +187,10 @@ extern "C" int sls_create(const sls_options* opts, sls_handle** out) {
     if (!h) return fail(nullptr, -2, "sls_create: out of host memory");
     if (opts) h->opt = *opts;
     if (h->opt.rank_tol <= 0) h->opt.rank_tol = 1e-10;
-    // 1e-13: the normal-equations solve is accurate to ~2e-16 cond(G)^2 and the residual tracks that error (error <~ 1e3 x
-    // residual, tests/parity_cases.py::check_random_banded), so this flags every column whose Phi may miss the 1e-9 bar
-    if (h->opt.feas_tol <= 0) h->opt.feas_tol = 1e-13;
+    // kernel 2 takes refinement sweeps while the residual exceeds feas_tol / 10 (1e-13: 15x the largest residual of the
+    // BASELINE configs, so those never refine); what is still above feas_tol afterwards is infeasible, rank-deficient beyond
+    // rank_tol or has cond(G) >~ 1e6 and is flagged (tests/parity_cases.py::check_random_banded)
+    if (h->opt.feas_tol <= 0) h->opt.feas_tol = 1e-12;
     h->device = h->opt.device;
     if (h->device < 0 || h->device >= ndev) { delete h; return fail(nullptr, -1, "sls_create: device ordinal out of range"); }
     int e = rt::set_device(h->device);
@@ -985,7 +986,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
             a.hist_stride = sls_solve_hist_doubles(c.N, (int)T);
             a.status = h->status.as<int32_t>(); a.resid = h->resid.as<double>();
             a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
-            a.refine_tol = h->opt.feas_tol; a.max_refine = (h->opt.flags & 4) ? 0 : 3; a.refined = h->d_flag.as<int32_t>() + 1;
+            a.refine_tol = 0.1 * h->opt.feas_tol; a.max_refine = (h->opt.flags & 4) ? 0 : 3; a.refined = h->d_flag.as<int32_t>() + 1;
             int warps = 0;
             SLS_CK(sls_launch_solve(c.N, a, h->sm_count, h->max_smem, &warps, h->stream));
             launches++;
@@ -1307,7 +1308,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
             a.hist_stride = sls_solve_hist_doubles(cl.N, (int)T);
             a.status = x.status.as<int32_t>(); a.resid = x.resid.as<double>();
             a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
-            a.refine_tol = h->opt.feas_tol; a.max_refine = (h->opt.flags & 4) ? 0 : 3; a.refined = h->d_flag.as<int32_t>() + 1;
+            a.refine_tol = 0.1 * h->opt.feas_tol; a.max_refine = (h->opt.flags & 4) ? 0 : 3; a.refined = h->d_flag.as<int32_t>() + 1;
             int warps = 0;
             PIPE_CK(sls_launch_solve(cl.N, a, h->sm_count, h->max_smem, &warps, h->stream));
             launches++;

@@ -46,6 +46,11 @@ int64_t sls_solve_hist_doubles(int N, int T);
 int sls_launch_solve(int N, const SlsSolveArgs& a, int sm_count, int max_smem, int* warps_launched,
                      sls_stream_t stream);
 int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem);
+// large size classes (32 < N <= 64): one CTA per column (sls_solve_wide.cu); a history slot per resident CTA
+int sls_launch_solve_wide(int N, const SlsSolveArgs& a, int sm_count, int max_smem, int* slots_launched, sls_stream_t stream);
+int sls_solve_wide_max_slots(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem);
+int64_t sls_solve_wide_hist_doubles(int N, int T);
+size_t sls_solve_wide_smem(int N, int mcap, int nnzcap, int T, int wu);
 
 // ---- kernel 3 (sls_scatter.cu) ----
 struct SlsScatterArgs {

@@ -26,6 +26,14 @@ def test_emu_grid_9x9_subset(emu_api):
     assert worst < 1e-11
 
 
+def test_emu_wide_solver_grid_13x13_subset(emu_api):
+    """n = 36 and n = 61 columns: the one-CTA-per-column kernel of the large size classes (sls_solve_wide.cu)."""
+    from conftest import PHI_FLOOR
+    worst, info = pc.check_golden(emu_api, "grid_13x13_full_d4_T20_subset", O.grid_plant(13, 13, actuation="full"), cols=[6, 84],
+                                  floor=PHI_FLOOR)
+    assert info["n"].tolist() == [36, 61] and worst < 1e-10
+
+
 def test_emu_error_paths(emu_api):
     pc.check_error_paths(emu_api)
 

@@ -332,3 +332,6 @@ def test_random_banded_plants_vs_oracle(cuda_api):
     worst, nclean, nflag = pc.check_random_banded(cuda_api, seeds=tuple(range(12)))
     assert nclean >= 30 and nflag >= 8, (nclean, nflag)       # flagged = infeasible or cond(G) >= 1e6 only
     assert worst < 1e-9, worst
+    # wider band, n up to 37: the refinement sweeps of the one-CTA-per-column kernel (sls_solve_wide.cu)
+    worst, nclean, nflag = pc.check_random_banded(cuda_api, seeds=(0, 1, 2, 3), Nx=80, bw=3, d=5, T=9, cols=(0, 11, 40, 41, 79))
+    assert nclean >= 8 and worst < 1e-9, (worst, nclean, nflag)
