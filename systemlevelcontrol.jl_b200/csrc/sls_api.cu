@@ -1476,17 +1476,27 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     a.A = h->A.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();
     a.dcol = dcol.as<int64_t>(); a.dtime = dtime.as<int64_t>(); a.overflow = dovf.as<int>();
     // pass 1: window sizes (scratch capacity = as much as 4 warps can have)
-    int cap = 1024;
-    while ((size_t)4 * 3 * (cap * 2) * sizeof(int32_t) <= (size_t)h->max_smem && cap < 8192) cap *= 2;
-    SIM_CK(sls_launch_sim_size(a, dnw.as<int32_t>(), dnu.as<int32_t>(), cap, nullptr, nullptr, 0, 0, h->stream));
+    // scratch lists of the window pass: 3 x cap ints per warp.  Start small (occupancy: 4 warps x 3 x 512 ints = 24 KB per
+    // block) and grow only when a scenario overflows (the kernel reports -1), up to what shared memory allows.
+    int cap = 512;
     std::vector<int32_t> nw(nscen), nu(nscen);
-    SIM_CK(rt::d2h(nw.data(), dnw.p, nscen * 4, h->stream));
-    SIM_CK(rt::d2h(nu.data(), dnu.p, nscen * 4, h->stream));
-    SIM_CK(rt::sync(h->stream));
     int wmax = 1, umax = 1;
-    for (int64_t s = 0; s < nscen; s++) {
-        if (nw[s] < 0 || nu[s] < 0) { cleanup(); return fail(h, -4, "sls_simulate: a scenario's window does not fit shared memory"); }
-        wmax = std::max(wmax, nw[s]); umax = std::max(umax, nu[s]);
+    for (;;) {
+        SIM_CK(sls_launch_sim_size(a, dnw.as<int32_t>(), dnu.as<int32_t>(), cap, nullptr, nullptr, 0, 0, h->stream));
+        SIM_CK(rt::d2h(nw.data(), dnw.p, nscen * 4, h->stream));
+        SIM_CK(rt::d2h(nu.data(), dnu.p, nscen * 4, h->stream));
+        SIM_CK(rt::sync(h->stream));
+        bool ovf_ = false;
+        wmax = 1; umax = 1;
+        for (int64_t s = 0; s < nscen; s++) {
+            if (nw[s] < 0 || nu[s] < 0) ovf_ = true;
+            wmax = std::max(wmax, nw[s]); umax = std::max(umax, nu[s]);
+        }
+        if (!ovf_) break;
+        if ((size_t)4 * 3 * (cap * 2) * sizeof(int32_t) > (size_t)h->max_smem || cap >= 8192) {
+            cleanup(); return fail(h, -4, "sls_simulate: a scenario's window does not fit shared memory");
+        }
+        cap *= 2;
     }
     const int wcap = (wmax + 1) & ~1, ucap = (umax + 1) & ~1;
     // window pass: the same kernel again, now storing the windows with exact strides
@@ -1498,6 +1508,7 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     SIM_CK(dnent.ensure(nscen * 8)); SIM_CK(dtapcnt.ensure((size_t)nscen * 2 * T * 4)); SIM_CK(dpkoff.ensure(nscen * 8));
     SIM_CK(sls_launch_sim_pack(a, false, wcap, ucap, dnent.as<int64_t>(), dtapcnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, h->stream));
     double sim_bytes = 0;
+    int64_t nent_max = 0;
     {
         std::vector<int64_t> nent(nscen), off(nscen);
         std::vector<uint32_t> tapcnt((size_t)nscen * 2 * T);
@@ -1513,7 +1524,7 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
                 sim_bytes += reps * ent * 10.0;
             }
         int64_t run = 0;
-        for (int64_t s = 0; s < nscen; s++) { off[s] = run; run += nent[s]; }
+        for (int64_t s = 0; s < nscen; s++) { off[s] = run; run += nent[s]; nent_max = std::max(nent_max, nent[s]); }
         SIM_CK(rt::h2d(dpkoff.p, off.data(), nscen * 8, h->stream));
         SIM_CK(dpkcnt.ensure((size_t)nscen * 2 * T * wcap * 2));
         SIM_CK(dpkrow.ensure((size_t)std::max<int64_t>(run, 1) * 2));
@@ -1535,7 +1546,12 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     if (x_out) { SIM_CK(dxo.ensure(nn * Nx * 8)); SIM_CK(rt::zero(dxo.p, nn * Nx * 8, h->stream)); a.xout = dxo.as<double>(); }
     if (u_out) { SIM_CK(duo.ensure(nn * std::max<int64_t>(Nu, 1) * 8)); SIM_CK(rt::zero(duo.p, nn * std::max<int64_t>(Nu, 1) * 8, h->stream)); a.uout = duo.as<double>(); }
     h->ev[0].record(h->stream);
-    SIM_CK(sls_launch_sim(a, cap2, wcap, ucap, h->stream));
+    // fast path: the scenario's packed window fits shared memory -> one CTA per scenario, Phi read from HBM once
+    const int nent_cap = (int)((nent_max + 1) & ~(int64_t)1);
+    const bool cta_path = !getenv("SLS_SIM_STREAM") && 2 * T <= 256 && wcap <= 256 && ucap <= 256 && nent_max < ((int64_t)1 << 24) &&
+                          sls_sim_cta_smem(nent_cap, wcap, ucap, (int)T) <= (size_t)h->max_smem;
+    if (cta_path) SIM_CK(sls_launch_sim_cta(a, wcap, ucap, nent_cap, h->sm_count, h->stream));
+    else SIM_CK(sls_launch_sim(a, cap2, wcap, ucap, h->stream));
     h->ev[1].record(h->stream);
     int ovf = 0;
     SIM_CK(rt::d2h(&ovf, dovf.p, 4, h->stream));

@@ -93,6 +93,9 @@ __host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, in
 int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, int32_t* Wg, int32_t* Wug,
                         int wcap, int ucap, sls_stream_t stream);
 int sls_launch_sim(const SlsSimArgs& a, int cap, int wcap, int ucap, sls_stream_t stream);
+// fast path: one CTA per scenario, packed Phi window resident in shared memory (needs 2T <= 256, windows <= 256, nent_cap entries fit)
+size_t sls_sim_cta_smem(int nent_cap, int wcap, int ucap, int T);
+int sls_launch_sim_cta(const SlsSimArgs& a, int wcap, int ucap, int nent_cap, int sm_count, sls_stream_t stream);
 int sls_launch_sim_pack(const SlsSimArgs& a, bool fill, int wcap, int ucap, int64_t* nent, uint32_t* tapcnt, const int64_t* pk_off,
                         uint16_t* pk_cnt, uint16_t* pk_row, double* pk_val, sls_stream_t stream);
 

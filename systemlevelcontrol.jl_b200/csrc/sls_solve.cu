@@ -81,7 +81,7 @@ sls_solve_kernel(SlsSolveArgs a) {
     double* hist = a.hist + (size_t)slot * a.hist_stride;      // [T+1][N] yh history, then [T][tri(N)] packed -Z_k
     double* yhist = hist;
     double* zhist = hist + (size_t)(T + 1) * N;
-    constexpr int TRI = N * (N + 1) / 2;
+    constexpr int HB = NB * (NB + 1) / 2 * 64;             // doubles of one stored -Z_k: lower-triangle blocks in register order
 
     for (int idx = slot; idx < a.count; idx += nslots) {
         const int c = a.list[idx];
@@ -210,13 +210,11 @@ sls_solve_kernel(SlsSolveArgs a) {
 
         // ------------------------------------------------------------------ tap 0:  S_0 = diag(mx_1), yh_0 = e
         double S[NB][NB][2];                                  // -Z_k ("swept" S_k) in accumulator layout
-        int rowoff[NB];                                       // r(r+1)/2 of the lane's row in each block row
         {
             const mask_t m1 = mxs[0];
 #pragma unroll
             for (int bi = 0; bi < NB; bi++) {
                 const int r = 8 * bi + g;
-                rowoff[bi] = r * (r + 1) / 2;
 #pragma unroll
                 for (int bj = 0; bj < NB; bj++) {
                     const int c0 = 8 * bj + 2 * q;
@@ -421,17 +419,19 @@ sls_solve_kernel(SlsSolveArgs a) {
                 S[p][p][0] = d0; S[p][p][1] = d1;
             }
             if (keep != nonempty) status |= SLS_ST_RANK_SKIPPED;
-            // (8) history: packed lower triangle (row-major) of -Z_k, k = 1..T-1 (Z_0 is diag(mx_1)); -Z_T, which the back
-            //     substitution uses straight from the registers, goes to slot 0 for the refinement sweeps
+            // (8) history: the lower-triangle blocks of -Z_k in REGISTER order (block b at hk + 64 b, a lane's two entries at
+            //     2*lane: one coalesced 16-byte store per block, read back the same way — no index arithmetic, no predicates;
+            //     rows / columns beyond n are exact zeros), k = 1..T-1 (Z_0 is diag(mx_1)); -Z_T, which the back substitution
+            //     uses straight from the registers, goes to slot 0 for the refinement sweeps
             {
-                double* hk = zhist + (size_t)(k < T ? k : 0) * TRI;
+                double* hk = zhist + (size_t)(k < T ? k : 0) * HB + 2 * lane;
+                int b = 0;
 #pragma unroll
                 for (int bi = 0; bi < NB; bi++)
 #pragma unroll
                     for (int bj = 0; bj <= bi; bj++) {
-                        const int r = 8 * bi + g, c0 = 8 * bj + 2 * q;
-                        if (r < n && c0 <= r) hk[rowoff[bi] + c0] = S[bi][bj][0];
-                        if (r < n && c0 + 1 <= r) hk[rowoff[bi] + c0 + 1] = S[bi][bj][1];
+                        *reinterpret_cast<double2*>(hk + 64 * b) = make_double2(S[bi][bj][0], S[bi][bj][1]);
+                        b++;
                     }
             }
             __syncwarp();
@@ -476,34 +476,13 @@ sls_solve_kernel(SlsSolveArgs a) {
         constexpr bool PRELOAD = (NB <= 4);
         constexpr int NZB = PRELOAD ? NB * (NB + 1) / 2 : 1;
         double zn[NZB][2], yn[RPL];
-        // element offsets of the lane's accumulator-layout entries inside a tap's packed lower triangle (-1: none);
-        // the diagonal blocks are completed by symmetric addressing.  Computed once per column.
-        int zoff[NZB][2];
-        if (PRELOAD) {
-            int idx = 0;
-#pragma unroll
-            for (int bi = 0; bi < NB; bi++) {
-                const int r = 8 * bi + g;
-#pragma unroll
-                for (int bj = 0; bj <= bi; bj++) {
-                    const int c0 = 8 * bj + 2 * q;
-                    int o0 = -1, o1 = -1;
-                    if (bj < bi) {
-                        if (r < n) { o0 = rowoff[bi] + c0; o1 = o0 + 1; }
-                    } else {
-                        if (r < n && c0 < n) o0 = (c0 <= r) ? rowoff[bi] + c0 : c0 * (c0 + 1) / 2 + r;
-                        if (r < n && c0 + 1 < n) o1 = (c0 + 1 <= r) ? rowoff[bi] + c0 + 1 : (c0 + 1) * (c0 + 2) / 2 + r;
-                    }
-                    zoff[PRELOAD ? idx : 0][0] = o0; zoff[PRELOAD ? idx : 0][1] = o1; idx++;
-                }
-            }
-        }
         auto load_hist = [&](int kk, double (&z)[NZB][2], double (&yv)[RPL]) {
-            const double* hk = zhist + (size_t)kk * TRI;
+            const double* hk = zhist + (size_t)kk * HB + 2 * lane;
 #pragma unroll
             for (int i = 0; i < NZB; i++) {
-                z[i][0] = (kk >= 1 && zoff[i][0] >= 0) ? hk[zoff[i][0]] : 0.0;
-                z[i][1] = (kk >= 1 && zoff[i][1] >= 0) ? hk[zoff[i][1]] : 0.0;
+                double2 v = make_double2(0.0, 0.0);
+                if (kk >= 1) v = *reinterpret_cast<const double2*>(hk + 64 * i);
+                z[i][0] = v.x; z[i][1] = v.y;
             }
 #pragma unroll
             for (int rr = 0; rr < RPL; rr++) { const int i = lane + 32 * rr; yv[rr] = (i < n) ? yhist[(size_t)kk * N + i] : 0.0; }
@@ -520,18 +499,6 @@ sls_solve_kernel(SlsSolveArgs a) {
                 for (int rr = 0; rr < RPL; rr++) yc[rr] = yn[rr];
                 if (k >= 2) load_hist(k - 2, zn, yn);
             }
-#ifndef SLS_EMU
-            // the next iteration's history (-Z_{k-2}, yh_{k-2}) is fetched towards L1 now: its loads sit at the head
-            // of a serial chain and would otherwise pay L2/HBM latency every tap
-            if (!PRELOAD && k >= 3) {
-                const char* hz = reinterpret_cast<const char*>(zhist + (size_t)(k - 2) * TRI);
-#pragma unroll 1
-                for (int o = lane * 128; o < (int)(n * (n + 1) / 2 * sizeof(double)); o += 32 * 128)
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(hz + o));
-                if (lane == 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(yhist + (size_t)(k - 2) * N));
-                if (lane == 1 && N > 16) asm volatile("prefetch.global.L1 [%0];" :: "l"(yhist + (size_t)(k - 2) * N + 16));
-            }
-#endif
             __syncwarp();
             // t = C~^T lambda_k
 #pragma unroll 1
@@ -576,7 +543,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                     if (i < N) gbuf[i] = (i < n && sls_mbit(mxs[0], i)) ? -rhs_s[i] : 0.0;
                 }
             } else {
-                const double* hk = zhist + (size_t)(k - 1) * TRI;
+                const double* hk = zhist + (size_t)(k - 1) * HB + 2 * lane;
                 double racc[NB], cacc[NB][2];
 #pragma unroll
                 for (int b = 0; b < NB; b++) { racc[b] = 0.0; cacc[b][0] = 0.0; cacc[b][1] = 0.0; }
@@ -589,16 +556,14 @@ sls_solve_kernel(SlsSolveArgs a) {
                     for (int bj = 0; bj <= bi; bj++) {
                         const int c0 = 8 * bj + 2 * q;
                         const double2 vc = *reinterpret_cast<const double2*>(rhs_s + c0);
-                        double z0 = 0.0, z1 = 0.0;
+                        double z0, z1;
                         if (PRELOAD) {
-                            z0 = zc[PRELOAD ? zi : 0][0]; z1 = zc[PRELOAD ? zi : 0][1]; zi++;
-                        } else if (bj < bi) {
-                            if (r < n) { z0 = hk[rowoff[bi] + c0]; z1 = hk[rowoff[bi] + c0 + 1]; }
+                            z0 = zc[PRELOAD ? zi : 0][0]; z1 = zc[PRELOAD ? zi : 0][1];
                         } else {
-                            // diagonal block: full 8x8 from the packed lower triangle by symmetric addressing
-                            if (r < n && c0 < n) z0 = (c0 <= r) ? hk[rowoff[bi] + c0] : hk[c0 * (c0 + 1) / 2 + r];
-                            if (r < n && c0 + 1 < n) z1 = (c0 + 1 <= r) ? hk[rowoff[bi] + c0 + 1] : hk[(c0 + 1) * (c0 + 2) / 2 + r];
+                            const double2 zv = *reinterpret_cast<const double2*>(hk + 64 * zi);
+                            z0 = zv.x; z1 = zv.y;
                         }
+                        zi++;
                         if (bj < bi) {
                             cacc[bj][0] = fma(z0, vr, cacc[bj][0]);
                             cacc[bj][1] = fma(z1, vr, cacc[bj][1]);
@@ -741,7 +706,8 @@ sls_solve_kernel(SlsSolveArgs a) {
                     if (i < N) gbuf[i] = (i < n && sls_mbit(mxs[0], i)) ? -rhs_s[i] : 0.0;
                 }
             } else {
-                const double* hk = zhist + (size_t)(k - 1 < T ? k - 1 : 0) * TRI;
+                const double* hk = zhist + (size_t)(k - 1 < T ? k - 1 : 0) * HB + 2 * lane;
+                int zi = 0;
                 double racc[NB], cacc[NB][2];
 #pragma unroll
                 for (int b = 0; b < NB; b++) { racc[b] = 0.0; cacc[b][0] = 0.0; cacc[b][1] = 0.0; }
@@ -753,13 +719,9 @@ sls_solve_kernel(SlsSolveArgs a) {
                     for (int bj = 0; bj <= bi; bj++) {
                         const int c0 = 8 * bj + 2 * q;
                         const double2 vc = *reinterpret_cast<const double2*>(rhs_s + c0);
-                        double z0 = 0.0, z1 = 0.0;
-                        if (bj < bi) {
-                            if (r < n) { z0 = hk[rowoff[bi] + c0]; z1 = hk[rowoff[bi] + c0 + 1]; }
-                        } else {
-                            if (r < n && c0 < n) z0 = (c0 <= r) ? hk[rowoff[bi] + c0] : hk[c0 * (c0 + 1) / 2 + r];
-                            if (r < n && c0 + 1 < n) z1 = (c0 + 1 <= r) ? hk[rowoff[bi] + c0 + 1] : hk[(c0 + 1) * (c0 + 2) / 2 + r];
-                        }
+                        const double2 zv = *reinterpret_cast<const double2*>(hk + 64 * zi);
+                        const double z0 = zv.x, z1 = zv.y;
+                        zi++;
                         if (bj < bi) { cacc[bj][0] = fma(z0, vr, cacc[bj][0]); cacc[bj][1] = fma(z1, vr, cacc[bj][1]); }
                         racc[bi] = fma(z0, vc.x, racc[bi]);
                         racc[bi] = fma(z1, vc.y, racc[bi]);
@@ -842,12 +804,12 @@ size_t sls_solve_smem_per_warp(int N, int mcap, int nnzcap, int T, int wu) {
 }
 // size classes above 32 run one CTA per column (sls_solve_wide.cu); SLS_WIDE=0 keeps them on the one-warp kernel (A/B)
 static bool use_wide(int N) {
-    static const bool off = [] { const char* e = getenv("SLS_WIDE"); return e && atoi(e) == 0; }();
-    return N > 32 && !off;
+    static const int minN = [] { const char* e = getenv("SLS_WIDE"); return e ? (atoi(e) == 0 ? 1 << 30 : atoi(e)) : 40; }();   // SLS_WIDE=<smallest N on the CTA kernel>
+    return N >= minN && N >= 16;
 }
 int64_t sls_solve_hist_doubles(int N, int T) {
     if (use_wide(N)) return sls_solve_wide_hist_doubles(N, T);
-    return (int64_t)(T + 1) * N + (int64_t)T * (N * (N + 1) / 2);
+    return (int64_t)(T + 1) * N + (int64_t)T * ((N / 8) * (N / 8 + 1) / 2 * 64);
 }
 
 template <int NB>

@@ -34,7 +34,7 @@ struct SlsWideLayout {
         SLS_SEC(oLam, 8 * N);
         SLS_SEC(oRhs, 8 * N);
         SLS_SEC(oXa, 8 * N);
-        SLS_SEC(oMisc, 128);
+        SLS_SEC(oMisc, 128 + 1024);
         SLS_SEC(oSx, 4 * N);
         SLS_SEC(oRptr, 2 * (N + 2));
         SLS_SEC(oRsplit, 2 * (N + 2));
@@ -54,14 +54,16 @@ struct SlsWideLayout {
     }
 };
 
+// resident CTAs per SM the register allocation aims at (shared memory allows about as many)
+template <int NB> struct SlsWideCfg { static const int MINB = (NB >= 5) ? 2 : ((NB == 4) ? 4 : ((NB == 3) ? 7 : 10)); };
+
 template <int NB>
-__global__ void __launch_bounds__(NB * 32, 2)
+__global__ void __launch_bounds__(NB * 32, SlsWideCfg<NB>::MINB)
 sls_solve_wide_kernel(SlsSolveArgs a) {
     constexpr int N = 8 * NB;
     constexpr int NT = NB * 32;              // threads per CTA = per column
-    constexpr int RPL = (N + 31) / 32;       // rows per lane in warp 0's per-column setup
     constexpr int BLK = NB * NB * 64;        // doubles of one full matrix (blocked)
-    typedef uint64_t mask_t;
+    typedef typename SlsMask<NB>::type mask_t;
     SLS_DYN_SMEM(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;   // accumulator-layout coordinates
@@ -95,6 +97,9 @@ sls_solve_wide_kernel(SlsSolveArgs a) {
     uint16_t* rowc = reinterpret_cast<uint16_t*>(base + L.oRowC);
     uint64_t* misc64 = reinterpret_cast<uint64_t*>(base + L.oMisc);   // [0] nzA, [1..2] non-empty ballots
     double* miscd = reinterpret_cast<double*>(base + L.oMisc + 32);   // [0..NB) per-warp residual maxima
+    int* rankflag = reinterpret_cast<int*>(base + L.oMisc + 104);     // a pivot block dropped a non-empty row
+    double* Pbuf = reinterpret_cast<double*>(base + L.oMisc + 128);   // -P of the current pivot block (row-major 8 x 8), two buffers:
+                                                                      // the owner of block p+1 may post while block p's is still being read
     const int wu = P.wu;
 
     double* hist = a.hist + (size_t)blockIdx.x * a.hist_stride;       // [T+1][N] yh history, then [T][BLK] -Z_k in register order
@@ -115,10 +120,10 @@ sls_solve_wide_kernel(SlsSolveArgs a) {
         for (int t = tid; t < T; t += NT) {
             const uint32_t* w = P.maskx + ((size_t)c * T + t) * P.wx;
             mask_t v = (mask_t)w[0];
-            if (P.wx > 1) v |= (mask_t)((uint64_t)w[1] << 32);
+            if (sizeof(mask_t) == 8 && P.wx > 1) v |= (mask_t)((uint64_t)w[1] << 32);
             mxs[t] = v;
         }
-        if (tid == 0) mxs[T] = (mask_t)0;
+        if (tid == 0) { mxs[T] = (mask_t)0; *rankflag = 0; }
 #pragma unroll 1
         for (int t = tid; t < T * wu; t += NT) mus[t] = P.masku[(size_t)c * T * wu + t];
 #pragma unroll 1
@@ -126,53 +131,51 @@ sls_solve_wide_kernel(SlsSolveArgs a) {
 #pragma unroll 1
         for (int e = tid; e < N * N; e += NT) Am[e] = 0.0;
         __syncthreads();
-        // ------------------------------------------------------------------ local CSR / CSC of C~ = [A~ B~]  (warp 0)
-        if (warp == 0) {
-            uint64_t nzA = 0ull;
-            int carry = 0;
+        // ------------------------------------------------------------------ local CSR / CSC of C~ = [A~ B~]
+        // one thread per local row (CSR) / per local column (CSC); offsets by a serial prefix over <= N + mcap counts in
+        // shared memory (the column's `tx` vector doubles as integer scratch here)
+        {
+            int32_t* cnts = reinterpret_cast<int32_t*>(tx);
+            if (tid == 0) misc64[0] = 0ull;
+            int cntA = 0, cntB = 0;
+            int64_t ea0 = 0, ea1 = 0, eb0 = 0, eb1 = 0;
+            if (tid < n) {
+                const int64_t gr = sx[tid];
+                ea0 = a.Ar.colptr[gr] - 1; ea1 = a.Ar.colptr[gr + 1] - 1;
+                eb0 = a.B2r.colptr[gr] - 1; eb1 = a.B2r.colptr[gr + 1] - 1;
 #pragma unroll 1
-            for (int rr = 0; rr < RPL; rr++) {
-                const int i = lane + 32 * rr;
-                const bool act = i < n;
-                int cntA = 0, cntB = 0;
-                int64_t ea0 = 0, ea1 = 0, eb0 = 0, eb1 = 0;
-                if (act) {
-                    const int64_t gr = sx[i];
-                    ea0 = a.Ar.colptr[gr] - 1; ea1 = a.Ar.colptr[gr + 1] - 1;
-                    eb0 = a.B2r.colptr[gr] - 1; eb1 = a.B2r.colptr[gr + 1] - 1;
+                for (int64_t e = ea0; e < ea1; e++) cntA += (sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1)) >= 0);
 #pragma unroll 1
-                    for (int64_t e = ea0; e < ea1; e++) cntA += (sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1)) >= 0);
-#pragma unroll 1
-                    for (int64_t e = eb0; e < eb1; e++) cntB += (sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1)) >= 0);
-                }
-                int incl = cntA + cntB;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(SLS_FULL, incl, d); if (lane >= d) incl += o; }
-                const int excl = carry + incl - (cntA + cntB);
-                if (act) {
-                    rptr[i] = (uint16_t)excl; rsplit[i] = (uint16_t)(excl + cntA);
-                    int o = excl;
-#pragma unroll 1
-                    for (int64_t e = ea0; e < ea1; e++) {
-                        const int l = sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
-                        if (l >= 0) { colr[o] = (uint16_t)l; valr[o] = a.Ar.nzval[e]; o++; nzA |= 1ull << ((i >> 3) * NB + (l >> 3)); }
-                    }
-#pragma unroll 1
-                    for (int64_t e = eb0; e < eb1; e++) {
-                        const int l = sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1));
-                        if (l >= 0) { colr[o] = (uint16_t)(n + l); valr[o] = a.B2r.nzval[e]; o++; }
-                    }
-                }
-                carry += __shfl_sync(SLS_FULL, incl, 31);
+                for (int64_t e = eb0; e < eb1; e++) cntB += (sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1)) >= 0);
+                cnts[tid] = cntA + cntB;
             }
-            if (lane == 0) rptr[n] = (uint16_t)carry;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) nzA |= __shfl_xor_sync(SLS_FULL, nzA, d);
-            if (lane == 0) misc64[0] = nzA;
-            carry = 0;
+            __syncthreads();
+            if (tid < n) {
+                int excl = 0;
 #pragma unroll 1
-            for (int p0 = 0; p0 < n + m; p0 += 32) {
-                const int p = p0 + lane;
+                for (int i = 0; i < tid; i++) excl += cnts[i];
+                rptr[tid] = (uint16_t)excl; rsplit[tid] = (uint16_t)(excl + cntA);
+                if (tid == n - 1) rptr[n] = (uint16_t)(excl + cntA + cntB);
+                int o = excl;
+                uint64_t nz = 0ull;
+#pragma unroll 1
+                for (int64_t e = ea0; e < ea1; e++) {
+                    const int l = sls_find_cold(sx, n, (int32_t)(a.Ar.rowval[e] - 1));
+                    if (l >= 0) { colr[o] = (uint16_t)l; valr[o] = a.Ar.nzval[e]; o++; nz |= 1ull << ((tid >> 3) * NB + (l >> 3)); }
+                }
+#pragma unroll 1
+                for (int64_t e = eb0; e < eb1; e++) {
+                    const int l = sls_find_cold(su, m, (int32_t)(a.B2r.rowval[e] - 1));
+                    if (l >= 0) { colr[o] = (uint16_t)(n + l); valr[o] = a.B2r.nzval[e]; o++; }
+                }
+                if (nz) atomicOr(reinterpret_cast<unsigned long long*>(misc64), (unsigned long long)nz);
+            }
+            if (n == 0 && tid == 0) rptr[0] = 0;
+            __syncthreads();
+            // CSC: columns 0..n of A~, then the m columns of B~
+#pragma unroll 1
+            for (int p0 = 0; p0 < n + m; p0 += NT) {
+                const int p = p0 + tid;
                 int cnt = 0;
                 int64_t e0 = 0, e1 = 0;
                 const SlsCsc& M = (p < n) ? a.A : a.B2;
@@ -181,22 +184,30 @@ sls_solve_wide_kernel(SlsSolveArgs a) {
                     e0 = M.colptr[gc] - 1; e1 = M.colptr[gc + 1] - 1;
 #pragma unroll 1
                     for (int64_t e = e0; e < e1; e++) cnt += (sls_find_cold(sx, n, (int32_t)(M.rowval[e] - 1)) >= 0);
+                    cnts[p] = cnt;
                 }
-                int incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(SLS_FULL, incl, d); if (lane >= d) incl += o; }
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int p0 = 0; p0 < n + m; p0 += NT) {
+                const int p = p0 + tid;
                 if (p < n + m) {
-                    int o = carry + incl - cnt;
+                    int o = 0;
+#pragma unroll 1
+                    for (int i = 0; i < p; i++) o += cnts[i];
                     cptr[p] = (uint16_t)o;
+                    if (p == n + m - 1) cptr[n + m] = (uint16_t)(o + cnts[p]);
+                    const SlsCsc& M = (p < n) ? a.A : a.B2;
+                    const int64_t gc = (p < n) ? sx[p] : su[p - n];
+                    const int64_t e0 = M.colptr[gc] - 1, e1 = M.colptr[gc + 1] - 1;
 #pragma unroll 1
                     for (int64_t e = e0; e < e1; e++) {
                         const int r = sls_find_cold(sx, n, (int32_t)(M.rowval[e] - 1));
                         if (r >= 0) { rowc[o] = (uint16_t)r; valc[o] = M.nzval[e]; o++; }
                     }
                 }
-                carry += __shfl_sync(SLS_FULL, incl, 31);
             }
-            if (lane == 0) cptr[n + m] = (uint16_t)carry;
+            if (n + m == 0 && tid == 0) cptr[0] = 0;
         }
         __syncthreads();
         const uint64_t nzA = misc64[0];
@@ -275,12 +286,13 @@ sls_solve_wide_kernel(SlsSolveArgs a) {
                 }
                 if (tid < N) thrs[tid] = (dref != 0.0) ? a.rank_tol * dref : SLS_INF;
                 const uint32_t bal = __ballot_sync(SLS_FULL, dref != 0.0);
-                if (lane == 0 && warp < 2) misc64[1 + warp] = bal;
+                if (lane == 0 && warp < 2) misc64[1 + warp] = (tid < N) ? bal : 0u;
 #pragma unroll
                 for (int w = 0; w < 4; w++) if (w < wu) mu_prev[w] = muk[w];
                 mk_prev = mk; mk1_prev = mk1; cache_valid = true;
                 __syncthreads();
                 nonempty = misc64[1] | ((NB > 4) ? (misc64[2] << 32) : 0ull);
+                if (NB == 1) nonempty &= 0xffull;
             } else {
                 __syncthreads();
             }
@@ -330,17 +342,15 @@ sls_solve_wide_kernel(SlsSolveArgs a) {
                     }
                 }
             }
-            // (7) block symmetric sweep with rank skipping: S <- -(S^+)
-            uint64_t keep = 0ull;
-#pragma unroll
-            for (int p = 0; p < NB; p++) {
-                *reinterpret_cast<double2*>(Ssm + ((warp * NB + p) << 6) + frag) = make_double2(Sr[p][0], Sr[p][1]);
-                __syncthreads();                               // column p of the current S is in shared memory
-                const double2 dv2 = *reinterpret_cast<const double2*>(Ssm + ((p * NB + p) << 6) + frag);
-                double d0 = dv2.x, d1 = dv2.y;
+            // (7) block symmetric sweep with rank skipping: S <- -(S^+), with one block of look-ahead.
+            //     The owner of pivot block p inverts it ALONE (8 scalar symmetric sweeps through shuffles on its registers)
+            //     and posts -P; in step p the owner of block p+1 only brings its diagonal block up to date (its other
+            //     blocks are recomputed from the column panel when its row becomes the pivot row) and inverts it while the
+            //     other warps run their DMMA updates, so the serial scalar chain overlaps the tensor work.
+            auto sweep_post = [&](double d0, double d1, int pb) {      // pb = pivot block whose owner this warp is
                 uint32_t kb = 0u;
-                const uint32_t actp = (uint32_t)(nonempty >> (8 * p)) & 0xffu;
-                const int npair = (actp == 0u) ? 0 : ((min(8, n - 8 * p) + 1) >> 1);
+                const uint32_t actp = (uint32_t)(nonempty >> (8 * pb)) & 0xffu;
+                const int npair = (actp == 0u) ? 0 : ((min(8, n - 8 * pb) + 1) >> 1);
 #pragma unroll 1
                 for (int rp = 0; rp < npair; rp++) {
 #pragma unroll
@@ -351,7 +361,7 @@ sls_solve_wide_kernel(SlsSolveArgs a) {
                         const double cg = __shfl_sync(SLS_FULL, src, (lane & ~3) | rp);
                         const double rr0 = __shfl_sync(SLS_FULL, d0, 4 * r + q);
                         const double rr1 = __shfl_sync(SLS_FULL, d1, 4 * r + q);
-                        const bool ok = dv > thrs[8 * p + r];
+                        const bool ok = dv > thrs[8 * pb + r];
                         const double pinv = ok ? sls_rcp(dv) : 0.0;
                         const bool isrow = (g == r);
                         const double cp = cg * pinv;
@@ -363,21 +373,20 @@ sls_solve_wide_kernel(SlsSolveArgs a) {
                         kb |= (ok ? 1u : 0u) << r;
                     }
                 }
-                keep |= (uint64_t)kb << (8 * p);
-                const double Pn[2] = {d0, d1};                // -P, symmetric
-                if (warp != p) {
-                    double Tn[2] = {0.0, 0.0};                // -S_wp P
-                    sls_dmma(Tn[0], Tn[1], Sr[p][0], Pn[0]);
-                    sls_dmma(Tn[0], Tn[1], Sr[p][1], Pn[1]);
+                if (lane == 0 && kb != actp) *rankflag = 1;
+                *reinterpret_cast<double2*>(Pbuf + 64 * (pb & 1) + frag) = make_double2(d0, d1);   // -P (symmetric), row-major
+            };
+            *reinterpret_cast<double2*>(Ssm + ((warp * NB) << 6) + frag) = make_double2(Sr[0][0], Sr[0][1]);   // column panel 0
+            if (warp == 0) sweep_post(Sr[0][0], Sr[0][1], 0);
+            __syncthreads();
 #pragma unroll
-                    for (int bj = 0; bj < NB; bj++) {
-                        if (bj == p) continue;
-                        const double2 sv = *reinterpret_cast<const double2*>(Ssm + ((bj * NB + p) << 6) + frag);   // S_jp before the step
-                        sls_dmma(Sr[bj][0], Sr[bj][1], Tn[0], sv.x);                                                // S_wj -= (S_wp P) S_jp^T
-                        sls_dmma(Sr[bj][0], Sr[bj][1], Tn[1], sv.y);
-                    }
-                    Sr[p][0] = -Tn[0]; Sr[p][1] = -Tn[1];
-                } else {
+            for (int p = 0; p < NB; p++) {
+                // here: column p of the current S (blocks (j,p), j != p) and -P_p are in shared memory
+                const double2 pv2 = *reinterpret_cast<const double2*>(Pbuf + 64 * (p & 1) + frag);
+                const double Pn[2] = {pv2.x, pv2.y};           // -P, symmetric
+                const int pn = (p + 1 < NB) ? p + 1 : p;       // next pivot block (a compile-time constant after unrolling)
+                if (warp == p) {
+                    // pivot row: S_pj = P (S_jp)^T from the panel (its own stale blocks are not read)
 #pragma unroll
                     for (int bj = 0; bj < NB; bj++) {
                         if (bj == p) continue;
@@ -387,10 +396,37 @@ sls_solve_wide_kernel(SlsSolveArgs a) {
                         sls_dmma(t0, t1, Pn[1], sv.y);
                         Sr[bj][0] = -t0; Sr[bj][1] = -t1;
                     }
-                    Sr[p][0] = d0; Sr[p][1] = d1;
+                    Sr[p][0] = Pn[0]; Sr[p][1] = Pn[1];
+                    if (p + 1 < NB) *reinterpret_cast<double2*>(Ssm + ((warp * NB + p + 1) << 6) + frag) = make_double2(Sr[pn][0], Sr[pn][1]);
+                } else {
+                    double Tn[2] = {0.0, 0.0};                // -S_wp P
+                    sls_dmma(Tn[0], Tn[1], Sr[p][0], Pn[0]);
+                    sls_dmma(Tn[0], Tn[1], Sr[p][1], Pn[1]);
+                    if (p + 1 < NB && warp == p + 1) {
+                        // next pivot owner: diagonal block only, S_ww -= (S_wp P)(S_wp)^T with S_wp still in the registers
+                        sls_dmma(Sr[pn][0], Sr[pn][1], Tn[0], Sr[p][0]);
+                        sls_dmma(Sr[pn][0], Sr[pn][1], Tn[1], Sr[p][1]);
+                        Sr[p][0] = -Tn[0]; Sr[p][1] = -Tn[1];
+                        sweep_post(Sr[pn][0], Sr[pn][1], p + 1);
+                    } else {
+                        if (p + 1 < NB) {                      // the next panel column first: the owner of block p+1 is waiting for nothing else
+                            const double2 sv = *reinterpret_cast<const double2*>(Ssm + ((pn * NB + p) << 6) + frag);
+                            sls_dmma(Sr[pn][0], Sr[pn][1], Tn[0], sv.x);
+                            sls_dmma(Sr[pn][0], Sr[pn][1], Tn[1], sv.y);
+                            *reinterpret_cast<double2*>(Ssm + ((warp * NB + p + 1) << 6) + frag) = make_double2(Sr[pn][0], Sr[pn][1]);
+                        }
+#pragma unroll
+                        for (int bj = 0; bj < NB; bj++) {
+                            if (bj == p || bj == p + 1) continue;
+                            const double2 sv = *reinterpret_cast<const double2*>(Ssm + ((bj * NB + p) << 6) + frag);   // S_jp before the step
+                            sls_dmma(Sr[bj][0], Sr[bj][1], Tn[0], sv.x);                                                // S_wj -= (S_wp P) S_jp^T
+                            sls_dmma(Sr[bj][0], Sr[bj][1], Tn[1], sv.y);
+                        }
+                        Sr[p][0] = -Tn[0]; Sr[p][1] = -Tn[1];
+                    }
                 }
+                if (p + 1 < NB) __syncthreads();               // panel p+1 and -P_{p+1} are complete
             }
-            if (keep != nonempty) status |= SLS_ST_RANK_SKIPPED;
             __syncthreads();                                   // the last column panel has been read by everybody
             // (8) -Z_k: own block row to shared memory (next tap's B fragments) and to the history (register order);
             //     -Z_T goes to slot 0 (refinement sweeps)
@@ -594,7 +630,7 @@ sls_solve_wide_kernel(SlsSolveArgs a) {
             __syncthreads();
         }
         if (!(resmax <= a.feas_tol)) status |= SLS_ST_RESIDUAL;
-        if (tid == 0) { a.status[c] = status; a.resid[c] = resmax; }
+        if (tid == 0) { if (*rankflag) status |= SLS_ST_RANK_SKIPPED; a.status[c] = status; a.resid[c] = resmax; }
     }
 }
 
@@ -630,6 +666,9 @@ static int wide_launch(const SlsSolveArgs& a, int sm_count, int max_smem, int* s
 
 int sls_solve_wide_max_slots(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem) {
     switch (N / 8) {
+        case 2: return wide_resident_blocks<2>(mcap, nnzcap, T, wu, sm_count, max_smem);
+        case 3: return wide_resident_blocks<3>(mcap, nnzcap, T, wu, sm_count, max_smem);
+        case 4: return wide_resident_blocks<4>(mcap, nnzcap, T, wu, sm_count, max_smem);
         case 5: return wide_resident_blocks<5>(mcap, nnzcap, T, wu, sm_count, max_smem);
         case 6: return wide_resident_blocks<6>(mcap, nnzcap, T, wu, sm_count, max_smem);
         case 7: return wide_resident_blocks<7>(mcap, nnzcap, T, wu, sm_count, max_smem);
@@ -642,6 +681,9 @@ int sls_launch_solve_wide(int N, const SlsSolveArgs& a, int sm_count, int max_sm
     *slots_launched = 0;
     if (a.count == 0) return 0;
     switch (N / 8) {
+        case 2: return wide_launch<2>(a, sm_count, max_smem, slots_launched, stream);
+        case 3: return wide_launch<3>(a, sm_count, max_smem, slots_launched, stream);
+        case 4: return wide_launch<4>(a, sm_count, max_smem, slots_launched, stream);
         case 5: return wide_launch<5>(a, sm_count, max_smem, slots_launched, stream);
         case 6: return wide_launch<6>(a, sm_count, max_smem, slots_launched, stream);
         case 7: return wide_launch<7>(a, sm_count, max_smem, slots_launched, stream);
