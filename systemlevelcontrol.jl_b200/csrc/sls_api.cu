@@ -158,6 +158,7 @@ struct sls_handle {
     DevBuf d_flag; PinVec<int32_t> h_flag;   // set by sls_validate_supports_kernel (malformed support rows)
     rt::Event gev[4];                        // around kernel 1a and kernels 1b + scan (gather_gpu_ms)
     std::vector<void*> registered;           // host ranges page-locked through sls_host_register
+    DevBuf supp[8]; PinVec<int64_t> supp_h; int supp_cap = 0;   // scratch of sls_make_supports (kept across calls)
 };
 
 static thread_local std::string g_create_err;
@@ -229,6 +230,8 @@ extern "C" void sls_destroy(sls_handle* h) {
     h->pipe.clear();
     h->pipe_colptr.release(); h->pipe_status.release(); h->pipe_resid.release();
     h->d_wx.release(); h->d_wu.release(); h->d_flag.release(); h->h_flag.release();
+    for (DevBuf& b : h->supp) b.release();
+    h->supp_h.release();
     for (void* q : h->registered) rt::host_unregister(q);
     h->registered.clear();
     for (int i = 0; i < 4; i++) h->gev[i].destroy();
@@ -442,6 +445,7 @@ extern "C" int sls_set_supports(sls_handle* h, int64_t T,
 }
 
 // ---- supports generated on the device (README.md:52-54) ----------------------------------------
+// Scratch of sls_make_supports lives in the handle (no cudaMalloc / cudaFree per call, which also synchronise the device).
 static int make_both_families(sls_handle* h, int64_t T, const std::vector<int>& kx, const std::vector<int>& ku,
                               int nlev, int64_t* nnz_x, int64_t* nnz_u) {
     const int64_t Nx = h->Nx;
@@ -456,38 +460,52 @@ static int make_both_families(sls_handle* h, int64_t T, const std::vector<int>& 
     std::vector<int32_t> sx(nlev + 1, -1), su(nlev + 1, -1);
     for (int k = 0; k < nsx; k++) sx[dx[k]] = k;
     for (int k = 0; k < nsu; k++) su[du[k]] = k;
-    DevBuf dsx, dsu, dcpx, dcpu, dtot, doffx, doffu, dovf;
-    int e = 0;
-    auto cleanup = [&]() { DevBuf* all[] = {&dsx, &dsu, &dcpx, &dcpu, &dtot, &doffx, &doffu, &dovf}; for (DevBuf* b : all) b->release(); };
-#define MS_CK(expr) do { e = (expr); if (e) { cleanup(); return fail(h, e, #expr); } } while (0)
+    DevBuf& dsx = h->supp[0]; DevBuf& dsu = h->supp[1]; DevBuf& dcpx = h->supp[2]; DevBuf& dcpu = h->supp[3];
+    DevBuf& dtot = h->supp[4]; DevBuf& doffx = h->supp[5]; DevBuf& doffu = h->supp[6]; DevBuf& dflags = h->supp[7];
+#define MS_CK(expr) do { int e_ = (expr); if (e_) return fail(h, e_, #expr); } while (0)
     MS_CK(dsx.ensure((nlev + 1) * 4)); MS_CK(dsu.ensure((nlev + 1) * 4));
     MS_CK(dcpx.ensure((size_t)nsx * (Nx + 1) * 8)); MS_CK(dcpu.ensure((size_t)nsu * (Nx + 1) * 8));
-    MS_CK(dtot.ensure(16)); MS_CK(doffx.ensure((size_t)nsx * 8)); MS_CK(doffu.ensure((size_t)nsu * 8)); MS_CK(dovf.ensure(4));
+    MS_CK(dtot.ensure(16)); MS_CK(doffx.ensure((size_t)nsx * 8)); MS_CK(doffu.ensure((size_t)nsu * 8)); MS_CK(dflags.ensure(16));
+    MS_CK(h->supp_h.resize(4 + nsx + nsu));
     MS_CK(rt::h2d(dsx.p, sx.data(), (nlev + 1) * 4, h->stream));
     MS_CK(rt::h2d(dsu.p, su.data(), (nlev + 1) * 4, h->stream));
-    MS_CK(rt::zero(dcpx.p, (size_t)nsx * (Nx + 1) * 8, h->stream));
-    MS_CK(rt::zero(dcpu.p, (size_t)nsu * (Nx + 1) * 8, h->stream));
-    MS_CK(rt::zero(dtot.p, 16, h->stream)); MS_CK(rt::zero(dovf.p, 4, h->stream));
+    MS_CK(rt::sync(h->stream));                                // sx / su are locals
     SlsSuppArgs a{};
-    a.A = h->A.view(); a.B2r = h->B2r.view(); a.Nx = Nx; a.Nu = h->Nu; a.nlev = nlev; a.cap = 2048;
+    a.A = h->A.view(); a.B2r = h->B2r.view(); a.Nx = Nx; a.Nu = h->Nu; a.nlev = nlev;
     a.ex_slot = dsx.as<int32_t>(); a.eu_slot = dsu.as<int32_t>();
     a.xcolptr = dcpx.as<int64_t>(); a.ucolptr = dcpu.as<int64_t>();
-    a.overflow = dovf.as<int>();
-    MS_CK(sls_launch_supports(a, false, h->stream));
-    MS_CK(sls_launch_scan(dcpx.as<int64_t>(), Nx + 1, nsx, dtot.as<int64_t>(), 1, 0, Nx + 1, h->stream));
-    MS_CK(sls_launch_scan(dcpu.as<int64_t>(), Nx + 1, nsu, dtot.as<int64_t>(), 1, 0, Nx + 1, h->stream));
+    a.overflow = dflags.as<int>(); a.maxlen = dflags.as<int>() + 1;
+    a.xlast_slot = sx[kx[T - 1]]; a.ulast_slot = su[ku[T - 1]];
+    // set capacity of the per-warp scratch (3 x cap ints): start small for occupancy, double while a set overflows
     std::vector<int64_t> lastx(nsx), lastu(nsu), offx(nsx + 1, 0), offu(nsu + 1, 0);
-    int ovf = 0;
-    MS_CK(rt::d2h_strided(lastx.data(), dcpx.as<int64_t>() + Nx, 8, (size_t)(Nx + 1) * 8, (size_t)nsx, h->stream));
-    MS_CK(rt::d2h_strided(lastu.data(), dcpu.as<int64_t>() + Nx, 8, (size_t)(Nx + 1) * 8, (size_t)nsu, h->stream));
-    MS_CK(rt::d2h(&ovf, dovf.p, 4, h->stream));
-    MS_CK(rt::sync(h->stream));
-    if (ovf) { cleanup(); return fail(h, -4, "sls_make_supports: a reachability set does not fit shared memory"); }
-    for (int k = 0; k < nsx; k++) offx[k + 1] = offx[k] + lastx[k] - 1;
-    for (int k = 0; k < nsu; k++) offu[k + 1] = offu[k] + lastu[k] - 1;
+    int64_t* hs = h->supp_h.data();                            // pinned: [0] overflow|maxlen x|maxlen u (ints), [2..] last colptr entries
+    int cap = h->supp_cap > 0 ? h->supp_cap : 128;
+    for (;;) {
+        a.cap = cap;
+        MS_CK(rt::zero(dcpx.p, (size_t)nsx * (Nx + 1) * 8, h->stream));
+        MS_CK(rt::zero(dcpu.p, (size_t)nsu * (Nx + 1) * 8, h->stream));
+        MS_CK(rt::zero(dtot.p, 16, h->stream)); MS_CK(rt::zero(dflags.p, 16, h->stream));
+        MS_CK(sls_launch_supports(a, false, h->stream));
+        MS_CK(sls_launch_scan(dcpx.as<int64_t>(), Nx + 1, nsx, dtot.as<int64_t>(), 1, 0, Nx + 1, h->stream));
+        MS_CK(sls_launch_scan(dcpu.as<int64_t>(), Nx + 1, nsu, dtot.as<int64_t>(), 1, 0, Nx + 1, h->stream));
+        MS_CK(sls_kcopy(hs, dflags.p, 16, h->stream));
+        MS_CK(sls_kgather64(hs + 2, dcpx.as<int64_t>() + Nx, (size_t)(Nx + 1), nsx, h->stream));
+        MS_CK(sls_kgather64(hs + 2 + nsx, dcpu.as<int64_t>() + Nx, (size_t)(Nx + 1), nsu, h->stream));
+        MS_CK(rt::sync(h->stream));
+        const int32_t* fl = reinterpret_cast<const int32_t*>(hs);
+        if (!fl[0]) break;
+        if ((size_t)4 * 3 * (cap * 2) * sizeof(int32_t) > (size_t)h->max_smem)
+            return fail(h, -4, "sls_make_supports: a reachability set does not fit shared memory");
+        cap *= 2;
+    }
+    h->supp_cap = cap;
+    const int32_t* fl = reinterpret_cast<const int32_t*>(hs);
+    for (int k = 0; k < nsx; k++) { lastx[k] = hs[2 + k]; offx[k + 1] = offx[k] + lastx[k] - 1; }
+    for (int k = 0; k < nsu; k++) { lastu[k] = hs[2 + nsx + k]; offu[k + 1] = offu[k] + lastu[k] - 1; }
     DevSupports& X = h->Sx; DevSupports& U = h->Su;
     X.row_off = U.row_off = 0;
     X.nnz = offx[nsx]; U.nnz = offu[nsu]; X.has_nzval = U.has_nzval = false;
+    X.maxlen_last = fl[1]; U.maxlen_last = fl[2];
     MS_CK(X.rowval.ensure(std::max<int64_t>(X.nnz, 1) * 8));
     MS_CK(U.rowval.ensure(std::max<int64_t>(U.nnz, 1) * 8));
     MS_CK(rt::h2d(doffx.p, offx.data(), (size_t)nsx * 8, h->stream));
@@ -510,20 +528,8 @@ static int make_both_families(sls_handle* h, int64_t T, const std::vector<int>& 
     X.h_tap_off[T] = X.nnz; U.h_tap_off[T] = U.nnz;
     MS_CK(rt::h2d(X.tap_off.p, X.h_tap_off.data(), (T + 1) * 8, h->stream));
     MS_CK(rt::h2d(U.tap_off.p, U.h_tap_off.data(), (T + 1) * 8, h->stream));
-    // longest column of the last tap of each family (bounds kernel 1's candidate list)
-    {
-        std::vector<int64_t> cpx(Nx + 1), cpu_(Nx + 1);
-        MS_CK(rt::d2h(cpx.data(), dcpx.as<int64_t>() + (int64_t)sx[kx[T - 1]] * (Nx + 1), (Nx + 1) * 8, h->stream));
-        MS_CK(rt::d2h(cpu_.data(), dcpu.as<int64_t>() + (int64_t)su[ku[T - 1]] * (Nx + 1), (Nx + 1) * 8, h->stream));
-        MS_CK(rt::d2h(&ovf, dovf.p, 4, h->stream));
-        MS_CK(rt::sync(h->stream));
-        int mlx = 0, mlu = 0;
-        for (int64_t c = 0; c < Nx; c++) { mlx = std::max<int>(mlx, (int)(cpx[c + 1] - cpx[c])); mlu = std::max<int>(mlu, (int)(cpu_[c + 1] - cpu_[c])); }
-        X.maxlen_last = mlx; U.maxlen_last = mlu;
-    }
+    MS_CK(rt::sync(h->stream));                                // offx / offu are locals
 #undef MS_CK
-    cleanup();
-    if (ovf) return fail(h, -4, "sls_make_supports: a reachability set does not fit shared memory");
     return 0;
 }
 
@@ -1458,9 +1464,9 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     if (h->have_weights) return fail(h, -1, "sls_simulate: not available with cost weights (the plant on the device is the scaled one)");
     if (nscen == 0) return 0;
     const Plan& p = h->plan;
-    DevBuf dcol, dtime, dnw, dnu, dxn, dun, dxo, duo, dovf, dW, dWu, dnent, dtapcnt, dpkoff, dpkcnt, dpkrow, dpkval;
+    DevBuf dcol, dtime, dnw, dnu, dxn, dun, dxo, duo, dovf, dW, dWu, dnent, dtapcnt, dpkoff, dpkcnt, dpkrow, dpkval, dctav, dctam;
     int e = 0;
-    auto cleanup = [&]() { DevBuf* all[] = {&dcol, &dtime, &dnw, &dnu, &dxn, &dun, &dxo, &duo, &dovf, &dW, &dWu, &dnent, &dtapcnt, &dpkoff, &dpkcnt, &dpkrow, &dpkval}; for (DevBuf* b : all) b->release(); };
+    auto cleanup = [&]() { DevBuf* all[] = {&dcol, &dtime, &dnw, &dnu, &dxn, &dun, &dxo, &duo, &dovf, &dW, &dWu, &dnent, &dtapcnt, &dpkoff, &dpkcnt, &dpkrow, &dpkval, &dctav, &dctam}; for (DevBuf* b : all) b->release(); };
 #define SIM_CK(expr) do { e = (expr); if (e) { cleanup(); return fail(h, e, #expr); } } while (0)
     h->ev[2].record(h->stream);
     SIM_CK(dcol.ensure(nscen * 8)); SIM_CK(dtime.ensure(nscen * 8));
@@ -1549,9 +1555,15 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     // fast path: the scenario's packed window fits shared memory -> one CTA per scenario, Phi read from HBM once
     const int nent_cap = (int)((nent_max + 1) & ~(int64_t)1);
     const bool cta_path = !getenv("SLS_SIM_STREAM") && 2 * T <= 256 && wcap <= 256 && ucap <= 256 && nent_max < ((int64_t)1 << 24) &&
-                          sls_sim_cta_smem(nent_cap, wcap, ucap, (int)T) <= (size_t)h->max_smem;
-    if (cta_path) SIM_CK(sls_launch_sim_cta(a, wcap, ucap, nent_cap, h->sm_count, h->stream));
-    else SIM_CK(sls_launch_sim(a, cap2, wcap, ucap, h->stream));
+                          sls_sim_cta_smem(0, wcap, ucap, (int)T) <= (size_t)h->max_smem;
+    if (cta_path) {
+        if (getenv("SLS_SIM_GLOBAL") || sls_sim_cta_smem(nent_cap, wcap, ucap, (int)T) > (size_t)h->max_smem) {
+            const size_t grid = (size_t)std::min<int64_t>(nscen, h->sm_count);
+            SIM_CK(dctav.ensure(grid * nent_cap * 8)); SIM_CK(dctam.ensure(grid * nent_cap * 2));
+            a.cta_vals = dctav.as<double>(); a.cta_meta = dctam.as<uint16_t>();
+        }
+        SIM_CK(sls_launch_sim_cta(a, wcap, ucap, nent_cap, h->sm_count, h->stream));
+    } else SIM_CK(sls_launch_sim(a, cap2, wcap, ucap, h->stream));
     h->ev[1].record(h->stream);
     int ovf = 0;
     SIM_CK(rt::d2h(&ovf, dovf.p, 4, h->stream));

@@ -88,13 +88,15 @@ struct SlsSimArgs {
     const uint16_t* pk_cnt;                     // [nscen][2T][wcap] packed entries per (tap, window column)
     const uint16_t* pk_row; const double* pk_val;   // packed Phi restricted to the window: local row, value
     int* overflow;
+    double* cta_vals; uint16_t* cta_meta;       // CTA kernel: per-CTA scratch for the row-ordered window when it does not fit
+                                                // shared memory ([grid][nent_cap] each; the wave's windows then live in L2), or null
 };
 __host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, int T);
 int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, int32_t* Wg, int32_t* Wug,
                         int wcap, int ucap, sls_stream_t stream);
 int sls_launch_sim(const SlsSimArgs& a, int cap, int wcap, int ucap, sls_stream_t stream);
 // fast path: one CTA per scenario, packed Phi window resident in shared memory (needs 2T <= 256, windows <= 256, nent_cap entries fit)
-size_t sls_sim_cta_smem(int nent_cap, int wcap, int ucap, int T);
+size_t sls_sim_cta_smem(int nent_cap, int wcap, int ucap, int T);   // nent_cap = 0: window in the global scratch
 int sls_launch_sim_cta(const SlsSimArgs& a, int wcap, int ucap, int nent_cap, int sm_count, sls_stream_t stream);
 int sls_launch_sim_pack(const SlsSimArgs& a, bool fill, int wcap, int ucap, int64_t* nent, uint32_t* tapcnt, const int64_t* pk_off,
                         uint16_t* pk_cnt, uint16_t* pk_row, double* pk_val, sls_stream_t stream);
@@ -110,5 +112,7 @@ struct SlsSuppArgs {
     int64_t* xrow; int64_t* urow;           // rowval of all slots back to back (fill pass)
     const int64_t* xoff; const int64_t* uoff;   // [nslots] offsets of each slot inside xrow / urow
     int* overflow;
+    int xlast_slot, ulast_slot;       // pattern slots of the last tap: their longest column goes to maxlen[0], maxlen[1]
+    int* maxlen;
 };
 int sls_launch_supports(const SlsSuppArgs& a, bool fill, sls_stream_t stream);

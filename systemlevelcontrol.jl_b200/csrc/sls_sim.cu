@@ -362,9 +362,11 @@ sls_sim_cta_kernel(SlsSimArgs a, int wcap, int ucap, int nent_cap) {
     SLS_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.T;
-    const SlsSimCtaLayout L(nent_cap, wcap, ucap, T);
-    double* vals = reinterpret_cast<double*>(smem + L.oVal);
-    uint16_t* meta = reinterpret_cast<uint16_t*>(smem + L.oMeta);
+    const SlsSimCtaLayout L(a.cta_vals ? 0 : nent_cap, wcap, ucap, T);
+    // the row-ordered window: shared memory when it fits, else this CTA's slice of a global scratch (148 CTAs x ~260 KB stay
+    // L2-resident, where the one-warp-per-scenario kernel's 4 096 concurrent windows did not)
+    double* vals = a.cta_vals ? a.cta_vals + (size_t)blockIdx.x * nent_cap : reinterpret_cast<double*>(smem + L.oVal);
+    uint16_t* meta = a.cta_meta ? a.cta_meta + (size_t)blockIdx.x * nent_cap : reinterpret_cast<uint16_t*>(smem + L.oMeta);
     double* what = reinterpret_cast<double*>(smem + L.oWhat);
     double* x = reinterpret_cast<double*>(smem + L.oX);
     double* xn = reinterpret_cast<double*>(smem + L.oXn);
@@ -479,7 +481,7 @@ sls_sim_cta_kernel(SlsSimArgs a, int wcap, int ucap, int nent_cap) {
                 double acc = 0.0;
                 if (r < nrows) {
                     const int e1 = rowptr[r + 1];
-#pragma unroll 1
+#pragma unroll 4
                     for (int e = rowptr[r] + (tid & 3); e < e1; e += 4) {
                         const int mt = meta[e];
                         const int sb = slot[mt >> 8];
@@ -540,7 +542,7 @@ sls_sim_cta_kernel(SlsSimArgs a, int wcap, int ucap, int nent_cap) {
 
 int sls_launch_sim_cta(const SlsSimArgs& a, int wcap, int ucap, int nent_cap, int sm_count, sls_stream_t stream) {
     if (a.nscen == 0) return 0;
-    const size_t smem = sls_sim_cta_smem(nent_cap, wcap, ucap, a.T);
+    const size_t smem = sls_sim_cta_smem(a.cta_vals ? 0 : nent_cap, wcap, ucap, a.T);
     auto kp = &sls_sim_cta_kernel;
     if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
     const int grid = a.nscen < sm_count ? a.nscen : sm_count;

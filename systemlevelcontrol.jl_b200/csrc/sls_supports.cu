@@ -60,7 +60,7 @@ sls_supp_kernel(SlsSuppArgs a) {
         const int xs = a.ex_slot[s], us = a.eu_slot[s];
         if (xs >= 0) {
             int64_t* cp = a.xcolptr + (int64_t)xs * (a.Nx + 1);
-            if (!FILL) { if (lane == 0) cp[j] = n; }
+            if (!FILL) { if (lane == 0) { cp[j] = n; if (xs == a.xlast_slot) atomicMax(a.maxlen, n); } }
             else {
                 int64_t* dst = a.xrow + a.xoff[xs] + cp[j] - 1;
 #pragma unroll 1
@@ -71,7 +71,7 @@ sls_supp_kernel(SlsSuppArgs a) {
             const int m = sls_supp_expand(a.B2r, cur, n, ub, a.cap);
             if (m < 0) { if (lane == 0) atomicOr(a.overflow, 1); return; }
             int64_t* cp = a.ucolptr + (int64_t)us * (a.Nx + 1);
-            if (!FILL) { if (lane == 0) cp[j] = m; }
+            if (!FILL) { if (lane == 0) { cp[j] = m; if (us == a.ulast_slot) atomicMax(a.maxlen + 1, m); } }
             else {
                 int64_t* dst = a.urow + a.uoff[us] + cp[j] - 1;
 #pragma unroll 1
