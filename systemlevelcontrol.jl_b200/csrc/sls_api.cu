@@ -159,6 +159,7 @@ struct sls_handle {
     rt::Event gev[4];                        // around kernel 1a and kernels 1b + scan (gather_gpu_ms)
     std::vector<void*> registered;           // host ranges page-locked through sls_host_register
     DevBuf supp[8]; PinVec<int64_t> supp_h; int supp_cap = 0;   // scratch of sls_make_supports (kept across calls)
+    DevBuf simb[17];                                            // scratch of sls_simulate (kept across calls)
 };
 
 static thread_local std::string g_create_err;
@@ -231,6 +232,7 @@ extern "C" void sls_destroy(sls_handle* h) {
     h->pipe_colptr.release(); h->pipe_status.release(); h->pipe_resid.release();
     h->d_wx.release(); h->d_wu.release(); h->d_flag.release(); h->h_flag.release();
     for (DevBuf& b : h->supp) b.release();
+    for (DevBuf& b : h->simb) b.release();
     h->supp_h.release();
     for (void* q : h->registered) rt::host_unregister(q);
     h->registered.clear();
@@ -1464,9 +1466,15 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     if (h->have_weights) return fail(h, -1, "sls_simulate: not available with cost weights (the plant on the device is the scaled one)");
     if (nscen == 0) return 0;
     const Plan& p = h->plan;
-    DevBuf dcol, dtime, dnw, dnu, dxn, dun, dxo, duo, dovf, dW, dWu, dnent, dtapcnt, dpkoff, dpkcnt, dpkrow, dpkval, dctav, dctam;
+    // scratch lives in the handle and is reused by later calls (no cudaMalloc / cudaFree — and the device synchronisation
+    // they imply — per call); the dense trajectory buffers (x_out / u_out: test-sized) are the exception
+    DevBuf& dcol = h->simb[0]; DevBuf& dtime = h->simb[1]; DevBuf& dnw = h->simb[2]; DevBuf& dnu = h->simb[3]; DevBuf& dxn = h->simb[4];
+    DevBuf& dun = h->simb[5]; DevBuf& dovf = h->simb[6]; DevBuf& dW = h->simb[7]; DevBuf& dWu = h->simb[8]; DevBuf& dnent = h->simb[9];
+    DevBuf& dtapcnt = h->simb[10]; DevBuf& dpkoff = h->simb[11]; DevBuf& dpkcnt = h->simb[12]; DevBuf& dpkrow = h->simb[13];
+    DevBuf& dpkval = h->simb[14]; DevBuf& dctav = h->simb[15]; DevBuf& dctam = h->simb[16];
+    DevBuf dxo, duo;
     int e = 0;
-    auto cleanup = [&]() { DevBuf* all[] = {&dcol, &dtime, &dnw, &dnu, &dxn, &dun, &dxo, &duo, &dovf, &dW, &dWu, &dnent, &dtapcnt, &dpkoff, &dpkcnt, &dpkrow, &dpkval, &dctav, &dctam}; for (DevBuf* b : all) b->release(); };
+    auto cleanup = [&]() { dxo.release(); duo.release(); };
 #define SIM_CK(expr) do { e = (expr); if (e) { cleanup(); return fail(h, e, #expr); } } while (0)
     h->ev[2].record(h->stream);
     SIM_CK(dcol.ensure(nscen * 8)); SIM_CK(dtime.ensure(nscen * 8));
@@ -1551,19 +1559,22 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     a.xnorm = dxn.as<double>(); a.unorm = dun.as<double>();
     if (x_out) { SIM_CK(dxo.ensure(nn * Nx * 8)); SIM_CK(rt::zero(dxo.p, nn * Nx * 8, h->stream)); a.xout = dxo.as<double>(); }
     if (u_out) { SIM_CK(duo.ensure(nn * std::max<int64_t>(Nu, 1) * 8)); SIM_CK(rt::zero(duo.p, nn * std::max<int64_t>(Nu, 1) * 8, h->stream)); a.uout = duo.as<double>(); }
-    h->ev[0].record(h->stream);
-    // fast path: the scenario's packed window fits shared memory -> one CTA per scenario, Phi read from HBM once
+    // fast path: one CTA per scenario, the packed window read from HBM once (then shared-memory or L2 resident)
     const int nent_cap = (int)((nent_max + 1) & ~(int64_t)1);
     const bool cta_path = !getenv("SLS_SIM_STREAM") && 2 * T <= 256 && wcap <= 256 && ucap <= 256 && nent_max < ((int64_t)1 << 24) &&
                           sls_sim_cta_smem(0, wcap, ucap, (int)T) <= (size_t)h->max_smem;
     if (cta_path) {
         if (getenv("SLS_SIM_GLOBAL") || sls_sim_cta_smem(nent_cap, wcap, ucap, (int)T) > (size_t)h->max_smem) {
-            const size_t grid = (size_t)std::min<int64_t>(nscen, h->sm_count);
+            const size_t grid = (size_t)std::min<int64_t>(nscen, 2 * h->sm_count);
             SIM_CK(dctav.ensure(grid * nent_cap * 8)); SIM_CK(dctam.ensure(grid * nent_cap * 2));
             a.cta_vals = dctav.as<double>(); a.cta_meta = dctam.as<uint16_t>();
         }
+        h->ev[0].record(h->stream);
         SIM_CK(sls_launch_sim_cta(a, wcap, ucap, nent_cap, h->sm_count, h->stream));
-    } else SIM_CK(sls_launch_sim(a, cap2, wcap, ucap, h->stream));
+    } else {
+        h->ev[0].record(h->stream);
+        SIM_CK(sls_launch_sim(a, cap2, wcap, ucap, h->stream));
+    }
     h->ev[1].record(h->stream);
     int ovf = 0;
     SIM_CK(rt::d2h(&ovf, dovf.p, 4, h->stream));

@@ -357,7 +357,7 @@ struct SlsSimCtaLayout {
 };
 size_t sls_sim_cta_smem(int nent_cap, int wcap, int ucap, int T) { return (size_t)SlsSimCtaLayout(nent_cap, wcap, ucap, T).total; }
 
-__global__ void __launch_bounds__(SIMC_NT, 1)
+__global__ void __launch_bounds__(SIMC_NT, 2)
 sls_sim_cta_kernel(SlsSimArgs a, int wcap, int ucap, int nent_cap) {
     SLS_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -481,8 +481,8 @@ sls_sim_cta_kernel(SlsSimArgs a, int wcap, int ucap, int nent_cap) {
                 double acc = 0.0;
                 if (r < nrows) {
                     const int e1 = rowptr[r + 1];
-#pragma unroll 4
-                    for (int e = rowptr[r] + (tid & 3); e < e1; e += 4) {
+#pragma unroll 8
+                    for (int e = rowptr[r] + (tid & 3); e < e1; e += 4) {        // (unrolled: 8 independent L2 loads in flight per lane)
                         const int mt = meta[e];
                         const int sb = slot[mt >> 8];
                         if (sb >= 0) acc = fma(vals[e], what[sb + (mt & 255)], acc);
@@ -545,7 +545,8 @@ int sls_launch_sim_cta(const SlsSimArgs& a, int wcap, int ucap, int nent_cap, in
     const size_t smem = sls_sim_cta_smem(a.cta_vals ? 0 : nent_cap, wcap, ucap, a.T);
     auto kp = &sls_sim_cta_kernel;
     if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
-    const int grid = a.nscen < sm_count ? a.nscen : sm_count;
+    const int per_sm = a.cta_vals ? 2 : 1;                   // L2 mode: two CTAs per SM hide the L2 latency; 2 x 148 windows still fit L2
+    const int grid = a.nscen < per_sm * sm_count ? a.nscen : per_sm * sm_count;
     SLS_LAUNCH(kp, grid, SIMC_NT, smem, stream, a, wcap, ucap, nent_cap);
     return rt::last_error();
 }
