@@ -966,7 +966,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         SlsScatterArgs s{};
         s.P = v; s.c_begin = 0; s.c_end = p.ncols;
         s.rowval = reinterpret_cast<int64_t* const*>(h->out_ptrs.as<void*>());
-        s.row_off_x = h->Sx.row_off; s.row_off_u = h->Su.row_off;
+        s.row_off_x = h->Sx.row_off; s.row_off_u = h->Su.row_off; s.sorted = p.cols_sorted ? 1 : 0;
         h->ev[5].record(h->copy_stream);
         SLS_CK(sls_launch_scatter(s, h->copy_stream));
         h->chunk_ev[15].record(h->copy_stream);
@@ -1303,7 +1303,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
             SlsScatterArgs sa{};
             sa.P = v; sa.c_begin = 0; sa.c_end = p.ncols;
             sa.rowval = reinterpret_cast<int64_t* const*>(x.out_ptrs.as<void*>());
-            sa.row_off_x = h->Sx.row_off; sa.row_off_u = h->Su.row_off;
+            sa.row_off_x = h->Sx.row_off; sa.row_off_u = h->Su.row_off; sa.sorted = p.cols_sorted ? 1 : 0;
             PIPE_CK(sls_launch_scatter(sa, h->scat_stream));
         }
         x.ev_scat.record(h->scat_stream);

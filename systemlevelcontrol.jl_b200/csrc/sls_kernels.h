@@ -59,6 +59,7 @@ struct SlsScatterArgs {
     // destination arrays: per tap tt in [0,2T): base pointers (device arrays of pointers)
     int64_t* const* rowval;  // [2T] -> int64 rowval buffers (1-based out)
     int64_t row_off_x, row_off_u;   // added to the stored rows (global numbering of a sub-plant window's outputs)
+    int sorted;              // the planned columns ascend: 32 consecutive planned columns own one contiguous rowval range
 };
 int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream);
 int sls_launch_unscale(const SlsPlanView& P, int c_begin, int c_end, const int64_t* const* rowval, double* const* nzval,

@@ -134,6 +134,17 @@ def check_error_paths(api):
         syn.close()
 
 
+def check_unsorted_plan(api):
+    """A column list in arbitrary order (kernel 3's non-contiguous store path) gives the same Φ as the sorted list, bit for bit."""
+    A, B1, B2, S = chain(40)
+    P = slc_b200.Plant(A, B1, B2)
+    cols = [35, 3, 20, 21, 0, 39, 7]
+    X1, U1 = slc_b200.SLS_H2(P, S, I=[[c] for c in cols], api=api)
+    X2, U2 = slc_b200.SLS_H2(P, S, I=[[c] for c in sorted(cols)], api=api)
+    for a, b in zip(X1 + U1, X2 + U2):
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)
+
+
 def check_masks_and_flags(api):
     """stored-false support entries, stored zeros in A, non-nested supports, an infeasible column."""
     A, B1, B2, S = chain(59)

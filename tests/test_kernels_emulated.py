@@ -40,6 +40,7 @@ def test_emu_error_paths(emu_api):
 
 def test_emu_masks_and_flags(emu_api):
     pc.check_masks_and_flags(emu_api)
+    pc.check_unsorted_plan(emu_api)
 
 
 def test_emu_closed_loop_simulation(emu_api):

@@ -131,6 +131,7 @@ def test_error_paths(cuda_api):
 
 def test_masks_and_flags(cuda_api):
     pc.check_masks_and_flags(cuda_api)
+    pc.check_unsorted_plan(cuda_api)
 
 
 def test_config2_chain_5000(cuda_api):
