@@ -43,7 +43,9 @@ typedef struct sls_options {
     int32_t device;      /* CUDA device ordinal                                                        */
     int32_t flags;       /* bit 0: also validate the supports' rowval (range, strictly ascending) on the host;
                             bit 1: sls_solve copies the outputs back after kernel 2 instead of chunk by chunk;
-                            bit 2: no refinement sweeps in kernel 2 (columns whose residual exceeds feas_tol are only flagged) */
+                            bit 2: no refinement sweeps in kernel 2 (columns whose residual exceeds feas_tol are only flagged);
+                            bit 3: measurement mode — sls_solve* runs kernel 3 alone before kernel 2 instead of beside it, so
+                                   that sls_timing.scatter_ms is its stand-alone device time */
     double  rank_tol;    /* pivot <= rank_tol * diag(D_k) => constraint row treated as redundant; 0 -> 1e-10 */
     double  feas_tol;    /* max-abs achievability residual above which SLS_STATUS_RESIDUAL is set; 0 -> 1e-12.  Columns above
                             feas_tol / 10 first take up to 3 refinement sweeps on the stored factors (flags bit 2: none) */

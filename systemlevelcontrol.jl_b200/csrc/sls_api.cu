@@ -78,7 +78,9 @@ struct SolveClass { int N, count, mcap, nnzcap; size_t list_off; };
 struct Plan {
     bool valid = false;
     int ncols = 0, nstride = 1, mstride = 1, wx = 1, wu = 1, nmax = 0, mmax = 0, cap = 32;
-    DevBuf cols, n, m, sx, su, maskx, masku, jloc, lnnz, lnnzA, lnnzB, pre, tot, colptr, lists, keepx, keepu;
+    DevBuf cols, n, m, sx, su, maskx, masku, jloc, lnnz, lnnzA, lnnzB, pre, tot, colptr, lists, keepx, keepu, stats;
+    PinVec<int32_t> h_stats;            // [36] plan statistics computed by kernel 1a (sls_gather.cu)
+    bool sizes_on_host = false, lists_on_host = false;   // h_n / h_m and h_lists are fetched on demand
     PinVec<int32_t> h_cols, h_lists;    // pinned: read by kernel copies (sls_kcopy)
     bool cols_sorted = true;            // planned columns strictly ascending => a planned-index range is a CSC column range
     PinVec<int32_t> h_status; PinVec<double> h_resid;
@@ -95,7 +97,8 @@ struct Plan {
     int64_t col_lo = 0, col_hi = 0;     // planned columns lie in [col_lo, col_hi)
     int identity_cols = 0;              // h_cols currently holds 0..identity_cols-1 (the cols == NULL plan)
     void release() {
-        DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists, &keepx, &keepu};
+        DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists, &keepx, &keepu, &stats};
+        h_stats.release();
         for (DevBuf* b : all) b->release();
         h_seg.release(); h_status.release(); h_resid.release(); h_cols.release(); h_lists.release();
         h_n.release(); h_m.release(); h_lnnz.release(); h_lA.release(); h_lB.release(); h_tot.release(); h_last.release();
@@ -657,37 +660,29 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     // kernel 1a leaves the index sets for kernel 1b (row stride cap) unless that would take more than 1 GB
     const bool keep = (size_t)nc1 * cap * 2 * sizeof(int32_t) <= ((size_t)1 << 30);
     if (keep) { SLS_CK(p.keepx.ensure((size_t)nc1 * cap * sizeof(int32_t))); SLS_CK(p.keepu.ensure((size_t)nc1 * cap * sizeof(int32_t))); }
+    SLS_CK(p.stats.ensure(36 * sizeof(int32_t))); SLS_CK(p.h_stats.resize(36));
+    SLS_CK(p.lists.ensure(nc1 * sizeof(int32_t)));
+    SLS_CK(rt::zero(p.stats.p, 36 * sizeof(int32_t), h->stream));
     h->gev[0].record(h->stream);
     SLS_CK(sls_launch_gather_count(h->A.view(), h->Sx.view(), h->Su.view(), (int)T, Nx, p.cols.as<int32_t>(), p.ncols,
                                    p.n.as<int32_t>(), p.m.as<int32_t>(), cap, keep ? p.keepx.as<int32_t>() : nullptr,
-                                   keep ? p.keepu.as<int32_t>() : nullptr, h->d_flag.as<int32_t>(), h->stream));
+                                   keep ? p.keepu.as<int32_t>() : nullptr, h->d_flag.as<int32_t>(), p.stats.as<int32_t>(), h->stream));
     h->gev[1].record(h->stream);
     SLS_CK(sls_kcopy(h->h_flag.data(), h->d_flag.p, sizeof(int32_t), h->stream));
-    SLS_CK(p.h_n.resize(nc1)); SLS_CK(p.h_m.resize(nc1));
-    p.h_n[0] = 0; p.h_m[0] = 0;
-    SLS_CK(sls_kcopy(p.h_n.data(), p.n.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
-    SLS_CK(sls_kcopy(p.h_m.data(), p.m.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    // sizes, class histogram and the kernel-2 work lists stay on the device; the host reads 36 integers
+    SLS_CK(sls_kcopy(p.h_stats.data(), p.stats.p, 36 * sizeof(int32_t), h->stream));
+    SLS_CK(sls_launch_class_lists(p.n.as<int32_t>(), p.ncols, p.stats.as<int32_t>(), sls_solve_class_count(), p.lists.as<int32_t>(), h->stream));
+    p.sizes_on_host = false; p.lists_on_host = false;
     if (trace) t1 = now();
     SLS_CK(rt::sync(h->stream));
     if (trace) t2 = now();
     if (h->h_flag[0]) return fail(h, -2, "plan: support rowval out of range or not strictly ascending inside a column");
-    int nmax = 0, mmax = 0;
-    // one pass over the sizes: maxima, overflow check and the histogram of kernel 2's size classes (class = ceil(n/8) - 1;
-    // everything beyond the last class lands in a catch-all bin and is rejected by sls_solve)
     const int nk_ = sls_solve_class_count();
+    const int32_t* st = p.h_stats.data();
+    if (st[2]) return fail(h, -4, "plan: candidate index list overflow in kernel 1");
+    const int nmax = st[0], mmax = st[1];
     int cls_count[16] = {0};
-    {
-        int bad = 0;
-        const int32_t* hn = p.h_n.data(); const int32_t* hm = p.h_m.data();
-        for (int i = 0; i < p.ncols; i++) {
-            const int n_ = hn[i], m_ = hm[i];
-            bad |= (n_ | m_);
-            nmax = std::max(nmax, n_); mmax = std::max(mmax, m_);
-            int k = n_ > 0 ? (n_ - 1) >> 3 : 0;
-            cls_count[k < nk_ ? k : nk_]++;
-        }
-        if (bad < 0) return fail(h, -4, "plan: candidate index list overflow in kernel 1");
-    }
+    for (int k = 0; k < 16; k++) cls_count[k < nk_ ? k : nk_] += st[4 + k];
     p.nmax = nmax; p.mmax = mmax;
     p.nstride = std::max(nmax, 1); p.mstride = std::max(mmax, 1);
     p.wx = (p.nstride + 31) / 32; p.wu = (p.mstride + 31) / 32;
@@ -724,29 +719,16 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     SLS_CK(sls_kcopy(tot.data() + p.ncols, p.tot.as<int64_t>() + p.ncols, sizeof(int64_t), h->stream));
     SLS_CK(sls_kgather64(p.h_last.data(), v.colptr + Nx, (size_t)(Nx + 1), (int)(2 * T), h->stream));
     (void)lA; (void)lB;
-    // size classes of kernel 2 (by n, known since the count pass): binned on the host while kernel 1b runs
+    // size classes of kernel 2 (by n): counts and largest m per class from kernel 1a's statistics; the lists were written
+    // by sls_class_lists_kernel (ascending inside a class, classes back to back)
     p.classes.clear();
-    SLS_CK(p.h_lists.resize(nc1));
     {
         size_t off = 0;
-        const int nk = nk_;
-        std::vector<SolveClass> cls(nk);
-        int fillpos[17], mcapk[17] = {0};
-        for (int k = 0; k < nk; k++) { cls[k] = SolveClass{sls_solve_class_N(k), cls_count[k], 0, 0, off}; fillpos[k] = (int)off; off += cls_count[k]; }
-        fillpos[nk] = -1;
-        {
-            const int32_t* hn = p.h_n.data(); const int32_t* hm = p.h_m.data(); int32_t* hl = p.h_lists.data();
-            for (int i = 0; i < p.ncols; i++) {
-                const int n_ = hn[i];
-                int k = n_ > 0 ? (n_ - 1) >> 3 : 0;
-                if (k >= nk) continue;                         // larger than the largest class: reported by sls_solve (nmax check)
-                hl[fillpos[k]++] = i;
-                mcapk[k] = std::max(mcapk[k], hm[i]);
-            }
+        for (int k = 0; k < nk_; k++) {
+            SolveClass c_{sls_solve_class_N(k), cls_count[k], st[20 + k], 0, off};
+            off += cls_count[k];
+            if (c_.count) p.classes.push_back(c_);
         }
-        for (int k = 0; k < nk; k++) { cls[k].mcap = mcapk[k]; if (cls[k].count) p.classes.push_back(cls[k]); }
-        SLS_CK(p.lists.ensure(nc1 * sizeof(int32_t)));
-        SLS_CK(sls_kcopy(p.lists.p, p.h_lists.data(), off * sizeof(int32_t), h->stream));
     }
     if (trace) t4 = now();
     SLS_CK(rt::sync(h->stream));
@@ -767,9 +749,33 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     return 0;
 }
 
+// per-column sizes / kernel-2 lists on the host: only for callers that ask (sls_plan's n_out / m_out, sls_reduce,
+// sls_local_problem, the statistics, the chunk boundaries of sls_solve's D2H pipeline)
+static int plan_fetch_sizes(sls_handle* h, Plan& p) {
+    if (p.sizes_on_host) return 0;
+    const int nc1 = std::max(p.ncols, 1);
+    SLS_CK(p.h_n.resize(nc1)); SLS_CK(p.h_m.resize(nc1));
+    p.h_n[0] = 0; p.h_m[0] = 0;
+    SLS_CK(sls_kcopy(p.h_n.data(), p.n.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(sls_kcopy(p.h_m.data(), p.m.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(rt::sync(h->stream));
+    p.sizes_on_host = true;
+    return 0;
+}
+static int plan_fetch_lists(sls_handle* h, Plan& p) {
+    if (p.lists_on_host) return 0;
+    const int nc1 = std::max(p.ncols, 1);
+    SLS_CK(p.h_lists.resize(nc1));
+    SLS_CK(sls_kcopy(p.h_lists.data(), p.lists.p, (size_t)p.ncols * sizeof(int32_t), h->stream));
+    SLS_CK(rt::sync(h->stream));
+    p.lists_on_host = true;
+    return 0;
+}
+
 // SURVEY §8d algorithmic work of a plan (reported by sls_get_timing; not needed to run the kernels)
 static void plan_stats(sls_handle* h, Plan& p, int64_t T) {
     if (p.stats_valid) return;
+    if (plan_fetch_sizes(h, p)) return;
     p.alg_flops = 0; p.alg_bytes = 0;
     if (p.ncols > 0) {
         int e = sls_kcopy(p.h_lnnz.data(), p.lnnz.p, (size_t)p.ncols * sizeof(int32_t), h->stream);
@@ -806,9 +812,13 @@ extern "C" int sls_plan(sls_handle* h, const int64_t* cols, int64_t ncols,
         if (nnz_x) nnz_x[t] = h->plan.nnz_tap[t];
         if (nnz_u) nnz_u[t] = h->plan.nnz_tap[T + t];
     }
-    for (int i = 0; i < h->plan.ncols; i++) {
-        if (n_out) n_out[i] = h->plan.h_n[i];
-        if (m_out) m_out[i] = h->plan.h_m[i];
+    if (n_out || m_out) {
+        e = plan_fetch_sizes(h, h->plan);
+        if (e) return e;
+        for (int i = 0; i < h->plan.ncols; i++) {
+            if (n_out) n_out[i] = h->plan.h_n[i];
+            if (m_out) m_out[i] = h->plan.h_m[i];
+        }
     }
     return 0;
 }
@@ -831,6 +841,8 @@ extern "C" int sls_reduce(sls_handle* h, const int64_t* cj, int64_t q,
     }
     Plan p;
     int e = build_plan(h, p, cju.data(), (int64_t)cju.size(), false);
+    if (e) { p.release(); return e; }
+    e = plan_fetch_sizes(h, p);
     if (e) { p.release(); return e; }
     std::vector<int32_t> sx((size_t)p.ncols * p.nstride), su((size_t)p.ncols * p.mstride);
     e = rt::d2h(sx.data(), p.sx.p, sx.size() * sizeof(int32_t), h->stream);
@@ -870,6 +882,7 @@ extern "C" int sls_local_problem(sls_handle* h, int64_t k, double* At, double* B
     SLS_ARG(h->plan.valid, "sls_local_problem: no plan");
     SLS_ARG(k >= 0 && k < h->plan.ncols, "sls_local_problem: column position out of range");
     SLS_CK(rt::set_device(h->device));
+    SLS_CK(plan_fetch_sizes(h, h->plan));
     const int n = h->plan.h_n[k], m = h->plan.h_m[k];
     const int64_t T = h->T;
     DevBuf dA, dB, dMx, dMu;
@@ -921,6 +934,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
     }
     std::vector<int> cb(nchunk + 1);
     for (int c = 0; c <= nchunk; c++) cb[c] = (int)((int64_t)p.ncols * c / nchunk);
+    if (nchunk > 1) SLS_CK(plan_fetch_lists(h, p));
     {
         std::vector<void*> ptrs(4 * T);
         for (int64_t tt = 0; tt < 2 * T; tt++) {
@@ -967,9 +981,16 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         s.P = v; s.c_begin = 0; s.c_end = p.ncols;
         s.rowval = reinterpret_cast<int64_t* const*>(h->out_ptrs.as<void*>());
         s.row_off_x = h->Sx.row_off; s.row_off_u = h->Su.row_off; s.sorted = p.cols_sorted ? 1 : 0;
-        h->ev[5].record(h->copy_stream);
-        SLS_CK(sls_launch_scatter(s, h->copy_stream));
-        h->chunk_ev[15].record(h->copy_stream);
+        if (h->opt.flags & 8) {                                // measurement mode: kernel 3 alone on the device, then kernel 2
+            h->ev[5].record(h->stream);
+            SLS_CK(sls_launch_scatter(s, h->stream));
+            h->chunk_ev[15].record(h->stream);
+            SLS_CK(rt::stream_wait(h->copy_stream, h->chunk_ev[15]));
+        } else {
+            h->ev[5].record(h->copy_stream);
+            SLS_CK(sls_launch_scatter(s, h->copy_stream));
+            h->chunk_ev[15].record(h->copy_stream);
+        }
         if (p.ncols) scatters++;
         // rowval is final now (it does not depend on kernel 2): its device->host copies start at once, whole taps, so the
         // D2H engine works from the first millisecond of kernel 2 and only the values trail the solve chunks
@@ -982,9 +1003,12 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
     }
     for (int ch = 0; ch < nchunk; ch++) {
         for (const SolveClass& c : p.classes) {
-            const int32_t* lb = p.h_lists.data() + c.list_off;
-            const int lo = (int)(std::lower_bound(lb, lb + c.count, cb[ch]) - lb);
-            const int hi = (int)(std::lower_bound(lb, lb + c.count, cb[ch + 1]) - lb);
+            int lo = 0, hi = c.count;
+            if (nchunk > 1) {
+                const int32_t* lb = p.h_lists.data() + c.list_off;
+                lo = (int)(std::lower_bound(lb, lb + c.count, cb[ch]) - lb);
+                hi = (int)(std::lower_bound(lb, lb + c.count, cb[ch + 1]) - lb);
+            }
             if (hi <= lo) continue;
             SlsSolveArgs a{};
             a.A = h->A.view(); a.B2 = h->B2.view(); a.Ar = h->Ar.view(); a.B2r = h->B2r.view();

@@ -45,7 +45,7 @@ __device__ int sls_warp_index_set(const SlsCsc& A, const SlsSupports& S, int T, 
 __global__ void __launch_bounds__(GATHER_WPB * 32)
 sls_gather_count_kernel(SlsCsc A, SlsSupports Sx, SlsSupports Su, int T, int64_t Nx,
                         const int32_t* __restrict__ cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
-                        int32_t* keep_x, int32_t* keep_u, const int32_t* __restrict__ bad_supports) {
+                        int32_t* keep_x, int32_t* keep_u, const int32_t* __restrict__ bad_supports, int32_t* stats) {
     SLS_DYN_SMEM(smem);
     const int warp = threadIdx.x >> 5, lane = sls_lane();
     const int c = blockIdx.x * GATHER_WPB + warp;
@@ -63,7 +63,57 @@ sls_gather_count_kernel(SlsCsc A, SlsSupports Sx, SlsSupports Su, int T, int64_t
     if (keep_u)
 #pragma unroll 1
         for (int i = lane; i < m; i += 32) keep_u[(size_t)c * cap + i] = buf[i];
-    if (lane == 0) { n_out[c] = n; m_out[c] = m; }
+    if (lane == 0) {
+        n_out[c] = n; m_out[c] = m;
+        // plan statistics on the device (the host reads 34 integers instead of 2 x ncols sizes): [0] max n, [1] max m,
+        // [2] overflow, [3] unused, [4 + k] columns of size class k (n in 8k+1..8k+8; class 15 = everything larger),
+        // [20 + k] largest m of class k
+        if (stats) {
+            if (n < 0 || m < 0) atomicOr(stats + 2, 1);
+            else {
+                atomicMax(stats + 0, n); atomicMax(stats + 1, m);
+                int k = n > 0 ? (n - 1) >> 3 : 0; if (k > 15) k = 15;
+                atomicAdd(stats + 4 + k, 1); atomicMax(stats + 20 + k, m);
+            }
+        }
+    }
+}
+
+// Kernel-2 work lists: block k writes the planned-column indices of size class k, ascending, behind those of the smaller
+// classes (stable stream compaction by block scans; one pass over n[] per class).
+__global__ void __launch_bounds__(1024)
+sls_class_lists_kernel(const int32_t* __restrict__ n, int ncols, const int32_t* __restrict__ stats, int nclass, int32_t* lists) {
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    const int k = blockIdx.x;
+    int off = 0;
+    for (int kk = 0; kk < k; kk++) off += stats[4 + kk];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < ncols; i0 += 1024) {
+        const int i = i0 + tid;
+        bool mine = false;
+        if (i < ncols) { const int nn = n[i]; int kc = nn > 0 ? (nn - 1) >> 3 : 0; if (kc > 15) kc = 15; mine = (kc == k) && k < nclass; }
+        const unsigned bal = __ballot_sync(SLS_FULL, mine);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; w++) before += wsum[w];
+        int total = 0;
+        for (int w = 0; w < 32; w++) total += wsum[w];
+        if (mine) lists[off + carry_s + before + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (tid == 0) carry_s += total;
+        __syncthreads();
+    }
+}
+
+int sls_launch_class_lists(const int32_t* n, int ncols, const int32_t* stats, int nclass, int32_t* lists, sls_stream_t stream) {
+    if (ncols == 0 || nclass <= 0) return 0;
+    auto kp = &sls_class_lists_kernel;
+    SLS_LAUNCH(kp, nclass, 1024, 0, stream, n, ncols, stats, nclass, lists);
+    return rt::last_error();
 }
 
 // 32-bit words of shared memory one warp of kernel 1b needs (kept even so that the int64 section stays aligned)
@@ -356,13 +406,13 @@ int sls_launch_validate_supports(const SlsSupports& S, int T, int64_t Nx, int64_
 // ---- host launchers -------------------------------------------------------------------------
 int sls_launch_gather_count(const SlsCsc& A, const SlsSupports& Sx, const SlsSupports& Su, int T, int64_t Nx,
                             const int32_t* cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
-                            int32_t* keep_x, int32_t* keep_u, const int32_t* bad_supports, sls_stream_t stream) {
+                            int32_t* keep_x, int32_t* keep_u, const int32_t* bad_supports, int32_t* stats, sls_stream_t stream) {
     if (ncols == 0) return 0;
     const int grid = (ncols + GATHER_WPB - 1) / GATHER_WPB;
     const size_t smem = (size_t)GATHER_WPB * cap * sizeof(int32_t);
     auto kp = &sls_gather_count_kernel;
     if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
-    SLS_LAUNCH(kp, grid, GATHER_WPB * 32, smem, stream, A, Sx, Su, T, Nx, cols, ncols, n_out, m_out, cap, keep_x, keep_u, bad_supports);
+    SLS_LAUNCH(kp, grid, GATHER_WPB * 32, smem, stream, A, Sx, Su, T, Nx, cols, ncols, n_out, m_out, cap, keep_x, keep_u, bad_supports, stats);
     return rt::last_error();
 }
 

@@ -5,7 +5,9 @@
 // ---- kernel 1 (sls_gather.cu) ----
 int sls_launch_gather_count(const SlsCsc& A, const SlsSupports& Sx, const SlsSupports& Su, int T, int64_t Nx,
                             const int32_t* cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
-                            int32_t* keep_x, int32_t* keep_u, const int32_t* bad_supports, sls_stream_t stream);   // keep_*: [ncols][cap] index sets for kernel 1b, or null
+                            int32_t* keep_x, int32_t* keep_u, const int32_t* bad_supports, int32_t* stats, sls_stream_t stream);
+// stats (36 ints, zeroed by the caller): [0] max n, [1] max m, [2] overflow, [4+k] columns of size class k, [20+k] max m of class k
+int sls_launch_class_lists(const int32_t* n, int ncols, const int32_t* stats, int nclass, int32_t* lists, sls_stream_t stream);   // keep_*: [ncols][cap] index sets for kernel 1b, or null
 // layout check (rows in 1..nrow, strictly ascending per column) of the support columns [c0, c1) of every tap; sets *flag
 int sls_launch_validate_supports(const SlsSupports& S, int T, int64_t Nx, int64_t nrow, int64_t c0, int64_t c1, int32_t* flag,
                                  sls_stream_t stream);

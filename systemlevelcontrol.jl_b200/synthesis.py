@@ -232,8 +232,9 @@ class Synthesizer:
         return out
 
     # -- kernel 1 -------------------------------------------------------------------------------
-    def plan(self, cols=None):
-        """cols: 0-based disturbance columns (None = all).  Returns (nnz_x[T], nnz_u[T], n[ncols], m[ncols])."""
+    def plan(self, cols=None, sizes=True):
+        """cols: 0-based disturbance columns (None = all).  Returns (nnz_x[T], nnz_u[T], n[ncols], m[ncols]).
+        sizes=False: n / m are not fetched (NULL n_out / m_out: the per-column sizes then stay on the device)."""
         T = self.T
         nnz_x = np.zeros(T, np.int64)
         nnz_u = np.zeros(T, np.int64)
@@ -243,12 +244,13 @@ class Synthesizer:
         else:
             c1 = np.ascontiguousarray(np.asarray(cols, dtype=np.int64) + 1)
             ncols = c1.size
-        n = np.zeros(max(ncols, 1), np.int32)
-        m = np.zeros(max(ncols, 1), np.int32)
-        self._ck(self.api.sls_plan(self.h, ptr(c1, i64p), ncols, ptr(nnz_x, i64p), ptr(nnz_u, i64p), ptr(n, i32p), ptr(m, i32p)))
+        n = np.zeros(max(ncols, 1) if sizes else 1, np.int32)
+        m = np.zeros(max(ncols, 1) if sizes else 1, np.int32)
+        self._ck(self.api.sls_plan(self.h, ptr(c1, i64p), ncols, ptr(nnz_x, i64p), ptr(nnz_u, i64p),
+                                   ptr(n, i32p) if sizes else None, ptr(m, i32p) if sizes else None))
         self.ncols = ncols
         self.nnz_x, self.nnz_u = nnz_x, nnz_u
-        self.n, self.m = n[:ncols], m[:ncols]
+        self.n, self.m = (n[:ncols], m[:ncols]) if sizes else (None, None)
         return nnz_x, nnz_u, self.n, self.m
 
     def reduce(self, cj):
