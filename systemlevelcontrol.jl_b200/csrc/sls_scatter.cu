@@ -9,8 +9,7 @@
 #include "sls_common.h"
 #include "sls_kernels.h"
 
-#define SCATTER_WPB 8
-#define SCATTER_STAGE 2048            // staged row indices per warp (32 columns of one tap); larger groups take the per-entry path
+#define SCATTER_MAXW 8
 
 __device__ __forceinline__ int sls_select_bit(const uint32_t* words, int nwords, int r) {
     // index of the r-th (0-based) set bit across `nwords` mask words
@@ -24,13 +23,16 @@ __device__ __forceinline__ int sls_select_bit(const uint32_t* words, int nwords,
     return -1;
 }
 
-// One warp handles 32 consecutive planned columns of one tap.  Every lane expands ITS column's mask bits into row
-// indices (a find-first-set loop: ~6 instructions per entry, against ~40 for a per-entry binary search + select-nth-bit)
-// into a per-warp staging area in shared memory at the offset a warp scan gives it; the warp then streams the staged
-// rows out as full 256-byte coalesced stores.  When the planned columns ascend (a.sorted: every plan but an unsorted
-// explicit column list) the 32 columns' segments are contiguous in rowval and the store address is base + e.
-__global__ void __launch_bounds__(SCATTER_WPB * 32)
-sls_scatter_kernel(SlsScatterArgs a) {
+// One warp handles 32 consecutive planned columns of one tap.  Their index-set rows (s_x or s_u: 32 x stride ints,
+// contiguous in the plan) are copied to shared memory with coalesced loads; every lane then expands ITS column's mask bits
+// into row indices (find-first-set loop, ~6 instructions per entry against ~40 for a per-entry binary search +
+// select-nth-bit) into a per-warp staging area at the offset a warp scan gives it, and the warp streams the staged rows
+// out as full 256-byte coalesced stores.  When the planned columns ascend (a.sorted: every plan but an unsorted explicit
+// column list) the 32 columns' segments are contiguous in rowval and the store address is base + e.
+// Shared memory per warp: 33 + 2 * 32 * stride ints (stride = nstride for the Φx taps, mstride for the Φu taps); the
+// launcher picks the warps per block that fit.
+__global__ void __launch_bounds__(SCATTER_MAXW * 32)
+sls_scatter_kernel(SlsScatterArgs a, int wpb, int per_warp) {
     SLS_DYN_SMEM(smem);
     const SlsPlanView& P = a.P;
     const int warp = threadIdx.x >> 5, lane = sls_lane();
@@ -38,15 +40,23 @@ sls_scatter_kernel(SlsScatterArgs a) {
     const int T = P.T;
     const bool isu = tt >= T;
     const int t = isu ? tt - T : tt;
-    const int c0 = a.c_begin + (blockIdx.x * SCATTER_WPB + warp) * 32;
+    const int c0 = a.c_begin + (blockIdx.x * wpb + warp) * 32;
     if (c0 >= a.c_end) return;
-    int32_t* pref = reinterpret_cast<int32_t*>(smem) + warp * (33 + SCATTER_STAGE);
-    int32_t* stage = pref + 33;
+    const int stride = isu ? P.mstride : P.nstride;
+    int32_t* pref = reinterpret_cast<int32_t*>(smem) + (size_t)warp * per_warp;
+    int32_t* rows = pref + 33;                                // [32][stride] index sets of the 32 columns
+    int32_t* stage = rows + 32 * stride;
     const int c = c0 + lane;
     const bool valid = c < a.c_end;
+    const int ncol = min(32, a.c_end - c0);
     const int nw = isu ? P.wu : P.wx;
     const uint32_t* mbase = isu ? P.masku : P.maskx;
     const uint32_t* mw = mbase + ((size_t)(valid ? c : c0) * T + t) * nw;
+    {
+        const int32_t* src = (isu ? P.su : P.sx) + (size_t)c0 * stride;
+#pragma unroll 4
+        for (int i = lane; i < ncol * stride; i += 32) rows[i] = src[i];
+    }
     int cnt = 0;
     if (valid) for (int w = 0; w < nw; w++) cnt += __popc(mw[w]);
     int incl = cnt;
@@ -59,55 +69,44 @@ sls_scatter_kernel(SlsScatterArgs a) {
     const int64_t* colptr = P.colptr + (int64_t)tt * (P.Nx + 1);
     int64_t* rowval = a.rowval[tt];
     const int64_t roff = 1 + (isu ? a.row_off_u : a.row_off_x);
-    if (E <= SCATTER_STAGE) {
-        if (valid) {
-            const int32_t* rows = isu ? P.su + (size_t)c * P.mstride : P.sx + (size_t)c * P.nstride;
-            int o = incl - cnt;
+    if (valid) {
+        const int32_t* myrows = rows + lane * stride;
+        int o = incl - cnt;
 #pragma unroll 1
-            for (int w = 0; w < nw; w++) {
-                uint32_t v = mw[w];
+        for (int w = 0; w < nw; w++) {
+            uint32_t v = mw[w];
 #pragma unroll 1
-                while (v) { const int b = __ffs(v) - 1; stage[o++] = rows[32 * w + b]; v &= v - 1; }
-            }
+            while (v) { const int b = __ffs(v) - 1; stage[o++] = myrows[32 * w + b]; v &= v - 1; }
         }
-        __syncwarp();
-        if (a.sorted) {
-            int64_t* dst = rowval + (colptr[P.cols[c0]] - 1);
-#pragma unroll 1
-            for (int e = lane; e < E; e += 32) dst[e] = (int64_t)stage[e] + roff;
-        } else {
-#pragma unroll 1
-            for (int e = lane; e < E; e += 32) {
-                int lo = 0, hi = 32;                          // largest cc with pref[cc] <= e
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pref[mid] <= e) lo = mid; else hi = mid; }
-                rowval[colptr[P.cols[c0 + lo]] - 1 + (e - pref[lo])] = (int64_t)stage[e] + roff;
-            }
-        }
-        return;
     }
-    // very wide groups: per entry, (column, rank) by binary search and select-nth-bit
-    for (int e = lane; e < E; e += 32) {
-        int lo = 0, hi = 32;
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pref[mid] <= e) lo = mid; else hi = mid; }
-        const int cc = c0 + lo;
-        const int r = e - pref[lo];
-        const int64_t j = P.cols[cc];
-        const uint32_t* mwc = mbase + ((size_t)cc * T + t) * nw;
-        const int li = sls_select_bit(mwc, nw, r);
-        const int32_t grow = isu ? P.su[(size_t)cc * P.mstride + li] : P.sx[(size_t)cc * P.nstride + li];
-        rowval[colptr[j] - 1 + r] = (int64_t)grow + roff;
+    __syncwarp();
+    if (a.sorted) {
+        int64_t* dst = rowval + (colptr[P.cols[c0]] - 1);
+#pragma unroll 4
+        for (int e = lane; e < E; e += 32) dst[e] = (int64_t)stage[e] + roff;
+    } else {
+#pragma unroll 1
+        for (int e = lane; e < E; e += 32) {
+            int lo = 0, hi = 32;                              // largest cc with pref[cc] <= e
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pref[mid] <= e) lo = mid; else hi = mid; }
+            rowval[colptr[P.cols[c0 + lo]] - 1 + (e - pref[lo])] = (int64_t)stage[e] + roff;
+        }
     }
 }
 
 int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream) {
     if (a.c_end <= a.c_begin) return 0;
-    const int per_block = SCATTER_WPB * 32;
-    dim3 grid((a.c_end - a.c_begin + per_block - 1) / per_block, 2 * a.P.T, 1);
+    const int stride = a.P.nstride > a.P.mstride ? a.P.nstride : a.P.mstride;
+    const int per_warp = (33 + 2 * 32 * stride + 3) & ~3;     // ints
+    int wpb = (int)((96 * 1024) / ((size_t)per_warp * sizeof(int32_t)));
+    if (wpb > SCATTER_MAXW) wpb = SCATTER_MAXW;
+    if (wpb < 1) wpb = 1;
+    const size_t smem = (size_t)wpb * per_warp * sizeof(int32_t);
     auto kp = &sls_scatter_kernel;
-    const size_t smem = (size_t)SCATTER_WPB * (33 + SCATTER_STAGE) * sizeof(int32_t);
-    static bool attr_set = false;
-    if (!attr_set) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; attr_set = true; }
-    SLS_LAUNCH(kp, grid, SCATTER_WPB * 32, smem, stream, a);
+    if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
+    const int per_block = wpb * 32;
+    dim3 grid((a.c_end - a.c_begin + per_block - 1) / per_block, 2 * a.P.T, 1);
+    SLS_LAUNCH(kp, grid, wpb * 32, smem, stream, a, wpb, per_warp);
     return rt::last_error();
 }
 
