@@ -162,7 +162,7 @@ struct sls_handle {
     rt::Event gev[4];                        // around kernel 1a and kernels 1b + scan (gather_gpu_ms)
     std::vector<void*> registered;           // host ranges page-locked through sls_host_register
     DevBuf supp[8]; PinVec<int64_t> supp_h; int supp_cap = 0;   // scratch of sls_make_supports (kept across calls)
-    DevBuf simb[17];                                            // scratch of sls_simulate (kept across calls)
+    DevBuf simb[19]; int sim_cap = 0;                           // scratch of sls_simulate (kept across calls)
 };
 
 static thread_local std::string g_create_err;
@@ -1516,11 +1516,14 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
     // pass 1: window sizes (scratch capacity = as much as 4 warps can have)
     // scratch lists of the window pass: 3 x cap ints per warp.  Start small (occupancy: 4 warps x 3 x 512 ints = 24 KB per
     // block) and grow only when a scenario overflows (the kernel reports -1), up to what shared memory allows.
-    int cap = 512;
+    // The windows are stored by the same launch at stride cap and compacted to their exact strides afterwards.
+    int cap = h->sim_cap > 0 ? h->sim_cap : 512;
     std::vector<int32_t> nw(nscen), nu(nscen);
     int wmax = 1, umax = 1;
+    DevBuf& dWt = h->simb[17]; DevBuf& dWut = h->simb[18];
     for (;;) {
-        SIM_CK(sls_launch_sim_size(a, dnw.as<int32_t>(), dnu.as<int32_t>(), cap, nullptr, nullptr, 0, 0, h->stream));
+        SIM_CK(dWt.ensure((size_t)nscen * cap * 4)); SIM_CK(dWut.ensure((size_t)nscen * cap * 4));
+        SIM_CK(sls_launch_sim_size(a, dnw.as<int32_t>(), dnu.as<int32_t>(), cap, dWt.as<int32_t>(), dWut.as<int32_t>(), cap, cap, h->stream));
         SIM_CK(rt::d2h(nw.data(), dnw.p, nscen * 4, h->stream));
         SIM_CK(rt::d2h(nu.data(), dnu.p, nscen * 4, h->stream));
         SIM_CK(rt::sync(h->stream));
@@ -1536,10 +1539,11 @@ extern "C" int sls_simulate(sls_handle* h, int64_t nscen, int64_t steps, const i
         }
         cap *= 2;
     }
+    h->sim_cap = cap;
     const int wcap = (wmax + 1) & ~1, ucap = (umax + 1) & ~1;
-    // window pass: the same kernel again, now storing the windows with exact strides
     SIM_CK(dW.ensure((size_t)nscen * wcap * 4)); SIM_CK(dWu.ensure((size_t)nscen * ucap * 4));
-    SIM_CK(sls_launch_sim_size(a, dnw.as<int32_t>(), dnu.as<int32_t>(), cap, dW.as<int32_t>(), dWu.as<int32_t>(), wcap, ucap, h->stream));
+    SIM_CK(sls_launch_sim_compact(dWt.as<int32_t>(), dWut.as<int32_t>(), cap, dnw.as<int32_t>(), dnu.as<int32_t>(), (int)nscen,
+                                  dW.as<int32_t>(), dWu.as<int32_t>(), wcap, ucap, h->stream));
     a.nw = dnw.as<int32_t>(); a.nu = dnu.as<int32_t>(); a.Wg = dW.as<int32_t>(); a.Wug = dWu.as<int32_t>();
     // pack pass: Phi restricted to every scenario's window, local row indices, in consumption order
     if (wcap > 65535 || ucap > 65535) { cleanup(); return fail(h, -4, "sls_simulate: window too large"); }

@@ -80,29 +80,43 @@ sls_gather_count_kernel(SlsCsc A, SlsSupports Sx, SlsSupports Su, int T, int64_t
 }
 
 // Kernel-2 work lists: block k writes the planned-column indices of size class k, ascending, behind those of the smaller
-// classes (stable stream compaction by block scans; one pass over n[] per class).
+// classes (stable stream compaction: 4 columns per thread per round, warp-shuffle scans, one pass over n[] per non-empty
+// class).
 __global__ void __launch_bounds__(1024)
 sls_class_lists_kernel(const int32_t* __restrict__ n, int ncols, const int32_t* __restrict__ stats, int nclass, int32_t* lists) {
     __shared__ int wsum[32];
     __shared__ int carry_s;
     const int k = blockIdx.x;
+    if (k >= nclass || stats[4 + k] == 0) return;
     int off = 0;
     for (int kk = 0; kk < k; kk++) off += stats[4 + kk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int i0 = 0; i0 < ncols; i0 += 1024) {
-        const int i = i0 + tid;
-        bool mine = false;
-        if (i < ncols) { const int nn = n[i]; int kc = nn > 0 ? (nn - 1) >> 3 : 0; if (kc > 15) kc = 15; mine = (kc == k) && k < nclass; }
-        const unsigned bal = __ballot_sync(SLS_FULL, mine);
-        if (lane == 0) wsum[warp] = __popc(bal);
+    for (int i0 = 0; i0 < ncols; i0 += 4096) {
+        const int i = i0 + 4 * tid;
+        bool mine[4];
+        int cnt = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            mine[e] = false;
+            if (i + e < ncols) { const int nn = n[i + e]; int kc = nn > 0 ? (nn - 1) >> 3 : 0; if (kc > 15) kc = 15; mine[e] = (kc == k); }
+            cnt += mine[e];
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(SLS_FULL, incl, d); if (lane >= d) incl += o; }
+        if (lane == 31) wsum[warp] = incl;
         __syncthreads();
-        int before = 0;
-        for (int w = 0; w < warp; w++) before += wsum[w];
-        int total = 0;
-        for (int w = 0; w < 32; w++) total += wsum[w];
-        if (mine) lists[off + carry_s + before + __popc(bal & ((1u << lane) - 1u))] = i;
+        int wv = wsum[lane];                                   // 32 warps: one more warp-level scan, done redundantly by every warp
+        int winc = wv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(SLS_FULL, winc, d); if (lane >= d) winc += o; }
+        const int before = __shfl_sync(SLS_FULL, winc - wv, warp);
+        const int total = __shfl_sync(SLS_FULL, winc, 31);
+        int pos = off + carry_s + before + incl - cnt;
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (mine[e]) lists[pos++] = i + e;
         __syncthreads();
         if (tid == 0) carry_s += total;
         __syncthreads();

@@ -98,6 +98,8 @@ __host__ __device__ size_t sls_sim_smem_per_warp(int cap, int wcap, int ucap, in
 int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, int32_t* Wg, int32_t* Wug,
                         int wcap, int ucap, sls_stream_t stream);
 int sls_launch_sim(const SlsSimArgs& a, int cap, int wcap, int ucap, sls_stream_t stream);
+int sls_launch_sim_compact(const int32_t* Wt, const int32_t* Wut, int cap, const int32_t* nw, const int32_t* nu, int nscen,
+                           int32_t* W, int32_t* Wu, int wcap, int ucap, sls_stream_t stream);
 // fast path: one CTA per scenario, packed Phi window resident in shared memory (needs 2T <= 256, windows <= 256, nent_cap entries fit)
 size_t sls_sim_cta_smem(int nent_cap, int wcap, int ucap, int T);   // nent_cap = 0: window in the global scratch
 int sls_launch_sim_cta(const SlsSimArgs& a, int wcap, int ucap, int nent_cap, int sm_count, sls_stream_t stream);

@@ -551,6 +551,21 @@ int sls_launch_sim_cta(const SlsSimArgs& a, int wcap, int ucap, int nent_cap, in
     return rt::last_error();
 }
 
+// windows stored at stride `cap` by the window pass -> exact strides wcap / ucap
+__global__ void sls_sim_compact_kernel(const int32_t* Wt, const int32_t* Wut, int cap, const int32_t* nw, const int32_t* nu,
+                                       int32_t* W, int32_t* Wu, int wcap, int ucap) {
+    const int s = blockIdx.x;
+    for (int i = threadIdx.x; i < nw[s]; i += blockDim.x) W[(size_t)s * wcap + i] = Wt[(size_t)s * cap + i];
+    for (int i = threadIdx.x; i < nu[s]; i += blockDim.x) Wu[(size_t)s * ucap + i] = Wut[(size_t)s * cap + i];
+}
+int sls_launch_sim_compact(const int32_t* Wt, const int32_t* Wut, int cap, const int32_t* nw, const int32_t* nu, int nscen,
+                           int32_t* W, int32_t* Wu, int wcap, int ucap, sls_stream_t stream) {
+    if (nscen == 0) return 0;
+    auto kp = &sls_sim_compact_kernel;
+    SLS_LAUNCH(kp, nscen, 64, 0, stream, Wt, Wut, cap, nw, nu, W, Wu, wcap, ucap);
+    return rt::last_error();
+}
+
 int sls_launch_sim_size(const SlsSimArgs& a, int32_t* nw_out, int32_t* nu_out, int cap, int32_t* Wg, int32_t* Wug,
                         int wcap, int ucap, sls_stream_t stream) {
     if (a.nscen == 0) return 0;

@@ -1,5 +1,6 @@
-// sls_solve.cu — kernel 2: batched FP64 equality-constrained least squares, one warp per column,
-// dense O(n^3) work on the FP64 tensor cores (DMMA m8n8k4), everything register-resident.
+// sls_solve.cu — kernel 2 for local state dimensions n <= 32: batched FP64 equality-constrained least squares, one warp
+// per column, dense O(n^3) work on the FP64 tensor cores (DMMA m8n8k4), everything register-resident.
+// (32 < n <= 64: one CTA per column, sls_solve_wide.cu.)
 //
 // Replaces the JuMP/Ipopt solve of reference src/synthesis.jl:46-62 for plants built by
 // Plant(A,B1=I,B2) ([C1 D12] = I, D11 = 0; GeneralizedPlant.jl:105-110).  Per column the reference's QP is
@@ -13,7 +14,7 @@
 // S_k^+ is the inverse on the rows whose pivot exceeds rank_tol * diag(D_k); redundant constraint rows are
 // eliminated (what Ipopt's inertia correction does implicitly).
 //
-// Data layout: an n x n matrix (n <= N = 8*NB <= 64) lives in the registers (spilling to L1-backed local memory for N > 32) of one warp as NB x NB blocks
+// Data layout: an n x n matrix (n <= N = 8*NB <= 32) lives in the registers of one warp as NB x NB blocks
 // of 8 x 8 in the DMMA accumulator layout: lane 4g+q holds X[8bi+g][8bj+2q], X[8bi+g][8bj+2q+1].
 // With the k index of the MMA mapped to even / odd columns, a product  X * W^T  of two blocks that are both
 // in accumulator layout needs NO data movement: A-fragment = (x0 | x1), B-fragment = (w0 | w1).  All
@@ -22,7 +23,7 @@
 //     block symmetric sweep (Gauss-Jordan) with pivot block p, P = S_pp^+ :
 //         S_ij -= (S_ip P) * (S_jp)^T,   S_ip <- S_ip P = S_ip * P^T,   S_pi <- P * (S_ip)^T,   S_pp <- -P
 // The 8 x 8 pivot blocks are inverted by 8 scalar symmetric sweeps with rank skipping through warp shuffles.
-// -Z_k goes to a per-warp history slot (packed lower triangle, L2/HBM) for the back substitution
+// -Z_k goes to a per-warp history slot (lower-triangle blocks in register order, L2/HBM) for the back substitution
 //     lambda_{k-1} = Z_{k-1}(yh_{k-1} + mx_k o A~^T lambda_k),
 //     x_k = mx_k o (lambda_{k-1} - A~^T lambda_k),   u_k = -mu_k o (B~^T lambda_k).
 // Sparse pieces (A~ x, B~ diag(mu) B~^T, diagonals) use a local CSR/CSC of C~ = [A~ B~] gathered from the
@@ -34,7 +35,7 @@
 #include "sls_solve_common.h"
 
 // warps per block / minimum resident blocks per SM of each size class (registers: 128 per thread up to N = 24)
-template <int NB> struct SlsCfg { static const int WPB = (NB <= 4) ? 4 : 1; static const int MINB = (NB <= 3) ? 4 : ((NB == 4) ? 2 : 1); };
+template <int NB> struct SlsCfg { static const int WPB = 4; static const int MINB = (NB <= 3) ? 4 : 2; };
 
 template <int NB>
 __global__ void __launch_bounds__(SlsCfg<NB>::WPB * 32, SlsCfg<NB>::MINB)
@@ -802,11 +803,10 @@ int sls_solve_class_of(int n) {
 size_t sls_solve_smem_per_warp(int N, int mcap, int nnzcap, int T, int wu) {
     return (size_t)SlsSolveLayout(N, mcap, nnzcap, T, wu).total;
 }
-// size classes above 32 run one CTA per column (sls_solve_wide.cu); SLS_WIDE=0 keeps them on the one-warp kernel (A/B)
-static bool use_wide(int N) {
-    static const int minN = [] { const char* e = getenv("SLS_WIDE"); return e ? (atoi(e) == 0 ? 1 << 30 : atoi(e)) : 40; }();   // SLS_WIDE=<smallest N on the CTA kernel>
-    return N >= minN && N >= 16;
-}
+// size classes above 32 run one CTA per column (sls_solve_wide.cu).  Measured both ways on B200: the one-warp kernel
+// needs 278 ms for the 300 x 300 grid (matrix spilled to local memory) against 131 ms here; the CTA kernel needs 19.5 ms for
+// the chain's N = 24 class against 12.5 ms for the one-warp kernel (profiles/r02_ab_logs.txt).
+static bool use_wide(int N) { return N > 32; }
 int64_t sls_solve_hist_doubles(int N, int T) {
     if (use_wide(N)) return sls_solve_wide_hist_doubles(N, T);
     return (int64_t)(T + 1) * N + (int64_t)T * ((N / 8) * (N / 8 + 1) / 2 * 64);
@@ -841,7 +841,7 @@ static int launch_class(const SlsSolveArgs& a, int sm_count, int max_smem, int* 
     return rt::last_error();
 }
 
-#define SLS_FOR_CLASSES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#define SLS_FOR_CLASSES(X) X(1) X(2) X(3) X(4)
 
 int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem) {
     if (use_wide(N)) return sls_solve_wide_max_slots(N, mcap, nnzcap, T, wu, sm_count, max_smem);

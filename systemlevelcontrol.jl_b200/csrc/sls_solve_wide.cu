@@ -55,7 +55,7 @@ struct SlsWideLayout {
 };
 
 // resident CTAs per SM the register allocation aims at (shared memory allows about as many)
-template <int NB> struct SlsWideCfg { static const int MINB = (NB >= 5) ? 2 : ((NB == 4) ? 4 : ((NB == 3) ? 7 : 10)); };
+template <int NB> struct SlsWideCfg { static const int MINB = 2; };
 
 template <int NB>
 __global__ void __launch_bounds__(NB * 32, SlsWideCfg<NB>::MINB)
@@ -666,9 +666,6 @@ static int wide_launch(const SlsSolveArgs& a, int sm_count, int max_smem, int* s
 
 int sls_solve_wide_max_slots(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem) {
     switch (N / 8) {
-        case 2: return wide_resident_blocks<2>(mcap, nnzcap, T, wu, sm_count, max_smem);
-        case 3: return wide_resident_blocks<3>(mcap, nnzcap, T, wu, sm_count, max_smem);
-        case 4: return wide_resident_blocks<4>(mcap, nnzcap, T, wu, sm_count, max_smem);
         case 5: return wide_resident_blocks<5>(mcap, nnzcap, T, wu, sm_count, max_smem);
         case 6: return wide_resident_blocks<6>(mcap, nnzcap, T, wu, sm_count, max_smem);
         case 7: return wide_resident_blocks<7>(mcap, nnzcap, T, wu, sm_count, max_smem);
@@ -681,9 +678,6 @@ int sls_launch_solve_wide(int N, const SlsSolveArgs& a, int sm_count, int max_sm
     *slots_launched = 0;
     if (a.count == 0) return 0;
     switch (N / 8) {
-        case 2: return wide_launch<2>(a, sm_count, max_smem, slots_launched, stream);
-        case 3: return wide_launch<3>(a, sm_count, max_smem, slots_launched, stream);
-        case 4: return wide_launch<4>(a, sm_count, max_smem, slots_launched, stream);
         case 5: return wide_launch<5>(a, sm_count, max_smem, slots_launched, stream);
         case 6: return wide_launch<6>(a, sm_count, max_smem, slots_launched, stream);
         case 7: return wide_launch<7>(a, sm_count, max_smem, slots_launched, stream);
