@@ -439,6 +439,8 @@ def run_ours(args, rank, world, local_rank):
         tm = syn.timing()
         res = {"total_ms": float(np.sum(step_ms)), "k_ms": {k: float(np.mean(v)) for k, v in k_ms.items()}, "launches": launches, "tm": tm,
                "e2e_ms": None}
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"[rank {rank}] steps {[round(x, 2) for x in step_ms]} kernels {res['k_ms']}", file=sys.stderr, flush=True)
         if e2e_reps:
             out = shard.alloc_slab()
             for _ in range(2):
@@ -458,23 +460,6 @@ def run_ours(args, rank, world, local_rank):
     main = measure(shard, args.steps, args.warmup, e2e_reps)
     clocks = sampler.stop() if sampler else None
     tm = main["tm"]
-
-    # kernels 1 + 3 stand-alone (kernel 3 normally overlaps kernel 2 on a second stream, which inflates its event time):
-    # a second handle in measurement mode (flags bit 3) on the same inputs
-    gs_alone = None
-    if rank == 0:
-        syn_m = slc_b200.Synthesizer(device=local_rank, flags=8)
-        try:
-            syn_m.set_plant(shard.Aj, shard.B2j); syn_m.set_supports(shard.Sx, shard.Su)
-            g_, s_ = [], []
-            for it in range(5):
-                syn_m.plan(shard.cols, sizes=False); syn_m.solve_device()
-                tmm = syn_m.timing()
-                if it >= 2:
-                    g_.append(tmm["gather_gpu_ms"]); s_.append(tmm["scatter_ms"])
-            gs_alone = (float(np.mean(g_)), float(np.mean(s_)))
-        finally:
-            syn_m.close()
 
     # ---------------------------------------------------------------- variants of the host path (N = 1 only)
     variants = {}
@@ -656,7 +641,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         k = main["k_ms"]
         solve_ms = k["solve_ms"]
-        gs_ms = (gs_alone[0] + gs_alone[1]) if gs_alone else (k["gather_gpu_ms"] + k["scatter_ms"])
+        gs_ms = k["gather_gpu_ms"] + k["scatter_ms"]
         ach_tf = tm["alg_flops"] / (solve_ms * 1e-3) / 1e12
         bytes13 = tm["alg_bytes"] - 8.0 * tm["nnz_out"]              # B_col minus the nzval half of the writes (kernel 2's)
         ach_gbs = bytes13 / (gs_ms * 1e-3) / 1e9
@@ -676,15 +661,15 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64["dmma"], "unit": "TFLOP/s", "frac": ach_tf / fp64["dmma"],
                          "frac_of_dfma_peak": ach_tf / fp64["dfma"], "dfma_peak": fp64["dfma"],
                          "traffic": t_solve, "traffic_source": src_solve,
-                         "kernel": "sls_solve_kernel (kernel 2, all size classes of one step; kernel 3 overlaps on a 2nd stream)",
+                         "kernel": "sls_solve_kernel (kernel 2, all size classes of one step)",
                          "flops_per_launch": tm["alg_flops"],
                          "peak_source": "sls_fp64_peak DMMA (mma.sync m8n8k4 f64) chain, measured in this run; the contraction runs on DMMA",
                          "refined_columns": int(tm["refined"])},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                              "traffic": t_gs, "traffic_source": src_gs,
-                             "kernel": "kernels 1a + 1b + colptr scan (GPU time, CUDA events around the launches) + kernel 3 (rowval scatter) timed "
-                                       "stand-alone on a handle in measurement mode (flags bit 3); in the product step kernel 3 overlaps kernel 2",
-                             "gather_gpu_ms": gs_alone[0] if gs_alone else None, "scatter_alone_ms": gs_alone[1] if gs_alone else None,
+                             "kernel": "kernels 1a + class lists + 1b + colptr scan (GPU time, CUDA events around the launches) + kernel 3 (rowval "
+                                       "scatter; runs alone before kernel 2)",
+                             "gather_gpu_ms": k["gather_gpu_ms"], "scatter_ms": k["scatter_ms"],
                              "bytes_per_launch": bytes13, "gpu_ms": gs_ms, "host_round_trip_ms": k["gather_ms"] - k["gather_gpu_ms"],
                              "bytes_definition": "SURVEY 8d B_col summed over the columns minus the 8 B/entry nzval writes (those are kernel 2's)",
                              "peak_source": hbm_src},

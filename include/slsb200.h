@@ -44,8 +44,7 @@ typedef struct sls_options {
     int32_t flags;       /* bit 0: also validate the supports' rowval (range, strictly ascending) on the host;
                             bit 1: sls_solve copies the outputs back after kernel 2 instead of chunk by chunk;
                             bit 2: no refinement sweeps in kernel 2 (columns whose residual exceeds feas_tol are only flagged);
-                            bit 3: measurement mode — sls_solve* runs kernel 3 alone before kernel 2 instead of beside it, so
-                                   that sls_timing.scatter_ms is its stand-alone device time */
+                            bit 3: reserved (was: kernel 3 before kernel 2 — that is the only order since ABI v6) */
     double  rank_tol;    /* pivot <= rank_tol * diag(D_k) => constraint row treated as redundant; 0 -> 1e-10 */
     double  feas_tol;    /* max-abs achievability residual above which SLS_STATUS_RESIDUAL is set; 0 -> 1e-12.  Columns above
                             feas_tol / 10 first take up to 3 refinement sweeps on the stored factors (flags bit 2: none) */
@@ -54,7 +53,7 @@ typedef struct sls_options {
 typedef struct sls_timing {      /* device times (CUDA events on the handle's stream) of the last plan+solve */
     float gather_ms;             /* kernel 1: index sets, masks, counts (+ scans)                       */
     float solve_ms;              /* kernel 2: batched FP64 equality-constrained LS                      */
-    float scatter_ms;            /* kernel 3: CSC scatter                                               */
+    float scatter_ms;            /* kernel 3: CSC scatter (runs alone, before kernel 2)                 */
     float h2d_ms, d2h_ms;        /* host<->device copies done inside sls_set_* / sls_solve              */
     int64_t solve_launches, gather_launches, scatter_launches;
     int64_t ncols, nnz_out;      /* columns synthesised, total stored entries of Φx+Φu                 */
