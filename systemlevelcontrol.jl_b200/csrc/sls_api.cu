@@ -611,21 +611,24 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     p.ncols = (int)ncols;
     SLS_CK(p.h_cols.resize(std::max<int64_t>(ncols, 1)));
     p.col_lo = 0; p.col_hi = cols ? 0 : ncols;
-    if (cols && ncols > 0) {
-        int64_t lo = cols[0], hi = cols[0];
-        for (int64_t i = 1; i < ncols; i++) { lo = std::min(lo, cols[i]); hi = std::max(hi, cols[i]); }
-        p.col_lo = std::max<int64_t>(lo - 1, 0); p.col_hi = std::min<int64_t>(hi, Nx);    // 1-based in, 0-based half-open out
-    }
     if (!cols) {
         if (p.identity_cols != ncols) { for (int64_t i = 0; i < ncols; i++) p.h_cols[i] = (int32_t)i; p.identity_cols = (int)ncols; }
     } else {
+        // one pass: range check, extent, ascending?; the uniqueness bitmap is only needed for a list that does not ascend
         p.identity_cols = 0;
-        std::vector<uint8_t> seen(unique_cols ? Nx : 0, 0);
+        int64_t lo = Nx, hi = -1;
+        bool ascending = true;
         for (int64_t i = 0; i < ncols; i++) {
             const int64_t j = cols[i] - 1;
             if (j < 0 || j >= Nx) return fail(h, -3, "plan: column index out of range (1-based, 1..Nx)");
-            if (unique_cols) { if (seen[j]) return fail(h, -3, "plan: duplicate column"); seen[j] = 1; }
+            if (j <= hi) ascending = false;
+            lo = std::min(lo, j); hi = std::max(hi, j);
             p.h_cols[i] = (int32_t)j;
+        }
+        if (ncols > 0) { p.col_lo = lo; p.col_hi = hi + 1; }
+        if (unique_cols && !ascending) {
+            std::vector<uint8_t> seen(Nx, 0);
+            for (int64_t i = 0; i < ncols; i++) { if (seen[p.h_cols[i]]) return fail(h, -3, "plan: duplicate column"); seen[p.h_cols[i]] = 1; }
         }
     }
     // every support column kernel 1 reads (the rows of nz(A[:,j])) must be on the device: after sls_synthesize of a
