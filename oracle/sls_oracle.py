@@ -354,7 +354,10 @@ def solve_group_general(At, B2t, It, Mxs, Mus, L, R, D, rcond=1e-11):
 
 def SLS_H2_general(P: Plant, S, I=None):
     """synthesis.jl:11-72 in full generality for state-feedback plants: column groups of any size (the 𝓘 keyword,
-    synthesis.jl:15), general [C1 D12], B1 and D11 in the cost (synthesis.jl:42-43,50,76-77).  Dense, slow: small cases."""
+    synthesis.jl:15), general [C1 D12], B1 and D11 in the cost (synthesis.jl:42-43,50,76-77).  Dense, slow: small cases.
+    Scatter ordering (the `# TODO: Verify dimensions` of synthesis.jl:64): `vec(repeat(s_x, q, 1)')` cycles through s_x
+    fastest and `vec(repeat(c_j, 1, n)')` repeats each group column n times, which is exactly the column-major order of
+    `vec(value.(Phi~_x[t]))` (n x q) — entry (i, c) of the local solution lands at (s_x[i], c_j[c]), as below."""
     Sx, Su = S
     T = len(Sx)
     groups = [[j] for j in range(P.Nx)] if I is None else [list(map(int, np.atleast_1d(g))) for g in I]
