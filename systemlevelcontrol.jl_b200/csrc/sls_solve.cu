@@ -471,11 +471,10 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
         for (int rr = 0; rr < RPL; rr++) xnext_r[rr] = 0.0;
         resmax = 0.0;
-        // History double buffer (size classes up to N = 32): -Z_{k-1} and yh_{k-1} of the NEXT tap are loaded into
-        // registers one full iteration ahead (the matrix registers of the forward pass are dead here), so the L2/HBM
-        // latency of the history hides behind a whole tap instead of heading its serial chain.
-        constexpr bool PRELOAD = (NB <= 4);
-        constexpr int NZB = PRELOAD ? NB * (NB + 1) / 2 : 1;
+        // History double buffer: -Z_{k-1} and yh_{k-1} of the NEXT tap are loaded into registers one full iteration ahead
+        // (the matrix registers of the forward pass are dead here), so the L2/HBM latency of the history hides behind a
+        // whole tap instead of heading its serial chain.
+        constexpr int NZB = NB * (NB + 1) / 2;
         double zn[NZB][2], yn[RPL];
         auto load_hist = [&](int kk, double (&z)[NZB][2], double (&yv)[RPL]) {
             const double* hk = zhist + (size_t)kk * HB + 2 * lane;
@@ -488,18 +487,16 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
             for (int rr = 0; rr < RPL; rr++) { const int i = lane + 32 * rr; yv[rr] = (i < n) ? yhist[(size_t)kk * N + i] : 0.0; }
         };
-        if (PRELOAD) load_hist(T - 1, zn, yn);
+        load_hist(T - 1, zn, yn);
         for (int k = T; k >= 1; k--) {
             const mask_t mk = mxs[k - 1];
             const uint32_t* muk = mus + (size_t)(k - 1) * wu;
             double zc[NZB][2], yc[RPL];
-            if (PRELOAD) {
 #pragma unroll
-                for (int i = 0; i < NZB; i++) { zc[i][0] = zn[i][0]; zc[i][1] = zn[i][1]; }
+            for (int i = 0; i < NZB; i++) { zc[i][0] = zn[i][0]; zc[i][1] = zn[i][1]; }
 #pragma unroll
-                for (int rr = 0; rr < RPL; rr++) yc[rr] = yn[rr];
-                if (k >= 2) load_hist(k - 2, zn, yn);
-            }
+            for (int rr = 0; rr < RPL; rr++) yc[rr] = yn[rr];
+            if (k >= 2) load_hist(k - 2, zn, yn);
             __syncwarp();
             // t = C~^T lambda_k
 #pragma unroll 1
@@ -532,7 +529,7 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
             for (int rr = 0; rr < RPL; rr++) {
                 const int i = lane + 32 * rr;
-                const double yprev_k = PRELOAD ? yc[rr] : ((i < n) ? yhist[(size_t)(k - 1) * N + i] : 0.0);
+                const double yprev_k = yc[rr];
                 if (i < N) rhs_s[i] = (i < n) ? (yprev_k + (sls_mbit(mk, i) ? tx[i] : 0.0)) : 0.0;
             }
             __syncwarp();
@@ -544,7 +541,6 @@ sls_solve_kernel(SlsSolveArgs a) {
                     if (i < N) gbuf[i] = (i < n && sls_mbit(mxs[0], i)) ? -rhs_s[i] : 0.0;
                 }
             } else {
-                const double* hk = zhist + (size_t)(k - 1) * HB + 2 * lane;
                 double racc[NB], cacc[NB][2];
 #pragma unroll
                 for (int b = 0; b < NB; b++) { racc[b] = 0.0; cacc[b][0] = 0.0; cacc[b][1] = 0.0; }
@@ -557,13 +553,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                     for (int bj = 0; bj <= bi; bj++) {
                         const int c0 = 8 * bj + 2 * q;
                         const double2 vc = *reinterpret_cast<const double2*>(rhs_s + c0);
-                        double z0, z1;
-                        if (PRELOAD) {
-                            z0 = zc[PRELOAD ? zi : 0][0]; z1 = zc[PRELOAD ? zi : 0][1];
-                        } else {
-                            const double2 zv = *reinterpret_cast<const double2*>(hk + 64 * zi);
-                            z0 = zv.x; z1 = zv.y;
-                        }
+                        const double z0 = zc[zi][0], z1 = zc[zi][1];
                         zi++;
                         if (bj < bi) {
                             cacc[bj][0] = fma(z0, vr, cacc[bj][0]);
