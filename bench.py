@@ -341,7 +341,7 @@ def sim_config5(syn, nx, hbm_peak, hbm_src):
     ns, steps = 4096, 250
     rng = np.random.default_rng(0)
     js = rng.integers(0, nx, ns); ts = rng.integers(1, steps - T, ns)
-    syn.simulate(js[:64], ts[:64], steps)                        # warm-up (allocations, module load)
+    syn.simulate(js, ts, steps)                                  # warm-up: the handle's scratch (1.4 GB) is allocated once
     t0 = time.perf_counter()
     sim = syn.simulate(js, ts, steps)
     wall = time.perf_counter() - t0
@@ -610,7 +610,7 @@ def run_ours(args, rank, world, local_rank):
         g = np.random.default_rng(0)
         js = g.integers(0, nx5, ns5); ts = g.integers(1, steps5 - T, ns5)
         mine = (js >= a5) & (js < b5)
-        syn.simulate(js[mine][:16] - sh5.p0, ts[mine][:16], steps5)
+        syn.simulate(js[mine] - sh5.p0, ts[mine], steps5)              # warm-up: scratch allocated once
         sim = syn.simulate(js[mine] - sh5.p0, ts[mine], steps5)
         tm5 = syn.timing()
         for k in range(0, int(mine.sum()), 53):

@@ -330,11 +330,12 @@ sls_sim_kernel(SlsSimArgs a, int cap, int wcap, int ucap) {
 // `steps` time steps (112 GB at config #5, 0.37 s).  Here the window is read once: the CTA re-orders it into CSR by
 // destination row (entries of a row in a fixed order: by warp chunk of taps, then tap, then window column — a stable,
 // timing-independent order, so results are reproducible bit for bit) with the (tap, window column) of every entry in a
-// 16-bit tag, and each step is a conflict-free row gather: 4 lanes per row accumulate
+// 16-bit tag, and each step is a conflict-free row gather: 8 lanes per row accumulate
 //     beta(t+1)[r] / u(t)[r] = sum_e val[e] * what[(t+1-tau_e) mod T][col_e]
-// and are combined by two shuffles in a fixed order.  No atomics, no HBM traffic inside the time loop.
+// and are combined by three shuffles in a fixed order.  No atomics, no HBM traffic inside the time loop.
 // Requires 2T <= 256, windows <= 256 and the packed window to fit shared memory; otherwise the streaming kernel runs.
-#define SIMC_WARPS 8
+#define SIMC_WARPS 16
+#define SIMC_LPR 8                    // lanes per destination row in the gather
 #define SIMC_NT (SIMC_WARPS * 32)
 struct SlsSimCtaLayout {
     int oVal, oMeta, oWhat, oX, oXn, oBeta, oU, oW, oWu, oRowptr, oSlot, oCnt, oRed, oTap, total;
@@ -474,23 +475,23 @@ sls_sim_cta_kernel(SlsSimArgs a, int wcap, int ucap, int nent_cap) {
                 slot[tt] = on ? (int)(src % T) * wcap : -1;
             }
             __syncthreads();
-            // beta(t+1) and u(t): 4 lanes per row
+            // beta(t+1) and u(t): SIMC_LPR lanes per row
 #pragma unroll 1
-            for (int r0 = 0; r0 < nrows; r0 += SIMC_NT / 4) {
-                const int r = r0 + (tid >> 2);
+            for (int r0 = 0; r0 < nrows; r0 += SIMC_NT / SIMC_LPR) {
+                const int r = r0 + tid / SIMC_LPR;
                 double acc = 0.0;
                 if (r < nrows) {
                     const int e1 = rowptr[r + 1];
 #pragma unroll 8
-                    for (int e = rowptr[r] + (tid & 3); e < e1; e += 4) {        // (unrolled: 8 independent L2 loads in flight per lane)
+                    for (int e = rowptr[r] + (tid % SIMC_LPR); e < e1; e += SIMC_LPR) {   // (unrolled: 8 independent L2 loads in flight per lane)
                         const int mt = meta[e];
                         const int sb = slot[mt >> 8];
                         if (sb >= 0) acc = fma(vals[e], what[sb + (mt & 255)], acc);
                     }
                 }
-                acc += __shfl_xor_sync(SLS_FULL, acc, 1);
-                acc += __shfl_xor_sync(SLS_FULL, acc, 2);
-                if (r < nrows && (tid & 3) == 0) { if (r < nw) beta[r] = acc; else u[r - nw] = acc; }
+#pragma unroll
+                for (int d = 1; d < SIMC_LPR; d <<= 1) acc += __shfl_xor_sync(SLS_FULL, acc, d);
+                if (r < nrows && (tid % SIMC_LPR) == 0) { if (r < nw) beta[r] = acc; else u[r - nw] = acc; }
             }
             __syncthreads();
             // x(t+1) = A x(t) + w(t) + B2 u(t) on the window rows
