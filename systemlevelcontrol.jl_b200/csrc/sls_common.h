@@ -10,6 +10,8 @@
 #define SLS_ST_RESIDUAL 1
 #define SLS_ST_RANK_SKIPPED 2
 #define SLS_ST_NO_IMPULSE 4
+#define SLS_ST_COST_SINGULAR 8
+#define SLS_ST_GROUP_PATTERN 16
 
 struct SlsCsc {                 // Julia SparseMatrixCSC{Float64,Int64} on the device
     const int64_t* colptr;      // ncol+1, 1-based

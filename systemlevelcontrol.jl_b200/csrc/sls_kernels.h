@@ -54,6 +54,28 @@ int sls_solve_wide_max_slots(int N, int mcap, int nnzcap, int T, int wu, int sm_
 int64_t sls_solve_wide_hist_doubles(int N, int T);
 size_t sls_solve_wide_smem(int N, int mcap, int nnzcap, int T, int wu);
 
+// ---- kernel 2g (sls_solve_general.cu): general cost / coupled column groups, one CTA per group ----
+struct SlsGeneralArgs {
+    SlsCsc A, B2;                     // CSC
+    SlsCsc C1, D12, D11, B1;          // cost matrices by columns (valid when the has_* flag is set)
+    int has_cost, has_d11, has_b1;    // has_cost = 0: [C1 D12] = I
+    SlsSupports Sx, Su;
+    SlsPlanView P;
+    const int32_t* grp_ptr;           // [ngroups+1] offsets of each group's members in the planned-column order, or null (singletons)
+    int ngroups;
+    int pc, Nc, nb, pb, qc, cap;      // launch-wide maxima: q(n+m), q n, n, n+m, q; sort-buffer capacity (power of two)
+    double* const* out_nzval;         // [2T]
+    double* scratch; int64_t scratch_stride;   // per resident CTA (sls_general_scratch_doubles)
+    int32_t* status; double* resid;
+    double rank_tol, feas_tol, refine_tol;
+    int max_refine;
+};
+size_t sls_general_smem(int pc, int Nc, int nb, int pb, int qc, int T, int cap);
+int64_t sls_general_scratch_doubles(int pc, int Nc, int T);
+// stats (8 ints, zeroed by the caller): max q, max n, max n+m, max q n, max q(n+m), overflow
+int sls_launch_general_size(const SlsPlanView& P, const int32_t* grp_ptr, int ngroups, int cap, int32_t* stats, sls_stream_t stream);
+int sls_launch_solve_general(const SlsGeneralArgs& a, int grid, sls_stream_t stream);
+
 // ---- kernel 3 (sls_scatter.cu) ----
 struct SlsScatterArgs {
     SlsPlanView P;
