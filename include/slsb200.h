@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SLS_ABI_VERSION 6
+#define SLS_ABI_VERSION 7
 
 /* per-column status bits written by sls_solve* (improves on the reference, which ignores the
  * solver's termination status: src/synthesis.jl:62-65) */
@@ -36,6 +36,10 @@ extern "C" {
                                         localisation, rank-deficient beyond rank_tol, or cond(G) >~ 1e6   */
 #define SLS_STATUS_RANK_SKIPPED  2   /* informational: >=1 redundant constraint row was eliminated      */
 #define SLS_STATUS_NO_IMPULSE    4   /* column j is not in its own s_x (Ĩ is a zero column) => Φ = 0    */
+#define SLS_STATUS_COST_SINGULAR 8  /* general cost only: [C1~ D12~]' [C1~ D12~] is singular on the free entries of a tap (the
+                                       reference's minimiser is then not unique); those entries were fixed to 0 */
+#define SLS_STATUS_GROUP_PATTERN 16 /* column groups only: a member column's support reaches rows of the group's union index set
+                                       that its own index set does not hold; nothing was written for the group */
 
 typedef struct sls_handle sls_handle;
 
@@ -89,6 +93,27 @@ int sls_set_plant(sls_handle* h, int64_t Nx, int64_t Nu,
  * of the similarity-scaled plant Wx A Wx^-1, Wx B2 Wu^-1 and Φ is scaled back on the device).  resid[] then refers
  * to the scaled variables.  A diagonal B1 only rescales the cost of each column and does not change Φ. */
 int sls_set_weights(sls_handle* h, int64_t Nx, int64_t Nu, const double* wx, const double* wu);
+
+/* General cost — the 6-argument `Plant(A,B1,B2,C1,D11,D12)` (GeneralizedPlant.jl:101-103) with arbitrary sparse matrices,
+ * Julia CSC like the plant: C1 (Nz x Nx), D12 (Nz x Nu), D11 (Nz x Nw; NULL colptr = zero), B1 (Nx x Nw; NULL colptr = I).
+ * Replaces, per column group c_j, the objective of synthesis.jl:42-43,50,76-77:
+ *     sum_t || [C1~ D12~] [Φx~[t]; Φu~[t]] B1~[ii_x,:] + D11~ ||_F^2,   [C1~ D12~] = rows [s_x; Nx+s_u], columns s_x / s_u
+ * (reduction.jl:15, GeneralizedPlant.jl:266-271).  Call after sls_set_plant; all four colptr NULL clears the cost (back to
+ * the identity).  The columns are then solved by the general kernel (one CTA per group, q(n+m) bounded by shared memory:
+ * about 64 for q n <= 48) through sls_set_supports + sls_plan + sls_solve; sls_synthesize refuses.  Not combinable with
+ * sls_set_weights.  Where the cost is singular on a tap's free entries the column is flagged SLS_STATUS_COST_SINGULAR. */
+int sls_set_cost(sls_handle* h, int64_t Nz, int64_t Nw,
+                 const int64_t* C1_colptr, const int64_t* C1_rowval, const double* C1_nzval,
+                 const int64_t* D12_colptr, const int64_t* D12_rowval, const double* D12_nzval,
+                 const int64_t* D11_colptr, const int64_t* D11_rowval, const double* D11_nzval,
+                 const int64_t* B1_colptr, const int64_t* B1_rowval, const double* B1_nzval);
+
+/* Column groups — the `𝓘` keyword of SLS_𝓗₂ (synthesis.jl:15) with q > 1 columns per group: group g holds the planned
+ * columns grp_ptr[g] .. grp_ptr[g+1]-1 (0-based offsets into the column list of the NEXT sls_plan / sls_solve;
+ * grp_ptr[ngroups] must equal its ncols; the columns of a group ascend).  A group is solved as ONE problem on the union of
+ * its columns' index sets (reduction.jl:14), coupled through B1~[ii_x,:] (synthesis.jl:42) when B1 is not diagonal.
+ * grp_ptr NULL clears the groups (single columns). */
+int sls_set_groups(sls_handle* h, int64_t ngroups, const int64_t* grp_ptr);
 
 /* 𝓢ₓ[t] (Nx x Nx) and 𝓢ᵤ[t] (Nu x Nx), t = 1..T: arrays of T pointers.  *_nzval (Bool) may be NULL
  * (= all true).  Index sets use the stored pattern of 𝓢[T] (reduction.jl:14); masks use nzval

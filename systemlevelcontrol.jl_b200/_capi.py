@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libslsb200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 STATUS_OK, STATUS_RESIDUAL, STATUS_RANK_SKIPPED, STATUS_NO_IMPULSE = 0, 1, 2, 4
 
 i64p = C.POINTER(C.c_int64)
@@ -59,6 +59,8 @@ SIGNATURES = {
     "sls_solve": (C.c_int, [C.c_void_p, i64pp, i64pp, f64pp, i64pp, i64pp, f64pp, i32p, f64p]),
     "sls_solve_device": (C.c_int, [C.c_void_p]),
     "sls_set_weights": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, f64p, f64p]),
+    "sls_set_cost": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, i64p, i64p, f64p, i64p, i64p, f64p, i64p, i64p, f64p, i64p, i64p, f64p]),
+    "sls_set_groups": (C.c_int, [C.c_void_p, C.c_int64, i64p]),
     "sls_synthesize": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(i64p), C.POINTER(i64p), C.POINTER(u8p),
                                  C.POINTER(i64p), C.POINTER(i64p), C.POINTER(u8p), C.c_int64, C.c_int64, i64p, i64p,
                                  C.POINTER(i64p), C.POINTER(i64p), C.POINTER(f64p),

@@ -163,6 +163,11 @@ struct sls_handle {
     std::vector<void*> registered;           // host ranges page-locked through sls_host_register
     DevBuf supp[8]; PinVec<int64_t> supp_h; int supp_cap = 0;   // scratch of sls_make_supports (kept across calls)
     DevBuf simb[19]; int sim_cap = 0;                           // scratch of sls_simulate (kept across calls)
+    // general cost / column groups (sls_set_cost, sls_set_groups -> kernel 2g)
+    DevCsc C1, D12, D11, B1;
+    bool have_cost = false, have_d11 = false, have_b1 = false, have_groups = false;
+    int64_t Nz = 0, Nw = 0;
+    std::vector<int32_t> h_grp; DevBuf d_grp, gen_scratch, gen_stats; PinVec<int32_t> h_gen_stats;
 };
 
 static thread_local std::string g_create_err;
@@ -254,6 +259,8 @@ extern "C" void sls_destroy(sls_handle* h) {
     for (int i = 0; i < 8; i++) h->ev[i].destroy();
     for (int i = 0; i < 2; i++) h->marks[i].destroy();
     for (int i = 0; i < 16; i++) h->chunk_ev[i].destroy();
+    h->C1.release(); h->D12.release(); h->D11.release(); h->B1.release();
+    h->d_grp.release(); h->gen_scratch.release(); h->gen_stats.release(); h->h_gen_stats.release();
     rt::stream_destroy(h->copy_stream);
     rt::stream_destroy(h->stream);
     delete h;
@@ -380,6 +387,64 @@ extern "C" int sls_set_weights(sls_handle* h, int64_t Nx, int64_t Nu, const doub
     SLS_CK(rt::h2d(h->d_wu.p, h->h_wu.data(), Nu * sizeof(double), h->stream));
     SLS_CK(rt::sync(h->stream));
     h->have_weights = true;
+    return 0;
+}
+
+// General cost: the 6-argument Plant(A,B1,B2,C1,D11,D12) (GeneralizedPlant.jl:101-103) with arbitrary sparse
+// C1 (Nz x Nx), D12 (Nz x Nu), D11 (Nz x Nw, NULL = 0) and B1 (Nx x Nw, NULL = I) in the objective
+// || [C1~ D12~] [Φx~;Φu~] B1~[ii_x,:] + D11~ ||  (synthesis.jl:42-43,50,76-77).  Solved by kernel 2g (sls_solve_general.cu).
+static int upload_cost_csc(sls_handle* h, DevCsc& d, const char* name, int64_t nrow, int64_t ncol,
+                           const int64_t* cp, const int64_t* rv, const double* nz) {
+    const char* m = check_csc(nrow, ncol, cp, rv, true);
+    if (m) return fail(h, -2, (std::string("sls_set_cost: ") + name + ": " + m).c_str());
+    if (!nz && cp[ncol] != 1) return fail(h, -1, (std::string("sls_set_cost: ") + name + " nzval is NULL").c_str());
+    for (int64_t e = 0; e < cp[ncol] - 1; e++)
+        if (!std::isfinite(nz[e])) return fail(h, -3, (std::string("sls_set_cost: ") + name + " holds a non-finite value").c_str());
+    return upload_csc(h, d, ncol, cp, rv, nz);
+}
+
+extern "C" int sls_set_cost(sls_handle* h, int64_t Nz, int64_t Nw,
+                            const int64_t* C1_colptr, const int64_t* C1_rowval, const double* C1_nzval,
+                            const int64_t* D12_colptr, const int64_t* D12_rowval, const double* D12_nzval,
+                            const int64_t* D11_colptr, const int64_t* D11_rowval, const double* D11_nzval,
+                            const int64_t* B1_colptr, const int64_t* B1_rowval, const double* B1_nzval) {
+    if (!h) return -1;
+    SLS_CK(rt::set_device(h->device));
+    h->solved = false;
+    if (!C1_colptr && !D12_colptr && !D11_colptr && !B1_colptr) { h->have_cost = h->have_d11 = h->have_b1 = false; return 0; }
+    SLS_ARG(h->have_plant, "sls_set_cost: call sls_set_plant first (the cost matrices are sized by Nx, Nu)");
+    SLS_ARG(!h->have_weights, "sls_set_cost: diagonal weights (sls_set_weights) are installed; put them into C1 / D12 instead");
+    SLS_ARG((C1_colptr != nullptr) == (D12_colptr != nullptr), "sls_set_cost: C1 and D12 must be given together");
+    SLS_ARG(Nz >= 0 && Nw >= 0 && Nz < (int64_t)1 << 31 && Nw < (int64_t)1 << 31, "sls_set_cost: bad dimensions");
+    h->have_cost = h->have_d11 = h->have_b1 = false;
+    if (C1_colptr) {
+        if (int e = upload_cost_csc(h, h->C1, "C1", Nz, h->Nx, C1_colptr, C1_rowval, C1_nzval)) return e;
+        if (int e = upload_cost_csc(h, h->D12, "D12", Nz, h->Nu, D12_colptr, D12_rowval, D12_nzval)) return e;
+    }
+    if (D11_colptr) { if (int e = upload_cost_csc(h, h->D11, "D11", Nz, Nw, D11_colptr, D11_rowval, D11_nzval)) return e; }
+    if (B1_colptr) { if (int e = upload_cost_csc(h, h->B1, "B1", h->Nx, Nw, B1_colptr, B1_rowval, B1_nzval)) return e; }
+    SLS_CK(rt::sync(h->stream));
+    h->have_cost = C1_colptr != nullptr; h->have_d11 = D11_colptr != nullptr && D11_colptr[Nw] > 1; h->have_b1 = B1_colptr != nullptr;
+    h->Nz = Nz; h->Nw = Nw;
+    return 0;
+}
+
+// Column groups (the 𝓘 keyword, synthesis.jl:15): group g = planned columns grp_ptr[g] .. grp_ptr[g+1]-1 of the NEXT
+// sls_solve (0-based offsets into the column list given to sls_plan; each group's columns ascending).  NULL clears.
+extern "C" int sls_set_groups(sls_handle* h, int64_t ngroups, const int64_t* grp_ptr) {
+    if (!h) return -1;
+    SLS_CK(rt::set_device(h->device));
+    h->solved = false;
+    if (!grp_ptr) { h->have_groups = false; h->h_grp.clear(); return 0; }
+    SLS_ARG(ngroups >= 0 && ngroups < (int64_t)1 << 31, "sls_set_groups: bad group count");
+    SLS_ARG(grp_ptr[0] == 0, "sls_set_groups: grp_ptr[0] must be 0");
+    for (int64_t g = 0; g < ngroups; g++)
+        SLS_ARG(grp_ptr[g + 1] > grp_ptr[g] && grp_ptr[g + 1] < (int64_t)1 << 31, "sls_set_groups: every group needs at least one column");
+    h->h_grp.assign(grp_ptr, grp_ptr + ngroups + 1);
+    SLS_CK(h->d_grp.ensure((size_t)(ngroups + 1) * sizeof(int32_t)));
+    SLS_CK(rt::h2d(h->d_grp.p, h->h_grp.data(), (size_t)(ngroups + 1) * sizeof(int32_t), h->stream));
+    SLS_CK(rt::sync(h->stream));
+    h->have_groups = true;
     return 0;
 }
 
@@ -923,7 +988,12 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
     const int64_t T = h->T, Nx = h->Nx;
     const int nc1 = std::max(p.ncols, 1);
     h->solved = false;
-    if (p.nmax > sls_solve_class_N(sls_solve_class_count() - 1))
+    const bool general = h->have_cost || h->have_groups;       // kernel 2g instead of the size-class kernels
+    if (general) {
+        SLS_ARG(!h->have_weights, "sls_solve: diagonal weights and a general cost / column groups cannot be combined");
+        if (h->have_groups) SLS_ARG(h->h_grp.back() == p.ncols, "sls_solve: the column groups (sls_set_groups) do not cover the planned columns");
+    }
+    if (!general && p.nmax > sls_solve_class_N(sls_solve_class_count() - 1))
         return fail(h, -6, "sls_solve: a column's local state dimension |s_x| exceeds the largest solver size class");
     SLS_CK(h->status.ensure(nc1 * sizeof(int32_t)));
     SLS_CK(h->resid.ensure(nc1 * sizeof(double)));
@@ -931,7 +1001,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
     SLS_CK(h->out_nzval.ensure((size_t)std::max<int64_t>(p.tot_packed, 1) * sizeof(double)));
     SLS_CK(h->out_ptrs.ensure((size_t)4 * T * sizeof(void*)));
     int nchunk = 1;
-    if (ho && p.cols_sorted && p.ncols >= 16384) {
+    if (ho && p.cols_sorted && p.ncols >= 16384 && !general) {
         nchunk = (h->opt.flags & 2) ? 1 : 4;                   // flags bit 1: no D2H pipeline
         if (const char* ev = getenv("SLS_D2H_CHUNKS")) { const int c = atoi(ev); if (c >= 1 && c <= 16) nchunk = c; }
     }
@@ -959,7 +1029,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
     // history slots: sized for the most demanding class
     size_t hist_bytes = 8;
     const SlsPlanView v = plan_view(h, p);
-    for (const SolveClass& c : p.classes) {
+    if (!general) for (const SolveClass& c : p.classes) {
         const int maxw = sls_solve_max_resident_warps(c.N, c.mcap, c.nnzcap, (int)T, p.wu, h->sm_count, h->max_smem);
         if (maxw <= 0) return fail(h, -4, "sls_solve: local problem does not fit shared memory");
         const int64_t warps = std::min<int64_t>(maxw, ((int64_t)c.count + 3) / 4 * 4);
@@ -1001,8 +1071,52 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
                     SLS_CK(rt::d2h(ho->rvs[x][t], h->out_rowval.as<int64_t>() + p.out_off[tt], (size_t)p.nnz_tap[tt] * sizeof(int64_t), h->copy_stream));
             }
     }
+    if (general && p.ncols) {
+        // one CTA per column group: sizes of the union index sets first (device), then the shared-memory carve-up
+        const int ngroups = h->have_groups ? (int)h->h_grp.size() - 1 : p.ncols;
+        int qmax = 1;
+        if (h->have_groups) for (int g = 0; g < ngroups; g++) qmax = std::max(qmax, h->h_grp[g + 1] - h->h_grp[g]);
+        int cap = 32;
+        while (cap < qmax * std::max(p.nstride, p.mstride)) cap <<= 1;
+        if (cap > 8192) return fail(h, -4, "sls_solve: a column group's index sets exceed the general solver's capacity");
+        SLS_CK(h->gen_stats.ensure(8 * sizeof(int32_t))); SLS_CK(h->h_gen_stats.resize(8));
+        SLS_CK(rt::zero(h->gen_stats.p, 8 * sizeof(int32_t), h->stream));
+        const int32_t* gp = h->have_groups ? h->d_grp.as<int32_t>() : nullptr;
+        SLS_CK(sls_launch_general_size(v, gp, ngroups, cap, h->gen_stats.as<int32_t>(), h->stream));
+        SLS_CK(sls_kcopy(h->h_gen_stats.data(), h->gen_stats.p, 8 * sizeof(int32_t), h->stream));
+        SLS_CK(rt::sync(h->stream));
+        const int32_t* gs = h->h_gen_stats.data();
+        if (gs[5]) return fail(h, -4, "sls_solve: a column group's index sets exceed the general solver's capacity");
+        SlsGeneralArgs a{};
+        a.A = h->A.view(); a.B2 = h->B2.view();
+        a.has_cost = h->have_cost; a.has_d11 = h->have_d11; a.has_b1 = h->have_b1;
+        if (h->have_cost) { a.C1 = h->C1.view(); a.D12 = h->D12.view(); }
+        if (h->have_d11) a.D11 = h->D11.view();
+        if (h->have_b1) a.B1 = h->B1.view();
+        a.Sx = h->Sx.view(); a.Su = h->Su.view(); a.P = v; a.grp_ptr = gp; a.ngroups = ngroups;
+        a.qc = gs[0]; a.nb = gs[1]; a.pb = gs[2]; a.Nc = gs[3]; a.pc = gs[4]; a.cap = cap;
+        const size_t smem = sls_general_smem(a.pc, a.Nc, a.nb, a.pb, a.qc, (int)T, cap);
+        if (smem > (size_t)h->max_smem)
+            return fail(h, -4, "sls_solve: a group's local problem does not fit the general solver's shared memory (q(n+m) too large)");
+        if (h->have_b1 || h->have_d11) {
+            // B1 / D11 are indexed by the group's columns: they must exist as columns of these matrices
+            if (p.col_hi > h->Nw) return fail(h, -1, "sls_solve: a planned column exceeds Nw (B1 / D11 have no such column)");
+        }
+        const int per_sm = std::max(1, std::min(4, (int)((size_t)(h->max_smem + 1024) / (smem + 1024))));
+        const int grid = std::min(ngroups, h->sm_count * per_sm);
+        a.scratch_stride = sls_general_scratch_doubles(a.pc, a.Nc, (int)T);
+        SLS_CK(h->gen_scratch.ensure((size_t)grid * a.scratch_stride * sizeof(double)));
+        a.scratch = h->gen_scratch.as<double>();
+        a.out_nzval = reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T);
+        a.status = h->status.as<int32_t>(); a.resid = h->resid.as<double>();
+        a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol; a.refine_tol = 0.1 * h->opt.feas_tol;
+        a.max_refine = (h->opt.flags & 4) ? 0 : 3;
+        SLS_CK(sls_launch_solve_general(a, grid, h->stream));
+        launches++;
+    }
     for (int ch = 0; ch < nchunk; ch++) {
         for (const SolveClass& c : p.classes) {
+            if (general) break;
             int lo = 0, hi = c.count;
             if (nchunk > 1) {
                 const int32_t* lb = p.h_lists.data() + c.list_off;
@@ -1185,6 +1299,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
                            int64_t* nnz_x, int64_t* nnz_u, int32_t* status, double* resid) {
     if (!h) return -1;
     SLS_ARG(h->have_plant, "sls_synthesize: call sls_set_plant first");
+    SLS_ARG(!h->have_cost && !h->have_groups, "sls_synthesize: a general cost / column groups are installed: use sls_set_supports + sls_plan + sls_solve");
     SLS_ARG(T >= 1 && T < 4096, "sls_synthesize: bad T");
     SLS_ARG(Sx_colptr && Sx_rowval && Su_colptr && Su_rowval, "sls_synthesize: NULL array of pointers");
     SLS_CK(rt::set_device(h->device));

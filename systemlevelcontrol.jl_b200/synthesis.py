@@ -196,6 +196,30 @@ class Synthesizer:
         self._ck(self.api.sls_set_plant(self.h, A.n, B2.n, ptr(A.colptr, i64p), ptr(A.rowval, i64p), ptr(A.nzval, f64p),
                                         ptr(B2.colptr, i64p), ptr(B2.rowval, i64p), ptr(B2.nzval, f64p)))
 
+    def set_cost(self, C1, D12, D11=None, B1=None):
+        """General cost matrices (sls_set_cost); call after set_plant.  D11 None = 0, B1 None = I; all None clears."""
+        if C1 is None and D12 is None and D11 is None and B1 is None:
+            n = ptr(None, i64p); z = ptr(None, f64p)
+            self._ck(self.api.sls_set_cost(self.h, 0, 0, n, n, z, n, n, z, n, n, z, n, n, z))
+            return
+        mats = [None if M is None else _as_julia(M, np.float64) for M in (C1, D12, D11, B1)]
+        Nz = mats[0].m if mats[0] is not None else (mats[2].m if mats[2] is not None else 0)
+        Nw = mats[2].n if mats[2] is not None else (mats[3].n if mats[3] is not None else self.Nx)
+        args = []
+        for M in mats:
+            args += [ptr(None if M is None else M.colptr, i64p), ptr(None if M is None else M.rowval, i64p),
+                     ptr(None if M is None else M.nzval, f64p)]
+        self._keep_cost = mats
+        self._ck(self.api.sls_set_cost(self.h, Nz, Nw, *args))
+
+    def set_groups(self, grp_ptr):
+        """Column groups over the planned column list (sls_set_groups): 0-based offsets, None clears."""
+        if grp_ptr is None:
+            self._ck(self.api.sls_set_groups(self.h, 0, ptr(None, i64p)))
+            return
+        g = np.ascontiguousarray(grp_ptr, dtype=np.int64)
+        self._ck(self.api.sls_set_groups(self.h, g.size - 1, ptr(g, i64p)))
+
     def set_supports(self, Sx, Su, pass_nzval=True):
         Sx = [_as_julia(M, np.bool_) for M in Sx]
         Su = [_as_julia(M, np.bool_) for M in Su]
@@ -472,39 +496,59 @@ def _check_plant(P):
     return True
 
 
-def SLS_H2(P, S, I=None, *, device: int = 0, return_info: bool = False, api=None):
-    """`SLS_𝓗₂(P, 𝓢; 𝓘=nothing)` (src/synthesis.jl:11-32).
-
-    P: Plant (state feedback).  S = [Sx, Su]: two length-T lists of Bool sparse matrices (Nx x Nx, Nu x Nx).
-    I: optional list of column groups; each group must be a single 0-based column (`[[j] for j in ...]`, the
-       reference's default shape, synthesis.jl:15) — plain ints are accepted too.
-    Returns (Phi_x, Phi_u): two length-T lists of scipy CSC matrices, the layout `eachcol(Φ)` gives in Julia
-    (synthesis.jl:27).  The stored pattern is the full in-support mask (explicit zeros kept).
-    Like the reference, a plant that is not state-feedback returns None (synthesis.jl:13 falls through)."""
-    if not _check_plant(P):
-        return None
+def _route(P, S, I):
+    """Host-side dispatch of SLS_H2: which kernel family solves (P, 𝓘).  Returns (wx, wu, general, cols, grp_ptr):
+    diagonal weights for sls_set_weights (or None), whether the general kernel 2g is needed (sls_set_cost), the planned
+    column list (None = all) and the group offsets for sls_set_groups (None = single columns)."""
     wx, wu, why = P.diagonal_cost()
-    if why is not None:
-        raise NotImplementedError("libslsb200 covers diagonal cost weights [C1 D12] = blockdiag(diag(wx), diag(wu)) > 0 with "
-                                  f"D11 = 0 and a diagonal B1 (SURVEY §8f-3); this plant: {why}")
+    general = why is not None            # general [C1 D12] / D11 / B1: kernel 2g (sls_set_cost)
     Sx, Su = S
     cols = None
+    grp_ptr = None
     if I is not None:
         groups = [[int(c) for c in np.atleast_1d(np.asarray(g))] for g in I]
         cols = [c for g in groups for c in g]
         if any(len(g) != 1 for g in groups):
             if len(set(cols)) != len(cols):
                 raise ValueError("a column appears in more than one group")
-            if not _groups_decouple(P, Sx, Su, groups):
-                raise NotImplementedError("a column group's union index set adds non-empty constraint rows to a member column "
-                                          "(supports not closed under the plant's pattern): coupled group problems are not "
-                                          "implemented (SURVEY §8f-3)")
+            if any(any(b <= a for a, b in zip(g, g[1:])) for g in groups):
+                raise ValueError("the columns of a group must ascend (the reference pairs the impulses I~ with the group's "
+                                 "columns by their order in s_x, reduction.jl:22-23)")
+            if general or not _groups_decouple(P, Sx, Su, groups):
+                grp_ptr = np.concatenate([[0], np.cumsum([len(g) for g in groups])]).astype(np.int64)
+    if grp_ptr is not None and wx is not None:
+        general, wx, wu = True, None, None       # coupled groups with diagonal weights: the weights travel as C1 / D12
+    if general and P.Nw < P.Nx and (cols is None or max(cols) >= P.Nw):
+        raise ValueError("B1 / D11 have fewer columns than the disturbance columns asked for")
+    return wx, wu, general, cols, grp_ptr
+
+
+def SLS_H2(P, S, I=None, *, device: int = 0, return_info: bool = False, api=None):
+    """`SLS_𝓗₂(P, 𝓢; 𝓘=nothing)` (src/synthesis.jl:11-32).
+
+    P: Plant (state feedback).  S = [Sx, Su]: two length-T lists of Bool sparse matrices (Nx x Nx, Nu x Nx).
+    I: optional list of column groups of 0-based columns (`[[j] for j in ...]` is the reference's default shape,
+       synthesis.jl:15; plain ints are accepted too).  Groups with q > 1 ascending columns are solved as one problem
+       on the union index set (kernel 2g) unless they provably decouple into their single columns.
+    Cost: the identity and diagonal [C1 D12] with a diagonal B1 run on the DMMA kernels; any other C1, D12, D11, B1
+       (6-argument Plant) runs on the general kernel (sls_set_cost).
+    Returns (Phi_x, Phi_u): two length-T lists of scipy CSC matrices, the layout `eachcol(Φ)` gives in Julia
+    (synthesis.jl:27).  The stored pattern is the full in-support mask (explicit zeros kept).
+    Like the reference, a plant that is not state-feedback returns None (synthesis.jl:13 falls through)."""
+    if not _check_plant(P):
+        return None
+    wx, wu, general, cols, grp_ptr = _route(P, S, I)
+    Sx, Su = S
     syn = Synthesizer(device=device, api=api)
     try:
         if wx is not None:
             syn.set_weights(wx, wu, P.Nx, P.Nu)
         syn.set_plant(P.A, P.B2)
-        if cols is None and not return_info:
+        if general:
+            syn.set_cost(P.C1, P.D12, P.D11 if P.D11.nnz else None, None if P._b1_is_identity() else P.B1)
+        if grp_ptr is not None:
+            syn.set_groups(grp_ptr)
+        if cols is None and not return_info and not general:
             out = syn.synthesize(Sx, Su)              # the default 𝓘 = 1..Nx: one pipelined call
             Phix, Phiu = syn.outputs_to_scipy(out)
             info = None

@@ -5,7 +5,7 @@
 set -e
 ROOT=$(cd "$(dirname "$0")/../.." && pwd)
 OUT=${TMPDIR:-/tmp}/sls_asan; mkdir -p "$OUT"
-for f in sls_api sls_gather sls_solve sls_solve_wide sls_scatter sls_sim sls_supports; do
+for f in sls_api sls_gather sls_solve sls_solve_wide sls_solve_general sls_scatter sls_sim sls_supports; do
   g++ -O1 -g -std=c++17 -DSLS_EMU -fPIC -w -fsanitize=address -fno-omit-frame-pointer -x c++ -I "$ROOT/tests/emu" \
       -c "$ROOT/systemlevelcontrol.jl_b200/csrc/$f.cu" -o "$OUT/$f.o" &
 done; wait
@@ -44,5 +44,10 @@ syn.simulate([20, 0, 39], [5, 3, 20], 40); print("sim (L2 scratch mode) ok"); sy
 A, B1, B2 = W.grid_plant(13, 13); Sx, Su = W.grid_supports(13, 13, 4, 20, 1.5)
 syn = slc_b200.Synthesizer(api=api); syn.set_plant(A, B2); syn.set_supports(Sx, Su); syn.plan([0, 6, 84]); out = syn.solve()
 print("grid ok (CTA kernel, n = 21 / 36 / 61)", out["resid"][:3].max(), syn.n); syn.close()
+sys.path.insert(0, "$ROOT/tests")
+import parity_cases as pc
+print("general cost / groups ok (kernel 2g)", pc.check_general_cost(api, cases=[
+    dict(kw=dict(dense_cost=True, b1_band=True, d11=True), I=[[0, 1], [10, 11, 12], [29]])]))
+pc.check_general_error_paths(api); print("general error paths ok")
 PY
 LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 python "$OUT/run.py"

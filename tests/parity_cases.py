@@ -467,6 +467,119 @@ def check_weighted_cost(api, cols=(3, 14, 39)):
     return worst
 
 
+def _general_plant(Nx, seed, dense_cost=True, b1_band=True, d11=True):
+    """Chain plant with a non-diagonal cost: banded SPD-ish C1 / D12 blocks (rows [x; u] as the reduced plant selects
+    rows [s_x; Nx+s_u], reduction.jl:15), a tridiagonal B1 and a sparse D11."""
+    A, B1, B2 = O.chain_plant(Nx)
+    Nu = B2.shape[1]
+    rng = np.random.default_rng(seed)
+    if dense_cost:
+        Qh = sp.diags([rng.uniform(1.0, 2.0, Nx), rng.uniform(-0.4, 0.4, Nx - 1), rng.uniform(-0.3, 0.3, Nx - 1)], [0, 1, -1])
+        Rh = sp.diags([rng.uniform(1.0, 2.0, Nu), rng.uniform(-0.3, 0.3, Nu - 1)], [0, 1])
+        Xu = sp.random(Nx, Nu, density=0.05, random_state=seed, data_rvs=lambda k: rng.uniform(-0.2, 0.2, k))
+        C1 = sp.vstack([Qh, 0.1 * Xu.T]).tocsc()                # state rows, then input rows
+        D12 = sp.vstack([Xu, Rh]).tocsc()
+    else:
+        CD = sp.identity(Nx + Nu, format="csc"); C1, D12 = CD[:, :Nx], CD[:, Nx:]
+    B1g = sp.diags([np.linspace(0.8, 1.5, Nx), rng.uniform(-0.5, 0.5, Nx - 1), rng.uniform(-0.5, 0.5, Nx - 1)], [0, 1, -1]).tocsc() if b1_band else B1
+    D11 = sp.random(Nx + Nu, Nx, density=0.04, random_state=seed + 1, data_rvs=lambda k: rng.uniform(-0.3, 0.3, k)).tocsc() if d11 else 0
+    return A, B1g, B2, C1, D11, D12
+
+
+def check_general_cost(api, Nx=30, d=6, T=12, cases=None):
+    """SURVEY §8 row f3 on the device: non-diagonal [C1 D12], D11 != 0, non-diagonal B1 and coupled q = 2 / q = 3 groups
+    through SLS_H2 -> sls_set_cost / sls_set_groups -> kernel 2g, against the oracle's null-space restatement of
+    synthesis.jl:42-43,50,76-77 (SLS_H2_general).  Patterns bit-exact, values to PHI_RTOL per tap."""
+    worst = 0.0
+    cases = cases or [
+        dict(kw=dict(dense_cost=True, b1_band=False, d11=False), I=[[3], [14], [29]]),          # dense cost, single columns
+        dict(kw=dict(dense_cost=True, b1_band=False, d11=True), I=[[0], [15]]),                  # + linear term D11
+        dict(kw=dict(dense_cost=False, b1_band=True, d11=False), I=[[4, 5], [20, 22]]),          # identity cost, B1 couples a group
+        dict(kw=dict(dense_cost=True, b1_band=True, d11=True), I=[[10, 11, 12], [0, 1], [29]]),  # everything at once
+    ]
+    for case in cases:
+        A, B1, B2, C1, D11, D12 = _general_plant(Nx, 3, **case["kw"])
+        S = O.make_supports(A, B2, d, T, 1.5)
+        Ox, Ou = O.SLS_H2_general(O.Plant(A, B1, B2, C1, D11, D12), S, I=case["I"])
+        Gx, Gu, info = slc_b200.SLS_H2(slc_b200.Plant(A, B1, B2, C1, D11, D12), S, I=case["I"], api=api, return_info=True)
+        assert (info["status"] & ~2 == 0).all(), info["status"]
+        assert info["resid"].max() < 1e-12, info["resid"]
+        for G, H in zip(Gx + Gu, Ox + Ou):
+            assert np.array_equal(G.indptr, H.indptr) and np.array_equal(G.indices, H.indices)
+            nb = np.linalg.norm(H.data)
+            if nb > 0:
+                worst = max(worst, np.linalg.norm(G.data - H.data) / nb)
+        assert worst < PHI_RTOL, (case, worst)
+    return worst
+
+
+def check_coupled_groups_identity_cost(api, Nx=30, d=6, T=12):
+    """A q = 2 group whose union index set adds non-empty constraint rows to a member (supports not closed under the
+    plant's pattern: the case _groups_decouple refuses) with the README cost: kernel 2g vs the oracle."""
+    A, B1, B2 = O.chain_plant(Nx)
+    S = O.make_supports(A, B2, d, T, 1.5)
+    groups = [[2, 9], [15, 16], [25]]
+    Ox, Ou = O.SLS_H2_general(O.Plant(A, B1, B2), S, I=groups)
+    Gx, Gu, info = slc_b200.SLS_H2(slc_b200.Plant(A, B1, B2), S, I=groups, api=api, return_info=True)
+    worst = 0.0
+    for G, H in zip(Gx + Gu, Ox + Ou):
+        assert np.array_equal(G.indptr, H.indptr) and np.array_equal(G.indices, H.indices)
+        nb = np.linalg.norm(H.data)
+        if nb > 0:
+            worst = max(worst, np.linalg.norm(G.data - H.data) / nb)
+    assert worst < PHI_RTOL, worst
+    return worst, info
+
+
+def check_general_error_paths(api):
+    """Refusals and flags of the general path: one-shot call refused, weights + cost refused, groups that do not cover the
+    plan, a singular cost (flag, not garbage), a group too large for shared memory."""
+    Nx, d, T = 30, 6, 12
+    A, B1, B2 = O.chain_plant(Nx)
+    Nu = B2.shape[1]
+    S = O.make_supports(A, B2, d, T, 1.5)
+    CD = sp.identity(Nx + Nu, format="csc")
+    syn = slc_b200.Synthesizer(api=api)
+    try:
+        with np.testing.assert_raises(_capi.SlsError):
+            syn.set_cost(CD[:, :Nx], CD[:, Nx:])                  # plant first
+        syn.set_plant(A, B2)
+        syn.set_cost(CD[:, :Nx], CD[:, Nx:])
+        with np.testing.assert_raises(_capi.SlsError):
+            syn.synthesize(*S)                                    # the pipelined one-shot path has no general kernel
+        syn.set_supports(*S); syn.plan([3, 4, 10])
+        syn.set_groups([0, 2])                                    # does not cover the three planned columns
+        with np.testing.assert_raises(_capi.SlsError):
+            syn.solve()
+        syn.set_groups([0, 2, 3])
+        ident = syn.solve()
+        assert (ident["status"][:3] & ~2 == 0).all()
+        # identity installed as a "general" cost == the DMMA kernels' answer (different algorithms: to rounding)
+        syn.set_cost(None, None); syn.set_groups(None)
+        ref = syn.solve()
+        for fam in ("x", "u"):
+            for t in range(T):
+                np.testing.assert_allclose(ident[fam]["nzval"][t], ref[fam]["nzval"][t], rtol=0, atol=1e-11)
+        # a cost that ignores the inputs entirely: singular on the free u entries -> flagged
+        Z12 = sp.csc_matrix((Nx + Nu, Nu))
+        syn.set_cost(CD[:, :Nx], Z12); syn.plan([10])
+        out = syn.solve()
+        assert out["status"][0] & 8, out["status"][:1]
+        # all columns as ONE group: q(n+m) far beyond shared memory
+        syn.set_cost(None, None); syn.plan(None); syn.set_groups([0, Nx])
+        with np.testing.assert_raises(_capi.SlsError):
+            syn.solve()
+        syn.set_groups(None)
+        # weights and a general cost exclude each other
+        syn.set_weights(np.full(Nx, 2.0), None, Nx, Nu); syn.set_plant(A, B2)
+        with np.testing.assert_raises(_capi.SlsError):
+            syn.set_cost(CD[:, :Nx], CD[:, Nx:])
+    finally:
+        syn.close()
+    with np.testing.assert_raises(ValueError):
+        slc_b200.SLS_H2(slc_b200.Plant(A, B1, B2), S, I=[[5, 3]], api=api)       # descending group
+
+
 def random_banded_plant(Nx, bw, seed, act_every=3):
     """Random banded A (bandwidth bw, unsymmetric values, stable-ish scaling) and a random column-selection-like B2 with
     random gains: exercises non-tridiagonal index sets, several nonzeros per B2 column and non-unit actuator gains."""

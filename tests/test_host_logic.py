@@ -44,25 +44,38 @@ def test_non_state_feedback_returns_none_like_reference():
     assert slc_b200.SLS_H2(OF(), [[], []]) is None
 
 
-def test_unsupported_shapes_raise():
-    """Cost shapes outside the diagonal family and coupled column groups are refused loudly."""
+def test_cost_and_group_routing():
+    """Which kernel family SLS_H2 picks (SURVEY §8f-3): identity / diagonal costs -> DMMA kernels (+ sls_set_weights);
+    non-diagonal [C1 D12], D11 != 0, non-diagonal B1 -> kernel 2g (sls_set_cost); q > 1 groups -> kernel 2g unless they
+    provably decouple.  Host logic only."""
+    from slc_b200.synthesis import _route
     A, B1, B2 = O.chain_plant(12)
     Nx, Nu = 12, B2.shape[1]
-    B1c = sp.csc_matrix(B1 + sp.diags([0.1 * np.ones(Nx - 1)], [1]))          # R = B1~[ii_x,:] would couple group columns
-    with pytest.raises(NotImplementedError):
-        slc_b200.SLS_H2(Plant(A, B1c, B2), [[], []])
+    S = O.make_supports(A, B2, 3, 6, 1.5)
+    assert _route(Plant(A, B1, B2), S, None) == (None, None, False, None, None)
+    B1c = sp.csc_matrix(B1 + sp.diags([0.1 * np.ones(Nx - 1)], [1]))          # R = B1~[ii_x,:] couples group columns
+    assert _route(Plant(A, B1c, B2), S, None)[2] is True
     C1 = sp.vstack([sp.identity(Nx) + sp.diags([0.1 * np.ones(Nx - 1)], [1]), sp.csc_matrix((Nu, Nx))])
     D12 = sp.vstack([sp.csc_matrix((Nx, Nu)), sp.identity(Nu)])
-    with pytest.raises(NotImplementedError):
-        slc_b200.SLS_H2(Plant(A, B1, B2, C1, 0, D12), [[], []])
+    assert _route(Plant(A, B1, B2, C1, 0, D12), S, None)[2] is True
     D11 = sp.csc_matrix(np.ones((Nx + Nu, Nx)))
-    with pytest.raises(NotImplementedError):
-        slc_b200.SLS_H2(Plant(A, B1, B2, sp.vstack([sp.identity(Nx), sp.csc_matrix((Nu, Nx))]), D11, D12), [[], []])
-    # supports not closed under the plant's pattern: a group's union adds non-empty rows to a member -> refused
-    P = Plant(A, B1, B2)
+    assert _route(Plant(A, B1, B2, sp.vstack([sp.identity(Nx), sp.csc_matrix((Nu, Nx))]), D11, D12), S, None)[2] is True
+    # diagonal weights stay on the DMMA kernels ...
+    wx = np.linspace(0.5, 2, Nx)
+    Cw = sp.vstack([sp.diags(wx), sp.csc_matrix((Nu, Nx))])
+    r = _route(Plant(A, B1, B2, Cw, 0, D12), S, [[3], [4]])
+    assert r[2] is False and np.array_equal(r[0], wx) and r[3] == [3, 4] and r[4] is None
+    # ... unless a coupled group needs kernel 2g: the weights then travel inside C1 / D12
     wide = sp.csc_matrix(O._pat_power(O._pat(A), 3) != 0)
-    with pytest.raises(NotImplementedError):
-        slc_b200.SLS_H2(P, [[wide, sp.identity(12, format="csc", dtype=bool)], [sp.csc_matrix((Nu, 12), dtype=bool)] * 2], I=[[0, 1]])
+    Sw = [[wide, sp.identity(12, format="csc", dtype=bool)], [sp.csc_matrix((Nu, 12), dtype=bool)] * 2]
+    r = _route(Plant(A, B1, B2, Cw, 0, D12), Sw, [[0, 1], [5]])
+    assert r[0] is None and r[2] is True and r[3] == [0, 1, 5] and r[4].tolist() == [0, 2, 3]
+    r = _route(Plant(A, B1, B2), Sw, [[0, 1]])
+    assert r[2] is False and r[4].tolist() == [0, 2]                         # identity cost, coupled group: groups only
+    with pytest.raises(ValueError):
+        _route(Plant(A, B1, B2), S, [[4, 3]])                                 # descending group
+    with pytest.raises(ValueError):
+        _route(Plant(A, B1, B2), S, [[3, 4], [4]])                            # a column in two groups
 
 
 def test_diagonal_cost_classification():

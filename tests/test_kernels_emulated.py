@@ -67,6 +67,13 @@ def test_emu_weighted_cost_and_groups(emu_api):
     pc.check_weighted_cost(emu_api, cols=(3, 39, 14))
 
 
+def test_emu_general_cost_and_coupled_groups(emu_api):
+    """kernel 2g (sls_solve_general.cu) vs the oracle's null-space restatement."""
+    assert pc.check_coupled_groups_identity_cost(emu_api)[0] < 1e-10
+    assert pc.check_general_cost(emu_api) < 1e-10
+    pc.check_general_error_paths(emu_api)
+
+
 def test_emu_pipelined_ring_plant_long_range_coupling(emu_api):
     """A ring (A[0,Nx-1], A[Nx-1,0] != 0): the first column chunk reaches the last support columns and vice versa, so the
     copy-in / plan dependency logic of sls_synthesize degenerates to waiting for every upload; results must not change."""

@@ -327,6 +327,17 @@ def test_weighted_cost_and_column_groups_vs_general_oracle(cuda_api):
     assert pc.check_weighted_cost(cuda_api, cols=(3, 14, 39, 0, 20, 27)) < 1e-10
 
 
+def test_general_cost_and_coupled_groups_vs_general_oracle(cuda_api):
+    """SURVEY §8f-3 in full: non-diagonal [C1 D12], D11 != 0, non-diagonal B1, coupled q = 2 / q = 3 groups
+    (synthesis.jl:42-43,50,76-77; reduction.jl:14-23) on kernel 2g, against SLS_H2_general."""
+    assert pc.check_coupled_groups_identity_cost(cuda_api)[0] < 1e-10
+    assert pc.check_general_cost(cuda_api) < 1e-10
+    assert pc.check_general_cost(cuda_api, Nx=60, d=9, T=29, cases=[
+        dict(kw=dict(dense_cost=True, b1_band=True, d11=True), I=[[0, 1], [29, 30], [31], [58, 59]]),
+        dict(kw=dict(dense_cost=True, b1_band=False, d11=False), I=[[j] for j in range(0, 60, 7)])]) < 1e-10
+    pc.check_general_error_paths(cuda_api)
+
+
 def test_random_banded_plants_vs_oracle(cuda_api):
     """Pentadiagonal random plants with two-state actuators and random gains (not a chain, not a grid): the accuracy /
     flagging contract on well-conditioned, ill-conditioned and infeasible columns (parity_cases.check_random_banded)."""
