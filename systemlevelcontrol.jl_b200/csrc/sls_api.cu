@@ -1102,8 +1102,8 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
             // B1 / D11 are indexed by the group's columns: they must exist as columns of these matrices
             if (p.col_hi > h->Nw) return fail(h, -1, "sls_solve: a planned column exceeds Nw (B1 / D11 have no such column)");
         }
-        const int per_sm = std::max(1, std::min(4, (int)((size_t)(h->max_smem + 1024) / (smem + 1024))));
-        const int grid = std::min(ngroups, h->sm_count * per_sm);
+        const int grid = sls_general_grid(a, h->sm_count);
+        if (grid <= 0) return fail(h, -4, "sls_solve: the general solver cannot be launched with this shared-memory size");
         a.scratch_stride = sls_general_scratch_doubles(a.pc, a.Nc, (int)T);
         SLS_CK(h->gen_scratch.ensure((size_t)grid * a.scratch_stride * sizeof(double)));
         a.scratch = h->gen_scratch.as<double>();

@@ -74,6 +74,7 @@ size_t sls_general_smem(int pc, int Nc, int nb, int pb, int qc, int T, int cap);
 int64_t sls_general_scratch_doubles(int pc, int Nc, int T);
 // stats (8 ints, zeroed by the caller): max q, max n, max n+m, max q n, max q(n+m), overflow
 int sls_launch_general_size(const SlsPlanView& P, const int32_t* grp_ptr, int ngroups, int cap, int32_t* stats, sls_stream_t stream);
+int sls_general_grid(const SlsGeneralArgs& a, int sm_count);
 int sls_launch_solve_general(const SlsGeneralArgs& a, int grid, sls_stream_t stream);
 
 // ---- kernel 3 (sls_scatter.cu) ----

@@ -23,7 +23,9 @@
 #include "sls_kernels.h"
 #include <cmath>
 
+#ifndef GEN_NT
 #define GEN_NT 256
+#endif
 #define SLS_INF_D ((double)INFINITY)
 
 struct GenLayout {
@@ -142,6 +144,22 @@ struct GenCtx {
     int Nc, pc;
 };
 
+// y[r] = alpha * sum_j M[r*ld + j] x[j] (+ add[r]) for r < rows: one warp per row, lanes across the row (coalesced), the
+// partial sums combined by shuffles in a fixed order.  M may live in the scratch slot (L2) or in shared memory.
+__device__ __forceinline__ void gen_matvec(const double* M, int ld, int rows, int cols, const double* x, double* y,
+                                           double alpha, const double* add) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int r = warp; r < rows; r += GEN_NT / 32) {
+        double s = 0.0;
+#pragma unroll 1
+        for (int j = lane; j < cols; j += 32) s += M[(size_t)r * ld + j] * x[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(SLS_FULL, s, o);
+        if (lane == 0) y[r] = alpha * s + (add ? add[r] : 0.0);
+    }
+}
+
 // mu <- solution of S mu = r (r in scratch[oR], T+1 blocks of Nb): forward sweep with the stored C_k, -Z_k, then back
 // substitution.  y, tmp: Nb doubles of shared memory each.
 __device__ void gen_solve_mu(const GenCtx& c, double* y, double* tmp) {
@@ -149,28 +167,15 @@ __device__ void gen_solve_mu(const GenCtx& c, double* y, double* tmp) {
     double* r = c.scratch + c.oR; double* mu = c.scratch + c.oMu; double* rt = c.scratch + c.oY;
     // forward: rt_0 = r_0, rt_k = r_k + C_k (Zb_{k-1} rt_{k-1})   (Zb = -Z)
 #pragma unroll 1
-    for (int k = 0; k <= T; k++) {
-        if (k == 0) {
+    for (int i = tid; i < Nb; i += GEN_NT) rt[i] = r[i];
+    __syncthreads();
 #pragma unroll 1
-            for (int i = tid; i < Nb; i += GEN_NT) rt[i] = r[i];
-        } else {
-            const double* Zb = c.scratch + c.oZ + (int64_t)(k - 1) * c.Nc * c.Nc;
-            const double* Ck = c.scratch + c.oC + (int64_t)k * c.Nc * c.Nc;
-            const double* rp = rt + (size_t)(k - 1) * c.Nc;
-#pragma unroll 1
-            for (int i = tid; i < Nb; i += GEN_NT) {
-                double s = 0.0;
-                for (int j = 0; j < Nb; j++) s += Zb[(size_t)i * c.Nc + j] * rp[j];
-                y[i] = s;
-            }
-            __syncthreads();
-#pragma unroll 1
-            for (int i = tid; i < Nb; i += GEN_NT) {
-                double s = r[(size_t)k * c.Nc + i];
-                for (int j = 0; j < Nb; j++) s += Ck[(size_t)i * c.Nc + j] * y[j];
-                rt[(size_t)k * c.Nc + i] = s;
-            }
-        }
+    for (int k = 1; k <= T; k++) {
+        const double* Zb = c.scratch + c.oZ + (int64_t)(k - 1) * c.Nc * c.Nc;
+        const double* Ck = c.scratch + c.oC + (int64_t)k * c.Nc * c.Nc;
+        gen_matvec(Zb, c.Nc, Nb, Nb, rt + (size_t)(k - 1) * c.Nc, y, 1.0, nullptr);
+        __syncthreads();
+        gen_matvec(Ck, c.Nc, Nb, Nb, y, rt + (size_t)k * c.Nc, 1.0, r + (size_t)k * c.Nc);
         __syncthreads();
     }
     // back: mu_T = -Zb_T rt_T;  mu_k = -Zb_k (rt_k - C_{k+1}^T mu_{k+1})
@@ -183,17 +188,13 @@ __device__ void gen_solve_mu(const GenCtx& c, double* y, double* tmp) {
             if (k < T) {
                 const double* Cn = c.scratch + c.oC + (int64_t)(k + 1) * c.Nc * c.Nc;
                 const double* mn = mu + (size_t)(k + 1) * c.Nc;
-                for (int j = 0; j < Nb; j++) s -= Cn[(size_t)j * c.Nc + i] * mn[j];
+#pragma unroll 4
+                for (int j = 0; j < Nb; j++) s -= Cn[(size_t)j * c.Nc + i] * mn[j];     // column i of C: coalesced across threads
             }
             tmp[i] = s;
         }
         __syncthreads();
-#pragma unroll 1
-        for (int i = tid; i < Nb; i += GEN_NT) {
-            double s = 0.0;
-            for (int j = 0; j < Nb; j++) s += Zb[(size_t)i * c.Nc + j] * tmp[j];
-            mu[(size_t)k * c.Nc + i] = -s;
-        }
+        gen_matvec(Zb, c.Nc, Nb, Nb, tmp, mu + (size_t)k * c.Nc, -1.0, nullptr);
         __syncthreads();
     }
 }
@@ -209,18 +210,13 @@ __device__ void gen_primal(const GenCtx& c, double* dst, bool with_g, double* av
         for (int v = tid; v < pbar; v += GEN_NT) {
             const int cc = v / p, a = v - cc * p;
             double s = (a < n) ? m0[cc * n + a] : 0.0;
+#pragma unroll 4
             for (int i = 0; i < n; i++) s -= c.F[(size_t)i * p + a] * m1[cc * n + i];
             if (with_g) s -= c.gb[v];
             avec[v] = s;
         }
         __syncthreads();
-        const double* W = c.scratch + c.oW + (int64_t)t * c.pc * c.pc;
-#pragma unroll 1
-        for (int v = tid; v < pbar; v += GEN_NT) {
-            double s = 0.0;
-            for (int w = 0; w < pbar; w++) s += W[(size_t)v * c.pc + w] * avec[w];
-            dst[(size_t)t * c.pc + v] = s;
-        }
+        gen_matvec(c.scratch + c.oW + (int64_t)t * c.pc * c.pc, c.pc, pbar, pbar, avec, dst + (size_t)t * c.pc, 1.0, nullptr);
         __syncthreads();
     }
 }
@@ -257,7 +253,10 @@ __device__ double gen_residual(const GenCtx& c, const double* z, const double* e
     return all;
 }
 
-__global__ void __launch_bounds__(GEN_NT, 1)
+#ifndef GEN_MINB
+#define GEN_MINB 4
+#endif
+__global__ void __launch_bounds__(GEN_NT, GEN_MINB)
 sls_solve_general_kernel(SlsGeneralArgs a) {
     SLS_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -659,6 +658,17 @@ int sls_launch_general_size(const SlsPlanView& P, const int32_t* grp_ptr, int ng
     if (smem > 48 * 1024) { if (rt::set_max_smem(kp, (int)smem)) return -1; }
     SLS_LAUNCH(kp, (ngroups + 3) / 4, 128, smem, stream, P, grp_ptr, ngroups, cap, stats);
     return rt::last_error();
+}
+
+// resident CTAs of kernel 2g for these sizes (the scratch holds one slot per CTA)
+int sls_general_grid(const SlsGeneralArgs& a, int sm_count) {
+    auto kp = &sls_solve_general_kernel;
+    const size_t smem = GenLayout(a.pc, a.Nc, a.nb, a.pb, a.qc, a.P.T, a.cap).total;
+    if (smem > 48 * 1024) { if (rt::set_max_smem(kp, (int)smem)) return -1; }
+    int per_sm = rt::max_blocks_per_sm(kp, GEN_NT, smem);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t g = (int64_t)sm_count * per_sm;
+    return (int)(g < a.ngroups ? g : a.ngroups);
 }
 
 int sls_launch_solve_general(const SlsGeneralArgs& a, int grid, sls_stream_t stream) {

@@ -496,6 +496,31 @@ def _check_plant(P):
     return True
 
 
+def _impulse_pairing_matches(P, Sx, groups):
+    """The reference builds I~ = I[:, ii_x] (reduction.jl:22-23): its c-th column is the impulse of the c-th member of the
+    group IN THE ORDER OF s_x (first occurrence over the group's columns, reduction.jl:14), while the c-th local column is
+    scattered to c_j[c] (synthesis.jl:65-66).  The device pairs every column with its own impulse; that equals the
+    reference exactly when the members' first occurrences in s_x follow the group's order — checked here on the patterns."""
+    if all(len(g) < 2 for g in groups):
+        return True
+    pA = (P.A != 0).astype(np.int64).tocsc()
+    own = ((sp.csc_matrix(Sx[-1]) != 0).astype(np.int64) @ pA).tocsc()       # column j: its s_x (ascending rows)
+    own.sort_indices()
+    for g in groups:
+        if len(g) < 2:
+            continue
+        rows = [own.indices[own.indptr[c]:own.indptr[c + 1]] for c in g]
+        keys = []
+        for c in g:
+            first = next((i for i, r in enumerate(rows) if np.searchsorted(r, c) < r.size and r[np.searchsorted(r, c)] == c), None)
+            if first is None:
+                return False                                                 # a member outside s_x: R is not square in Julia
+            keys.append((first, c))
+        if any(b <= a for a, b in zip(keys, keys[1:])):
+            return False
+    return True
+
+
 def _route(P, S, I):
     """Host-side dispatch of SLS_H2: which kernel family solves (P, 𝓘).  Returns (wx, wu, general, cols, grp_ptr):
     diagonal weights for sls_set_weights (or None), whether the general kernel 2g is needed (sls_set_cost), the planned
@@ -511,9 +536,10 @@ def _route(P, S, I):
         if any(len(g) != 1 for g in groups):
             if len(set(cols)) != len(cols):
                 raise ValueError("a column appears in more than one group")
-            if any(any(b <= a for a, b in zip(g, g[1:])) for g in groups):
-                raise ValueError("the columns of a group must ascend (the reference pairs the impulses I~ with the group's "
-                                 "columns by their order in s_x, reduction.jl:22-23)")
+            if not _impulse_pairing_matches(P, Sx, groups):
+                raise ValueError("a group's columns are not in the order in which they first occur in its index set s_x: the "
+                                 "reference would pair the impulses I~ with other columns of the group (reduction.jl:14,"
+                                 "22-23); list the group's columns in ascending order")
             if general or not _groups_decouple(P, Sx, Su, groups):
                 grp_ptr = np.concatenate([[0], np.cumsum([len(g) for g in groups])]).astype(np.int64)
     if grp_ptr is not None and wx is not None:

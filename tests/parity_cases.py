@@ -577,7 +577,7 @@ def check_general_error_paths(api):
     finally:
         syn.close()
     with np.testing.assert_raises(ValueError):
-        slc_b200.SLS_H2(slc_b200.Plant(A, B1, B2), S, I=[[5, 3]], api=api)       # descending group
+        slc_b200.SLS_H2(slc_b200.Plant(A, B1, B2), S, I=[[5, 3]], api=api)       # 3 occurs in s_x before 5: reference pairing differs
 
 
 def random_banded_plant(Nx, bw, seed, act_every=3):

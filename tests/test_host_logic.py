@@ -73,7 +73,8 @@ def test_cost_and_group_routing():
     r = _route(Plant(A, B1, B2), Sw, [[0, 1]])
     assert r[2] is False and r[4].tolist() == [0, 2]                         # identity cost, coupled group: groups only
     with pytest.raises(ValueError):
-        _route(Plant(A, B1, B2), S, [[4, 3]])                                 # descending group
+        _route(Plant(A, B1, B2), S, [[4, 3]])                                 # 3 is first seen among column 4's rows, before 4
+    assert _route(Plant(A, B1, B2), S, [[11, 0]])[3] == [11, 0]               # far apart: first occurrences follow the group order
     with pytest.raises(ValueError):
         _route(Plant(A, B1, B2), S, [[3, 4], [4]])                            # a column in two groups
 
