@@ -46,10 +46,12 @@ end
 """
 function synthesize(A::SparseMatrixCSC{Float64,Int64}, B₂::SparseMatrixCSC{Float64,Int64},
                     𝓢ₓ::Vector{SparseMatrixCSC{Bool,Int64}}, 𝓢ᵤ::Vector{SparseMatrixCSC{Bool,Int64}},
-                    cols::Union{Nothing,Vector{Int64}}; wx=nothing, wu=nothing, device::Integer=0)
+                    cols::Union{Nothing,Vector{Int64}}; wx=nothing, wu=nothing, cost=nothing, grp_ptr=nothing, device::Integer=0)
+    # cost = (C₁, D₁₂, D₁₁ or nothing, B₁ or nothing): general cost -> sls_set_cost (kernel 2g); grp_ptr::Vector{Int64}: 0-based
+    # offsets of the column groups inside `cols` -> sls_set_groups
     Nx, Nu, T = size(A, 1), size(B₂, 2), length(𝓢ₓ)
     h = Handle(device=device)
-    GC.@preserve A B₂ 𝓢ₓ 𝓢ᵤ cols wx wu begin
+    GC.@preserve A B₂ 𝓢ₓ 𝓢ᵤ cols wx wu cost grp_ptr begin
         if wx !== nothing || wu !== nothing        # before sls_set_plant: the device holds the similarity-scaled plant
             check(h.ptr, ccall((:sls_set_weights, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
                   h.ptr, Nx, Nu, wx === nothing ? C_NULL : wx, wu === nothing ? C_NULL : wu))
@@ -57,6 +59,15 @@ function synthesize(A::SparseMatrixCSC{Float64,Int64}, B₂::SparseMatrixCSC{Flo
         check(h.ptr, ccall((:sls_set_plant, LIB), Cint,
               (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
               h.ptr, Nx, Nu, A.colptr, A.rowval, A.nzval, B₂.colptr, B₂.rowval, B₂.nzval))
+        if cost !== nothing                        # after sls_set_plant: the cost matrices are sized by Nx, Nu
+            C₁, D₁₂, D₁₁, B₁ = cost
+            f3(M) = M === nothing ? (Ptr{Int64}(C_NULL), Ptr{Int64}(C_NULL), Ptr{Float64}(C_NULL)) : (pointer(M.colptr), pointer(M.rowval), pointer(M.nzval))
+            check(h.ptr, ccall((:sls_set_cost, LIB), Cint,
+                  (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
+                   Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                  h.ptr, size(C₁, 1), B₁ === nothing ? (D₁₁ === nothing ? Nx : size(D₁₁, 2)) : size(B₁, 2),
+                  f3(C₁)..., f3(D₁₂)..., f3(D₁₁)..., f3(B₁)...))
+        end
         ptrs(f, S) = [pointer(f(M)) for M in S]
         xcp, xrv, xnz = ptrs(M -> M.colptr, 𝓢ₓ), ptrs(M -> M.rowval, 𝓢ₓ), [Ptr{UInt8}(pointer(M.nzval)) for M in 𝓢ₓ]
         ucp, urv, unz = ptrs(M -> M.colptr, 𝓢ᵤ), ptrs(M -> M.rowval, 𝓢ᵤ), [Ptr{UInt8}(pointer(M.nzval)) for M in 𝓢ᵤ]
@@ -68,6 +79,8 @@ function synthesize(A::SparseMatrixCSC{Float64,Int64}, B₂::SparseMatrixCSC{Flo
         check(h.ptr, ccall((:sls_plan, LIB), Cint,
               (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}),
               h.ptr, cols === nothing ? C_NULL : cols, ncols, nnzx, nnzu, C_NULL, C_NULL))
+        grp_ptr === nothing || check(h.ptr, ccall((:sls_set_groups, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}),
+                                                  h.ptr, length(grp_ptr) - 1, grp_ptr))
         # two-phase sizing: Julia owns every output buffer
         mk(nnz, nrow) = [SparseMatrixCSC{Float64,Int64}(nrow, Nx, ones(Int64, Nx + 1), Vector{Int64}(undef, nnz[t]), Vector{Float64}(undef, nnz[t])) for t in 1:T]
         Φₓ, Φᵤ = mk(nnzx, Nx), mk(nnzu, Nu)
@@ -200,20 +213,19 @@ function synthesize_shard(h::Handle, A::SparseMatrixCSC{Float64,Int64}, B₂::Sp
 end
 
 """
-    diagonal_cost(P) -> (wx, wu)  or error(...)
+    diagonal_cost(P) -> (wx, wu)  or  :general
 
-The cost family libslsb200 solves on the device (the Python mirror's `Plant.diagonal_cost`): `[C₁ D₁₂]` = blockdiag(
-Diagonal(wx), Diagonal(wu)) > 0, `D₁₁ = 0`, diagonal `B₁` without zeros (a diagonal B₁ rescales each column's cost and does
-not change Φ).  Anything else would silently give a Φ that differs from the reference's, so it is refused here.
+The cost family the DMMA kernels solve (the Python mirror's `Plant.diagonal_cost`): `[C₁ D₁₂]` = blockdiag(Diagonal(wx),
+Diagonal(wu)) > 0, `D₁₁ = 0`, diagonal `B₁` without zeros (a diagonal B₁ rescales each column's cost and does not change Φ).
+Anything else returns `:general`: the caller then passes `cost = (C₁, D₁₂, D₁₁, B₁)` and the general kernel 2g solves it
+(sls_set_cost; synthesis.jl:42-43,50,76-77).
 """
 function diagonal_cost(P)
     Nx, Nu = P.Nx, P.Nu
-    size(P.B₁) == (Nx, Nx) && isdiag(P.B₁) && all(!iszero, diag(P.B₁)) ||
-        error("libslsb200: B₁ must be diagonal without zeros (R = B̃₁[iiₓ,:] otherwise couples the columns of a group)")
-    iszero(P.D₁₁) || error("libslsb200: D₁₁ ≠ 0 adds a linear term to the cost (not implemented on the device)")
+    size(P.B₁) == (Nx, Nx) && isdiag(P.B₁) && all(!iszero, diag(P.B₁)) || return :general
+    iszero(P.D₁₁) || return :general
     L = [P.C₁ P.D₁₂]
-    size(L) == (Nx + Nu, Nx + Nu) && isdiag(L) && all(>(0), diag(L)) ||
-        error("libslsb200: [C₁ D₁₂] must be diagonal with positive entries (general cost: SURVEY §8f-3)")
+    size(L) == (Nx + Nu, Nx + Nu) && isdiag(L) && all(>(0), diag(L)) || return :general
     w = diag(L)
     all(==(1.0), w) ? (nothing, nothing) : (Vector{Float64}(w[1:Nx]), Vector{Float64}(w[Nx+1:end]))
 end
@@ -239,15 +251,21 @@ end # module
 #         default = 𝓘 === nothing                                               # captured BEFORE the reassignment below
 #         𝓘 = default ? [[i] for i in 1:P.Nx] : 𝓘;                             # :15
 #         𝓢ₓ,𝓢ᵤ = 𝓢;  T = length(𝓢ₓ)                                           # :19-20
-#         wx, wu = SLSB200.diagonal_cost(P)                                     # error(...) for costs the device does not solve
-#         # q > 1 groups: with a diagonal B₁ the cost is separable, and the group problem equals its columns' problems only
-#         # when the union index set adds just EMPTY constraint rows to every member column (supports closed under the
-#         # plant's pattern): check it on the patterns as synthesis.py::_groups_decouple does, else error(...)
-#         all(g -> length(g) == 1, 𝓘) || SLSB200.groups_decouple(P, 𝓢ₓ, 𝓢ᵤ, 𝓘) ||
-#             error("libslsb200: coupled column groups are not implemented on the device (SURVEY §8f-3)")
+#         dc = SLSB200.diagonal_cost(P)                                         # (wx, wu) for the DMMA kernels, or :general
 #         cols = Int64[c for g in 𝓘 for c in g]
-#         Φₓ,Φᵤ,status,resid = default ? SLSB200.synthesize_pipelined(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ; wx=wx, wu=wu) :
-#                                        SLSB200.synthesize(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ, cols; wx=wx, wu=wu)
+#         # q > 1 groups: solved as ONE problem on the union index set (kernel 2g) unless the group provably equals its
+#         # columns' problems (diagonal B₁ and a union that adds only empty constraint rows: groups_decouple).  List each
+#         # group's columns ascending (I~ pairs the impulses with the columns by their order in s_x, reduction.jl:22-23).
+#         coupled = any(g -> length(g) > 1, 𝓘) && (dc === :general || !SLSB200.groups_decouple(P, 𝓢ₓ, 𝓢ᵤ, 𝓘))
+#         grp = coupled ? Int64[0; cumsum(length.(𝓘))] : nothing
+#         if dc === :general || coupled                                         # weights travel inside C₁ / D₁₂ on this path
+#             Φₓ,Φᵤ,status,resid = SLSB200.synthesize(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ, cols; grp_ptr=grp,
+#                                      cost=(sparse(P.C₁), sparse(P.D₁₂), iszero(P.D₁₁) ? nothing : sparse(P.D₁₁), sparse(P.B₁)))
+#         else
+#             wx, wu = dc
+#             Φₓ,Φᵤ,status,resid = default ? SLSB200.synthesize_pipelined(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ; wx=wx, wu=wu) :
+#                                            SLSB200.synthesize(P.A, P.B₂, 𝓢ₓ, 𝓢ᵤ, cols; wx=wx, wu=wu)
+#         end
 #         any(!iszero, status .& 1) && @warn "SLS_𝓗₂: $(count(!iszero, status .& 1)) column(s) infeasible / not converged (status bit 0)"
 #         # optional: dropzeros!.(Φₓ); dropzeros!.(Φᵤ) reproduces the zero-dropping of `Φ̃ += …` (:67)
 #         Φ = [Φₓ Φᵤ]                                                           # T×2 Matrix{SparseMatrixCSC}
