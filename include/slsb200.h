@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SLS_ABI_VERSION 7
+#define SLS_ABI_VERSION 8
 
 /* per-column status bits written by sls_solve* (improves on the reference, which ignores the
  * solver's termination status: src/synthesis.jl:62-65) */
@@ -145,6 +145,18 @@ int sls_reduce(sls_handle* h, const int64_t* cj, int64_t q,
                int64_t* sx_out, int64_t sx_cap, int64_t* n_sx,
                int64_t* su_out, int64_t su_cap, int64_t* n_su,
                uint8_t* iix_out);
+
+/* Output-feedback branch of sparsity_dim_reduction (reduction.jl:16-18):
+ *     s_x, s_u, s_y = (unique(findnz(𝓢ⱼ[end][:,cⱼ])[1]) for 𝓢ⱼ in 𝓢),   𝓢 = [𝓢ₓ, 𝓢ᵤ, 𝓢ᵧ]
+ * — the stored rows of the listed columns of each family's LAST tap, first occurrences in CSC order (no product with the
+ * pattern of A on this branch).  The caller passes that last tap per family (Julia colptr of ncols_S+1 entries, rowval;
+ * nrows[f] rows); s_out[f] (capacity s_cap[f], 1-based) may be NULL to query n_s[f].  iix_out (n_s[0] Bools, may be NULL)
+ * is indexin(s_x, cⱼ) .≠ nothing (reduction.jl:22); Ĩ = [I(|s_x|)[:,ii_x] 0] (reduction.jl:23) is implied by it.
+ * No output-feedback synthesis exists in the reference (SLS_𝓗₂ returns nothing for such plants, synthesis.jl:13,29-31) and
+ * its L⁺ regulariser hook is identically 0 (synthesis.jl:21,52), so nothing else of that branch crosses the ABI. */
+int sls_reduce_of(sls_handle* h, int64_t nfam, const int64_t* const* S_colptr, const int64_t* const* S_rowval,
+                  const int64_t* nrows, int64_t ncols_S, const int64_t* cj, int64_t q,
+                  int64_t* const* s_out, const int64_t* s_cap, int64_t* n_s, uint8_t* iix_out);
 
 /* After sls_plan: the local sub-plant blocks of listed column `k` (0-based position in the plan's
  * list): dense column-major A~ = A[s_x,s_x] (n x n), B2~ = B2[s_x,s_u] (n x m), and the free-variable

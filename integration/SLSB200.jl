@@ -284,3 +284,10 @@ end # module
 #   ccall((:sls_reduce, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ref{Int64}, Ptr{Int64}, Int64, Ref{Int64}, Ptr{UInt8}),
 #         h, cⱼ, length(cⱼ), sx, length(sx), nsx, su, length(su), nsu, iix)
 #   then P̃ = view(P, (sₓ, [sₓ; P.Nx .+ sᵤ]), (sₓ, cⱼ, sᵤ)) and Ĩ = [I(P̃.Nx)[:,iiₓ] spzeros(P̃.Nx, P̃.Nw-sum(iiₓ))] as in :15,:23.
+# The OutputFeedback branch (src/reduction.jl:16-18; 𝓢 = [𝓢ₓ, 𝓢ᵤ, 𝓢ᵧ]) maps to sls_reduce_of, which takes the LAST tap of each family:
+#   cp = [S[end].colptr for S in 𝓢]; rv = [S[end].rowval for S in 𝓢]; nr = Int64[size(S[end],1) for S in 𝓢]
+#   ccall((:sls_reduce_of, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Int64}, Int64, Ptr{Int64}, Int64,
+#                                       Ptr{Ptr{Int64}}, Ptr{Int64}, Ptr{Int64}, Ptr{UInt8}),
+#         h, 3, pointer.(cp), pointer.(rv), nr, size(𝓢[1][end],2), cⱼ, length(cⱼ), pointer.(s_out), Int64.(length.(s_out)), ns, iix)
+#   then P̃ = view(P, (sₓ, [sₓ; P.Nx .+ sᵤ], sᵧ), (sₓ, cⱼ, sᵤ)) and Ĩ as above (:17,:22-23).  No OutputFeedback synthesis exists in the
+#   reference (SLS_𝓗₂ returns nothing for such plants) and L⁺ ≡ 0 (src/synthesis.jl:21,52), so the hook has no ABI counterpart.

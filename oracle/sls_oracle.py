@@ -216,6 +216,36 @@ def sparsity_dim_reduction(P: Plant, cj, S, _prod=None):
     return (At, B1t, B2t), It, iix, sx, su
 
 
+def sparsity_dim_reduction_of(mats, cj, S):
+    """reduction.jl:16-18, the OutputFeedback branch:  s_x, s_u, s_y = (unique(findnz(𝓢ⱼ[end][:,cⱼ])[1]) for 𝓢ⱼ in 𝓢)
+    — stored rows (findnz lists stored entries, whatever their value) of the listed columns of each family's last tap,
+    first occurrences in CSC order; no product with the pattern of A.  `mats` = dict of the nine plant matrices
+    (A, B1, B2, C1, D11, D12, C2, D21, D22; scipy sparse), cj 0-based.  Returns (sub, I_tilde, ii_x, s_x, s_u, s_y) where
+    sub = view(P, (s_x, [s_x; Nx+s_u], s_y), (s_x, c_j, s_u)) materialised block by block
+    (GeneralizedPlant.jl:266-285, OutputFeedback rows I[3] for C2/D21/D22) and I_tilde = [I(n)[:,ii_x] 0] (reduction.jl:22-23)."""
+    cj = np.asarray(cj, dtype=np.int64)
+    ss = []
+    for Sj in S:
+        M = sp.csc_matrix(Sj[-1])
+        M.sort_indices()
+        rows = [M.indices[M.indptr[c]:M.indptr[c + 1]] for c in cj]
+        rows = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+        ss.append(_unique_first(rows.astype(np.int64)))
+    sx, su, sy = ss
+    Nx = mats["A"].shape[0]
+    zr = np.concatenate([sx, Nx + su])
+    cut = lambda M, r, c: sp.csc_matrix(M)[r, :][:, c].toarray()
+    sub = dict(A=cut(mats["A"], sx, sx), B1=cut(mats["B1"], sx, cj), B2=cut(mats["B2"], sx, su),
+               C1=cut(mats["C1"], zr, sx), D11=cut(mats["D11"], zr, cj), D12=cut(mats["D12"], zr, su),
+               C2=cut(mats["C2"], sy, sx), D21=cut(mats["D21"], sy, cj), D22=cut(mats["D22"], sy, su))
+    iix = np.isin(sx, cj)
+    n, q = sx.size, cj.size
+    It = np.zeros((n, q))
+    sel = np.nonzero(iix)[0]
+    It[sel, np.arange(sel.size)] = 1.0
+    return sub, It, iix, sx, su, sy
+
+
 def cost_blocks(P: Plant, cj, sx, su):
     """[C1~ D12~] and D11~ of the reduced plant: rows [s_x; Nx+s_u] of C1, D12, D11 (reduction.jl:15,
     GeneralizedPlant.jl:266-271), columns s_x / s_u / c_j.  Returns (L, D11t) dense."""

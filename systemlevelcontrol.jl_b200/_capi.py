@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libslsb200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 STATUS_OK, STATUS_RESIDUAL, STATUS_RANK_SKIPPED, STATUS_NO_IMPULSE = 0, 1, 2, 4
 
 i64p = C.POINTER(C.c_int64)
@@ -55,6 +55,8 @@ SIGNATURES = {
     "sls_get_supports": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, i64p, i64p, u8p]),
     "sls_plan": (C.c_int, [C.c_void_p, i64p, C.c_int64, i64p, i64p, i32p, i32p]),
     "sls_reduce": (C.c_int, [C.c_void_p, i64p, C.c_int64, i64p, C.c_int64, i64p, i64p, C.c_int64, i64p, u8p]),
+    "sls_reduce_of": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(i64p), C.POINTER(i64p), i64p, C.c_int64, i64p, C.c_int64,
+                                C.POINTER(i64p), i64p, i64p, u8p]),
     "sls_local_problem": (C.c_int, [C.c_void_p, C.c_int64, f64p, f64p, u8p, u8p]),
     "sls_solve": (C.c_int, [C.c_void_p, i64pp, i64pp, f64pp, i64pp, i64pp, f64pp, i32p, f64p]),
     "sls_solve_device": (C.c_int, [C.c_void_p]),

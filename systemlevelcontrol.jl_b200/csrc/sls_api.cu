@@ -945,6 +945,71 @@ extern "C" int sls_reduce(sls_handle* h, const int64_t* cj, int64_t q,
     return 0;
 }
 
+// Output-feedback branch of sparsity_dim_reduction (reduction.jl:16-18): s_f = unique(findnz(𝓢_f[end][:,cⱼ])[1]) for every
+// support family f (𝓢 = [𝓢ₓ,𝓢ᵤ,𝓢ᵧ]); the caller passes the LAST tap of each family.  Only the listed columns' segments are
+// uploaded; the union runs on the device (sls_union_first_kernel).
+extern "C" int sls_reduce_of(sls_handle* h, int64_t nfam, const int64_t* const* S_colptr, const int64_t* const* S_rowval,
+                             const int64_t* nrows, int64_t ncols_S, const int64_t* cj, int64_t q,
+                             int64_t* const* s_out, const int64_t* s_cap, int64_t* n_s, uint8_t* iix_out) {
+    if (!h) return -1;
+    SLS_ARG(nfam >= 1 && nfam <= 8, "sls_reduce_of: nfam must be 1..8 (the reference uses 3: S_x, S_u, S_y)");
+    SLS_ARG(S_colptr && S_rowval && nrows && n_s, "sls_reduce_of: NULL argument");
+    SLS_ARG(cj && q >= 1, "sls_reduce_of: empty column group");
+    SLS_ARG(ncols_S >= 1, "sls_reduce_of: supports without columns");
+    for (int64_t i = 0; i < q; i++)
+        if (cj[i] < 1 || cj[i] > ncols_S) return fail(h, -3, "sls_reduce_of: column index out of range (1-based, 1..ncols)");
+    SLS_CK(rt::set_device(h->device));
+    std::vector<int64_t> first;                               // s of family 0 (for ii_x)
+    for (int64_t f = 0; f < nfam; f++) {
+        SLS_ARG(S_colptr[f] && S_rowval[f] && nrows[f] >= 0, "sls_reduce_of: NULL support arrays");
+        const int64_t* cp = S_colptr[f];
+        std::vector<int64_t> seg((size_t)q + 1, 0), rows;
+        for (int64_t i = 0; i < q; i++) {
+            const int64_t e0 = cp[cj[i] - 1], e1 = cp[cj[i]];
+            if (e0 < 1 || e1 < e0) return fail(h, -2, "sls_reduce_of: colptr is not a 1-based non-decreasing Julia colptr");
+            rows.insert(rows.end(), S_rowval[f] + (e0 - 1), S_rowval[f] + (e1 - 1));
+            seg[(size_t)i + 1] = (int64_t)rows.size();
+        }
+        const int64_t C = (int64_t)rows.size();
+        const size_t words = (size_t)((nrows[f] + 31) / 32) + 1;
+        DevBuf d_rows, d_seg, d_seen, d_out, d_meta;
+        auto drop = [&]() { d_rows.release(); d_seg.release(); d_seen.release(); d_out.release(); d_meta.release(); };
+        int e = d_rows.ensure((size_t)std::max<int64_t>(C, 1) * 8);
+        if (!e) e = d_seg.ensure(seg.size() * 8);
+        if (!e) e = d_seen.ensure(words * 4);
+        if (!e) e = d_out.ensure((size_t)std::max<int64_t>(C, 1) * 8);
+        if (!e) e = d_meta.ensure(16);                        // [0..7] n_out (int64), [8..11] flag
+        if (!e && C) e = rt::h2d(d_rows.p, rows.data(), (size_t)C * 8, h->stream);
+        if (!e) e = rt::h2d(d_seg.p, seg.data(), seg.size() * 8, h->stream);
+        if (!e) e = rt::zero(d_seen.p, words * 4, h->stream);
+        if (!e) e = rt::zero(d_meta.p, 16, h->stream);
+        if (!e) e = sls_launch_union_first(d_rows.as<int64_t>(), d_seg.as<int64_t>(), (int)q, nrows[f], d_seen.as<uint32_t>(),
+                                           d_out.as<int64_t>(), d_meta.as<int64_t>(), reinterpret_cast<int32_t*>(d_meta.as<char>() + 8), h->stream);
+        int64_t meta[2] = {0, 0};
+        if (!e) e = rt::d2h(meta, d_meta.p, 16, h->stream);
+        if (!e) e = rt::sync(h->stream);
+        if (e) { drop(); return fail(h, e, "sls_reduce_of: device work failed"); }
+        if ((int32_t)(meta[1] & 0xffffffff)) { drop(); return fail(h, -2, "sls_reduce_of: support rows out of range or not strictly ascending inside a column"); }
+        const int64_t ns = meta[0];
+        n_s[f] = ns;
+        std::vector<int64_t> res((size_t)ns);
+        if (ns) { e = rt::d2h(res.data(), d_out.p, (size_t)ns * 8, h->stream); if (!e) e = rt::sync(h->stream); }
+        drop();
+        if (e) return fail(h, e, "sls_reduce_of: device to host copy");
+        if (s_out && s_out[f]) {
+            if (!s_cap || ns > s_cap[f]) return fail(h, -4, "sls_reduce_of: output capacity too small (sizes returned in n_s)");
+            std::copy(res.begin(), res.end(), s_out[f]);
+        }
+        if (f == 0) first.swap(res);
+    }
+    if (iix_out) {                                            // indexin(sₓ, cⱼ) .≠ nothing  (reduction.jl:22)
+        std::vector<int64_t> sorted(cj, cj + q);
+        std::sort(sorted.begin(), sorted.end());
+        for (size_t i = 0; i < first.size(); i++) iix_out[i] = std::binary_search(sorted.begin(), sorted.end(), first[i]) ? 1 : 0;
+    }
+    return 0;
+}
+
 extern "C" int sls_local_problem(sls_handle* h, int64_t k, double* At, double* B2t, uint8_t* Mx, uint8_t* Mu) {
     if (!h) return -1;
     SLS_ARG(h->plan.valid, "sls_local_problem: no plan");

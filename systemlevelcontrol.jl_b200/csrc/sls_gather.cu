@@ -417,6 +417,61 @@ int sls_launch_validate_supports(const SlsSupports& S, int T, int64_t Nx, int64_
     return rt::last_error();
 }
 
+// Output-feedback branch of sparsity_dim_reduction (reference src/reduction.jl:16-18): for one support family
+//     s = unique(findnz(𝓢ⱼ[end][:,cⱼ])[1])
+// i.e. the stored rows of the listed columns of the LAST tap, first occurrences in CSC order (cⱼ order, rows ascending
+// inside a column) — no product with the pattern of A on this branch.  `rows` holds the q column segments back to back
+// (1-based, seg[s]..seg[s+1]).  One block: the segments are taken in order; rows are distinct inside a segment, so one
+// test-and-set per row on a bitmap decides "seen before", and a block-wide rank keeps the order of first occurrence.
+// Malformed input (row outside 1..nrow, not strictly ascending inside a column) sets *flag.
+#define UNION_THREADS 256
+__global__ void __launch_bounds__(UNION_THREADS)
+sls_union_first_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict__ seg, int q, int64_t nrow,
+                       uint32_t* seen, int64_t* out, int64_t* n_out, int32_t* flag) {
+    __shared__ int wsum[UNION_THREADS / 32];
+    __shared__ int64_t base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = 0; s < q; s++) {
+        const int64_t e0 = seg[s], e1 = seg[s + 1];
+#pragma unroll 1
+        for (int64_t i0 = e0; i0 < e1; i0 += UNION_THREADS) {
+            const int64_t i = i0 + tid;
+            bool keep = false;
+            int64_t r = 0;
+            if (i < e1) {
+                r = rows[i];
+                const int64_t prev = (i > e0) ? rows[i - 1] : 0;
+                if (r < 1 || r > nrow || r <= prev) *flag = 1;
+                else {
+                    const uint32_t bit = 1u << ((r - 1) & 31);
+                    keep = !(atomicOr(&seen[(r - 1) >> 5], bit) & bit);
+                }
+            }
+            const uint32_t b = __ballot_sync(SLS_FULL, keep);
+            if (lane == 0) wsum[warp] = __popc(b);
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < UNION_THREADS / 32; w++) { if (w < warp) before += wsum[w]; total += wsum[w]; }
+            if (keep) out[base_s + before + __popc(b & ((1u << lane) - 1u))] = r;
+            __syncthreads();
+            if (tid == 0) base_s += total;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) *n_out = base_s;
+}
+
+int sls_launch_union_first(const int64_t* rows, const int64_t* seg, int q, int64_t nrow, uint32_t* seen, int64_t* out,
+                           int64_t* n_out, int32_t* flag, sls_stream_t stream) {
+    auto kp = &sls_union_first_kernel;
+    SLS_LAUNCH(kp, 1, UNION_THREADS, 0, stream, rows, seg, q, nrow, seen, out, n_out, flag);
+    return rt::last_error();
+}
+
 // ---- host launchers -------------------------------------------------------------------------
 int sls_launch_gather_count(const SlsCsc& A, const SlsSupports& Sx, const SlsSupports& Su, int T, int64_t Nx,
                             const int32_t* cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,

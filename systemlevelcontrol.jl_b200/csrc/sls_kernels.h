@@ -18,6 +18,10 @@ int sls_launch_gather_fill(const SlsCsc& A, const SlsCsc& B2, const SlsSupports&
 int sls_launch_scan(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, int64_t lo, int64_t hi, sls_stream_t stream);
 int sls_launch_local_dense(const SlsCsc& A, const SlsCsc& B2, const SlsPlanView& P, int c,
                            double* At, double* B2t, uint8_t* Mx, uint8_t* Mu, sls_stream_t stream);
+// output-feedback reduction (reduction.jl:16-18): first-occurrence union of q column segments (rows 1-based, seg[q+1]);
+// seen = zeroed bitmap of ceil(nrow/32) words; sets *flag on rows outside 1..nrow or not ascending inside a segment
+int sls_launch_union_first(const int64_t* rows, const int64_t* seg, int q, int64_t nrow, uint32_t* seen, int64_t* out,
+                           int64_t* n_out, int32_t* flag, sls_stream_t stream);
 
 // ---- kernel 2 (sls_solve.cu) ----
 struct SlsSolveArgs {

@@ -64,7 +64,7 @@ class Plant:
     Dimension checks follow validate_GeneralizedPlant (GeneralizedPlant.jl:291-311): a mismatch raises
     ValueError (the reference throws ErrorException)."""
 
-    def __init__(self, A, B1, B2, C1=None, D11=None, D12=None):
+    def __init__(self, A, B1, B2, C1=None, D11=None, D12=None, C2=None, D21=None, D22=None):
         self.A = sp.csc_matrix(A, dtype=np.float64)
         self.B1 = sp.csc_matrix(B1, dtype=np.float64)
         self.B2 = sp.csc_matrix(B2, dtype=np.float64)
@@ -93,8 +93,30 @@ class Plant:
                 raise ValueError("D11 must be Nz x Nw")
         for M in (self.A, self.B1, self.B2, self.C1, self.D11, self.D12):
             M.sort_indices()
-        self.Ny = self.Nx
-        self.feedback = "StateFeedback"
+        # 9-argument form (GeneralizedPlant.jl:69-99): C₂ == I with an empty / zero D₂₁ is state feedback, anything else is
+        # an OutputFeedback plant — which SLS_H2 does not synthesise (synthesis.jl:13 falls through) but
+        # sparsity_dim_reduction reduces (reduction.jl:16-18)
+        def _isempty(M):                                          # Julia isempty: no elements (not "no stored entries")
+            return M is not None and not np.isscalar(M) and int(np.prod(np.shape(M) if not sp.issparse(M) else M.shape)) == 0
+        d21_zero = D21 is None or (np.isscalar(D21) and D21 == 0) or _isempty(D21)     # isempty(D₂₁) || D₂₁ == 0
+        c2_eye = C2 is None or (sp.issparse(C2) and C2.shape == (self.Nx, self.Nx)
+                                and abs(sp.csc_matrix(C2) - sp.identity(self.Nx, format="csc")).nnz == 0)
+        if c2_eye and d21_zero:
+            self.Ny = self.Nx
+            self.feedback = "StateFeedback"
+        else:
+            self.C2 = sp.identity(self.Nx, format="csc", dtype=np.float64) if C2 is None else sp.csc_matrix(C2, dtype=np.float64)
+            self.Ny = self.C2.shape[0]
+            self.D21 = sp.csc_matrix((self.Ny, self.Nw), dtype=np.float64) if d21_zero else sp.csc_matrix(D21, dtype=np.float64)
+            self.D22 = sp.csc_matrix((self.Ny, self.Nu), dtype=np.float64) if (D22 is None or (np.isscalar(D22) and D22 == 0) or _isempty(D22)) \
+                else sp.csc_matrix(D22, dtype=np.float64)
+            if self.C2.shape[1] != self.Nx:
+                raise ValueError("C2 must have Nx columns")
+            if self.D21.shape != (self.Ny, self.Nw) or self.D22.shape != (self.Ny, self.Nu):
+                raise ValueError("D21 must be Ny x Nw and D22 must be Ny x Nu")
+            for M in (self.C2, self.D21, self.D22):
+                M.sort_indices()
+            self.feedback = "OutputFeedback"
 
     def diagonal_cost(self):
         """(wx, wu, why): the diagonal weights when [C₁ D₁₂] = blockdiag(diag(wx), diag(wu)) with positive entries,
@@ -288,6 +310,25 @@ class Synthesizer:
         self._ck(self.api.sls_reduce(self.h, ptr(cj1, i64p), cj1.size, ptr(sx, i64p), sx.size, C.byref(nsx),
                                      ptr(su, i64p), su.size, C.byref(nsu), ptr(iix, u8p)))
         return sx[:nsx.value] - 1, su[:nsu.value] - 1, iix[:nsx.value].astype(bool)
+
+    def reduce_of(self, last_taps, cj):
+        """Output-feedback branch of sparsity_dim_reduction (reduction.jl:16-18) through sls_reduce_of: `last_taps` = the last
+        tap 𝓢ⱼ[end] of every support family; returns ([s_x, s_u, s_y, ...], ii_x), 0-based."""
+        cj1 = np.ascontiguousarray(np.asarray(cj, dtype=np.int64) + 1)
+        fams = [_as_julia(M, np.bool_) for M in last_taps]
+        ncols = fams[0].n
+        if any(F.n != ncols for F in fams):
+            raise ValueError("the support families must have the same number of columns")
+        nrows = np.array([F.m for F in fams], dtype=np.int64)
+        outs = [np.zeros(max(F.m, 1), np.int64) for F in fams]
+        caps = np.array([o.size for o in outs], dtype=np.int64)
+        ns = np.zeros(len(fams), np.int64)
+        iix = np.zeros(max(fams[0].m, 1), np.uint8)
+        self._ck(self.api.sls_reduce_of(self.h, len(fams), ptr_array([F.colptr for F in fams], i64p),
+                                        ptr_array([F.rowval for F in fams], i64p), ptr(nrows, i64p), ncols,
+                                        ptr(cj1, i64p), cj1.size, ptr_array(outs, i64p), ptr(caps, i64p), ptr(ns, i64p),
+                                        ptr(iix, u8p)))
+        return [o[:int(k)] - 1 for o, k in zip(outs, ns)], iix[:int(ns[0])].astype(bool)
 
     def local_problem(self, k):
         n, m, T = int(self.n[k]), int(self.m[k]), self.T
@@ -597,6 +638,8 @@ def sparsity_dim_reduction(P, cj, S, *, device: int = 0, api=None):
     Returns (P̃, Ĩ, iiₓ, sₓ, sᵤ) with P̃ = Plant(A[sₓ,sₓ], B₁[sₓ,cⱼ], B₂[sₓ,sᵤ]) (the sub-plant the reference's
     `view` describes, GeneralizedPlant.jl:266-285), Ĩ = I(|sₓ|)[:, iiₓ] padded to |cⱼ| columns, and 0-based
     index vectors.  The index sets come from kernel 1 on the GPU."""
+    if getattr(P, "feedback", None) == "OutputFeedback":
+        return _sparsity_dim_reduction_of(P, cj, S, device=device, api=api)
     Sx, Su = S
     syn = Synthesizer(device=device, api=api)
     try:
@@ -611,4 +654,33 @@ def sparsity_dim_reduction(P, cj, S, *, device: int = 0, api=None):
     It = np.zeros((n, q))
     sel = np.nonzero(iix)[0]
     It[sel, np.arange(sel.size)] = 1.0
+    return Pt, It, iix, sx, su
+
+
+def _sparsity_dim_reduction_of(P, cj, S, *, device: int = 0, api=None):
+    """The OutputFeedback branch (src/reduction.jl:16-18): 𝓢 = [𝓢ₓ, 𝓢ᵤ, 𝓢ᵧ],
+    sₓ, sᵤ, sᵧ = (unique(findnz(𝓢ⱼ[end][:,cⱼ])[1]) for 𝓢ⱼ in 𝓢) and P̃ = view(P, (sₓ, [sₓ;Nx+sᵤ], sᵧ), (sₓ, cⱼ, sᵤ)).
+    Returns the reference's five values (P̃, Ĩ, iiₓ, sₓ, sᵤ) — sᵧ is not returned there either; it is kept on P̃.s_y.
+    The index sets come from the GPU (sls_reduce_of); P̃ is materialised block by block as the view describes
+    (GeneralizedPlant.jl:266-285)."""
+    if len(S) != 3:
+        raise ValueError("an OutputFeedback plant is reduced with three support families [Sx, Su, Sy] (reduction.jl:17)")
+    syn = Synthesizer(device=device, api=api)
+    try:
+        (sx, su, sy), iix = syn.reduce_of([Sj[-1] for Sj in S], cj)
+    finally:
+        syn.close()
+    cj = np.asarray(cj, dtype=np.int64)
+    zr = np.concatenate([sx, P.Nx + su])
+    if zr.size and zr.max() >= P.Nz:
+        raise ValueError("the view selects rows [s_x; Nx+s_u] of C1/D11/D12: needs Nz >= Nx+Nu rows")
+    cut = lambda M, r, c: M[r, :][:, c]
+    Pt = Plant(cut(P.A, sx, sx), cut(P.B1, sx, cj), cut(P.B2, sx, su),
+               cut(P.C1, zr, sx), cut(P.D11, zr, cj), cut(P.D12, zr, su),
+               cut(P.C2, sy, sx), cut(P.D21, sy, cj), cut(P.D22, sy, su))
+    Pt.s_y = sy
+    n, q = sx.size, cj.size
+    It = np.zeros((n, q))
+    sel = np.nonzero(iix)[0]
+    It[sel, np.arange(sel.size)] = 1.0                       # [I(n)[:,ii_x] 0]  (reduction.jl:22-23)
     return Pt, It, iix, sx, su

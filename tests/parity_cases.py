@@ -70,6 +70,62 @@ def check_reduction_fixture(api):
     assert sx2[0] == 30 and not np.all(np.diff(sx2) > 0)          # genuinely unsorted
 
 
+def of_fixture(Nx=59):
+    """An OutputFeedback plant on the README chain (every third state measured, D21 != 0) and single-tap supports of
+    radius 9 for the three families [Sx, Su, Sy] the reference's OF branch iterates over (reduction.jl:17)."""
+    A, B1, B2 = O.chain_plant(Nx)
+    Nu = B2.shape[1]
+    C2 = sp.identity(Nx, format="csc")[np.arange(0, Nx, 3), :]
+    Ny = C2.shape[0]
+    D21 = sp.csc_matrix(0.1 * np.ones((Ny, Nx)))
+    CD = sp.identity(Nx + Nu, format="csc")
+    mats = dict(A=A, B1=B1, B2=B2, C1=CD[:, :Nx], D11=sp.csc_matrix((Nx + Nu, Nx)), D12=CD[:, Nx:], C2=C2, D21=D21,
+                D22=sp.csc_matrix((Ny, Nu)))
+    pA = O._pat(A)
+    P9 = O._pat_power(pA, 9)
+    Sx = [sp.csc_matrix(P9 != 0)]
+    Su = [sp.csc_matrix((O._pat(sp.csc_matrix(B2).T) @ P9) != 0)]
+    Sy = [sp.csc_matrix((O._pat(C2) @ P9) != 0)]
+    return mats, [Sx, Su, Sy]
+
+
+def check_reduction_of(api):
+    """the OutputFeedback branch of sparsity_dim_reduction (reduction.jl:16-18) through sls_reduce_of
+    (sls_union_first_kernel) against the oracle's restatement — index sets in first-occurrence order, ii_x, I~, the
+    nine blocks of the view — plus its error paths."""
+    mats, S = of_fixture()
+    P = slc_b200.Plant(mats["A"], mats["B1"], mats["B2"], mats["C1"], mats["D11"], mats["D12"], mats["C2"], mats["D21"], mats["D22"])
+    assert P.feedback == "OutputFeedback" and P.Ny == 20
+    assert slc_b200.SLS_H2(P, S[:2], api=api) is None          # synthesis.jl:13: the guard falls through, nothing is returned
+    for cj in (np.arange(20), np.array([30, 5, 31]), np.array([58]), np.array([7, 7, 2])):
+        Pt, It, iix, sx, su = slc_b200.sparsity_dim_reduction(P, cj, S, api=api)
+        sub, oIt, oiix, osx, osu, osy = O.sparsity_dim_reduction_of(mats, cj, S)
+        assert np.array_equal(sx, osx) and np.array_equal(su, osu) and np.array_equal(Pt.s_y, osy)
+        assert np.array_equal(iix, oiix) and np.array_equal(It, oIt)
+        for name in ("A", "B1", "B2", "C1", "D11", "D12"):
+            assert np.array_equal(getattr(Pt, name).toarray(), sub[name]), name
+        if Pt.feedback == "OutputFeedback":
+            for name in ("C2", "D21", "D22"):
+                assert np.array_equal(getattr(Pt, name).toarray(), sub[name]), name
+    # the family sizes are what the branch is for: no product with pat(A), so s_x of column 30 is the radius-9 band
+    _, _, _, sx, su = slc_b200.sparsity_dim_reduction(P, np.array([30, 5, 31]), S, api=api)
+    assert np.array_equal(sx, np.r_[21:40, 0:15, 40])
+    # error paths: column out of range, malformed rows (descending inside a column), too small a capacity
+    syn = slc_b200.Synthesizer(api=api)
+    try:
+        with pytest.raises(_capi.SlsError):
+            syn.reduce_of([S[0][-1], S[1][-1], S[2][-1]], [59])
+        bad = slc_b200.JuliaCSC.from_scipy(S[0][-1], np.bool_)
+        bad.rowval = bad.rowval.copy()
+        bad.rowval[:2] = bad.rowval[:2][::-1]
+        with pytest.raises(_capi.SlsError):
+            syn.reduce_of([bad], [0])
+        (s0,), _ = syn.reduce_of([S[0][-1]], [0])               # the handle stays usable after an error
+        assert np.array_equal(s0, np.arange(10))
+    finally:
+        syn.close()
+
+
 def check_local_blocks(api, A, B1, B2, S, cols):
     """kernel 1 outputs (index sets, masks, local A~/B2~) bit-exact against the oracle's gather."""
     Po = O.Plant(A, B1, B2)

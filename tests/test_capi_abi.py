@@ -20,7 +20,7 @@ def header_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = header_symbols()
-    for s in ("sls_create", "sls_destroy", "sls_set_plant", "sls_set_supports", "sls_plan", "sls_reduce",
+    for s in ("sls_create", "sls_destroy", "sls_set_plant", "sls_set_supports", "sls_plan", "sls_reduce", "sls_reduce_of",
               "sls_solve", "sls_solve_device", "sls_last_error"):
         assert s in syms
 

@@ -11,6 +11,10 @@ def test_emu_reduction_fixture(emu_api):
     pc.check_reduction_fixture(emu_api)
 
 
+def test_emu_reduction_output_feedback_branch(emu_api):
+    pc.check_reduction_of(emu_api)
+
+
 def test_emu_readme_chain_subset_vs_golden(emu_api):
     worst, info = pc.check_golden(emu_api, "readme_chain_59", O.chain_plant(59), cols=[0, 1, 5, 29, 30, 57, 58])
     assert worst < 1e-11

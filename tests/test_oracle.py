@@ -38,6 +38,25 @@ def test_reduction_known_answer():
     assert np.array_equal(B2t, B2[:30, :10].toarray())
 
 
+def test_reduction_output_feedback_branch():
+    """reduction.jl:16-18: s = unique(findnz(𝓢ⱼ[end][:,cⱼ])[1]) per family, no product with pat(A).  The
+    reference has no fixture for this branch; the expected sets are derived by hand from the radius-9 band supports."""
+    from parity_cases import of_fixture
+    mats, S = of_fixture()
+    sub, It, iix, sx, su, sy = O.sparsity_dim_reduction_of(mats, np.arange(20), S)
+    assert np.array_equal(sx, np.arange(29))                       # column j stores rows j-9..j+9: union over 0..19 = 0..28
+    assert np.array_equal(su, np.arange(10))                       # actuators {6n, 6n+1}: states 0..28 hold actuators 0..9
+    assert np.array_equal(sy, np.arange(10))                       # measured states 0,3,...,27
+    assert np.array_equal(iix, np.r_[np.ones(20, bool), np.zeros(9, bool)])
+    assert np.array_equal(It, np.eye(29)[:, :20])
+    assert sub["C2"].shape == (10, 29) and sub["D21"].shape == (10, 20) and sub["C1"].shape == (39, 29)
+    # first-occurrence order over an unsorted group
+    _, _, iix, sx, _, sy = O.sparsity_dim_reduction_of(mats, np.array([30, 5, 31]), S)
+    assert np.array_equal(sx, np.r_[21:40, 0:15, 40])
+    assert np.array_equal(sy, np.r_[7:14, 0:5])                    # measured states 21..39 -> outputs 7..13; 0..14 -> 0..4
+    assert iix.sum() == 3 and iix[9] and iix[19 + 5] and iix[10]
+
+
 def test_supports_readme_counts():
     P, A, B1, B2 = readme()
     Sx, Su = O.make_supports(A, B2, 9, 29, 1.5)

@@ -24,6 +24,10 @@ def test_reduction_fixture(cuda_api):
     pc.check_reduction_fixture(cuda_api)
 
 
+def test_reduction_output_feedback_branch(cuda_api):
+    pc.check_reduction_of(cuda_api)
+
+
 def test_config1_readme_chain_vs_golden(cuda_api):
     worst, info = pc.check_golden(cuda_api, "readme_chain_59", O.chain_plant(59))
     assert worst < 1e-10
