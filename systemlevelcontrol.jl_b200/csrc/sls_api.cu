@@ -1312,8 +1312,10 @@ static int pipe_prepare(sls_handle* h, PipeSupp& f, int64_t T, int64_t Nx, int64
     SLS_CK(rt::h2d(d.tap_off.p, d.h_tap_off.data(), (T + 1) * sizeof(int64_t), h->in_stream));   // pageable: before the big copies
     for (int64_t t = 0; t < T; t++)
         SLS_CK(rt::h2d(d.colptr.as<int64_t>() + t * (Nx + 1) + w0, f.cps[t], (wn + 1) * sizeof(int64_t), h->in_stream));
-    // the Bool values are 1/9 of the bytes but would be half of the slice copies (each copy costs ~10 us of driver
-    // time): they go up whole, once per tap, ahead of the column chunks
+    // the Bool values are 1/9 of the bytes but would be half of the slice copies (each copy costs 10-14 us on the copy-in
+    // engine of this box): they go up whole, once per tap, ahead of the column chunks.  Measured the other way (slices
+    // travelling with their chunk, so that chunk 0 lands 0.9 ms earlier): the copy-in of the call ends at 21.9 instead of
+    // 17.2 ms and the call takes the same 32.1 ms — it is bound by the copy-out engine (profiles/r02_e2e_pipeline_trace.txt).
     if (any_nz)
         for (int64_t t = 0; t < T; t++)
             SLS_CK(rt::h2d(d.nzval.as<uint8_t>() + slot[t], f.nzs[t] + (f.cps[t][0] - 1), (size_t)(slot[t + 1] - slot[t]), h->in_stream));
@@ -1379,9 +1381,30 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
     // fill and drain time (measured on config #3: 4-5 chunks best, 8 chunks +2 ms)
     int K = (ncols >= 16384) ? 4 : 1;
     if (const char* ev = getenv("SLS_PIPE_CHUNKS")) { const int c = atoi(ev); if (c >= 1) K = c; }
+    // relative chunk sizes (tuning knob, "w0,w1,...").  Measured on config #3: no split beats equal chunks by more than 0.3 ms
+    // (small first chunks start the download earlier but add ~116 copies of 5-14 us each per chunk and direction)
+    std::vector<double> fr;
+    if (const char* ev = getenv("SLS_PIPE_FRACS")) {
+        for (const char* s = ev; *s;) {
+            char* end = nullptr;
+            const double w = strtod(s, &end);
+            if (end == s) break;
+            if (w > 0) fr.push_back(w);
+            s = (*end == ',') ? end + 1 : end;
+        }
+        if (!fr.empty() && ncols >= 16384) K = (int)fr.size(); else fr.clear();
+    }
     K = (int)std::min<int64_t>(std::min<int64_t>(K, SLS_PIPE_MAX), ncols);
     std::vector<int64_t> cb(K + 1), ub(K + 1);
     for (int c = 0; c <= K; c++) cb[c] = r0 + ncols * c / K;
+    if ((int)fr.size() == K && K > 1) {
+        double tot = 0, run = 0;
+        for (double w : fr) tot += w;
+        for (int c = 1; c < K; c++) {
+            run += fr[c - 1];
+            cb[c] = std::min(r1 - (K - c), std::max(cb[c - 1] + 1, r0 + (int64_t)llround((double)ncols * run / tot)));
+        }
+    }
     // support columns to upload: the range itself plus the columns kernel 1 reaches through nz(A[:,j]) (the halo)
     // upload chunk c ends where the reach of plan chunk c ends, so that chunk c never waits for chunk c+1's copy
     ub = cb;
