@@ -1,0 +1,37 @@
+"""pcie_probe.py — host<->device copy ceilings of the box (pinned memory, torch copies on side streams): one large copy per
+direction, both directions at once, and 1 GiB cut into 464 / 4096 copies (the per-copy cost the pipelined call pays).
+Numbers of this pool: profiles/r02_e2e_pipeline_trace.txt."""
+import torch, time
+torch.cuda.set_device(0)
+GB = 1 << 30
+n = GB // 8
+hd = torch.empty(n, dtype=torch.float64).pin_memory()
+hu = torch.empty(n, dtype=torch.float64).pin_memory()
+dd = torch.empty(n, dtype=torch.float64, device="cuda")
+du = torch.empty(n, dtype=torch.float64, device="cuda")
+s1, s2, s3 = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+def timed(fn, reps=3):
+    best = 1e9
+    for _ in range(reps):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
+    return best
+def d2h_one():
+    with torch.cuda.stream(s1): hd.copy_(dd, non_blocking=True)
+def h2d_one():
+    with torch.cuda.stream(s2): du.copy_(hu, non_blocking=True)
+def both():
+    d2h_one(); h2d_one()
+def d2h_pieces(k, streams=1):
+    step = n // k
+    for i in range(k):
+        st = s1 if (streams == 1 or i % 2 == 0) else s3
+        with torch.cuda.stream(st): hd[i*step:(i+1)*step].copy_(dd[i*step:(i+1)*step], non_blocking=True)
+def d2h_two_halves():
+    h = n // 2
+    with torch.cuda.stream(s1): hd[:h].copy_(dd[:h], non_blocking=True)
+    with torch.cuda.stream(s3): hd[h:].copy_(dd[h:], non_blocking=True)
+for name, fn, gb in (("D2H 1 GiB one copy", d2h_one, 1), ("H2D 1 GiB one copy", h2d_one, 1), ("D2H + H2D concurrently (1 GiB each)", both, 2),
+                     ("D2H 1 GiB as 464 copies, one stream", lambda: d2h_pieces(464), 1), ("D2H 1 GiB as 464 copies, two streams", lambda: d2h_pieces(464, 2), 1),
+                     ("D2H 1 GiB as 2 halves on two streams", d2h_two_halves, 1), ("D2H 1 GiB as 4096 copies, one stream", lambda: d2h_pieces(4096), 1)):
+    t = timed(fn)
+    print(f"{name}: {t*1e3:.2f} ms = {gb * GB / t / 1e9:.1f} GB/s total", flush=True)
