@@ -546,6 +546,27 @@ def run_ours(args, rank, world, local_rank):
         syn.set_plant(shard.Aj, shard.B2j)
         syn.set_supports(shard.Sx, shard.Su)
 
+    # N > 1: the values-only form of the host path as well.  The host's aggregate device-to-host ceiling (71-92 GB/s on
+    # these boxes whatever the GPU count, profiles/r02_e2e_pipeline_trace.txt) is what holds `e2e` at N = 8; this form
+    # moves half the bytes down.
+    if world > 1 and not args.no_e2e:
+        outv = shard.alloc_slab(values_only=True)
+        shard.e2e_step(outv, values_only=True)
+        barrier()
+        r = [shard.e2e_step(outv, values_only=True) for _ in range(3)]
+        barrier()
+        ok = all(int(r[-1][1][t]) == outv["x"]["nzval"][t].size for t in range(T)) and \
+            all(int(r[-1][2][t]) == outv["u"]["nzval"][t].size for t in range(T)) and float(outv["resid"].max()) < 1e-9
+        ok = allsum(0.0 if ok else 1.0) == 0.0
+        vo_ms = allmax(float(np.mean([x[0] for x in r])))
+        vo_d2h = int(allsum(float(shard.d2h_full)))
+        if ok:
+            variants["e2e_values_only"] = {"value": nx_local * world / (vo_ms * 1e-3), "unit": UNIT, "ms_per_step": vo_ms,
+                                           "d2h_bytes_per_step": vo_d2h,
+                                           "what": "sls_synthesize_window with NULL rowval outputs on every rank (nnz(Phi[t]) == nnz(S[t]) checked: "
+                                                   "the host aliases its own S[t].rowval); the documented Julia fast path, not the headline"}
+        del outv
+
     # ---------------------------------------------------------------- config #5 on the resident controller, config #4 (N = 1)
     config5 = config4 = None
     extra_launches = 0
