@@ -14,7 +14,9 @@ support window that range needs (`sls_synthesize_window`); there is no data-path
  value   : columns/s with plant and supports already resident in HBM (device time, CUDA events on the library's stream,
            max over ranks).
  e2e     : the same through the reference-facing call with HOST buffers (pinned): sls_set_plant + sls_synthesize_window
-           (H2D of the support window, kernels 1-3, D2H of every Φ tap's column slab in Julia CSC layout), pipelined.
+           (H2D of the support window, kernels 1-3, every Φ tap's column slab in Julia CSC layout back in the caller's arrays:
+           colptr and values by D2H copies, rowval by D2H or — for taps whose pattern the device proved equal to the
+           support's — from the caller's own S[t].rowval by host threads), pipelined.
  roofline: kernel 2 (dominant) against the FP64 DMMA peak measured on this device by sls_fp64_peak
            (MEASURED_PEAKS.json has no FP64 entry); roofline_hbm: kernels 1+3 against the measured copy peak.
  strong  : the same hot path on Nx = 100 000 columns TOTAL, cost-balanced contiguous ranges over the N GPUs
@@ -405,6 +407,8 @@ def run_ours(args, rank, world, local_rank):
         pass
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)")
 
+    # host threads the library may use for host-side copies, per rank (its own default assumes it owns the box)
+    os.environ.setdefault("SLS_HOST_COPY_THREADS", str(max(2, min(8, (os.cpu_count() or 8) // max(world, 1) // 2))))
     syn = slc_b200.Synthesizer(device=local_rank)
     import ctypes as C
     dfma, dmma = C.c_double(), C.c_double()
@@ -449,7 +453,10 @@ def run_ours(args, rank, world, local_rank):
             e2e = [shard.e2e_step(out)[0] for _ in range(e2e_reps)]
             barrier()
             assert out["resid"].max() < 1e-9, "e2e result failed its own feasibility check"
-            res.update(e2e_ms=float(np.mean(e2e)), out=out, d2h=shard.d2h_full)
+            # rowval outputs the library filled host-side from the caller's own S[t].rowval (pattern proven equal on the
+            # device) never crossed PCIe: they are not device-to-host bytes
+            hcb = int(syn.timing()["host_copied_bytes"])
+            res.update(e2e_ms=float(np.mean(e2e)), out=out, d2h=shard.d2h_full - hcb, host_copied=hcb)
         return res
 
     nx_local = args.nx
@@ -481,6 +488,18 @@ def run_ours(args, rank, world, local_rank):
                                            "what": "sls_synthesize_window with NULL rowval outputs: the returned nnz(Phi[t]) == nnz(S[t]) proves "
                                                    "the stored pattern is S[t]'s, so the host aliases its own S[t].rowval (0.53 GB less D2H); "
                                                    "the documented Julia fast path (integration/SLSB200.jl), not the headline"}
+        # (1b) every rowval output copied back from the device (flags bit 3 / SLS_PIPE_ROWS_FROM_DEVICE): the call as it was
+        #      before the library learnt to fill pattern-equal taps from the caller's own S[t].rowval
+        os.environ["SLS_PIPE_ROWS_FROM_DEVICE"] = "1"
+        try:
+            shard.e2e_step(out)
+            rd = float(np.mean([shard.e2e_step(out)[0] for _ in range(3)]))
+            assert int(syn.timing()["host_copied_bytes"]) == 0 and same_values(out)
+        finally:
+            os.environ.pop("SLS_PIPE_ROWS_FROM_DEVICE", None)
+        variants["e2e_rows_from_device"] = {"value": shard.ncols / (rd * 1e-3), "unit": UNIT, "ms_per_step": rd,
+                                            "d2h_bytes_per_step": int(main["d2h"] + main["host_copied"]),
+                                            "what": "same call, rowval outputs always copied from the device (sls_options.flags bit 3)"}
         # (2) the three-call form of the ABI
         out3 = None
         if shard.cols is None:
@@ -703,6 +722,11 @@ def run_ours(args, rank, world, local_rank):
             line["e2e"] = {"value": ncols_all / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                            "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                            "h2d_bytes_per_rank": int(shard.h2d), "d2h_bytes_per_rank": int(main.get("d2h", 0)),
+                           "host_copied_bytes_per_rank": int(main.get("host_copied", 0)),
+                           "host_copied_what": "rowval outputs of taps whose stored pattern the device proved equal to the support's "
+                                               "(equal stored-entry counts; stored rows are a subset of the support column) are filled "
+                                               "from the caller's own S[t].rowval by host threads instead of a device-to-host copy; "
+                                               "bit-identical (tests: check_pipelined_rowval_sources); e2e_rows_from_device is the call without it",
                            "api": "sls_set_plant (the rank's sub-plant) + sls_synthesize_window (support window in, Phi column slab out; "
                                   "column-chunked copy/compute pipeline), pinned host buffers, full CSC outputs (colptr + rowval + nzval)"}
             line.update(variants)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SLS_ABI_VERSION 8
+#define SLS_ABI_VERSION 9
 
 /* per-column status bits written by sls_solve* (improves on the reference, which ignores the
  * solver's termination status: src/synthesis.jl:62-65) */
@@ -48,7 +48,9 @@ typedef struct sls_options {
     int32_t flags;       /* bit 0: also validate the supports' rowval (range, strictly ascending) on the host;
                             bit 1: sls_solve copies the outputs back after kernel 2 instead of chunk by chunk;
                             bit 2: no refinement sweeps in kernel 2 (columns whose residual exceeds feas_tol are only flagged);
-                            bit 3: reserved (was: kernel 3 before kernel 2 — that is the only order since ABI v6) */
+                            bit 3: sls_synthesize* always copies the rowval outputs from the device (default: a tap whose stored-entry
+                                   count equals the support's over a column chunk — then its rows ARE the support's — is filled
+                                   from the caller's own S[t].rowval on the host, bit-identical, half the device-to-host bytes) */
     double  rank_tol;    /* pivot <= rank_tol * diag(D_k) => constraint row treated as redundant; 0 -> 1e-10 */
     double  feas_tol;    /* max-abs achievability residual above which SLS_STATUS_RESIDUAL is set; 0 -> 1e-12.  Columns above
                             feas_tol / 10 first take up to 3 refinement sweeps on the stored factors (flags bit 2: none) */
@@ -69,6 +71,8 @@ typedef struct sls_timing {      /* device times (CUDA events on the handle's st
     float sim_pack_ms;           /* sls_simulate: window + pack passes before the simulation kernel     */
     int64_t refined;             /* columns of the last solve that took >= 1 refinement sweep of kernel 2 */
     double  sim_bytes;           /* sls_simulate: packed Phi bytes the recursion consumed (sum over scenarios and steps) */
+    int64_t host_copied_bytes;   /* sls_synthesize*: bytes of rowval outputs filled from the caller's own S[t].rowval on the host
+                                    (taps whose stored pattern the device proved equal to the support's) instead of device-to-host copies */
 } sls_timing;
 
 int         sls_abi_version(void);

@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libslsb200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 STATUS_OK, STATUS_RESIDUAL, STATUS_RANK_SKIPPED, STATUS_NO_IMPULSE = 0, 1, 2, 4
 
 i64p = C.POINTER(C.c_int64)
@@ -36,7 +36,8 @@ class SlsTiming(C.Structure):
                 ("ncols", C.c_int64), ("nnz_out", C.c_int64),
                 ("alg_flops", C.c_double), ("alg_bytes", C.c_double),
                 ("sim_ms", C.c_float), ("sim_window", C.c_int32), ("sim_uwindow", C.c_int32),
-                ("gather_gpu_ms", C.c_float), ("sim_pack_ms", C.c_float), ("refined", C.c_int64), ("sim_bytes", C.c_double)]
+                ("gather_gpu_ms", C.c_float), ("sim_pack_ms", C.c_float), ("refined", C.c_int64), ("sim_bytes", C.c_double),
+                ("host_copied_bytes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

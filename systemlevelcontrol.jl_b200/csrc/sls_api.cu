@@ -18,6 +18,9 @@
 #include <chrono>
 #include <thread>
 #include <atomic>
+#include <mutex>
+#include <condition_variable>
+#include <deque>
 
 namespace {
 
@@ -1268,6 +1271,72 @@ extern "C" int sls_solve(sls_handle* h,
 // rowval/nzval arrive slice by slice, in final position), with its own output buffers.  Results are bit-for-bit
 // those of the three-call path.
 namespace {
+// Host-side copies of the pipelined call, off the calling thread: a few workers take (dst, src, bytes) pieces from a queue.
+// Used for the rowval outputs of sls_synthesize*: Phi[t][:,j] stores a SUBSET of the rows of S[t][:,j] (kernel 1 keeps the
+// support entries that are true and whose row lies in s_x), so when a tap's stored-entry count over a chunk's columns equals
+// the support's, its row indices ARE the caller's own S[t].rowval slice — they are copied host to host instead of coming back
+// over PCIe (on these hosts the device-to-host direction is the scarce one: 57 GB/s for one GPU, 71-92 GB/s for all eight
+// together, profiles/r02_e2e_pipeline_trace.txt).
+struct HostCopier {
+    struct Job { char* dst; const char* src; size_t n; };
+    std::deque<Job> q;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool closing = false;
+    std::vector<std::thread> th;
+    int64_t bytes = 0;
+    static int default_threads() {
+        if (const char* ev = getenv("SLS_HOST_COPY_THREADS")) { const int c = atoi(ev); if (c >= 1) return std::min(c, 64); }
+        const int hc = (int)std::thread::hardware_concurrency();
+        return std::max(2, std::min(8, hc / 4));
+    }
+    void start() {
+        const int nt = default_threads();
+        for (int i = 0; i < nt; i++)
+            th.emplace_back([this]() {
+                for (;;) {
+                    Job j;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [this]() { return closing || !q.empty(); });
+                        if (q.empty()) return;
+                        j = q.front(); q.pop_front();
+                    }
+                    memcpy(j.dst, j.src, j.n);
+                }
+            });
+    }
+    void add(void* dst, const void* src, size_t n) {            // pieces of at most 2 MB so that the workers stay balanced
+        if (!n || dst == src) { bytes += (int64_t)n; return; }
+        if (th.empty()) start();
+        const size_t piece = (size_t)2 << 20;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t o = 0; o < n; o += piece) q.push_back(Job{(char*)dst + o, (const char*)src + o, std::min(piece, n - o)});
+        }
+        cv.notify_all();
+        bytes += (int64_t)n;
+    }
+    void finish() {                                             // drains the queue; the calling thread helps
+        for (;;) {
+            Job j;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (q.empty()) break;
+                j = q.front(); q.pop_front();
+            }
+            memcpy(j.dst, j.src, j.n);
+        }
+        { std::lock_guard<std::mutex> lk(mu); closing = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+        th.clear();
+    }
+    ~HostCopier() { finish(); }
+};
+}
+
+namespace {
 struct CopyBatch {                                          // slice copies of one chunk and direction, issued as one call
     std::vector<void*> dst, src; std::vector<size_t> len;
     void add(void* d, const void* s_, size_t n) { if (n) { dst.push_back(d); src.push_back(const_cast<void*>(s_)); len.push_back(n); } }
@@ -1463,6 +1532,8 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
         return 0;
     };
     CopyBatch obatch;
+    HostCopier hcopy;
+    const bool host_rows = !(h->opt.flags & 8) && !getenv("SLS_PIPE_ROWS_FROM_DEVICE");   // flags bit 3: rowval always from the device
     auto chunk_of = [&](int64_t col) { int c = 0; while (c < K - 1 && col >= ub[c + 1]) c++; return c; };
     std::vector<int64_t> base(2 * T, 0);
     std::vector<int64_t> cols;
@@ -1571,7 +1642,14 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
         for (int64_t tt = 0; tt < 2 * T; tt++) {
             const int x_ = tt >= T; const int64_t t = x_ ? tt - T : tt;
             int64_t* const* hr = x_ ? Pu_rowval : Px_rowval;
-            if (hr && hr[t]) obatch.add(hr[t] + base[tt], x.out_rowval.as<int64_t>() + p.out_off[tt], (size_t)p.nnz_tap[tt] * sizeof(int64_t));
+            if (!(hr && hr[t])) continue;
+            // stored rows of a column are a subset of the support column's: equal counts over the chunk <=> the very same
+            // row indices, which the caller already holds (HostCopier above); otherwise they come from kernel 3's output
+            const int64_t* cp = fam[x_].cps[t] - w0;            // indexed by the global column
+            if (host_rows && p.nnz_tap[tt] == cp[c1] - cp[c0])
+                hcopy.add(hr[t] + base[tt], fam[x_].rvs[t] + (cp[c0] - 1), (size_t)p.nnz_tap[tt] * sizeof(int64_t));
+            else
+                obatch.add(hr[t] + base[tt], x.out_rowval.as<int64_t>() + p.out_off[tt], (size_t)p.nnz_tap[tt] * sizeof(int64_t));
         }
         PIPE_CK(obatch.flush(h->copy_stream));
         sls_stream_t vstream = getenv("SLS_PIPE_ONE_OUT") ? h->copy_stream : h->out2_stream;   // values on their own stream
@@ -1591,6 +1669,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
 #undef PIPE_CK
     if (e) feed_stop.store(true);
     feeder.join();
+    hcopy.finish();
     if (!e && feed_err.load()) e = fail(h, feed_err.load(), feed_msg.c_str());
     if (e) { pipe_drain(h); h->have_supports = false; return e; }
     h->pipe_done.record(h->copy_stream);
@@ -1615,7 +1694,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
                     rt::elapsed_ms(h->ev[0], h->pipe_in[c]), rt::elapsed_ms(h->ev[0], h->pipe[c]->ev_plan),
                     rt::elapsed_ms(h->ev[0], h->pipe[c]->ev_scat), rt::elapsed_ms(h->ev[0], h->pipe[c]->ev_solved),
                     rt::elapsed_ms(h->ev[0], h->pipe[c]->ev_out));
-        fprintf(stderr, "[pipe] total %.2f\n", rt::elapsed_ms(h->ev[0], h->ev[1]));
+        fprintf(stderr, "[pipe] total %.2f (rowval filled host-side: %.1f MB)\n", rt::elapsed_ms(h->ev[0], h->ev[1]), hcopy.bytes / 1e6);
     }
     h->tm = sls_timing{};
     h->tm.solve_ms = rt::elapsed_ms(h->ev[0], h->ev[1]);       // whole pipelined call (copies, kernels 1-3) on the device clock
@@ -1623,6 +1702,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
     h->pipe_chunks = K;                                        // alg_flops / alg_bytes: summed over the chunks' plans on demand (sls_get_timing)
     h->tm.ncols = ncols; h->tm.nnz_out = nnz_total; h->tm.alg_flops = flops; h->tm.alg_bytes = bytes;
     h->tm.refined = h->h_flag[1];
+    h->tm.host_copied_bytes = hcopy.bytes;
     h->tm_from_plan = false;
     // the support columns of the range (+halo) stay on the device; a later sls_plan of other columns needs
     // sls_set_supports.  The outputs live in per-chunk buffers, so the

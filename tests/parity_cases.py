@@ -348,6 +348,51 @@ def check_pipelined(api, plant, S, chunks, pass_nzval=True):
         syn.close()
 
 
+def check_pipelined_rowval_sources(api, Nx=24, d=3, T=8):
+    """sls_synthesize fills a tap's rowval output from the caller's own S[t].rowval when the stored-entry count over a column
+    chunk equals the support's (stored rows are a subset of the support column, so equal counts mean equal rows) and from the
+    device otherwise.  Supports with stored-false entries and with rows outside s_x take the device branch for the taps they
+    touch; every output must equal the three-call path bit for bit, whatever the source, and flags bit 3 turns the host
+    branch off."""
+    import os
+    A, B1, B2, S = chain(Nx, d=d, T=T)
+    Sx, Su = [sp.csc_matrix(M).copy() for M in S[0]], [sp.csc_matrix(M).copy() for M in S[1]]
+    for M in Sx + Su:
+        M.sort_indices()
+    M = Sx[3]; M.data[M.indptr[5] + 1] = False                      # stored false: the entry is fixed to 0, not stored in Phi
+    M = Su[2]; M.data[M.indptr[7]] = False
+    L = Sx[4].tolil(); L[min(Nx - 1, 10 + d + 4), 10] = True; Sx[4] = sp.csc_matrix(L.tocsc()); Sx[4].sort_indices()   # a row outside s_x
+    touched = {("x", 3), ("u", 2), ("x", 4)}
+    check_pipelined(api, (A, B1, B2), [Sx, Su], chunks=[1, 3])        # bit for bit against the three-call path
+    old = os.environ.get("SLS_PIPE_CHUNKS")
+    os.environ["SLS_PIPE_CHUNKS"] = "1"
+    try:
+        for flags in (0, 8):
+            syn = slc_b200.Synthesizer(api=api, flags=flags)
+            try:
+                syn.set_plant(A, B2)
+                out = syn.synthesize(Sx, Su)
+                hcb = syn.timing()["host_copied_bytes"]
+                expect = 0 if flags else 8 * sum(out[f]["rowval"][t].size for f in ("x", "u") for t in range(T) if (f, t) not in touched)
+                assert hcb == expect, (flags, hcb, expect)
+                for f, t in touched:                                  # the touched taps really store fewer entries than their support
+                    assert out[f]["rowval"][t].size < (Sx if f == "x" else Su)[t].nnz
+                if flags == 0:
+                    ref = out
+                else:
+                    for f in ("x", "u"):
+                        for t in range(T):
+                            for part in ("colptr", "rowval", "nzval"):
+                                assert np.array_equal(out[f][part][t], ref[f][part][t]), (f, t, part)
+            finally:
+                syn.close()
+    finally:
+        if old is None:
+            os.environ.pop("SLS_PIPE_CHUNKS", None)
+        else:
+            os.environ["SLS_PIPE_CHUNKS"] = old
+
+
 def check_window(api, plant, S, ranges, halo=1, chunks=(1, 3), sub_reach=None):
     """sls_synthesize_window (support window in, column slab out) == the three-call path on the same columns, bit for
     bit — for both ways of passing a window (a colptr view into the full matrices; rebased slices), and with the

@@ -62,6 +62,10 @@ def test_emu_pipelined_one_shot_equals_three_call(emu_api):
     pc.check_pipelined(emu_api, (A, B1, B2), S, chunks=[1, 5])
 
 
+def test_emu_pipelined_rowval_from_host_or_device(emu_api):
+    pc.check_pipelined_rowval_sources(emu_api)
+
+
 def test_emu_window_shard_form(emu_api):
     A, B1, B2, S = pc.chain(30, d=3, T=8)
     pc.check_window(emu_api, (A, B1, B2), S, ranges=[(0, 11), (9, 22), (20, 30)], sub_reach=5)

@@ -289,6 +289,13 @@ def test_pipelined_one_shot_equals_three_call_small(cuda_api):
     pc.check_pipelined(cuda_api, (A, B1, B2), S, chunks=[4], pass_nzval=False)
 
 
+def test_pipelined_rowval_from_host_or_device(cuda_api):
+    """sls_synthesize: rowval outputs filled from the caller's S[t].rowval (pattern proven equal) or from kernel 3's output
+    (stored-false entries, rows outside s_x) — bit for bit the three-call result either way; flags bit 3 = device only."""
+    pc.check_pipelined_rowval_sources(cuda_api, Nx=59, d=9, T=29)
+    pc.check_pipelined_rowval_sources(cuda_api)
+
+
 def test_pipelined_one_shot_config3_100k_bit_for_bit(cuda_api):
     """BASELINE config #3 through sls_synthesize (default 8 column chunks, pinned buffers, copies overlapped with the
     kernels) == the three-call path, bit for bit; plus a 2-shard split of the columns."""

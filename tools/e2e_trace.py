@@ -33,9 +33,6 @@ def main():
         shard.e2e_step(out, values_only=a.values_only)
     torch.cuda.synchronize()
     ms = [shard.e2e_step(out, values_only=a.values_only)[0] for _ in range(a.reps)]
-    if trace:
-        os.environ["SLS_PIPE_TRACE"] = trace
-        shard.e2e_step(out, values_only=a.values_only)
     assert out["resid"].max() < 1e-9
     import time
     sp, sw = [], []
@@ -45,8 +42,12 @@ def main():
                               out=out, values_only=a.values_only, row_off=(shard.p0, shard.u0))
         t2 = time.perf_counter()
         sp.append(1e3 * (t1 - t0)); sw.append(1e3 * (t2 - t1))
+    if trace:
+        os.environ["SLS_PIPE_TRACE"] = trace
+        shard.e2e_step(out, values_only=a.values_only)
     print(f"host wall: sls_set_plant {min(sp):.2f} ms, sls_synthesize_window {min(sw):.2f} ms (incl. the ctypes wrapper)", flush=True)
     print(f"e2e chunks={os.environ.get('SLS_PIPE_CHUNKS', 'default')} fracs={os.environ.get('SLS_PIPE_FRACS', '-')} "
+          f"host_copy_threads={os.environ.get('SLS_HOST_COPY_THREADS', 'default')} rows_from_device={os.environ.get('SLS_PIPE_ROWS_FROM_DEVICE', '0')} "
           f"values_only={a.values_only}: mean {np.mean(ms):.2f} ms, min {np.min(ms):.2f} ms over {a.reps} calls", flush=True)
     syn.close()
 
