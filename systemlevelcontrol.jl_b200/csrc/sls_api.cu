@@ -21,6 +21,10 @@
 #include <mutex>
 #include <condition_variable>
 #include <deque>
+#include <cstdint>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace {
 
@@ -1277,6 +1281,31 @@ namespace {
 // the support's, its row indices ARE the caller's own S[t].rowval slice — they are copied host to host instead of coming back
 // over PCIe (on these hosts the device-to-host direction is the scarce one: 57 GB/s for one GPU, 71-92 GB/s for all eight
 // together, profiles/r02_e2e_pipeline_trace.txt).
+// memcpy with non-temporal stores: the destination (an output array of hundreds of MB) is not read again by this call, so
+// the lines need not be fetched for ownership nor kept in cache — a third less DRAM traffic than memcpy, which on these
+// hosts is what the copy engines are competing for (glibc only switches to streaming stores far above the 2 MB pieces)
+static void stream_copy(char* d, const char* s, size_t n) {
+#if defined(__SSE2__)
+    static const bool nt = !getenv("SLS_HOST_COPY_NO_NT");
+    if (nt && n >= 256) {
+        size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+        memcpy(d, s, head); d += head; s += head; n -= head;
+        const size_t blocks = n / 64;
+        for (size_t i = 0; i < blocks; i++) {
+            const __m128i a = _mm_loadu_si128((const __m128i*)(s)), b = _mm_loadu_si128((const __m128i*)(s + 16));
+            const __m128i c = _mm_loadu_si128((const __m128i*)(s + 32)), e = _mm_loadu_si128((const __m128i*)(s + 48));
+            _mm_stream_si128((__m128i*)(d), a); _mm_stream_si128((__m128i*)(d + 16), b);
+            _mm_stream_si128((__m128i*)(d + 32), c); _mm_stream_si128((__m128i*)(d + 48), e);
+            s += 64; d += 64;
+        }
+        n -= blocks * 64;
+        memcpy(d, s, n);
+        _mm_sfence();
+        return;
+    }
+#endif
+    memcpy(d, s, n);
+}
 struct HostCopier {
     struct Job { char* dst; const char* src; size_t n; };
     std::deque<Job> q;
@@ -1288,7 +1317,7 @@ struct HostCopier {
     static int default_threads() {
         if (const char* ev = getenv("SLS_HOST_COPY_THREADS")) { const int c = atoi(ev); if (c >= 1) return std::min(c, 64); }
         const int hc = (int)std::thread::hardware_concurrency();
-        return std::max(2, std::min(8, hc / 4));
+        return std::max(2, std::min(4, hc / 4));   // streaming stores: two threads already keep up with the pipeline on config #3
     }
     void start() {
         const int nt = default_threads();
@@ -1302,7 +1331,7 @@ struct HostCopier {
                         if (q.empty()) return;
                         j = q.front(); q.pop_front();
                     }
-                    memcpy(j.dst, j.src, j.n);
+                    stream_copy(j.dst, j.src, j.n);
                 }
             });
     }
@@ -1325,7 +1354,7 @@ struct HostCopier {
                 if (q.empty()) break;
                 j = q.front(); q.pop_front();
             }
-            memcpy(j.dst, j.src, j.n);
+            stream_copy(j.dst, j.src, j.n);
         }
         { std::lock_guard<std::mutex> lk(mu); closing = true; }
         cv.notify_all();

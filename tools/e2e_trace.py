@@ -47,7 +47,7 @@ def main():
         shard.e2e_step(out, values_only=a.values_only)
     print(f"host wall: sls_set_plant {min(sp):.2f} ms, sls_synthesize_window {min(sw):.2f} ms (incl. the ctypes wrapper)", flush=True)
     print(f"e2e chunks={os.environ.get('SLS_PIPE_CHUNKS', 'default')} fracs={os.environ.get('SLS_PIPE_FRACS', '-')} "
-          f"host_copy_threads={os.environ.get('SLS_HOST_COPY_THREADS', 'default')} rows_from_device={os.environ.get('SLS_PIPE_ROWS_FROM_DEVICE', '0')} "
+          f"host_copy_threads={os.environ.get('SLS_HOST_COPY_THREADS', 'default')} nt_stores={0 if os.environ.get('SLS_HOST_COPY_NO_NT') else 1} rows_from_device={os.environ.get('SLS_PIPE_ROWS_FROM_DEVICE', '0')} "
           f"values_only={a.values_only}: mean {np.mean(ms):.2f} ms, min {np.min(ms):.2f} ms over {a.reps} calls", flush=True)
     syn.close()
 
