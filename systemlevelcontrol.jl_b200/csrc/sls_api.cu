@@ -85,7 +85,7 @@ struct SolveClass { int N, count, mcap, nnzcap; size_t list_off; };
 struct Plan {
     bool valid = false;
     int ncols = 0, nstride = 1, mstride = 1, wx = 1, wu = 1, nmax = 0, mmax = 0, cap = 32;
-    DevBuf cols, n, m, sx, su, maskx, masku, jloc, lnnz, lnnzA, lnnzB, pre, tot, colptr, lists, keepx, keepu, stats;
+    DevBuf cols, n, m, sx, su, maskx, masku, jloc, lnnz, lnnzA, lnnzB, pre, tot, colptr, lists, keepx, keepu, stats, scanws;
     PinVec<int32_t> h_stats;            // [36] plan statistics computed by kernel 1a (sls_gather.cu)
     bool sizes_on_host = false, lists_on_host = false;   // h_n / h_m and h_lists are fetched on demand
     PinVec<int32_t> h_cols, h_lists;    // pinned: read by kernel copies (sls_kcopy)
@@ -104,7 +104,7 @@ struct Plan {
     int64_t col_lo = 0, col_hi = 0;     // planned columns lie in [col_lo, col_hi)
     int identity_cols = 0;              // h_cols currently holds 0..identity_cols-1 (the cols == NULL plan)
     void release() {
-        DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists, &keepx, &keepu, &stats};
+        DevBuf* all[] = {&cols, &n, &m, &sx, &su, &maskx, &masku, &jloc, &lnnz, &lnnzA, &lnnzB, &pre, &tot, &colptr, &lists, &keepx, &keepu, &stats, &scanws};
         h_stats.release();
         for (DevBuf* b : all) b->release();
         h_seg.release(); h_status.release(); h_resid.release(); h_cols.release(); h_lists.release();
@@ -782,7 +782,8 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     h->gev[2].record(h->stream);
     SLS_CK(sls_launch_gather_fill(h->A.view(), h->B2.view(), h->Sx.view(), h->Su.view(), v, cap, keep ? p.keepx.as<int32_t>() : nullptr,
                                   keep ? p.keepu.as<int32_t>() : nullptr, h->stream));
-    SLS_CK(sls_launch_scan(v.colptr, Nx + 1, (int)(2 * T), v.tot, p.ncols + 1, p.col_lo, p.col_hi, h->stream));
+    SLS_CK(p.scanws.ensure(sls_scan_scratch_bytes((int)(2 * T), std::max<int64_t>(p.col_hi - p.col_lo, p.ncols + 1))));
+    SLS_CK(sls_launch_scan(v.colptr, Nx + 1, (int)(2 * T), v.tot, p.ncols + 1, p.col_lo, p.col_hi, h->stream, p.scanws.as<int64_t>()));
     h->gev[3].record(h->stream);
     // sizes back to the host
     SLS_CK(p.h_lnnz.resize(nc1)); SLS_CK(p.h_lA.resize(nc1)); SLS_CK(p.h_lB.resize(nc1));

@@ -14,17 +14,73 @@
 #include "sls_common.h"
 #include "sls_kernels.h"
 #include <climits>
+#include <algorithm>
 
 #define GATHER_WPB 4
 
 // Sorted-unique union of the rows of S[T-1][:,k] over the stored nonzeros k of A[:,j].
 // Result in buf[0..ret); ret = -1 if the candidate list overflows `cap` (a power of two).
+//
+// Fast path (banded plants: every segment is a run of consecutive rows).  Support rows are strictly ascending (validated on
+// the device behind their upload, sls_validate_supports_kernel), so a segment whose last row minus its first equals its length
+// minus one IS that run and only its two end rows are read.  The union of the runs is built as a bitmap over [min first, max
+// last] (one 32-bit word per lane) and expanded in order: no candidate list, no sort.  Anything else — a segment with a gap, more
+// than 32 segments, a span above 1024 rows — takes the general path below with identical results.
 __device__ int sls_warp_index_set(const SlsCsc& A, const SlsSupports& S, int T, int64_t Nx, int64_t j,
                                   int32_t* buf, int cap) {
     const int lane = sls_lane();
     const int64_t a0 = A.colptr[j] - 1, a1 = A.colptr[j + 1] - 1;
     const int64_t* scp = S.colptr + (int64_t)(T - 1) * (Nx + 1);
     const int64_t base = S.tap_off[T - 1];
+    if (a1 - a0 <= 32) {
+        int len = 0, first = 0, last = -1;
+        if (lane < a1 - a0 && A.nzval[a0 + lane] != 0.0) {    // `A .≠ 0` drops stored zeros
+            const int64_t k = A.rowval[a0 + lane] - 1;
+            const int64_t s0 = base + scp[k] - 1, s1 = base + scp[k + 1] - 1;
+            len = (int)(s1 - s0);
+            if (len > 0) {
+                first = (int32_t)(S.rowval[s0] - 1 - S.row_off);
+                last = (int32_t)(S.rowval[s1 - 1] - 1 - S.row_off);
+            }
+        }
+        const bool isrun = (len == 0) || (last - first == len - 1);
+        const int C = __reduce_add_sync(SLS_FULL, len);
+        if (C > cap) return -1;                               // same overflow rule as the general path (candidates, not distinct rows)
+        if (C == 0) return 0;
+        if (__all_sync(SLS_FULL, isrun)) {
+            const int lo = -__reduce_max_sync(SLS_FULL, len > 0 ? -first : INT_MIN);
+            const int hi = __reduce_max_sync(SLS_FULL, len > 0 ? last : INT_MIN);
+            if (hi - lo < 1024) {
+                const int nseg = (int)(a1 - a0);
+                uint32_t word = 0u;                           // rows lo + 32*lane .. lo + 32*lane + 31
+#pragma unroll 1
+                for (int e = 0; e < nseg; e++) {
+                    const int le = __shfl_sync(SLS_FULL, len, e);
+                    const int f = __shfl_sync(SLS_FULL, first, e) - lo - 32 * lane, l = __shfl_sync(SLS_FULL, last, e) - lo - 32 * lane;
+                    if (le > 0 && l >= 0 && f <= 31) {
+                        const uint32_t upto = (l >= 31) ? 0xffffffffu : ((2u << l) - 1u);
+                        const uint32_t from = (f <= 0) ? 0xffffffffu : ~((1u << f) - 1u);
+                        word |= upto & from;
+                    }
+                }
+                const int cw = __popc(word);
+                int incl = cw;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(SLS_FULL, incl, d); if (lane >= d) incl += o; }
+                const int excl = incl - cw;
+                const int nw = ((hi - lo) >> 5) + 1;
+                __syncwarp();
+#pragma unroll 1
+                for (int w = 0; w < nw; w++) {
+                    const uint32_t ww = __shfl_sync(SLS_FULL, word, w);
+                    const int off = __shfl_sync(SLS_FULL, excl, w);
+                    if ((ww >> lane) & 1u) buf[off + __popc(ww & ((1u << lane) - 1u))] = lo + 32 * w + lane;
+                }
+                __syncwarp();
+                return __shfl_sync(SLS_FULL, incl, 31);
+            }
+        }
+    }
     int C = 0;
 #pragma unroll 1
     for (int64_t e = a0; e < a1; e++) {
@@ -42,39 +98,57 @@ __device__ int sls_warp_index_set(const SlsCsc& A, const SlsSupports& S, int T, 
 }
 
 // kernel 1a: sizes only (n, m) so that the host can size the strided metadata exactly.
-__global__ void __launch_bounds__(GATHER_WPB * 32)
+// Plan statistics are reduced inside the block (shared-memory atomics) and flushed once per block: with one global
+// atomic per column and statistic, 100 000 columns queued ~500 000 atomics on five addresses of one L2 sector, and the
+// kernel ran at the L2's same-address atomic rate (0.28 ms) whatever else it did.
+#define COUNT_MAX_WPB 16
+__global__ void __launch_bounds__(COUNT_MAX_WPB * 32)
 sls_gather_count_kernel(SlsCsc A, SlsSupports Sx, SlsSupports Su, int T, int64_t Nx,
                         const int32_t* __restrict__ cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
                         int32_t* keep_x, int32_t* keep_u, const int32_t* __restrict__ bad_supports, int32_t* stats) {
     SLS_DYN_SMEM(smem);
+    __shared__ int s_stats[36];
+    const int wpb = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = sls_lane();
-    const int c = blockIdx.x * GATHER_WPB + warp;
-    if (c >= ncols) return;
-    if (bad_supports && *bad_supports) return;               // malformed support rows (sls_validate_supports_kernel): index nothing
-    int32_t* buf = reinterpret_cast<int32_t*>(smem) + (size_t)warp * cap;
-    const int64_t j = cols[c];
-    // the index sets are kept (row stride cap) so that kernel 1b does not gather and sort them a second time
-    const int n = sls_warp_index_set(A, Sx, T, Nx, j, buf, cap);
-    if (keep_x)
+    const int c = blockIdx.x * wpb + warp;
+    if (threadIdx.x < 36) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+    // malformed support rows (sls_validate_supports_kernel): index nothing
+    if (c < ncols && !(bad_supports && *bad_supports)) {
+        int32_t* buf = reinterpret_cast<int32_t*>(smem) + (size_t)warp * cap;
+        const int64_t j = cols[c];
+        // the index sets are kept (row stride cap) so that kernel 1b does not gather and sort them a second time
+        const int n = sls_warp_index_set(A, Sx, T, Nx, j, buf, cap);
+        if (keep_x)
 #pragma unroll 1
-        for (int i = lane; i < n; i += 32) keep_x[(size_t)c * cap + i] = buf[i];
-    __syncwarp();
-    const int m = sls_warp_index_set(A, Su, T, Nx, j, buf, cap);
-    if (keep_u)
+            for (int i = lane; i < n; i += 32) keep_x[(size_t)c * cap + i] = buf[i];
+        __syncwarp();
+        const int m = sls_warp_index_set(A, Su, T, Nx, j, buf, cap);
+        if (keep_u)
 #pragma unroll 1
-        for (int i = lane; i < m; i += 32) keep_u[(size_t)c * cap + i] = buf[i];
-    if (lane == 0) {
-        n_out[c] = n; m_out[c] = m;
-        // plan statistics on the device (the host reads 34 integers instead of 2 x ncols sizes): [0] max n, [1] max m,
-        // [2] overflow, [3] unused, [4 + k] columns of size class k (n in 8k+1..8k+8; class 15 = everything larger),
-        // [20 + k] largest m of class k
-        if (stats) {
-            if (n < 0 || m < 0) atomicOr(stats + 2, 1);
-            else {
-                atomicMax(stats + 0, n); atomicMax(stats + 1, m);
-                int k = n > 0 ? (n - 1) >> 3 : 0; if (k > 15) k = 15;
-                atomicAdd(stats + 4 + k, 1); atomicMax(stats + 20 + k, m);
+            for (int i = lane; i < m; i += 32) keep_u[(size_t)c * cap + i] = buf[i];
+        if (lane == 0) {
+            n_out[c] = n; m_out[c] = m;
+            // plan statistics on the device (the host reads 36 integers instead of 2 x ncols sizes): [0] max n, [1] max m,
+            // [2] overflow, [3] unused, [4 + k] columns of size class k (n in 8k+1..8k+8; class 15 = everything larger),
+            // [20 + k] largest m of class k
+            if (stats) {
+                if (n < 0 || m < 0) atomicOr(s_stats + 2, 1);
+                else {
+                    atomicMax(s_stats + 0, n); atomicMax(s_stats + 1, m);
+                    int k = n > 0 ? (n - 1) >> 3 : 0; if (k > 15) k = 15;
+                    atomicAdd(s_stats + 4 + k, 1); atomicMax(s_stats + 20 + k, m);
+                }
             }
+        }
+    }
+    __syncthreads();
+    if (stats && threadIdx.x < 36) {
+        const int i = threadIdx.x, v = s_stats[i];
+        if (v != 0) {                                         // every statistic starts at 0 and only grows
+            if (i == 2) atomicOr(stats + 2, v);
+            else if (i >= 4 && i < 20) atomicAdd(stats + i, v);
+            else atomicMax(stats + i, v);
         }
     }
 }
@@ -136,6 +210,24 @@ __host__ __device__ int sls_gather_fill_words(int cap, int nstride, int mstride,
     return (w + 1) & ~1;
 }
 
+// every one of the len bytes at p is non-zero: aligned 4-byte words in the middle (a zero byte shows as a set high bit of
+// (v - 0x01010101) & ~v), single bytes up to the first and after the last aligned word — nothing outside [p, p + len) is read
+__device__ __forceinline__ bool sls_all_true(const uint8_t* p, int len) {
+    bool ok = true;
+    int i = 0;
+    const int head = (int)((4 - (reinterpret_cast<uintptr_t>(p) & 3)) & 3);
+#pragma unroll 1
+    for (; i < head && i < len; i++) ok = ok && (p[i] != 0);
+#pragma unroll 1
+    for (; i + 4 <= len; i += 4) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(p + i);
+        ok = ok && (((v - 0x01010101u) & ~v & 0x80808080u) == 0u);
+    }
+#pragma unroll 1
+    for (; i < len; i++) ok = ok && (p[i] != 0);
+    return ok;
+}
+
 // kernel 1b: index sets, ii_x, masks, per-tap counts, packed-result offsets, local nnz.
 // The 2T support columns 𝓢ₓ[t][:,j], 𝓢ᵤ[t][:,j] of a disturbance column are read as ONE flattened list
 // (segment table + prefix sums in shared memory), so all their loads are independent and in flight together
@@ -192,8 +284,42 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
         __syncwarp();
     }
     if (lane == 0) { P.n[c] = n; P.m[c] = m; P.jloc[c] = sls_find(sx, n, (int32_t)j); }
+    // an index set that is a run of consecutive rows (banded plants) maps a row to its local index by subtraction
+    const bool runx = n > 0 && sx[n - 1] - sx[0] == n - 1, runu = m > 0 && su[m - 1] - su[0] == m - 1;
 
-    // prefix sums of the 2T segment lengths
+    // Fast path, one lane per support column 𝓢[t][:,j]: when the index set is a run and the column's stored rows are a run too
+    // (strictly ascending rows: last - first == len - 1 proves it from the two end rows) with every stored value true, the tap's
+    // mask is the bit range [first - s[0], last - s[0]] clipped to the index set: no per-entry work.  Such columns leave the
+    // flattened list below (length 0); everything else (gaps, stored-false entries, scattered index sets) stays on it.
+#pragma unroll 1
+    for (int tt = lane; tt < 2 * T; tt += 32) {
+        const int len = cnt[tt];
+        const bool isu = tt >= T;
+        bool fast = (len == 0);
+        if (len > 0 && (isu ? runu : runx)) {
+            const SlsSupports& S = isu ? Su : Sx;
+            const int64_t s0 = seg0[tt];
+            const int32_t first = (int32_t)(S.rowval[s0] - 1 - S.row_off), last = (int32_t)(S.rowval[s0 + len - 1] - 1 - S.row_off);
+            if (last - first == len - 1) {
+                const bool allon = !S.nzval || sls_all_true(S.nzval + s0, len);
+                if (allon) {
+                    const int b0 = isu ? su[0] : sx[0], nn = isu ? m : n;
+                    const int lo = max(first - b0, 0), hi = min(last - b0, nn - 1);
+                    uint32_t* w = mw + (isu ? tt - T : tt) * nmw + (isu ? P.wx : 0);
+#pragma unroll 1
+                    for (int q = lo >> 5; q <= (hi >> 5); q++) {           // empty when lo > hi
+                        const int l = max(lo - 32 * q, 0), h = min(hi - 32 * q, 31);
+                        if (l <= h) w[q] = ((h == 31) ? 0xffffffffu : ((2u << h) - 1u)) & ~((1u << l) - 1u);
+                    }
+                    fast = true;
+                }
+            }
+        }
+        if (fast) cnt[tt] = 0;
+    }
+    __syncwarp();
+
+    // prefix sums of the segment lengths still on the list
     {
         int carry = 0;
 #pragma unroll 1
@@ -210,8 +336,6 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
     }
     __syncwarp();
     const int total = pfx[2 * T];
-    // an index set that is a run of consecutive rows (banded plants) maps a row to its local index by subtraction
-    const bool runx = n > 0 && sx[n - 1] - sx[0] == n - 1, runu = m > 0 && su[m - 1] - su[0] == m - 1;
     int tt = 0;                                               // a lane's entries f = lane, lane+32, ... move forward through the taps
 #pragma unroll 1
     for (int f = lane; f < total; f += 32) {
@@ -268,14 +392,20 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
     for (int l = lane; l < n; l += 32) {
         const int64_t e0 = A.colptr[sx[l]] - 1, e1 = A.colptr[sx[l] + 1] - 1;
 #pragma unroll 1
-        for (int64_t e = e0; e < e1; e++) cntA += (sls_find(sx, n, (int32_t)(A.rowval[e] - 1)) >= 0);
+        for (int64_t e = e0; e < e1; e++) {
+            const int32_t r = (int32_t)(A.rowval[e] - 1);
+            cntA += runx ? (r >= sx[0] && r <= sx[n - 1]) : (sls_find(sx, n, r) >= 0);
+        }
     }
 #pragma unroll 1
     for (int l = lane; l < m; l += 32) {
         const int64_t e0 = B2.colptr[su[l]] - 1, e1 = B2.colptr[su[l] + 1] - 1;
         cntBfull += (int)(e1 - e0);
 #pragma unroll 1
-        for (int64_t e = e0; e < e1; e++) cntB += (sls_find(sx, n, (int32_t)(B2.rowval[e] - 1)) >= 0);
+        for (int64_t e = e0; e < e1; e++) {
+            const int32_t r = (int32_t)(B2.rowval[e] - 1);
+            cntB += runx ? (r >= sx[0] && r <= sx[n - 1]) : (sls_find(sx, n, r) >= 0);
+        }
     }
     cntA = __reduce_add_sync(SLS_FULL, cntA);
     cntB = __reduce_add_sync(SLS_FULL, cntB);
@@ -295,18 +425,69 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
 // Only the window [lo, hi) of a colptr array can hold non-zero counts (the planned columns): it is scanned, the
 // entries before it are set to 1 and the entries from hi on to 1 + total, so the serial part of the scan does not
 // grow with Nx when one GPU plans a shard of a larger plant (weak scaling).  Nothing outside [lo, hi) is read.
+// With a scratch array (`partial`, (narr+1) x nchunk sums written by sls_scan_sum_kernel) every array is cut into nchunk
+// pieces of `chunk` entries scanned by separate blocks (grid (narr+1) x nchunk): the 2T + 1 serial block-loops of the
+// one-block-per-array form (13 tiles of four barriers each at Nx = 100 000) become one tile per block.
+__device__ __forceinline__ void sls_scan_range(int b, int narr, int64_t len, int64_t totlen, int64_t lo, int64_t hi, int64_t chunk,
+                                               int ch, int64_t& T0, int64_t& L) {
+    const int64_t a0 = (b < narr) ? lo : 0, a1 = (b < narr) ? hi : totlen;
+    (void)len;
+    T0 = a0 + (int64_t)ch * chunk; if (T0 > a1) T0 = a1;
+    L = T0 + chunk; if (L > a1) L = a1;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS)
-sls_scan_kernel(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, int64_t lo, int64_t hi) {
+sls_scan_sum_kernel(const int64_t* colptr, int64_t len, int narr, const int64_t* tot, int64_t totlen, int64_t lo, int64_t hi,
+                    int64_t chunk, int64_t* partial) {
+    __shared__ int64_t wsum[SCAN_THREADS / 32];
+    const int b = blockIdx.x, ch = blockIdx.y;
+    const int64_t* arr = (b < narr) ? colptr + (int64_t)b * len : tot;
+    int64_t T0, L;
+    sls_scan_range(b, narr, len, totlen, lo, hi, chunk, ch, T0, L);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t sum = 0;
+#pragma unroll 1
+    for (int64_t i = T0 + tid; i < L; i += SCAN_THREADS) sum += arr[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(SLS_FULL, sum, d);
+    if (lane == 0) wsum[warp] = sum;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t w = wsum[lane];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(SLS_FULL, w, d);
+        if (lane == 0) partial[(int64_t)b * gridDim.y + ch] = w;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+sls_scan_kernel(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, int64_t lo, int64_t hi,
+                int64_t chunk, const int64_t* partial) {
     __shared__ int64_t wsum[SCAN_THREADS / 32];
     __shared__ int64_t carry_s, tile_total_s;
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, ch = blockIdx.y;
     int64_t* arr = (b < narr) ? colptr + (int64_t)b * len : tot;
-    const int64_t T0 = (b < narr) ? lo : 0;
-    const int64_t L = (b < narr) ? hi : totlen;
+    int64_t T0, L;
+    sls_scan_range(b, narr, len, totlen, lo, hi, chunk, ch, T0, L);
     const int64_t add = (b < narr) ? 1 : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
+    {   // carry into this chunk: the sums of the chunks before it
+        int64_t pre = 0;
+        if (partial)
+#pragma unroll 1
+            for (int c = tid; c < ch; c += SCAN_THREADS) pre += partial[(int64_t)b * gridDim.y + c];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) pre += __shfl_xor_sync(SLS_FULL, pre, d);
+        if (lane == 0) wsum[warp] = pre;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = wsum[lane];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(SLS_FULL, w, d);
+            if (lane == 0) carry_s = w;
+        }
+        __syncthreads();
+    }
     for (int64_t tile = T0; tile < L; tile += (int64_t)SCAN_THREADS * SCAN_ITEMS) {
         const int64_t i0 = tile + (int64_t)tid * SCAN_ITEMS;
         int64_t v[SCAN_ITEMS];
@@ -334,7 +515,8 @@ sls_scan_kernel(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t to
         if (tid == 0) carry_s += tile_total_s;
         __syncthreads();
     }
-    if (b < narr && tid == 0 && hi < len) arr[hi] = carry_s + 1;     // the value of every entry from hi on (sls_colptr_fill_kernel)
+    // the value of every entry from hi on (sls_colptr_fill_kernel): written by the block of the last chunk
+    if (b < narr && ch == (int)gridDim.y - 1 && tid == 0 && hi < len) arr[hi] = carry_s + 1;
 }
 
 // entries outside the scanned window: 1 before it, arr[hi] (= 1 + total, written by the scan) after it
@@ -477,11 +659,13 @@ int sls_launch_gather_count(const SlsCsc& A, const SlsSupports& Sx, const SlsSup
                             const int32_t* cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
                             int32_t* keep_x, int32_t* keep_u, const int32_t* bad_supports, int32_t* stats, sls_stream_t stream) {
     if (ncols == 0) return 0;
-    const int grid = (ncols + GATHER_WPB - 1) / GATHER_WPB;
-    const size_t smem = (size_t)GATHER_WPB * cap * sizeof(int32_t);
+    int wpb = COUNT_MAX_WPB;                                  // warps per block: as many as 32 KB of candidate buffers allow
+    while (wpb > 1 && (size_t)wpb * cap * sizeof(int32_t) > 32 * 1024) wpb >>= 1;
+    const int grid = (ncols + wpb - 1) / wpb;
+    const size_t smem = (size_t)wpb * cap * sizeof(int32_t);
     auto kp = &sls_gather_count_kernel;
     if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
-    SLS_LAUNCH(kp, grid, GATHER_WPB * 32, smem, stream, A, Sx, Su, T, Nx, cols, ncols, n_out, m_out, cap, keep_x, keep_u, bad_supports, stats);
+    SLS_LAUNCH(kp, grid, wpb * 32, smem, stream, A, Sx, Su, T, Nx, cols, ncols, n_out, m_out, cap, keep_x, keep_u, bad_supports, stats);
     return rt::last_error();
 }
 
@@ -496,15 +680,33 @@ int sls_launch_gather_fill(const SlsCsc& A, const SlsCsc& B2, const SlsSupports&
     return rt::last_error();
 }
 
-int sls_launch_scan(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, int64_t lo, int64_t hi, sls_stream_t stream) {
+size_t sls_scan_scratch_bytes(int narr, int64_t span) {
+    const int64_t tile = (int64_t)SCAN_THREADS * SCAN_ITEMS;
+    return (size_t)(narr + 1) * (size_t)((span + tile - 1) / tile + 1) * sizeof(int64_t);
+}
+
+// `scratch` (sls_scan_scratch_bytes(narr, max(hi - lo, totlen)) bytes) may be null: one block per array then.
+int sls_launch_scan(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, int64_t lo, int64_t hi, sls_stream_t stream,
+                    int64_t* scratch) {
     auto kp = &sls_scan_kernel;
     if (lo < 0) lo = 0;
     if (hi > len || hi < lo) hi = len;
-    SLS_LAUNCH(kp, narr + 1, SCAN_THREADS, 0, stream, colptr, len, narr, tot, totlen, lo, hi);
+    const int64_t tile = (int64_t)SCAN_THREADS * SCAN_ITEMS;
+    const int64_t span = std::max<int64_t>(narr > 0 ? hi - lo : 0, totlen);
+    int64_t nchunk = scratch ? (span + tile - 1) / tile : 1;
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 65535) nchunk = 65535;
+    const int64_t chunk = nchunk == 1 ? span : ((span + nchunk - 1) / nchunk + tile - 1) / tile * tile;
+    dim3 grid((unsigned)(narr + 1), (unsigned)nchunk, 1);
+    if (nchunk > 1) {
+        auto ks = &sls_scan_sum_kernel;
+        SLS_LAUNCH(ks, grid, SCAN_THREADS, 0, stream, (const int64_t*)colptr, len, narr, (const int64_t*)tot, totlen, lo, hi, chunk, scratch);
+    }
+    SLS_LAUNCH(kp, grid, SCAN_THREADS, 0, stream, colptr, len, narr, tot, totlen, lo, hi, chunk, (const int64_t*)(nchunk > 1 ? scratch : nullptr));
     if (narr > 0 && (lo > 0 || hi + 1 < len)) {
         auto kf = &sls_colptr_fill_kernel;
-        dim3 grid((unsigned)((len + 255) / 256), narr, 1);
-        SLS_LAUNCH(kf, grid, 256, 0, stream, colptr, len, lo, hi);
+        dim3 gridf((unsigned)((len + 255) / 256), narr, 1);
+        SLS_LAUNCH(kf, gridf, 256, 0, stream, colptr, len, lo, hi);
     }
     return rt::last_error();
 }

@@ -15,7 +15,9 @@ __host__ __device__ int sls_gather_fill_words(int cap, int nstride, int mstride,
 int sls_launch_gather_fill(const SlsCsc& A, const SlsCsc& B2, const SlsSupports& Sx, const SlsSupports& Su,
                            const SlsPlanView& P, int cap, const int32_t* keep_x, const int32_t* keep_u, sls_stream_t stream);
 // scans the window [lo, hi) of every colptr array (counts outside it are known to be zero and are not read)
-int sls_launch_scan(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, int64_t lo, int64_t hi, sls_stream_t stream);
+size_t sls_scan_scratch_bytes(int narr, int64_t span);
+int sls_launch_scan(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t totlen, int64_t lo, int64_t hi, sls_stream_t stream,
+                    int64_t* scratch = nullptr);
 int sls_launch_local_dense(const SlsCsc& A, const SlsCsc& B2, const SlsPlanView& P, int c,
                            double* At, double* B2t, uint8_t* Mx, uint8_t* Mu, sls_stream_t stream);
 // output-feedback reduction (reduction.jl:16-18): first-occurrence union of q column segments (rows 1-based, seg[q+1]);
