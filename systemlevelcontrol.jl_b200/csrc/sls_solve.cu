@@ -34,6 +34,10 @@
 
 #include "sls_solve_common.h"
 
+#ifndef SLS_K2_PIVOT_SMEM
+#define SLS_K2_PIVOT_SMEM 1
+#endif
+
 // warps per block / minimum resident blocks per SM of each size class (registers: 128 per thread up to N = 24)
 template <int NB> struct SlsCfg { static const int WPB = 4; static const int MINB = (NB <= 3) ? 4 : 2; };
 
@@ -354,11 +358,10 @@ sls_solve_kernel(SlsSolveArgs a) {
                 }
             // (7) block symmetric sweep with rank skipping:  S <- -(S^+).  A skipped pivot (<= threshold) gets
             //     pinv = 0, which zeroes its row and column at once (they never feed a kept row).
-            uint64_t keep = 0ull;
+            int nkept = 0;                                        // pivots kept in this tap (a kept pivot leaves a non-zero diagonal of -P)
 #pragma unroll
             for (int p = 0; p < NB; p++) {
                 double d0 = S[p][p][0], d1 = S[p][p][1];
-                uint32_t kb = 0u;
                 const uint32_t actp = (uint32_t)(nonempty >> (8 * p)) & 0xffu;   // non-empty rows of D_k in this block
                 // rows beyond n are never touched; an empty row inside the block (threshold +inf) takes the skip path of
                 // the arithmetic below (pinv = 0 on an all-zero row and column), so no per-pivot branch is needed
@@ -368,11 +371,26 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
                         const int r = 2 * rp + e;
+#if SLS_K2_PIVOT_SMEM
+                        // pivot row through shared memory (two alternating 8-double buffers: lam_s and rhs_s, which only the back
+                        // substitution uses; N >= 8 doubles each in every size class): the
+                        // four lanes of row r post it, everybody reads its two row entries, the pivot and — by symmetry,
+                        // S[g][r] = S[r][g] — its column entry from it.  1 STS + 3 LDS instead of 8 SHFL and the ~10 register
+                        // moves that re-pair the shuffled 32-bit halves.
+                        double* rb = e ? rhs_s : lam_s;
+                        if (g == r) *reinterpret_cast<double2*>(rb + 2 * q) = make_double2(d0, d1);
+                        __syncwarp();
+                        const double2 rrv = *reinterpret_cast<const double2*>(rb + 2 * q);
+                        const double rr0 = rrv.x, rr1 = rrv.y;
+                        const double cg = rb[g];
+                        const double dv = rb[r];
+#else
                         const double src = e ? d1 : d0;
                         const double dv = __shfl_sync(SLS_FULL, src, 4 * r + rp);
                         const double cg = __shfl_sync(SLS_FULL, src, (lane & ~3) | rp);
                         const double rr0 = __shfl_sync(SLS_FULL, d0, 4 * r + q);
                         const double rr1 = __shfl_sync(SLS_FULL, d1, 4 * r + q);
+#endif
                         const bool ok = dv > thrs[8 * p + r];
                         const double pinv = ok ? sls_rcp(dv) : 0.0;
                         const bool isrow = (g == r);
@@ -382,10 +400,11 @@ sls_solve_kernel(SlsSolveArgs a) {
                         const double cv = isrow ? -pinv : cp;
                         if (q == rp) { if (e) n1 = cv; else n0 = cv; }
                         d0 = n0; d1 = n1;
-                        kb |= (ok ? 1u : 0u) << r;
                     }
                 }
-                keep |= (uint64_t)kb << (8 * p);
+                // a kept pivot ends with a strictly negative diagonal entry of -P, a skipped one (and every row the sweep never
+                // touched: all-zero) with an exact zero, so the kept pivots are counted from the diagonal in one ballot
+                nkept += __popc(__ballot_sync(SLS_FULL, (q == (g >> 1)) && (((g & 1) ? d1 : d0) != 0.0)));
                 const double Pn[2] = {d0, d1};                // -P, symmetric
                 double Tn[NB][2], Tt[NB][2];                  // Tn_i = -S_ip P,  Tt_i = -P S_pi = -(S_ip P)^T
 #pragma unroll
@@ -419,7 +438,7 @@ sls_solve_kernel(SlsSolveArgs a) {
                 }
                 S[p][p][0] = d0; S[p][p][1] = d1;
             }
-            if (keep != nonempty) status |= SLS_ST_RANK_SKIPPED;
+            if (nkept != __popcll(nonempty)) status |= SLS_ST_RANK_SKIPPED;   // kept pivots are a subset of the non-empty rows
             // (8) history: the lower-triangle blocks of -Z_k in REGISTER order (block b at hk + 64 b, a lane's two entries at
             //     2*lane: one coalesced 16-byte store per block, read back the same way — no index arithmetic, no predicates;
             //     rows / columns beyond n are exact zeros), k = 1..T-1 (Z_0 is diag(mx_1)); -Z_T, which the back substitution
