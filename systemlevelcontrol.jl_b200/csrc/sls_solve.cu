@@ -110,7 +110,7 @@ sls_solve_kernel(SlsSolveArgs a) {
 #pragma unroll 1
         for (int t = lane; t < 2 * T; t += 32) obase[t] = P.colptr[(int64_t)t * (P.Nx + 1) + P.cols[c]] - 1;
 #pragma unroll 1
-        for (int e = lane; e < N * N; e += 32) Am[e] = 0.0;
+        for (int e = 2 * lane; e < N * N; e += 64) *reinterpret_cast<double2*>(Am + e) = make_double2(0.0, 0.0);
         __syncwarp();
         // ------------------------------------------------------------------ local CSR of C~ = [A~ B~]
         uint64_t nzA = 0ull;                                  // bit bi*NB+bj: block (bi,bj) of A~ has a stored entry
@@ -270,7 +270,7 @@ sls_solve_kernel(SlsSolveArgs a) {
             for (int w = 0; w < 4; w++) if (w < wu) same = same && (muk[w] == mu_prev[w]);
             if (!same) {
 #pragma unroll 1
-                for (int e = lane; e < N * N; e += 32) Dp[e] = 0.0;
+                for (int e = 2 * lane; e < N * N; e += 64) *reinterpret_cast<double2*>(Dp + e) = make_double2(0.0, 0.0);
                 __syncwarp();
                 nonempty = 0ull;
 #pragma unroll
