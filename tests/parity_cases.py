@@ -225,6 +225,38 @@ def check_masks_and_flags(api):
     return worst
 
 
+def check_gather_paths(api):
+    """Kernel 1's fast paths (index sets / masks of banded plants from the end rows of each support segment) against the
+    general paths and the oracle, bit for bit, on inputs that mix them inside one plan and one column:
+    a gap in a LAST-tap segment (1a: sorted-union path for the three columns that read it, bitmap path for the rest),
+    a gap in an intermediate tap (1b: that support column on the per-entry list, the other 2T-1 on the lane-per-tap path),
+    a stored `false` inside a run, a stored `false` at the END of a run (the end-row test alone would accept it), and a
+    long-range coupling in A that spreads a column's segments over more than 1 024 rows (bitmap path refused)."""
+    A, B1, B2, S = chain(80)
+    Sx, Su = [M.copy() for M in S[0]], [M.copy() for M in S[1]]
+    T = len(Sx)
+    def drop(M, r, c):
+        L = M.tolil(); L[r, c] = False; M2 = sp.csc_matrix(L.tocsc()); M2.eliminate_zeros(); M2.sort_indices(); return M2
+    Sx[T - 1] = drop(Sx[T - 1], 41, 40)                         # gap inside the last-tap segment of column 40
+    Sx[12] = drop(Sx[12], 52, 50)                               # gap in an intermediate tap of column 50
+    M = Sx[20]; M.data[M.indptr[30] + 2] = False                # stored false inside the run of column 30
+    M = Sx[21]; M.data[M.indptr[31 + 1] - 1] = False            # stored false at the end of the run of column 31
+    M = Su[15]; M.data[M.indptr[33]] = False                    # and at the start of an actuator run
+    cols = [0, 29, 30, 31, 33, 39, 40, 41, 49, 50, 51, 79]
+    check_local_blocks(api, A, B1, B2, [Sx, Su], cols)
+    worst, info, infos = check_against_oracle(api, A, B1, B2, [Sx, Su], cols)
+    ok = [k for k, j in enumerate(cols) if infos[j]["residual"] < 1e-10]
+    assert len(ok) >= len(cols) - 3                              # dropping a support row can make a column infeasible
+    assert not (info["status"][ok] & _capi.STATUS_RESIDUAL).any()
+    # long-range coupling: column 1300 of A also drives state 60, so its index set is two runs 1 240 rows apart
+    Nx = 1400
+    A2, B1b, B2b = O.chain_plant(Nx)
+    A2 = A2.tolil(); A2[60, 1300] = 0.2; A2 = sp.csc_matrix(A2.tocsc()); A2.sort_indices()
+    S2 = O.make_supports(A2, B2b, 4, 8, 1.5)
+    check_local_blocks(api, A2, B1b, B2b, S2, [59, 60, 61, 1299, 1300, 1301])
+    return worst
+
+
 def check_simulation(api, Nx, scenarios, steps=120, tol=1e-13):
     """sls_simulate (windowed, on device) against the oracle's dense README recursion, scenario by scenario."""
     A, B1, B2, S = chain(Nx)

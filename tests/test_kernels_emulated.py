@@ -42,6 +42,10 @@ def test_emu_error_paths(emu_api):
     pc.check_error_paths(emu_api)
 
 
+def test_emu_gather_fast_and_general_paths(emu_api):
+    assert pc.check_gather_paths(emu_api) < 1e-9
+
+
 def test_emu_masks_and_flags(emu_api):
     pc.check_masks_and_flags(emu_api)
     pc.check_unsorted_plan(emu_api)

@@ -133,6 +133,11 @@ def test_error_paths(cuda_api):
     pc.check_error_paths(cuda_api)
 
 
+def test_gather_fast_and_general_paths(cuda_api):
+    """kernel 1: run fast paths vs sorted-union / per-entry paths mixed in one plan, bit-exact vs the oracle's gather."""
+    assert pc.check_gather_paths(cuda_api) < 1e-9
+
+
 def test_masks_and_flags(cuda_api):
     pc.check_masks_and_flags(cuda_api)
     pc.check_unsorted_plan(cuda_api)
