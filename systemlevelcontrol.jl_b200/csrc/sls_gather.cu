@@ -428,10 +428,10 @@ sls_gather_fill_kernel(SlsCsc A, SlsCsc B2, SlsSupports Sx, SlsSupports Su, SlsP
 // With a scratch array (`partial`, (narr+1) x nchunk sums written by sls_scan_sum_kernel) every array is cut into nchunk
 // pieces of `chunk` entries scanned by separate blocks (grid (narr+1) x nchunk): the 2T + 1 serial block-loops of the
 // one-block-per-array form (13 tiles of four barriers each at Nx = 100 000) become one tile per block.
-__device__ __forceinline__ void sls_scan_range(int b, int narr, int64_t len, int64_t totlen, int64_t lo, int64_t hi, int64_t chunk,
+// entries [T0, L) of array b (a colptr array: the window [lo, hi); the tot array: [0, totlen)) that chunk ch covers
+__device__ __forceinline__ void sls_scan_range(int b, int narr, int64_t totlen, int64_t lo, int64_t hi, int64_t chunk,
                                                int ch, int64_t& T0, int64_t& L) {
     const int64_t a0 = (b < narr) ? lo : 0, a1 = (b < narr) ? hi : totlen;
-    (void)len;
     T0 = a0 + (int64_t)ch * chunk; if (T0 > a1) T0 = a1;
     L = T0 + chunk; if (L > a1) L = a1;
 }
@@ -443,7 +443,7 @@ sls_scan_sum_kernel(const int64_t* colptr, int64_t len, int narr, const int64_t*
     const int b = blockIdx.x, ch = blockIdx.y;
     const int64_t* arr = (b < narr) ? colptr + (int64_t)b * len : tot;
     int64_t T0, L;
-    sls_scan_range(b, narr, len, totlen, lo, hi, chunk, ch, T0, L);
+    sls_scan_range(b, narr, totlen, lo, hi, chunk, ch, T0, L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int64_t sum = 0;
 #pragma unroll 1
@@ -468,7 +468,7 @@ sls_scan_kernel(int64_t* colptr, int64_t len, int narr, int64_t* tot, int64_t to
     const int b = blockIdx.x, ch = blockIdx.y;
     int64_t* arr = (b < narr) ? colptr + (int64_t)b * len : tot;
     int64_t T0, L;
-    sls_scan_range(b, narr, len, totlen, lo, hi, chunk, ch, T0, L);
+    sls_scan_range(b, narr, totlen, lo, hi, chunk, ch, T0, L);
     const int64_t add = (b < narr) ? 1 : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {   // carry into this chunk: the sums of the chunks before it
