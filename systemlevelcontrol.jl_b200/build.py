@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libslsb200.so")
-SOURCES = ["sls_api.cu", "sls_gather.cu", "sls_solve.cu", "sls_solve_wide.cu", "sls_solve_general.cu", "sls_scatter.cu", "sls_sim.cu", "sls_supports.cu", "sls_peak.cu"]
+SOURCES = ["sls_api.cu", "sls_gather.cu", "sls_solve.cu", "sls_solve_wide.cu", "sls_solve_huge.cu", "sls_solve_general.cu", "sls_scatter.cu", "sls_sim.cu", "sls_supports.cu", "sls_peak.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

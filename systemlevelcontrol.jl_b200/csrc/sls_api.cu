@@ -1131,7 +1131,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         const int maxw = sls_solve_max_resident_warps(c.N, c.mcap, c.nnzcap, (int)T, p.wu, h->sm_count, h->max_smem);
         if (maxw <= 0) return fail(h, -4, "sls_solve: local problem does not fit shared memory");
         const int64_t warps = std::min<int64_t>(maxw, ((int64_t)c.count + 3) / 4 * 4);
-        hist_bytes = std::max(hist_bytes, (size_t)warps * sls_solve_hist_doubles(c.N, (int)T) * sizeof(double));
+        hist_bytes = std::max(hist_bytes, (size_t)warps * sls_solve_hist_doubles(c.N, (int)T, p.wu) * sizeof(double));
     }
     SLS_CK(h->hist.ensure(hist_bytes));
     SLS_CK(rt::zero(h->d_flag.as<int32_t>() + 1, sizeof(int32_t), h->stream));
@@ -1227,7 +1227,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
             a.P = v; a.list = p.lists.as<int32_t>() + c.list_off + lo; a.count = hi - lo;
             a.mcap = c.mcap; a.nnzcap = c.nnzcap;
             a.out_nzval = reinterpret_cast<double* const*>(h->out_ptrs.as<void*>() + 2 * T); a.hist = h->hist.as<double>();
-            a.hist_stride = sls_solve_hist_doubles(c.N, (int)T);
+            a.hist_stride = sls_solve_hist_doubles(c.N, (int)T, p.wu);
             a.status = h->status.as<int32_t>(); a.resid = h->resid.as<double>();
             a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
             a.refine_tol = 0.1 * h->opt.feas_tol; a.max_refine = (h->opt.flags & 4) ? 0 : 3; a.refined = h->d_flag.as<int32_t>() + 1;
@@ -1641,7 +1641,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
             const int maxw = sls_solve_max_resident_warps(cl.N, cl.mcap, cl.nnzcap, (int)T, p.wu, h->sm_count, h->max_smem);
             if (maxw <= 0) { e = fail(h, -4, "sls_synthesize: local problem does not fit shared memory"); break; }
             const int64_t warps = std::min<int64_t>(maxw, ((int64_t)cl.count + 3) / 4 * 4);
-            hist_bytes = std::max(hist_bytes, (size_t)warps * sls_solve_hist_doubles(cl.N, (int)T) * sizeof(double));
+            hist_bytes = std::max(hist_bytes, (size_t)warps * sls_solve_hist_doubles(cl.N, (int)T, p.wu) * sizeof(double));
         }
         if (e) break;
         PIPE_CK(h->hist.ensure(hist_bytes));
@@ -1664,7 +1664,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
             a.P = v; a.list = p.lists.as<int32_t>() + cl.list_off; a.count = cl.count;
             a.mcap = cl.mcap; a.nnzcap = cl.nnzcap;
             a.out_nzval = reinterpret_cast<double* const*>(x.out_ptrs.as<void*>() + 2 * T); a.hist = h->hist.as<double>();
-            a.hist_stride = sls_solve_hist_doubles(cl.N, (int)T);
+            a.hist_stride = sls_solve_hist_doubles(cl.N, (int)T, p.wu);
             a.status = x.status.as<int32_t>(); a.resid = x.resid.as<double>();
             a.rank_tol = h->opt.rank_tol; a.feas_tol = h->opt.feas_tol;
             a.refine_tol = 0.1 * h->opt.feas_tol; a.max_refine = (h->opt.flags & 4) ? 0 : 3; a.refined = h->d_flag.as<int32_t>() + 1;

@@ -49,7 +49,7 @@ int sls_solve_class_count();
 int sls_solve_class_N(int k);
 // shared memory (bytes per warp) and history doubles per warp for class N
 size_t sls_solve_smem_per_warp(int N, int mcap, int nnzcap, int T, int wu);
-int64_t sls_solve_hist_doubles(int N, int T);
+int64_t sls_solve_hist_doubles(int N, int T, int wu = 1);   // wu: mask words of the plan's inputs (> 4 routes every class to the n > 64 kernel)
 // launches one class; *slots_io: in = available history slots (warps), out = warps launched
 int sls_launch_solve(int N, const SlsSolveArgs& a, int sm_count, int max_smem, int* warps_launched,
                      sls_stream_t stream);
@@ -59,6 +59,11 @@ int sls_launch_solve_wide(int N, const SlsSolveArgs& a, int sm_count, int max_sm
 int sls_solve_wide_max_slots(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem);
 int64_t sls_solve_wide_hist_doubles(int N, int T);
 size_t sls_solve_wide_smem(int N, int mcap, int nnzcap, int T, int wu);
+
+// 64 < N <= 128: one CTA per column, matrices in the CTA's global scratch slot (sls_solve_huge.cu); a slot per resident CTA
+int sls_launch_solve_huge(int N, const SlsSolveArgs& a, int sm_count, int max_smem, int* slots_launched, sls_stream_t stream);
+int sls_solve_huge_max_slots(int N, int mcap, int nnzcap, int T, int wx, int wu, int sm_count, int max_smem);
+int64_t sls_solve_huge_hist_doubles(int N, int T);
 
 // ---- kernel 2g (sls_solve_general.cu): general cost / coupled column groups, one CTA per group ----
 struct SlsGeneralArgs {

@@ -802,7 +802,7 @@ sls_solve_kernel(SlsSolveArgs a) {
 }
 
 // ---- host side ------------------------------------------------------------------------------
-static const int kClasses[] = {8, 16, 24, 32, 40, 48, 56, 64};
+static const int kClasses[] = {8, 16, 24, 32, 40, 48, 56, 64, 72, 80, 88, 96, 104, 112, 120, 128};
 int sls_solve_class_count() { return (int)(sizeof(kClasses) / sizeof(int)); }
 int sls_solve_class_N(int k) { return kClasses[k]; }
 int sls_solve_class_of(int n) {
@@ -815,8 +815,12 @@ size_t sls_solve_smem_per_warp(int N, int mcap, int nnzcap, int T, int wu) {
 // size classes above 32 run one CTA per column (sls_solve_wide.cu).  Measured both ways on B200: the one-warp kernel
 // needs 278 ms for the 300 x 300 grid (matrix spilled to local memory) against 131 ms here; the CTA kernel needs 19.5 ms for
 // the chain's N = 24 class against 12.5 ms for the one-warp kernel (profiles/r02_ab_logs.txt).
-static bool use_wide(int N) { return N > 32; }
-int64_t sls_solve_hist_doubles(int N, int T) {
+static bool use_wide(int N) { return N > 32 && N <= 64; }
+// 64 < n <= 128: one CTA per column on matrices in global scratch (sls_solve_huge.cu) — a completeness path, not a DMMA kernel
+// (also every class of a plan whose input masks need more than four words, m > 128: the DMMA kernels keep mu_k in four registers)
+static bool use_huge(int N, int wu) { return N > 64 || wu > 4; }
+int64_t sls_solve_hist_doubles(int N, int T, int wu) {
+    if (use_huge(N, wu)) return sls_solve_huge_hist_doubles(N, T);
     if (use_wide(N)) return sls_solve_wide_hist_doubles(N, T);
     return (int64_t)(T + 1) * N + (int64_t)T * ((N / 8) * (N / 8 + 1) / 2 * 64);
 }
@@ -853,6 +857,7 @@ static int launch_class(const SlsSolveArgs& a, int sm_count, int max_smem, int* 
 #define SLS_FOR_CLASSES(X) X(1) X(2) X(3) X(4)
 
 int sls_solve_max_resident_warps(int N, int mcap, int nnzcap, int T, int wu, int sm_count, int max_smem) {
+    if (use_huge(N, wu)) return sls_solve_huge_max_slots(N, mcap, nnzcap, T, 4, wu, sm_count, max_smem);
     if (use_wide(N)) return sls_solve_wide_max_slots(N, mcap, nnzcap, T, wu, sm_count, max_smem);
     switch (N / 8) {
 #define X(nb) case nb: return resident_warps<nb>(mcap, nnzcap, T, wu, sm_count, max_smem);
@@ -866,6 +871,7 @@ int sls_launch_solve(int N, const SlsSolveArgs& a, int sm_count, int max_smem, i
                      sls_stream_t stream) {
     *warps_launched = 0;
     if (a.count == 0) return 0;
+    if (use_huge(N, a.P.wu)) return sls_launch_solve_huge(N, a, sm_count, max_smem, warps_launched, stream);
     if (use_wide(N)) return sls_launch_solve_wide(N, a, sm_count, max_smem, warps_launched, stream);
     switch (N / 8) {
 #define X(nb) case nb: return launch_class<nb>(a, sm_count, max_smem, warps_launched, stream);

@@ -5,7 +5,7 @@
 set -e
 ROOT=$(cd "$(dirname "$0")/../.." && pwd)
 OUT=${TMPDIR:-/tmp}/sls_asan; mkdir -p "$OUT"
-for f in sls_api sls_gather sls_solve sls_solve_wide sls_solve_general sls_scatter sls_sim sls_supports; do
+for f in sls_api sls_gather sls_solve sls_solve_wide sls_solve_huge sls_solve_general sls_scatter sls_sim sls_supports; do
   g++ -O1 -g -std=c++17 -DSLS_EMU -fPIC -w -fsanitize=address -fno-omit-frame-pointer -x c++ -I "$ROOT/tests/emu" \
       -c "$ROOT/systemlevelcontrol.jl_b200/csrc/$f.cu" -o "$OUT/$f.o" &
 done; wait

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "systemlevelcontrol.jl_b200", "csrc")
 OUT = os.path.join(HERE, "libslsb200_emu.so")
-SOURCES = ["sls_api.cu", "sls_gather.cu", "sls_solve.cu", "sls_solve_wide.cu", "sls_solve_general.cu", "sls_scatter.cu", "sls_sim.cu", "sls_supports.cu"]
+SOURCES = ["sls_api.cu", "sls_gather.cu", "sls_solve.cu", "sls_solve_wide.cu", "sls_solve_huge.cu", "sls_solve_general.cu", "sls_scatter.cu", "sls_sim.cu", "sls_supports.cu"]
 
 
 def build(force=False, opt="-O2"):

@@ -7,7 +7,7 @@ import scipy.sparse as sp
 
 import slc_b200
 from slc_b200 import _capi
-from conftest import PHI_RTOL, assert_phi_matches, golden_taps, load_golden
+from conftest import PHI_FLOOR, PHI_RTOL, assert_phi_matches, golden_taps, load_golden
 from oracle import sls_oracle as O
 
 
@@ -254,6 +254,24 @@ def check_gather_paths(api):
     A2 = A2.tolil(); A2[60, 1300] = 0.2; A2 = sp.csc_matrix(A2.tocsc()); A2.sort_indices()
     S2 = O.make_supports(A2, B2b, 4, 8, 1.5)
     check_local_blocks(api, A2, B1b, B2b, S2, [59, 60, 61, 1299, 1300, 1301])
+    return worst
+
+
+def check_large_local_problems(api):
+    """Local state dimensions above 64 (sls_solve_huge.cu): a fully actuated 15 x 15 grid with d = 5 (centre column n = 85,
+    m = 113: the n > 64 kernel beside the DMMA kernels of the smaller edge / corner columns in one plan) and d = 6 (n = 113,
+    m = 141: input masks of five words, every class on the n > 64 kernel).  Index sets / masks / local blocks bit-exact, Phi
+    against the oracle's exact minimiser."""
+    A, B1, B2 = O.grid_plant(15, 15, actuation="full")
+    worst = 0.0
+    for d, T, cols, nexp in ((5, 8, [112, 0, 7, 16], 85), (6, 8, [112, 0], 113)):
+        S = O.make_supports(A, B2, d, T, 1.5)
+        check_local_blocks(api, A, B1, B2, S, cols)
+        w, info, infos = check_against_oracle(api, A, B1, B2, S, cols, floor=PHI_FLOOR)
+        assert int(info["n"][0]) == nexp, info["n"]
+        assert max(i["residual"] for i in infos.values()) < 1e-12
+        assert not (info["status"] & _capi.STATUS_RESIDUAL).any() and float(info["resid"].max()) < 1e-13
+        worst = max(worst, w)
     return worst
 
 

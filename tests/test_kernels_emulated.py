@@ -46,6 +46,10 @@ def test_emu_gather_fast_and_general_paths(emu_api):
     assert pc.check_gather_paths(emu_api) < 1e-9
 
 
+def test_emu_large_local_problems_n_above_64(emu_api):
+    assert pc.check_large_local_problems(emu_api) < 1e-10
+
+
 def test_emu_masks_and_flags(emu_api):
     pc.check_masks_and_flags(emu_api)
     pc.check_unsorted_plan(emu_api)

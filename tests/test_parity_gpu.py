@@ -138,6 +138,11 @@ def test_gather_fast_and_general_paths(cuda_api):
     assert pc.check_gather_paths(cuda_api) < 1e-9
 
 
+def test_large_local_problems_n_above_64(cuda_api):
+    """64 < n <= 128: the one-CTA-per-column SIMT kernel (sls_solve_huge.cu), alone and beside the DMMA kernels."""
+    assert pc.check_large_local_problems(cuda_api) < 1e-10
+
+
 def test_masks_and_flags(cuda_api):
     pc.check_masks_and_flags(cuda_api)
     pc.check_unsorted_plan(cuda_api)
