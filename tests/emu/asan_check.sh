@@ -44,6 +44,11 @@ syn.simulate([20, 0, 39], [5, 3, 20], 40); print("sim (L2 scratch mode) ok"); sy
 A, B1, B2 = W.grid_plant(13, 13); Sx, Su = W.grid_supports(13, 13, 4, 20, 1.5)
 syn = slc_b200.Synthesizer(api=api); syn.set_plant(A, B2); syn.set_supports(Sx, Su); syn.plan([0, 6, 84]); out = syn.solve()
 print("grid ok (CTA kernel, n = 21 / 36 / 61)", out["resid"][:3].max(), syn.n); syn.close()
+A, B1, B2 = W.grid_plant(15, 15)
+for d_ in (5, 6):                                             # n = 85 beside the DMMA kernels; n = 113, m = 141: every class on the n > 64 kernel
+    Sx, Su = W.grid_supports(15, 15, d_, 6, 1.5)
+    syn = slc_b200.Synthesizer(api=api); syn.set_plant(A, B2); syn.set_supports(Sx, Su); syn.plan([112, 0, 7]); out = syn.solve()
+    print("grid ok (n > 64 kernel, d =", d_, ")", out["resid"][:3].max(), syn.n); syn.close()
 sys.path.insert(0, "$ROOT/tests")
 import parity_cases as pc
 print("general cost / groups ok (kernel 2g)", pc.check_general_cost(api, cases=[
