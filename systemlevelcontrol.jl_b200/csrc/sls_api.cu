@@ -91,6 +91,7 @@ struct Plan {
     PinVec<int32_t> h_cols, h_lists;    // pinned: read by kernel copies (sls_kcopy)
     bool cols_sorted = true;            // planned columns strictly ascending => a planned-index range is a CSC column range
     bool cols_contiguous = true;        // planned columns are first, first+1, ...: the list is generated on the device
+    bool sets_are_runs = false;         // every s_x / s_u of the plan is a run of consecutive rows (kernel 1a, stats[3])
     PinVec<int32_t> h_status; PinVec<double> h_resid;
     PinVec<int64_t> h_seg;              // [(nchunk+1)][2T] output offsets of the D2H pipeline's chunk boundaries
     PinVec<int32_t> h_n, h_m, h_lnnz, h_lA, h_lB;
@@ -781,6 +782,7 @@ static int build_plan(sls_handle* h, Plan& p, const int64_t* cols, int64_t ncols
     const int32_t* st = p.h_stats.data();
     if (st[2]) return fail(h, -4, "plan: candidate index list overflow in kernel 1");
     const int nmax = st[0], mmax = st[1];
+    p.sets_are_runs = (st[3] == 0);
     int cls_count[16] = {0};
     for (int k = 0; k < 16; k++) cls_count[k < nk_ ? k : nk_] += st[4 + k];
     p.nmax = nmax; p.mmax = mmax;
@@ -1154,7 +1156,7 @@ static int run_solve(sls_handle* h, const HostOut* ho) {
         SlsScatterArgs s{};
         s.P = v; s.c_begin = 0; s.c_end = p.ncols;
         s.rowval = reinterpret_cast<int64_t* const*>(h->out_ptrs.as<void*>());
-        s.row_off_x = h->Sx.row_off; s.row_off_u = h->Su.row_off; s.sorted = p.cols_sorted ? 1 : 0;
+        s.row_off_x = h->Sx.row_off; s.row_off_u = h->Su.row_off; s.sorted = p.cols_sorted ? 1 : 0; s.runs = p.sets_are_runs ? 1 : 0;
         h->ev[5].record(h->stream);
         SLS_CK(sls_launch_scatter(s, h->stream));
         h->chunk_ev[15].record(h->stream);
@@ -1654,7 +1656,7 @@ static int synthesize_impl(sls_handle* h, int64_t T, bool slab, int64_t w0, int6
             SlsScatterArgs sa{};
             sa.P = v; sa.c_begin = 0; sa.c_end = p.ncols;
             sa.rowval = reinterpret_cast<int64_t* const*>(x.out_ptrs.as<void*>());
-            sa.row_off_x = h->Sx.row_off; sa.row_off_u = h->Su.row_off; sa.sorted = p.cols_sorted ? 1 : 0;
+            sa.row_off_x = h->Sx.row_off; sa.row_off_u = h->Su.row_off; sa.sorted = p.cols_sorted ? 1 : 0; sa.runs = p.sets_are_runs ? 1 : 0;
             PIPE_CK(sls_launch_scatter(sa, h->stream));
         }
         x.ev_scat.record(h->stream);

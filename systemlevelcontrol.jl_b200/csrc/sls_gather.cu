@@ -119,22 +119,27 @@ sls_gather_count_kernel(SlsCsc A, SlsSupports Sx, SlsSupports Su, int T, int64_t
         const int64_t j = cols[c];
         // the index sets are kept (row stride cap) so that kernel 1b does not gather and sort them a second time
         const int n = sls_warp_index_set(A, Sx, T, Nx, j, buf, cap);
+        // [3]: some index set of the plan is NOT a run of consecutive rows (kernel 3 then stages the index sets; for banded
+        // plants it derives a row from the set's first row and the mask bit)
+        bool notrun = n > 1 && (buf[n - 1] - buf[0] != n - 1);
         if (keep_x)
 #pragma unroll 1
             for (int i = lane; i < n; i += 32) keep_x[(size_t)c * cap + i] = buf[i];
         __syncwarp();
         const int m = sls_warp_index_set(A, Su, T, Nx, j, buf, cap);
+        notrun = notrun || (m > 1 && (buf[m - 1] - buf[0] != m - 1));
         if (keep_u)
 #pragma unroll 1
             for (int i = lane; i < m; i += 32) keep_u[(size_t)c * cap + i] = buf[i];
         if (lane == 0) {
             n_out[c] = n; m_out[c] = m;
             // plan statistics on the device (the host reads 36 integers instead of 2 x ncols sizes): [0] max n, [1] max m,
-            // [2] overflow, [3] unused, [4 + k] columns of size class k (n in 8k+1..8k+8; class 15 = everything larger),
+            // [2] overflow, [3] some index set is not a run of consecutive rows, [4 + k] columns of size class k (n in 8k+1..8k+8; class 15 = everything larger),
             // [20 + k] largest m of class k
             if (stats) {
                 if (n < 0 || m < 0) atomicOr(s_stats + 2, 1);
                 else {
+                    if (notrun) atomicOr(s_stats + 3, 1);
                     atomicMax(s_stats + 0, n); atomicMax(s_stats + 1, m);
                     int k = n > 0 ? (n - 1) >> 3 : 0; if (k > 15) k = 15;
                     atomicAdd(s_stats + 4 + k, 1); atomicMax(s_stats + 20 + k, m);
@@ -146,7 +151,7 @@ sls_gather_count_kernel(SlsCsc A, SlsSupports Sx, SlsSupports Su, int T, int64_t
     if (stats && threadIdx.x < 36) {
         const int i = threadIdx.x, v = s_stats[i];
         if (v != 0) {                                         // every statistic starts at 0 and only grows
-            if (i == 2) atomicOr(stats + 2, v);
+            if (i == 2 || i == 3) atomicOr(stats + i, v);
             else if (i >= 4 && i < 20) atomicAdd(stats + i, v);
             else atomicMax(stats + i, v);
         }

@@ -6,7 +6,7 @@
 int sls_launch_gather_count(const SlsCsc& A, const SlsSupports& Sx, const SlsSupports& Su, int T, int64_t Nx,
                             const int32_t* cols, int ncols, int32_t* n_out, int32_t* m_out, int cap,
                             int32_t* keep_x, int32_t* keep_u, const int32_t* bad_supports, int32_t* stats, sls_stream_t stream);
-// stats (36 ints, zeroed by the caller): [0] max n, [1] max m, [2] overflow, [4+k] columns of size class k, [20+k] max m of class k
+// stats (36 ints, zeroed by the caller): [0] max n, [1] max m, [2] overflow, [3] some index set is not a run, [4+k] columns of size class k, [20+k] max m of class k
 int sls_launch_class_lists(const int32_t* n, int ncols, const int32_t* stats, int nclass, int32_t* lists, sls_stream_t stream);   // keep_*: [ncols][cap] index sets for kernel 1b, or null
 // layout check (rows in 1..nrow, strictly ascending per column) of the support columns [c0, c1) of every tap; sets *flag
 int sls_launch_validate_supports(const SlsSupports& S, int T, int64_t Nx, int64_t nrow, int64_t c0, int64_t c1, int32_t* flag,
@@ -96,6 +96,7 @@ struct SlsScatterArgs {
     int64_t* const* rowval;  // [2T] -> int64 rowval buffers (1-based out)
     int64_t row_off_x, row_off_u;   // added to the stored rows (global numbering of a sub-plant window's outputs)
     int sorted;              // the planned columns ascend: 32 consecutive planned columns own one contiguous rowval range
+    int runs;                // every index set of the plan is a run of consecutive rows: row = first row + mask bit (no staging)
 };
 int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream);
 int sls_launch_unscale(const SlsPlanView& P, int c_begin, int c_end, const int64_t* const* rowval, double* const* nzval,

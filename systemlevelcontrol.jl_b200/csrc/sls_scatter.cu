@@ -31,6 +31,9 @@ __device__ __forceinline__ int sls_select_bit(const uint32_t* words, int nwords,
 // column list) the 32 columns' segments are contiguous in rowval and the store address is base + e.
 // Shared memory per warp: 33 + 2 * 32 * stride ints (stride = nstride for the Φx taps, mstride for the Φu taps); the
 // launcher picks the warps per block that fit.
+// RUNS: every index set of the plan is a run of consecutive rows (banded plants; kernel 1a's statistics): a row is the set's
+// first row plus the mask bit, the index sets are not staged and a warp needs half the shared memory (twice the resident warps).
+template <bool RUNS>
 __global__ void __launch_bounds__(SCATTER_MAXW * 32)
 sls_scatter_kernel(SlsScatterArgs a, int wpb, int per_warp) {
     SLS_DYN_SMEM(smem);
@@ -44,15 +47,17 @@ sls_scatter_kernel(SlsScatterArgs a, int wpb, int per_warp) {
     if (c0 >= a.c_end) return;
     const int stride = isu ? P.mstride : P.nstride;
     int32_t* pref = reinterpret_cast<int32_t*>(smem) + (size_t)warp * per_warp;
-    int32_t* rows = pref + 33;                                // [32][stride] index sets of the 32 columns
-    int32_t* stage = rows + 32 * stride;
+    int32_t* rows = pref + 33;                                // [32][stride] index sets of the 32 columns (not with RUNS)
+    int32_t* stage = RUNS ? rows : rows + 32 * stride;
     const int c = c0 + lane;
     const bool valid = c < a.c_end;
     const int ncol = min(32, a.c_end - c0);
     const int nw = isu ? P.wu : P.wx;
     const uint32_t* mbase = isu ? P.masku : P.maskx;
     const uint32_t* mw = mbase + ((size_t)(valid ? c : c0) * T + t) * nw;
-    {
+    int32_t row0 = 0;
+    if (RUNS) { if (valid) row0 = ((isu ? P.su : P.sx))[(size_t)c * stride]; }
+    else {
         const int32_t* src = (isu ? P.su : P.sx) + (size_t)c0 * stride;
 #pragma unroll 4
         for (int i = lane; i < ncol * stride; i += 32) rows[i] = src[i];
@@ -76,7 +81,7 @@ sls_scatter_kernel(SlsScatterArgs a, int wpb, int per_warp) {
         for (int w = 0; w < nw; w++) {
             uint32_t v = mw[w];
 #pragma unroll 1
-            while (v) { const int b = __ffs(v) - 1; stage[o++] = myrows[32 * w + b]; v &= v - 1; }
+            while (v) { const int b = __ffs(v) - 1; stage[o++] = RUNS ? row0 + 32 * w + b : myrows[32 * w + b]; v &= v - 1; }
         }
     }
     __syncwarp();
@@ -97,16 +102,23 @@ sls_scatter_kernel(SlsScatterArgs a, int wpb, int per_warp) {
 int sls_launch_scatter(const SlsScatterArgs& a, sls_stream_t stream) {
     if (a.c_end <= a.c_begin) return 0;
     const int stride = a.P.nstride > a.P.mstride ? a.P.nstride : a.P.mstride;
-    const int per_warp = (33 + 2 * 32 * stride + 3) & ~3;     // ints
+    const bool runs = a.runs != 0;
+    const int per_warp = (33 + (runs ? 1 : 2) * 32 * stride + 3) & ~3;     // ints
     int wpb = (int)((96 * 1024) / ((size_t)per_warp * sizeof(int32_t)));
     if (wpb > SCATTER_MAXW) wpb = SCATTER_MAXW;
     if (wpb < 1) wpb = 1;
     const size_t smem = (size_t)wpb * per_warp * sizeof(int32_t);
-    auto kp = &sls_scatter_kernel;
-    if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
     const int per_block = wpb * 32;
     dim3 grid((a.c_end - a.c_begin + per_block - 1) / per_block, 2 * a.P.T, 1);
-    SLS_LAUNCH(kp, grid, wpb * 32, smem, stream, a, wpb, per_warp);
+    if (runs) {
+        auto kp = &sls_scatter_kernel<true>;
+        if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
+        SLS_LAUNCH(kp, grid, wpb * 32, smem, stream, a, wpb, per_warp);
+    } else {
+        auto kp = &sls_scatter_kernel<false>;
+        if (smem > 48 * 1024) { int e = rt::set_max_smem(kp, (int)smem); if (e) return e; }
+        SLS_LAUNCH(kp, grid, wpb * 32, smem, stream, a, wpb, per_warp);
+    }
     return rt::last_error();
 }
 
